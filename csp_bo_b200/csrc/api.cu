@@ -1,0 +1,272 @@
+// api.cu -- the C ABI of libcspbo_b200.so (include/cspbo_b200.h): error reporting, the resident
+// block builder and the 13 reference-compatible entry points built on top of it.
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "common.h"
+
+namespace cspbo {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
+                       double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
+                       cudaStream_t st);
+
+struct DevBuf {
+    double *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+};
+
+}  // namespace cspbo
+
+using namespace cspbo;
+
+extern "C" const char *cspbo_last_error(void) { return g_err; }
+extern "C" int cspbo_version(void) { return 100; }
+extern "C" long long cspbo_launch_count(void) { return g_launches.load(); }
+
+extern "C" int cspbo_set_device(int device)
+{
+    CSPBO_CUDA(cudaSetDevice(device));
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_device_count(int *count)
+{
+    if (!count) { set_error("device_count: null"); return CSPBO_E_ARG; }
+    *count = 0;
+    CSPBO_CUDA(cudaGetDeviceCount(count));
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_synchronize(void)
+{
+    CSPBO_CUDA(cudaDeviceSynchronize());
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b,
+                                 double *out, double *out_grad, int mem, int accumulate)
+{
+    if (!desc || !a || !b || !out) { set_error("block_build: null argument"); return CSPBO_E_ARG; }
+    const cspbo_block_desc &d = *desc;
+    if (d.family != CSPBO_DOT && d.family != CSPBO_RBF) { set_error("block_build: bad family %d", d.family); return CSPBO_E_ARG; }
+    if (d.block < CSPBO_KEE || d.block > CSPBO_KFF) { set_error("block_build: bad block %d", d.block); return CSPBO_E_ARG; }
+    const bool grad = d.family == CSPBO_RBF && d.with_grad;
+    if (grad && !out_grad) { set_error("block_build: with_grad needs out_grad"); return CSPBO_E_ARG; }
+    if (grad && d.stress) { set_error("block_build: with_grad and stress are exclusive"); return CSPBO_E_ARG; }
+    if (d.family == CSPBO_RBF && !(d.l > 0.0)) { set_error("block_build: RBF needs l > 0"); return CSPBO_E_ARG; }
+    if (d.symmetric && (a != b || d.stress || d.block == CSPBO_KEF)) {
+        set_error("block_build: symmetric needs a == b, no stress, K_EE or K_FF");
+        return CSPBO_E_ARG;
+    }
+    const long long m1 = a->m, m2 = b->m;
+    long long si, sk, sj, sl, n_out, n_grad = 0;
+    int passesA = 1, passesB = 1;
+    if (d.block == CSPBO_KEE) {
+        if (a->nc != 0 || b->nc != 0) { set_error("block_build: K_EE needs two energy packs"); return CSPBO_E_ARG; }
+        si = m2; sk = 0; sj = 1; sl = 0; n_out = m1 * m2; n_grad = n_out;
+    } else if (d.block == CSPBO_KEF) {
+        const int nc = d.stress ? 9 : 3;
+        if (a->nc != 0 || b->nc < nc) { set_error("block_build: K_EF needs (energy, force[nc>=%d]) packs", nc); return CSPBO_E_ARG; }
+        si = m2 * nc; sk = 0; sj = nc; sl = 1; n_out = m1 * m2 * nc; n_grad = m1 * m2 * 3;
+        passesB = nc / 3;
+    } else {
+        const int nc1 = d.stress ? 9 : 3;
+        if (a->nc < nc1 || b->nc < 3) { set_error("block_build: K_FF needs (force[nc>=%d], force) packs", nc1); return CSPBO_E_ARG; }
+        si = nc1 * m2 * 3; sk = m2 * 3; sj = 3; sl = 1; n_out = m1 * nc1 * m2 * 3; n_grad = m1 * 3 * m2 * 3;
+        passesA = nc1 / 3;
+    }
+    if (n_out == 0) return CSPBO_OK;
+
+    double *dout = out, *dgrad = out_grad;
+    DevBuf tmp, tmpg;
+    if (mem == CSPBO_MEM_HOST) {
+        CSPBO_CUDA(cudaMalloc(&tmp.p, (size_t)n_out * sizeof(double)));
+        dout = tmp.p;
+        if (accumulate) CSPBO_CUDA(cudaMemcpyAsync(dout, out, (size_t)n_out * sizeof(double), cudaMemcpyHostToDevice));
+        else CSPBO_CUDA(cudaMemsetAsync(dout, 0, (size_t)n_out * sizeof(double)));
+        if (grad) {
+            CSPBO_CUDA(cudaMalloc(&tmpg.p, (size_t)n_grad * sizeof(double)));
+            dgrad = tmpg.p;
+            if (accumulate) CSPBO_CUDA(cudaMemcpyAsync(dgrad, out_grad, (size_t)n_grad * sizeof(double), cudaMemcpyHostToDevice));
+            else CSPBO_CUDA(cudaMemsetAsync(dgrad, 0, (size_t)n_grad * sizeof(double)));
+        }
+    } else if (!accumulate) {
+        CSPBO_CUDA(cudaMemsetAsync(dout, 0, (size_t)n_out * sizeof(double)));
+        if (grad) CSPBO_CUDA(cudaMemsetAsync(dgrad, 0, (size_t)n_grad * sizeof(double)));
+    }
+
+    for (int pa = 0; pa < passesA; pa++)
+        for (int pb = 0; pb < passesB; pb++) {
+            // stress: the 9 derivative columns are processed as three independent triplets
+            const long long off = (d.block == CSPBO_KFF) ? (long long)pa * 3 * sk : (long long)pb * 3 * sl;
+            int rc = build_block_device(d, a, b, pa * 3, pb * 3, dout + off, dgrad, si, sk, sj, sl, 0);
+            if (rc) return rc;
+        }
+
+    if (mem == CSPBO_MEM_HOST) {
+        CSPBO_CUDA(cudaMemcpyAsync(out, dout, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost));
+        if (grad) CSPBO_CUDA(cudaMemcpyAsync(out_grad, dgrad, (size_t)n_grad * sizeof(double), cudaMemcpyDeviceToHost));
+        CSPBO_CUDA(cudaStreamSynchronize(0));
+    }
+    return CSPBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// reference-compatible entry points
+// ------------------------------------------------------------------------------------------
+namespace {
+
+struct PackGuard {
+    cspbo_pack *p = nullptr;
+    ~PackGuard() { cspbo_pack_destroy(p); }
+};
+
+int groups_of(const int *inds, int n)
+{
+    int m = 0;
+    for (int i = 0; i < n; i++) m = std::max(m, inds[i] + 1);
+    return m;
+}
+
+// `interleaved_grad`: RBF kef_many_with_grad writes K and dK/dl into one [m1,m2,6] array.
+int compat_block(int family, int block, int n1, int n2, int n2_start, int n2_end, int d, int x2i, double zeta,
+                 double sigma2, double sigma02, double l, double tol, int use_tol, int with_grad, int stress,
+                 const double *x1, const double *dx1dr, const int *ele1, const int *x1_inds,
+                 const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds,
+                 double *pout, double *dpout_dl)
+{
+    if (n1 < 0 || n2 < 0 || x2i < 0 || !pout) { set_error("bad sizes or null pout"); return CSPBO_E_ARG; }
+    if (n1 == 0 || n2 == 0 || x2i == 0) return CSPBO_OK;
+    const int m1 = groups_of(x1_inds, n1);
+    PackGuard A, B;
+    int rc;
+    const int nc1 = (block == CSPBO_KFF) ? (stress ? 9 : 3) : 0;
+    const int nc2 = (block == CSPBO_KEE) ? 0 : ((block == CSPBO_KEF && stress) ? 9 : 3);
+    rc = cspbo_pack_create(n1, d, nc1, m1, 0, n1, x1, nc1 ? dx1dr : nullptr, ele1, x1_inds, CSPBO_MEM_HOST, &A.p);
+    if (rc) return rc;
+    rc = cspbo_pack_create(n2, d, nc2, x2i, n2_start, n2_end, x2, nc2 ? dx2dr : nullptr, ele2, x2_inds,
+                           CSPBO_MEM_HOST, &B.p);
+    if (rc) return rc;
+    cspbo_block_desc desc;
+    memset(&desc, 0, sizeof(desc));
+    desc.family = family; desc.block = block; desc.zeta = zeta;
+    desc.sigma2 = sigma2; desc.sigma02 = sigma02; desc.l = l; desc.tol = tol; desc.use_tol = use_tol;
+    desc.with_grad = with_grad; desc.stress = stress;
+    // Dot K_EE: the reference multiplies by sigma2 inside C (dot_kernel.cpp:47); RBF carries sigma2 in K
+    desc.scale = (family == CSPBO_DOT && block == CSPBO_KEE) ? sigma2 : 1.0;
+    desc.scale_grad = 1.0;
+    desc.symmetric = 0;
+    if (with_grad && block == CSPBO_KEF) {
+        // interleaved [m1,m2,6] output: run K and dK/dl through the strided device path by hand
+        const long long m2 = x2i, n_out = (long long)m1 * m2 * 6;
+        DevBuf tmp;
+        CSPBO_CUDA(cudaMalloc(&tmp.p, (size_t)n_out * sizeof(double)));
+        CSPBO_CUDA(cudaMemcpyAsync(tmp.p, pout, (size_t)n_out * sizeof(double), cudaMemcpyHostToDevice));
+        rc = build_block_device(desc, A.p, B.p, 0, 0, tmp.p, tmp.p + 3, m2 * 6, 0, 6, 1, 0);
+        if (rc) return rc;
+        CSPBO_CUDA(cudaMemcpyAsync(pout, tmp.p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost));
+        CSPBO_CUDA(cudaStreamSynchronize(0));
+        return CSPBO_OK;
+    }
+    return cspbo_block_build(&desc, A.p, B.p, pout, dpout_dl, CSPBO_MEM_HOST, /*accumulate=*/1);
+}
+
+}  // namespace
+
+#define XE const double *x1, const int *ele1, const int *x1_inds
+#define XF2 const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds
+#define XF1 const double *x1, const double *dx1dr, const int *ele1, const int *x1_inds
+
+extern "C" int cspbo_dot_kee_many(int n1, int n2, int d, int x2i, double zeta, double sigma2, double sigma02, XE,
+                                  const double *x2, const int *ele2, const int *x2_inds, double *pout)
+{
+    return compat_block(CSPBO_DOT, CSPBO_KEE, n1, n2, 0, n2, d, x2i, zeta, sigma2, sigma02, 0, 0, 0, 0, 0,
+                        x1, nullptr, ele1, x1_inds, x2, nullptr, ele2, x2_inds, pout, nullptr);
+}
+extern "C" int cspbo_dot_kef_many(int n1, int n2, int d, int x2i, double zeta, XE, XF2, double *pout)
+{
+    return compat_block(CSPBO_DOT, CSPBO_KEF, n1, n2, 0, n2, d, x2i, zeta, 1, 0, 0, 0, 0, 0, 0,
+                        x1, nullptr, ele1, x1_inds, x2, dx2dr, ele2, x2_inds, pout, nullptr);
+}
+extern "C" int cspbo_dot_kef_many_stress(int n1, int n2, int d, int x2i, double zeta, XE, XF2, double *pout)
+{
+    return compat_block(CSPBO_DOT, CSPBO_KEF, n1, n2, 0, n2, d, x2i, zeta, 1, 0, 0, 0, 0, 0, 1,
+                        x1, nullptr, ele1, x1_inds, x2, dx2dr, ele2, x2_inds, pout, nullptr);
+}
+extern "C" int cspbo_dot_kff_many(int n1, int n2, int n2_start, int n2_end, int d, int x2i, double zeta, XF1, XF2,
+                                  double *pout)
+{
+    return compat_block(CSPBO_DOT, CSPBO_KFF, n1, n2, n2_start, n2_end, d, x2i, zeta, 1, 0, 0, 0, 0, 0, 0,
+                        x1, dx1dr, ele1, x1_inds, x2, dx2dr, ele2, x2_inds, pout, nullptr);
+}
+extern "C" int cspbo_dot_kff_many_stress(int n1, int n2, int n2_start, int n2_end, int d, int x2i, double zeta, XF1,
+                                         XF2, double *pout)
+{
+    return compat_block(CSPBO_DOT, CSPBO_KFF, n1, n2, n2_start, n2_end, d, x2i, zeta, 1, 0, 0, 0, 0, 0, 1,
+                        x1, dx1dr, ele1, x1_inds, x2, dx2dr, ele2, x2_inds, pout, nullptr);
+}
+
+extern "C" int cspbo_rbf_kee_many(int n1, int n2, int d, int x2i, double zeta, double sigma2, double l2, XE,
+                                  const double *x2, const int *ele2, const int *x2_inds, double *pout)
+{
+    return compat_block(CSPBO_RBF, CSPBO_KEE, n1, n2, 0, n2, d, x2i, zeta, sigma2, 0, sqrt(l2), 0, 0, 0, 0,
+                        x1, nullptr, ele1, x1_inds, x2, nullptr, ele2, x2_inds, pout, nullptr);
+}
+extern "C" int cspbo_rbf_kee_many_with_grad(int n1, int n2, int d, int x2i, double zeta, double sigma2, double l2, XE,
+                                            const double *x2, const int *ele2, const int *x2_inds, double *pout,
+                                            double *dpout_dl)
+{
+    if (!dpout_dl) { set_error("kee_many_with_grad: null dpout_dl"); return CSPBO_E_ARG; }
+    return compat_block(CSPBO_RBF, CSPBO_KEE, n1, n2, 0, n2, d, x2i, zeta, sigma2, 0, sqrt(l2), 0, 0, 1, 0,
+                        x1, nullptr, ele1, x1_inds, x2, nullptr, ele2, x2_inds, pout, dpout_dl);
+}
+extern "C" int cspbo_rbf_kef_many(int n1, int n2, int d, int x2i, double zeta, double sigma2, double l2, XE, XF2,
+                                  double *pout)
+{
+    return compat_block(CSPBO_RBF, CSPBO_KEF, n1, n2, 0, n2, d, x2i, zeta, sigma2, 0, sqrt(l2), 0, 0, 0, 0,
+                        x1, nullptr, ele1, x1_inds, x2, dx2dr, ele2, x2_inds, pout, nullptr);
+}
+extern "C" int cspbo_rbf_kef_many_with_grad(int n1, int n2, int d, int x2i, double zeta, double sigma2, double l, XE,
+                                            XF2, double *pout)
+{
+    return compat_block(CSPBO_RBF, CSPBO_KEF, n1, n2, 0, n2, d, x2i, zeta, sigma2, 0, l, 0, 0, 1, 0,
+                        x1, nullptr, ele1, x1_inds, x2, dx2dr, ele2, x2_inds, pout, nullptr);
+}
+extern "C" int cspbo_rbf_kef_many_stress(int n1, int n2, int d, int x2i, double zeta, double sigma2, double l2, XE,
+                                         XF2, double *pout)
+{
+    return compat_block(CSPBO_RBF, CSPBO_KEF, n1, n2, 0, n2, d, x2i, zeta, sigma2, 0, sqrt(l2), 0, 0, 0, 1,
+                        x1, nullptr, ele1, x1_inds, x2, dx2dr, ele2, x2_inds, pout, nullptr);
+}
+extern "C" int cspbo_rbf_kff_many(int n1, int n2, int n2_start, int n2_end, int d, int x2i, double zeta,
+                                  double sigma2, double l2, double tol, XF1, XF2, double *pout)
+{
+    return compat_block(CSPBO_RBF, CSPBO_KFF, n1, n2, n2_start, n2_end, d, x2i, zeta, sigma2, 0, sqrt(l2), tol, 1, 0,
+                        0, x1, dx1dr, ele1, x1_inds, x2, dx2dr, ele2, x2_inds, pout, nullptr);
+}
+extern "C" int cspbo_rbf_kff_many_with_grad(int n1, int n2, int n2_start, int n2_end, int d, int x2i, double zeta,
+                                            double sigma2, double l, XF1, XF2, double *pout, double *dpout_dl)
+{
+    if (!dpout_dl) { set_error("kff_many_with_grad: null dpout_dl"); return CSPBO_E_ARG; }
+    return compat_block(CSPBO_RBF, CSPBO_KFF, n1, n2, n2_start, n2_end, d, x2i, zeta, sigma2, 0, l, 0, 0, 1, 0,
+                        x1, dx1dr, ele1, x1_inds, x2, dx2dr, ele2, x2_inds, pout, dpout_dl);
+}
+extern "C" int cspbo_rbf_kff_many_stress(int n1, int n2, int n2_start, int n2_end, int d, int x2i, double zeta,
+                                         double sigma2, double l2, double tol, XF1, XF2, double *pout)
+{
+    return compat_block(CSPBO_RBF, CSPBO_KFF, n1, n2, n2_start, n2_end, d, x2i, zeta, sigma2, 0, sqrt(l2), tol, 1, 0,
+                        1, x1, dx1dr, ele1, x1_inds, x2, dx2dr, ele2, x2_inds, pout, nullptr);
+}

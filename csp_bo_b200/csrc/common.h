@@ -1,0 +1,65 @@
+// common.h -- shared declarations of libcspbo_b200 (host side)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "cspbo_b200.h"
+
+namespace cspbo {
+
+void set_error(const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define CSPBO_CUDA(call)                                                                     \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            cspbo::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                    \
+                             cudaGetErrorString(e__));                                       \
+            return (e__ == cudaErrorMemoryAllocation) ? CSPBO_E_NOMEM                        \
+                   : (e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver)        \
+                       ? CSPBO_E_NODEVICE                                                    \
+                       : CSPBO_E_CUDA;                                                       \
+        }                                                                                    \
+    } while (0)
+
+// Tile geometry.  A tile holds 8 row slots; slot r of every tile of a block belongs to the same
+// group (structure / force atom).  Each slot carries NV vectors (the unit descriptor u and,
+// for force packs, the nc projected+scaled derivative vectors) of 4*KS doubles, stored in
+// mma.m8n8k4 fragment order so that one 128-bit load per lane fetches a lane's operands for
+// two consecutive k-steps:
+//     index(v, f, slot) = ((v*(KS/2) + f/8)*32 + slot*4 + f%4)*2 + (f/4)%2
+constexpr int kSlots = 8;
+
+inline int ksteps_for(int d)
+{
+    if (d <= 0) return -1;
+    if (d <= 24) return 6;
+    if (d <= 56) return 14;
+    return -1;
+}
+
+}  // namespace cspbo
+
+// The opaque pack object of the C ABI.
+struct cspbo_pack {
+    int n = 0, d = 0, nc = 0, m = 0, nv = 0, ks = 0;
+    int device = 0;
+    long long n_tiles = 0, n_blocks = 0;
+    long long tile_doubles = 0;
+    // host-side plan
+    std::vector<int> species;      // sorted species ids present in the packed rows
+    std::vector<int> blk0;         // first block of each species bucket (size ns+1)
+    std::vector<int> h_tile_start; // first tile of each block (size n_blocks+1)
+    std::vector<long long> rows_per_species;
+    // device-side tables
+    double *d_tiles = nullptr;
+    int *d_tile_start = nullptr;
+    int *d_slot_group = nullptr;     // [n_blocks*8] group id of each slot, -1 = empty
+    unsigned *d_tile_valid = nullptr;  // [n_tiles] bit r set <=> slot r holds a row with |x|>1e-8
+    long long bytes = 0;
+};

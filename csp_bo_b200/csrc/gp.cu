@@ -1,0 +1,152 @@
+// gp.cu -- GP algebra that consumes the covariance blocks on the device
+// (reference cspbo/gaussianprocess.py:105-127 fit, :138-141 / :359-366 prediction).
+//   noise add + K*.alpha GEMV : hand-written HBM-bound kernels
+//   Cholesky factorisation / solve : cuSOLVER potrf / potrs (as BASELINE.json's north_star asks)
+#include <cusolverDn.h>
+
+#include <mutex>
+
+#include "common.h"
+
+namespace cspbo {
+
+__global__ void add_noise_kernel(double *K, int N, int n_energy, double ne2, double nf2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) K[(size_t)i * N + i] += (i < n_energy) ? ne2 : nf2;
+}
+
+// pred[r] = sum_j Kstar[r, j] alpha[j]; one warp per row, 128-bit coalesced loads, each K* byte read once
+__global__ void predict_gemv_kernel(const double *__restrict__ Ks, int n, int N, const double *__restrict__ alpha,
+                                    double *__restrict__ pred)
+{
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const double *kr = Ks + row * (long long)N;
+    double acc = 0.0;
+    if ((N & 1) == 0 && ((reinterpret_cast<size_t>(kr) & 15) == 0)) {
+        const double2 *k2 = reinterpret_cast<const double2 *>(kr);
+        const double2 *a2 = reinterpret_cast<const double2 *>(alpha);
+        for (int j = lane; j < (N >> 1); j += 32) {
+            const double2 kv = k2[j];
+            const double2 av = __ldg(a2 + j);
+            acc = fma(kv.x, av.x, acc);
+            acc = fma(kv.y, av.y, acc);
+        }
+    } else {
+        for (int j = lane; j < N; j += 32) acc = fma(kr[j], __ldg(alpha + j), acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) pred[row] = acc;
+}
+
+__global__ void logdet_kernel(const double *L, int N, double *out)
+{
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) acc += log(L[(size_t)i * N + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) *out = 2.0 * acc;
+    }
+}
+
+static std::mutex g_solver_mu;
+static cusolverDnHandle_t g_solver[64] = {nullptr};
+
+static int solver_handle(cusolverDnHandle_t *h)
+{
+    int dev = 0;
+    CSPBO_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_solver_mu);
+    if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return CSPBO_E_ARG; }
+    if (!g_solver[dev]) {
+        cusolverStatus_t s = cusolverDnCreate(&g_solver[dev]);
+        if (s != CUSOLVER_STATUS_SUCCESS) { set_error("cusolverDnCreate failed (%d)", (int)s); return CSPBO_E_SOLVER; }
+    }
+    *h = g_solver[dev];
+    return CSPBO_OK;
+}
+
+}  // namespace cspbo
+
+using namespace cspbo;
+
+extern "C" int cspbo_gp_add_noise(double *K, int N, int n_energy, double noise_e, double f_coef)
+{
+    if (!K || N < 0) { set_error("gp_add_noise: bad argument"); return CSPBO_E_ARG; }
+    if (N == 0) return CSPBO_OK;
+    const double nf = f_coef * noise_e;
+    add_noise_kernel<<<(N + 255) / 256, 256>>>(K, N, n_energy, noise_e * noise_e, nf * nf);
+    g_launches++;
+    CSPBO_CUDA(cudaGetLastError());
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_gp_cholesky_solve(double *K, int N, double *y, int nrhs, double *logdet)
+{
+    if (!K || N <= 0 || (nrhs > 0 && !y)) { set_error("gp_cholesky_solve: bad argument"); return CSPBO_E_ARG; }
+    cusolverDnHandle_t h;
+    int rc = solver_handle(&h);
+    if (rc) return rc;
+    int lwork = 0;
+    // K is symmetric, so its row-major image is also its column-major image.
+    const cublasFillMode_t uplo = CUBLAS_FILL_MODE_LOWER;
+    cusolverStatus_t s = cusolverDnDpotrf_bufferSize(h, uplo, N, K, N, &lwork);
+    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
+    double *work = nullptr;
+    int *info = nullptr;
+    CSPBO_CUDA(cudaMalloc(&work, (size_t)std::max(lwork, 1) * sizeof(double)));
+    cudaError_t e = cudaMalloc(&info, sizeof(int));
+    if (e != cudaSuccess) { cudaFree(work); set_error("cudaMalloc(info) failed"); return CSPBO_E_NOMEM; }
+    int hinfo = 0;
+    s = cusolverDnDpotrf(h, uplo, N, K, N, work, lwork, info);
+    cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
+    if (s != CUSOLVER_STATUS_SUCCESS || hinfo != 0) {
+        cudaFree(work); cudaFree(info);
+        if (hinfo > 0) { set_error("K is not positive definite (leading minor %d)", hinfo); return CSPBO_E_NOTPD; }
+        set_error("potrf failed (status %d, info %d)", (int)s, hinfo);
+        return CSPBO_E_SOLVER;
+    }
+    if (nrhs > 0) {
+        s = cusolverDnDpotrs(h, uplo, N, nrhs, K, N, y, N, info);
+        cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
+        if (s != CUSOLVER_STATUS_SUCCESS || hinfo != 0) {
+            cudaFree(work); cudaFree(info);
+            set_error("potrs failed (status %d, info %d)", (int)s, hinfo);
+            return CSPBO_E_SOLVER;
+        }
+    }
+    if (logdet) {
+        double *dl = nullptr;
+        if (cudaMalloc(&dl, sizeof(double)) == cudaSuccess) {
+            logdet_kernel<<<1, 1024>>>(K, N, dl);
+            g_launches++;
+            cudaMemcpy(logdet, dl, sizeof(double), cudaMemcpyDeviceToHost);
+            cudaFree(dl);
+        }
+    }
+    cudaFree(work);
+    cudaFree(info);
+    CSPBO_CUDA(cudaGetLastError());
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_gp_predict(const double *Kstar, int n, int N, const double *alpha, double *pred)
+{
+    if (n < 0 || N < 0 || (n > 0 && (!Kstar || !pred)) || (N > 0 && !alpha)) { set_error("gp_predict: bad argument"); return CSPBO_E_ARG; }
+    if (n == 0) return CSPBO_OK;
+    const int wpb = 8;
+    predict_gemv_kernel<<<(n + wpb - 1) / wpb, wpb * 32>>>(Kstar, n, N, alpha, pred);
+    g_launches++;
+    CSPBO_CUDA(cudaGetLastError());
+    return CSPBO_OK;
+}

@@ -1,0 +1,381 @@
+// tiles.cu -- the covariance-block tile kernels (K_EE / K_EF / K_FF, Dot and RBF) for sm_100a.
+//
+// One templated kernel family replaces the 13 scalar loops of the reference
+// (cspbo/kernels/dot_kernel.cpp:4-506, rbf_kernel.cpp:4-822).  For a pair of packed 8-group
+// blocks (pack.cu) of one species, every 8x8 tile pair costs NV1*NV2*KS FP64 tensor-core
+// instructions (DMMA.8x8x4, the only FP64 MMA shape sm_100a has natively) that produce, per
+// thread and for two (row a, row b) pairs, the full set of dot products
+//     H[0][0] = c = u_a.u_b      H[k][0] = P_k = A^_a[:,k].u_b
+//     H[0][l] = Q_l = u_a.A^_b[:,l]   H[k][l] = T_kl = A^_a[:,k].A^_b[:,l]
+// followed by the zeta / exp chain rule in registers:
+//     Dot K_FF  (dot_kernel.cpp:265-323):   F_kl = c^(z-1) T_kl + (z-1) c^(z-2) P_k Q_l
+//     RBF K_FF  (rbf_kernel.cpp:390-462):   F_kl = dK/dD [ z c^(z-1) T_kl
+//                                               + (z(z-1)c^(z-2) + z^2 c^(2z-2)/(2l^2)) P_k Q_l ]
+//     K_EF      (dot_kernel.cpp:102-121, rbf_kernel.cpp:141-164):  z c^(z-1) Q_l  (x -dK/dD for RBF)
+//     K_EE      (dot_kernel.cpp:45-47, rbf_kernel.cpp:41-43)
+// Because slot r of every tile of a block is the same group, the reference's scatter-add over
+// (row a in group i, row b in group j) is a plain register accumulation; each thread owns the
+// 3x3 (or 1x3, 1x1) output blocks of two fixed group pairs and writes them once.
+#include <algorithm>
+
+#include "common.h"
+
+namespace cspbo {
+
+struct SideDev {
+    const double *tiles;
+    const int *tile_start;
+    const int *slot_group;
+    const unsigned *tile_valid;
+    int tile_doubles;  // NV*KS*32
+    int voff;          // first derivative vector used is 1+voff
+};
+
+struct TileParams {
+    SideDev A, B;
+    int a_blk0, a_nblk, b_blk0, b_nblk;
+    int tbc;  // B tiles per shared-memory chunk
+    int symmetric;
+    double zeta, sigma2, sigma02, inv2l2, inv_l, inv_l3, tol;
+    int use_tol;
+    double scale, scale_grad;
+    double *out, *out_grad;
+    long long si, sk, sj, sl;  // out index = i*si + k*sk + j*sj + l*sl
+};
+
+enum { MODE_KEE = 0, MODE_KEF = 1, MODE_KFF = 2 };
+enum { FAM_DOT = 0, FAM_RBF = 1, FAM_RBF_GRAD = 2 };
+
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// Per-pair scalar weights of the chain rule.
+struct Weights {
+    double w1, w2;    // F = w1*T + w2*P*Q            (kff)   | kef: w1*Q | kee: w1
+    double g1, g2;    // d/dl companion: w1g*T + w2g*P*Q      | kef: g1*Q | kee: g1
+};
+
+template <int MODE, int FAM, bool Z2>
+__device__ __forceinline__ Weights pair_weights(double c, bool valid, const TileParams &p)
+{
+    Weights w;
+    w.g1 = w.g2 = 0.0;
+    const double z = p.zeta;
+    // powers of c
+    double cm2, cm1, cz;  // c^(z-2), c^(z-1), c^z
+    if (Z2) {
+        cm2 = 1.0; cm1 = c; cz = c * c;
+    } else {
+        cm2 = pow(c, z - 2.0);   // reference: d2 = pow(dx, zeta-2); d1 = dx*d2  (dot_kernel.cpp:265-267)
+        cm1 = c * cm2;
+        cz = (MODE == MODE_KFF) ? c * cm1 : pow(c, z);
+        if (MODE == MODE_KEF) cm1 = pow(c, z - 1.0);  // dot_kernel.cpp:102
+    }
+    if (FAM == FAM_DOT) {
+        if (MODE == MODE_KFF) { w.w1 = cm1; w.w2 = (z - 1.0) * cm2; }
+        else if (MODE == MODE_KEF) { w.w1 = z * cm1; w.w2 = 0.0; }
+        else { w.w1 = cz + p.sigma02; w.w2 = 0.0; }  // sigma2 applied through p.scale
+    } else {
+        const double K = p.sigma2 * exp(-(1.0 - cz) * p.inv2l2);
+        const double dKdD = K * p.inv2l2;
+        const double gl = (cz - 1.0) * p.inv_l3 + 2.0 * p.inv_l;  // (D-1)/l^3 + 2/l
+        if (MODE == MODE_KFF) {
+            const double dD = z * cm1;                 // dD/dc
+            const double ml = dD * dD * p.inv2l2;      // (1/(2l^2)) (dD/dc)^2
+            w.w1 = dKdD * dD;
+            w.w2 = dKdD * (z * (z - 1.0) * cm2 + ml);
+            if (FAM == FAM_RBF_GRAD) {
+                // dpout_dl -= F*gl + (2/l) dK/dD ml P Q      (rbf_kernel.cpp:621-629)
+                w.g1 = -gl * w.w1;
+                w.g2 = -(gl * w.w2 + 2.0 * p.inv_l * dKdD * ml);
+            }
+            if (p.use_tol && !(dKdD > p.tol)) valid = false;  // rbf_kernel.cpp:394
+        } else if (MODE == MODE_KEF) {
+            w.w1 = -dKdD * z * cm1;                    // pout -= C  (rbf_kernel.cpp:162-164)
+            w.w2 = 0.0;
+            if (FAM == FAM_RBF_GRAD) w.g1 = -w.w1 * gl;  // pout[3+l] += C*gl (rbf_kernel.cpp:244-246)
+        } else {
+            w.w1 = K; w.w2 = 0.0;
+            if (FAM == FAM_RBF_GRAD) w.g1 = K * (1.0 - cz);  // rbf_kernel.cpp:92
+        }
+    }
+    if (!valid) { w.w1 = w.w2 = w.g1 = w.g2 = 0.0; }
+    return w;
+}
+
+template <int MODE, int FAM, int KS, bool Z2>
+__global__ void __launch_bounds__(256) block_tile_kernel(const TileParams p)
+{
+    constexpr int NV1 = (MODE == MODE_KFF) ? 4 : 1;
+    constexpr int NV2 = (MODE == MODE_KEE) ? 1 : 4;
+    constexpr int NC1 = (MODE == MODE_KFF) ? 3 : 1;
+    constexpr int NC2 = (MODE == MODE_KEE) ? 1 : 3;
+    constexpr bool GRAD = (FAM == FAM_RBF_GRAD);
+    constexpr int HALF = KS / 2;
+
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int npg = (p.a_nblk + nwarps - 1) / nwarps;
+    const int pg = blockIdx.x % npg;
+    const int q = blockIdx.x / npg;
+    const int a_rel = pg * nwarps + warp;
+    const int b_rel = q;
+    bool active = a_rel < p.a_nblk;
+    // symmetric build: only blocks with b >= a are computed (mirrored at write time)
+    if (p.symmetric && b_rel < a_rel) active = false;
+    const int a_blk = p.a_blk0 + (active ? a_rel : 0);
+    const int b_blk = p.b_blk0 + b_rel;
+
+    const int a_t0 = p.A.tile_start[a_blk];
+    const int Ta = active ? p.A.tile_start[a_blk + 1] - a_t0 : 0;
+    const int b_t0 = p.B.tile_start[b_blk];
+    const int Tb = p.B.tile_start[b_blk + 1] - b_t0;
+
+    double *sB = smem;
+    unsigned *sBvalid = reinterpret_cast<unsigned *>(smem + (size_t)p.tbc * p.B.tile_doubles);
+
+    double acc[2][NC1][NC2];
+    double accg[2][GRAD ? NC1 : 1][GRAD ? NC2 : 1];
+#pragma unroll
+    for (int e = 0; e < 2; e++)
+#pragma unroll
+        for (int k = 0; k < NC1; k++)
+#pragma unroll
+            for (int l = 0; l < NC2; l++) {
+                acc[e][k][l] = 0.0;
+                if (GRAD) accg[e][k][l] = 0.0;
+            }
+
+    const int ar = lane >> 2;        // a slot of this thread's accumulator rows
+    const int bq = (lane & 3) * 2;   // first of its two b slots
+
+    for (int c0 = 0; c0 < Tb; c0 += p.tbc) {
+        const int nt = min(p.tbc, Tb - c0);
+        __syncthreads();
+        {   // cooperative, coalesced 128-bit copy of nt consecutive B tiles
+            const double2 *src = reinterpret_cast<const double2 *>(p.B.tiles + (size_t)(b_t0 + c0) * p.B.tile_doubles);
+            double2 *dst = reinterpret_cast<double2 *>(sB);
+            const int n2 = nt * (p.B.tile_doubles >> 1);
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
+            for (int i = threadIdx.x; i < nt; i += blockDim.x) sBvalid[i] = p.B.tile_valid[b_t0 + c0 + i];
+        }
+        __syncthreads();
+
+        for (int ta = 0; ta < Ta; ta++) {
+            // A fragments of this slab: registers for the whole sweep over the chunk
+            double a[NV1][KS];
+            const double2 *at = reinterpret_cast<const double2 *>(p.A.tiles + (size_t)(a_t0 + ta) * p.A.tile_doubles);
+#pragma unroll
+            for (int v = 0; v < NV1; v++) {
+                const int tv = (v == 0) ? 0 : (p.A.voff + v);
+#pragma unroll
+                for (int h = 0; h < HALF; h++) {
+                    const double2 t = __ldg(at + (tv * HALF + h) * 32 + lane);
+                    a[v][2 * h] = t.x;
+                    a[v][2 * h + 1] = t.y;
+                }
+            }
+            const unsigned va = p.A.tile_valid[a_t0 + ta];
+            const bool a_ok = (va >> ar) & 1u;
+
+            for (int tb = 0; tb < nt; tb++) {
+                double H[NV1][NV2][2];
+#pragma unroll
+                for (int v1 = 0; v1 < NV1; v1++)
+#pragma unroll
+                    for (int v2 = 0; v2 < NV2; v2++) H[v1][v2][0] = H[v1][v2][1] = 0.0;
+
+                const double2 *bt = reinterpret_cast<const double2 *>(sB + (size_t)tb * p.B.tile_doubles);
+#pragma unroll
+                for (int h = 0; h < HALF; h++) {
+#pragma unroll
+                    for (int v2 = 0; v2 < NV2; v2++) {
+                        const int tv = (v2 == 0) ? 0 : (p.B.voff + v2);
+                        const double2 b = bt[(tv * HALF + h) * 32 + lane];
+#pragma unroll
+                        for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h], b.x);
+#pragma unroll
+                        for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h + 1], b.y);
+                    }
+                }
+
+                const unsigned vb = sBvalid[tb];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const bool ok = a_ok && ((vb >> (bq + e)) & 1u);
+                    const double c = H[0][0][e];
+                    if (MODE == MODE_KFF && FAM == FAM_DOT && Z2) {
+                        // zeta = 2: F = c*T + P*Q; padded rows are all-zero so no masking is needed
+#pragma unroll
+                        for (int k = 0; k < 3; k++)
+#pragma unroll
+                            for (int l = 0; l < 3; l++) {
+                                acc[e][k][l] = fma(c, H[k + 1][l + 1][e], acc[e][k][l]);
+                                acc[e][k][l] = fma(H[k + 1][0][e], H[0][l + 1][e], acc[e][k][l]);
+                            }
+                    } else {
+                        const Weights w = pair_weights<MODE, FAM, Z2>(c, ok, p);
+                        if (MODE == MODE_KFF) {
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                const double pk = H[k + 1][0][e];
+                                const double w2p = w.w2 * pk;
+                                const double g2p = GRAD ? w.g2 * pk : 0.0;
+#pragma unroll
+                                for (int l = 0; l < 3; l++) {
+                                    acc[e][k][l] = fma(w.w1, H[k + 1][l + 1][e], acc[e][k][l]);
+                                    acc[e][k][l] = fma(w2p, H[0][l + 1][e], acc[e][k][l]);
+                                    if (GRAD) {
+                                        accg[e][k][l] = fma(w.g1, H[k + 1][l + 1][e], accg[e][k][l]);
+                                        accg[e][k][l] = fma(g2p, H[0][l + 1][e], accg[e][k][l]);
+                                    }
+                                }
+                            }
+                        } else if (MODE == MODE_KEF) {
+#pragma unroll
+                            for (int l = 0; l < 3; l++) {
+                                acc[e][0][l] = fma(w.w1, H[0][l + 1][e], acc[e][0][l]);
+                                if (GRAD) accg[e][0][l] = fma(w.g1, H[0][l + 1][e], accg[e][0][l]);
+                            }
+                        } else {
+                            acc[e][0][0] += w.w1;
+                            if (GRAD) accg[e][0][0] += w.g1;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    if (!active) return;
+    const int gi = p.A.slot_group[a_blk * 8 + ar];
+    if (gi < 0) return;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+        const int gj = p.B.slot_group[b_blk * 8 + bq + e];
+        if (gj < 0) continue;
+#pragma unroll
+        for (int k = 0; k < NC1; k++)
+#pragma unroll
+            for (int l = 0; l < NC2; l++) {
+                const long long o = gi * p.si + k * p.sk + gj * p.sj + l * p.sl;
+                p.out[o] += p.scale * acc[e][k][l];
+                if (GRAD) p.out_grad[o] += p.scale_grad * accg[e][k][l];
+            }
+        if (p.symmetric && b_rel != a_rel) {
+            // mirror: K[(j,l),(i,k)] = K[(i,k),(j,l)]   (only used for square K_EE / K_FF builds)
+#pragma unroll
+            for (int k = 0; k < NC1; k++)
+#pragma unroll
+                for (int l = 0; l < NC2; l++) {
+                    const long long o = gj * p.si + l * p.sk + gi * p.sj + k * p.sl;
+                    p.out[o] += p.scale * acc[e][k][l];
+                    if (GRAD) p.out_grad[o] += p.scale_grad * accg[e][k][l];
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int MODE, int FAM, int KS, bool Z2>
+static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t st)
+{
+    auto kern = block_tile_kernel<MODE, FAM, KS, Z2>;
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        CSPBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int npg = (p.a_nblk + nwarps - 1) / nwarps;
+    const long long grid = (long long)npg * p.b_nblk;
+    if (grid <= 0) return CSPBO_OK;
+    kern<<<(unsigned)grid, nwarps * 32, smem, st>>>(p);
+    g_launches++;
+    CSPBO_CUDA(cudaGetLastError());
+    return CSPBO_OK;
+}
+
+template <int MODE, int KS>
+static int launch_mode(int fam, bool z2, const TileParams &p, int nwarps, size_t smem, cudaStream_t st)
+{
+    if (fam == FAM_DOT) return z2 ? launch_one<MODE, FAM_DOT, KS, true>(p, nwarps, smem, st)
+                                  : launch_one<MODE, FAM_DOT, KS, false>(p, nwarps, smem, st);
+    if (fam == FAM_RBF) return z2 ? launch_one<MODE, FAM_RBF, KS, true>(p, nwarps, smem, st)
+                                  : launch_one<MODE, FAM_RBF, KS, false>(p, nwarps, smem, st);
+    return z2 ? launch_one<MODE, FAM_RBF_GRAD, KS, true>(p, nwarps, smem, st)
+              : launch_one<MODE, FAM_RBF_GRAD, KS, false>(p, nwarps, smem, st);
+}
+
+template <int KS>
+static int launch_ks(int mode, int fam, bool z2, const TileParams &p, int nwarps, size_t smem, cudaStream_t st)
+{
+    switch (mode) {
+        case MODE_KEE: return launch_mode<MODE_KEE, KS>(fam, z2, p, nwarps, smem, st);
+        case MODE_KEF: return launch_mode<MODE_KEF, KS>(fam, z2, p, nwarps, smem, st);
+        default: return launch_mode<MODE_KFF, KS>(fam, z2, p, nwarps, smem, st);
+    }
+}
+
+// Build one block between packs a and b into DEVICE memory `out` (accumulating).
+int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
+                       double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
+                       cudaStream_t st)
+{
+    if (a->ks != b->ks || a->d != b->d) {
+        set_error("block_build: packs have different descriptor lengths (%d vs %d)", a->d, b->d);
+        return CSPBO_E_ARG;
+    }
+    const int mode = d.block;
+    int fam = d.family == CSPBO_DOT ? FAM_DOT : (d.with_grad ? FAM_RBF_GRAD : FAM_RBF);
+    const bool z2 = (d.zeta == 2.0);
+    TileParams p;
+    p.A = {a->d_tiles, a->d_tile_start, a->d_slot_group, a->d_tile_valid, (int)a->tile_doubles, voffA};
+    p.B = {b->d_tiles, b->d_tile_start, b->d_slot_group, b->d_tile_valid, (int)b->tile_doubles, voffB};
+    p.zeta = d.zeta; p.sigma2 = d.sigma2; p.sigma02 = d.sigma02;
+    p.inv2l2 = d.family == CSPBO_RBF ? 1.0 / (2.0 * d.l * d.l) : 0.0;
+    p.inv_l = d.family == CSPBO_RBF ? 1.0 / d.l : 0.0;
+    p.inv_l3 = d.family == CSPBO_RBF ? p.inv_l / (d.l * d.l) : 0.0;
+    p.tol = d.tol; p.use_tol = d.use_tol;
+    p.scale = d.scale; p.scale_grad = d.scale_grad;
+    p.out = out; p.out_grad = out_grad;
+    p.si = si; p.sk = sk; p.sj = sj; p.sl = sl;
+    p.symmetric = d.symmetric;
+
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+
+    for (size_t ea = 0; ea < a->species.size(); ea++) {
+        size_t eb = 0;
+        for (; eb < b->species.size(); eb++)
+            if (b->species[eb] == a->species[ea]) break;
+        if (eb == b->species.size()) continue;
+        p.a_blk0 = a->blk0[ea]; p.a_nblk = a->blk0[ea + 1] - a->blk0[ea];
+        p.b_blk0 = b->blk0[eb]; p.b_nblk = b->blk0[eb + 1] - b->blk0[eb];
+        if (p.a_nblk == 0 || p.b_nblk == 0) continue;
+        // warps per CTA: one A block per warp; shrink for small problems so the grid covers the SMs
+        int nwarps = 8;
+        while (nwarps > 1 && (long long)((p.a_nblk + nwarps - 1) / nwarps) * p.b_nblk < 2LL * sms) nwarps >>= 1;
+        // B tiles per shared-memory chunk: all tiles of the largest B block if they fit in ~96 KB
+        int maxTb = 0;
+        for (int q = p.b_blk0; q < p.b_blk0 + p.b_nblk; q++)
+            maxTb = std::max(maxTb, b->h_tile_start[q + 1] - b->h_tile_start[q]);
+        const size_t tile_bytes = (size_t)b->tile_doubles * sizeof(double);
+        int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, (96 * 1024) / tile_bytes));
+        p.tbc = tbc;
+        const size_t smem = (size_t)tbc * tile_bytes + (size_t)tbc * sizeof(unsigned) + 16;
+        int rc;
+        if (a->ks == 6) rc = launch_ks<6>(mode, fam, z2, p, nwarps, smem, st);
+        else rc = launch_ks<14>(mode, fam, z2, p, nwarps, smem, st);
+        if (rc) return rc;
+    }
+    return CSPBO_OK;
+}
+
+}  // namespace cspbo

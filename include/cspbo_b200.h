@@ -1,0 +1,205 @@
+/*
+ * cspbo_b200.h -- C ABI of libcspbo_b200.so, the B200 (sm_100a) implementation of CSP_BO's
+ * Gaussian-process kernel-matrix hot path (K_EE / K_EF / K_FF of the Dot and RBF many-body
+ * kernels, K*.alpha prediction, Cholesky fit).
+ *
+ * Plain C: pointers and sizes only, no torch / C++ types.  Every function returns an int
+ * status (0 = ok, see CSPBO_E_*) and never throws.  cspbo_last_error() returns a static,
+ * thread-local, human readable message for the last non-zero status.
+ *
+ * Three layers, lowest first:
+ *
+ *  (1) reference-compatible entry points (host pointers, one call = one block)
+ *      cspbo_dot_* / cspbo_rbf_*  -- same argument lists as the reference's cffi cdefs
+ *      (reference cspbo/kernels/libdot_builder.py:5-9 and librbf_builder.py:5-12, implemented
+ *      by cspbo/kernels/dot_kernel.cpp and rbf_kernel.cpp) plus an int return.  Like the
+ *      reference they ACCUMULATE into the caller's `pout` (+= / -=), so `pout` must be
+ *      zero-initialised by the caller (dot_kernel.py:36,107-110,219-229).
+ *      The two shim libraries libdot_kernel_b200.so / librbf_kernel_b200.so export these under
+ *      the reference's exact unprefixed names (kee_many, kef_many, ...) for a cffi/ctypes
+ *      binding that wants a drop-in `lib` object.
+ *
+ *  (2) resident API: pack a stacked descriptor set once into HBM (cspbo_pack_*), then build any
+ *      number of blocks against it (cspbo_block_build) into host or device memory.  This is what
+ *      the Python kernel objects (csp_bo_b200.kernels.Dot_mb / RBF_mb) use: the training set is
+ *      packed once per fit and reused by every prediction.
+ *
+ *  (3) GP algebra on the device: K + noise -> Cholesky (cuSOLVER) -> alpha, and K*.alpha
+ *      (reference cspbo/gaussianprocess.py:105-127,138-141,359-366).
+ *
+ * Conventions (identical to the reference, dot_kernel.cpp:4-55):
+ *   x[n,d]            stacked descriptor rows, row-major float64
+ *   dxdr[n,d,nc]      per-row Cartesian derivative, nc = 3 (force) or 9 (3 force + 6 stress)
+ *   ele[n]            species id per row (int32); pairs of different species contribute 0
+ *   inds[n]           group id per row (structure for "energy" data, force atom for "force" data)
+ *   x2i               number of x2 groups (= row stride of pout)
+ *   rows with |x| <= 1e-8 are ignored.
+ */
+#ifndef CSPBO_B200_H
+#define CSPBO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSPBO_OK            0
+#define CSPBO_E_CUDA        1   /* a CUDA runtime call failed */
+#define CSPBO_E_ARG         2   /* invalid argument (null pointer, negative size, d unsupported) */
+#define CSPBO_E_NOMEM       3   /* host or device allocation failed */
+#define CSPBO_E_SOLVER      4   /* cuSOLVER failure; CSPBO_E_NOTPD for a non positive-definite K */
+#define CSPBO_E_NOTPD       5
+#define CSPBO_E_NODEVICE    6   /* no CUDA device: there is NO CPU fallback */
+
+#define CSPBO_MAX_D         64  /* largest descriptor length the tile kernels are compiled for */
+
+const char *cspbo_last_error(void);
+int cspbo_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long cspbo_launch_count(void);
+/* make `device` current for subsequent calls from this thread (cudaSetDevice) */
+int cspbo_set_device(int device);
+int cspbo_device_count(int *count);
+int cspbo_synchronize(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) reference-compatible entry points.  Host pointers.  pout is accumulated into.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Dot kernel.  Replaces dot_kernel.cpp:4-55 (kee_many) */
+int cspbo_dot_kee_many(int n1, int n2, int d, int x2i, double zeta, double sigma2, double sigma02,
+                       const double *x1, const int *ele1, const int *x1_inds,
+                       const double *x2, const int *ele2, const int *x2_inds, double *pout);
+/* dot_kernel.cpp:57-128 */
+int cspbo_dot_kef_many(int n1, int n2, int d, int x2i, double zeta,
+                       const double *x1, const int *ele1, const int *x1_inds,
+                       const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds,
+                       double *pout);
+/* dot_kernel.cpp:131-214 (dx2dr has 9 columns, pout[m1,m2,9]) */
+int cspbo_dot_kef_many_stress(int n1, int n2, int d, int x2i, double zeta,
+                              const double *x1, const int *ele1, const int *x1_inds,
+                              const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds,
+                              double *pout);
+/* dot_kernel.cpp:215-334.  Only x2 rows [n2_start, n2_end) are used (the reference's MPI split). */
+int cspbo_dot_kff_many(int n1, int n2, int n2_start, int n2_end, int d, int x2i, double zeta,
+                       const double *x1, const double *dx1dr, const int *ele1, const int *x1_inds,
+                       const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds,
+                       double *pout);
+/* dot_kernel.cpp:336-506 (dx1dr has 9 columns, pout[m1,9,m2*3]) */
+int cspbo_dot_kff_many_stress(int n1, int n2, int n2_start, int n2_end, int d, int x2i, double zeta,
+                              const double *x1, const double *dx1dr, const int *ele1, const int *x1_inds,
+                              const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds,
+                              double *pout);
+
+/* RBF kernel.  rbf_kernel.cpp:4-48 */
+int cspbo_rbf_kee_many(int n1, int n2, int d, int x2i, double zeta, double sigma2, double l2,
+                       const double *x1, const int *ele1, const int *x1_inds,
+                       const double *x2, const int *ele2, const int *x2_inds, double *pout);
+/* rbf_kernel.cpp:50-97 */
+int cspbo_rbf_kee_many_with_grad(int n1, int n2, int d, int x2i, double zeta, double sigma2, double l2,
+                                 const double *x1, const int *ele1, const int *x1_inds,
+                                 const double *x2, const int *ele2, const int *x2_inds,
+                                 double *pout, double *dpout_dl);
+/* rbf_kernel.cpp:100-170 */
+int cspbo_rbf_kef_many(int n1, int n2, int d, int x2i, double zeta, double sigma2, double l2,
+                       const double *x1, const int *ele1, const int *x1_inds,
+                       const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds,
+                       double *pout);
+/* rbf_kernel.cpp:172-252.  NB: takes l, not l^2; pout[m1,m2,6] = (K_EF[3], dK_EF/dl[3]) */
+int cspbo_rbf_kef_many_with_grad(int n1, int n2, int d, int x2i, double zeta, double sigma2, double l,
+                                 const double *x1, const int *ele1, const int *x1_inds,
+                                 const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds,
+                                 double *pout);
+/* rbf_kernel.cpp:255-337 */
+int cspbo_rbf_kef_many_stress(int n1, int n2, int d, int x2i, double zeta, double sigma2, double l2,
+                              const double *x1, const int *ele1, const int *x1_inds,
+                              const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds,
+                              double *pout);
+/* rbf_kernel.cpp:340-472.  Pairs with dK/dD <= tol are skipped (:394). */
+int cspbo_rbf_kff_many(int n1, int n2, int n2_start, int n2_end, int d, int x2i, double zeta,
+                       double sigma2, double l2, double tol,
+                       const double *x1, const double *dx1dr, const int *ele1, const int *x1_inds,
+                       const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds,
+                       double *pout);
+/* rbf_kernel.cpp:474-639.  NB: takes l, not l^2; no tol test. */
+int cspbo_rbf_kff_many_with_grad(int n1, int n2, int n2_start, int n2_end, int d, int x2i, double zeta,
+                                 double sigma2, double l,
+                                 const double *x1, const double *dx1dr, const int *ele1, const int *x1_inds,
+                                 const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds,
+                                 double *pout, double *dpout_dl);
+/* rbf_kernel.cpp:641-822 */
+int cspbo_rbf_kff_many_stress(int n1, int n2, int n2_start, int n2_end, int d, int x2i, double zeta,
+                              double sigma2, double l2, double tol,
+                              const double *x1, const double *dx1dr, const int *ele1, const int *x1_inds,
+                              const double *x2, const double *dx2dr, const int *ele2, const int *x2_inds,
+                              double *pout);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) resident API
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cspbo_pack cspbo_pack;   /* a stacked descriptor set, normalised and tiled in HBM */
+
+#define CSPBO_MEM_HOST   0
+#define CSPBO_MEM_DEVICE 1
+
+/* Pack rows [row_start,row_end) of a stacked set.
+ *   dxdr == NULL  -> "energy" pack (descriptor only: usable as the E side of K_EE / K_EF)
+ *   dxdr != NULL  -> "force" pack; nc = 3 or 9 columns per feature (9: 3 force + 6 stress)
+ *   m             number of groups (ids in inds must lie in [0,m))
+ *   mem           where x / dxdr live (CSPBO_MEM_HOST or CSPBO_MEM_DEVICE); ele / inds are
+ *                 always host arrays (the tile layout is planned on the host).
+ * Replaces the per-call ffi.new(...) deep copies of dot_kernel.py:207-216. */
+int cspbo_pack_create(int n, int d, int nc, int m, int row_start, int row_end,
+                      const double *x, const double *dxdr, const int *ele, const int *inds,
+                      int mem, cspbo_pack **out);
+int cspbo_pack_destroy(cspbo_pack *p);
+int cspbo_pack_groups(const cspbo_pack *p);          /* m */
+long long cspbo_pack_bytes(const cspbo_pack *p);     /* HBM footprint */
+/* same-species valid row pairs between two packs: the unit SURVEY 8(d) counts flops in */
+long long cspbo_pack_pair_count(const cspbo_pack *a, const cspbo_pack *b);
+
+#define CSPBO_DOT 0
+#define CSPBO_RBF 1
+
+#define CSPBO_KEE 0
+#define CSPBO_KEF 1
+#define CSPBO_KFF 2
+
+typedef struct {
+    int family;        /* CSPBO_DOT | CSPBO_RBF */
+    int block;         /* CSPBO_KEE | CSPBO_KEF | CSPBO_KFF */
+    double zeta;
+    double sigma2;     /* Dot K_EE and all RBF blocks (the reference's C argument) */
+    double sigma02;    /* Dot K_EE */
+    double l;          /* RBF length scale (l, not l^2) */
+    double tol;        /* RBF K_FF skip threshold */
+    int use_tol;       /* 1: apply the dK/dD > tol test (kff_many, kff_many_stress) */
+    int with_grad;     /* RBF only: also produce the d/dl companion (kee/kef/kff _with_grad) */
+    int stress;        /* 1: K_EF -> 9 columns from side b; K_FF -> 9 rows from side a */
+    double scale;      /* result multiplier applied on the device (1.0 = raw reference C output) */
+    double scale_grad; /* multiplier of the d/dl companion */
+    int symmetric;     /* 1: a and b are the same pack; only blocks j>=i are computed and mirrored */
+} cspbo_block_desc;
+
+/* out layouts (row-major, identical to the reference C functions):
+ *   KEE  out[m1, m2]                            grad -> out_grad[m1, m2]
+ *   KEF  out[m1, m2, nc]  nc = 3 | 9 (stress)   grad -> out_grad[m1, m2, 3]   (separate array)
+ *   KFF  out[m1, nc1, m2*3] nc1 = 3 | 9         grad -> out_grad[m1, 3, m2*3]
+ * mem tells where out/out_grad live.  accumulate = 0 overwrites, 1 adds to the existing content. */
+int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b,
+                      double *out, double *out_grad, int mem, int accumulate);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) GP algebra on the device (all pointers are DEVICE pointers, column count = N)
+ * ------------------------------------------------------------------------------------------ */
+/* K[i,i] += noise_e^2 (i < n_energy) or (f_coef*noise_e)^2 (else)   gaussianprocess.py:109-113 */
+int cspbo_gp_add_noise(double *K, int N, int n_energy, double noise_e, double f_coef);
+/* In-place lower Cholesky of the symmetric K (cuSOLVER potrf) followed by alpha = K^-1 y (potrs);
+ * y[N, nrhs] column-major == row-major for nrhs = 1.   gaussianprocess.py:116,127 */
+int cspbo_gp_cholesky_solve(double *K, int N, double *y_inout, int nrhs, double *logdet);
+/* pred[n] = Kstar[n, N] . alpha[N]    gaussianprocess.py:140,359 */
+int cspbo_gp_predict(const double *Kstar, int n, int N, const double *alpha, double *pred);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSPBO_B200_H */

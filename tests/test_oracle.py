@@ -1,0 +1,62 @@
+"""Pins the oracle: the C port (oracle/kernels_port.c) and, when present, the compiled unmodified
+reference (oracle/_ref) must reproduce tests/golden/golden_outputs.npz, which the unmodified
+reference C++ produced from the reference's own fixtures (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from tests._cases import OracleImpl, golden_cases, max_norm_err
+
+
+@pytest.fixture(scope="module")
+def port_outputs(oracle_built, fixtures):
+    return golden_cases(fixtures, OracleImpl("port"))
+
+
+def test_port_matches_reference_goldens(port_outputs, golden):
+    assert set(port_outputs) == set(golden)
+    worst = {k: max_norm_err(port_outputs[k], golden[k]) for k in golden}
+    bad = {k: v for k, v in worst.items() if not v <= 1e-13}
+    assert not bad, bad
+
+
+def test_compiled_reference_matches_goldens(oracle_built, fixtures, golden):
+    from oracle import cpu_reference as cr
+    if not cr.have_ref():
+        pytest.skip("oracle/_ref not built (reference tree not mounted)")
+    out = golden_cases(fixtures, OracleImpl("ref"))
+    for k in golden:
+        assert max_norm_err(out[k], golden[k]) <= 1e-14, k
+
+
+def test_kff_symmetry_and_psd(golden):
+    K = golden["dot_kff_bigbig"]
+    assert max_norm_err(K, K.T) < 1e-13
+    w = np.linalg.eigvalsh(0.5 * (K + K.T))
+    assert w.min() > -1e-8 * w.max()
+
+
+def test_dot_hyper_gradient_is_scaled_copy(golden):
+    # dot_kernel.py:55-57: dK_EE/dsigma = 2K/sigma
+    assert np.allclose(golden["dot_kee_ds"], 2 * golden["dot_kee"] / 18.55544058601137, rtol=1e-15)
+
+
+def test_rbf_dl_matches_finite_difference(oracle_built, fixtures):
+    from tests._cases import force_tuple
+    from oracle import cpu_reference as cr
+    x2 = force_tuple(fixtures, "x2")
+    s, l, h = 6.244955524643115, 0.5611029935713949, 1e-6
+    _, _, dl = cr.rbf_kff_C(x2, x2, s, l, 2.0, grad=True, backend="port")
+    kp = cr.rbf_kff_C(x2, x2, s, l + h, 2.0, tol=-1.0, backend="port")
+    km = cr.rbf_kff_C(x2, x2, s, l - h, 2.0, tol=-1.0, backend="port")
+    assert max_norm_err((kp - km) / (2 * h), dl) < 1e-6
+
+
+def test_gp_fit_oracle(oracle_built, golden):
+    from oracle import cpu_reference as cr
+    K = golden["dot_ktotal_train"]
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal(len(K))
+    L, alpha = cr.gp_fit(K, y, n_energy=4, noise_e=0.005, f_coef=30)
+    Kn = K.copy()
+    Kn[np.diag_indices(len(K))] += np.r_[np.full(4, 0.005 ** 2), np.full(len(K) - 4, (30 * 0.005) ** 2)]
+    assert np.allclose(Kn @ alpha[:, 0], y, atol=1e-8 * np.abs(y).max())
