@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the GP kernel-matrix hot path (BASELINE.json metric:
+"K_FF entries/s (fp64) + GP fit wall-time at 1/2/4/8 B200 vs host CPU").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one K_FF(X, X) build for a synthetic training set shaped like the reference's
+Cpp_code/X1_big.npy (csp_bo_b200/synthetic.py): 6667 force atoms = 20 001 force rows, 146 976
+stacked descriptor rows, d = 24, Pt/H/O species mix, Dot kernel sigma=18.555 zeta=2
+(examples/models/test_2.json).  `value` = entries of the [3m,3m] K_FF matrix delivered per
+second with the packed descriptors already resident in HBM; `e2e` = the same through the public
+kff_C() call with pinned HOST buffers in and the K_FF matrix back in pinned HOST memory.
+
+N > 1 (torchrun): the symmetric build is sharded over ranks by interleaved 8-atom row blocks
+(strong scaling, fixed total work, no data-path collective; the max over ranks of the
+device-timed region is reported).
+
+--impl reference times the reference's own CPU implementation (oracle/_ref = the unmodified
+cspbo/kernels/dot_kernel.cpp compiled with g++ -O2, threaded like its MPI split) on a bounded
+slab of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ATOMS = 6667
+SIGMA, SIGMA0, ZETA = 18.555440586011372, 0.01, 2.0
+FLOP_PER_PAIR = 32 * 24 + 100     # F_FF(d) = 2*16*d + 100 at d = 24
+FP64_PEAK_FALLBACK = 37.03        # TFLOP/s, DMMA.8x8x4 issue-bound peak measured on this pool (profiles/fp64_peak_r01.json)
+
+
+def fp64_peak():
+    """MEASURED_PEAKS.json carries no FP64 entry; the denominator is the DMMA peak measured on this
+    pool's B200 with tools/fp64_peak.cu and committed under profiles/."""
+    for name in sorted(os.listdir(os.path.join(ROOT, "profiles")), reverse=True):
+        if name.startswith("fp64_peak_r") and name.endswith(".json"):
+            try:
+                d = json.load(open(os.path.join(ROOT, "profiles", name)))
+                return float(d["dmma_peak_tflops"]), "profiles/" + name + " (tools/fp64_peak.cu, DMMA.8x8x4)"
+            except Exception:
+                pass
+    return FP64_PEAK_FALLBACK, "fallback constant"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload(single_element=False, n_atoms=N_ATOMS):
+    from csp_bo_b200 import synthetic
+    X = synthetic.force_set(n_atoms, seed=0, single_element=single_element)
+    pairs = synthetic.same_species_pairs(X[2], X[2])
+    return X, pairs
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference_rate(X, n_x1_atoms, threads, backend="auto"):
+    """K_FF slab (first n_x1_atoms x1 atoms against all x2) with the reference CPU code; returns
+    (entries/s, seconds, kind)."""
+    from oracle import cpu_reference as cr
+    be = cr.get_backend(backend)
+    x, dx, ele, counts = X
+    rows = int(np.sum(counts[:n_x1_atoms]))
+    X1 = (x[:rows], dx[:rows], ele[:rows], counts[:n_x1_atoms])
+    t0 = time.perf_counter()
+    C = cr.dot_kff_C(X1, X, SIGMA, SIGMA0, ZETA, backend=be.kind, threads=threads)
+    dt = time.perf_counter() - t0
+    return C.size / dt, dt, ("reference" if be.kind == "ref" else "port"), C
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path on the host cores, bounded slab per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X, pairs = workload()
+    cores = os.cpu_count() or 1
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=False, stdout=subprocess.DEVNULL)
+    n_x1 = max(1, cores // 2)     # ~0.25 s of one core per x1 atom => a few seconds per step
+    for _ in range(args.warmup):
+        cpu_reference_rate(X, 1, cores)
+    times, entries = [], 0
+    for _ in range(args.steps):
+        rate, dt, kind, C = cpu_reference_rate(X, n_x1, cores)
+        times.append(dt); entries = C.size
+    ms = 1e3 * float(np.mean(times))
+    value = entries / (ms * 1e-3)
+    sample = "K_FF slab: first %d of %d x1 atoms x all %d x2 atoms per step (%d entries)" % (n_x1, len(X[3]), len(X[3]), entries)
+    line = {"impl": "reference", "metric": "K_FF entries/s (fp64)", "value": value, "unit": "entries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(X, pairs), "gpu_launches": 0,
+            "cpu_baseline": {"value": value, "unit": "entries/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(X, pairs):
+    return {"workload": "K_FF(X,X) Dot zeta=2 d=24, synthetic X1_big-shaped Pt/H/O training set, "
+                        "%d force atoms = %d force rows, %d stacked rows" % (len(X[3]), 3 * len(X[3]), len(X[0])),
+            "force_rows": 3 * len(X[3]), "stacked_rows": int(len(X[0])), "d": 24, "kernel": "Dot_mb",
+            "sigma": SIGMA, "zeta": ZETA, "same_species_row_pairs": int(pairs),
+            "l2": "no explicit flush: each step streams a 3.2 GB output + 113 MB of packed rows, >> 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from csp_bo_b200 import _lib, packing
+    from csp_bo_b200.kernels.dot_kernel import kff_C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; csp_bo_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    lib = _lib.load()
+    _lib.check(lib.cspbo_set_device(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    X, pairs = workload()
+    m = len(X[3])
+    xd, dxd = torch.from_numpy(X[0]).cuda(), torch.from_numpy(X[1]).cuda()
+    full = packing.Pack(xd, dxd, X[2], X[3])
+    if world == 1:
+        mine, sym, m_mine = full, True, m
+    else:
+        # strong scaling: rank r owns every world-th 8-atom row block of K_FF (complete rows)
+        blocks = np.arange((m + 7) // 8)
+        own = np.concatenate([np.arange(b * 8, min(m, b * 8 + 8)) for b in blocks[rank::world]])
+        off = np.concatenate(([0], np.cumsum(X[3])))
+        rows = np.concatenate([np.arange(off[g], off[g + 1]) for g in own])
+        mine = packing.Pack(torch.from_numpy(X[0][rows]).cuda(), torch.from_numpy(X[1][rows]).cuda(), X[2][rows],
+                            [X[3][g] for g in own])
+        sym, m_mine = False, len(own)
+    out = torch.empty((m_mine, 3, m * 3), dtype=torch.float64, device="cuda")
+    my_pairs = mine.pair_count(full)
+    algo_pairs = (my_pairs + len(X[0])) / 2 if sym else my_pairs
+
+    def step():
+        packing.build_block(_lib.DOT, _lib.KFF, mine, full, ZETA, scale=SIGMA * SIGMA * ZETA, symmetric=sym, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_all0.record()
+    for e0, e1 in evs:
+        e0.record(); step(); e1.record()
+    t_all1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_all0.elapsed_time(t_all1)
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    entries = 9.0 * m * m
+    value = entries / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the public API: pinned host in, K_FF in pinned host memory out
+    e2e = None
+    if world == 1:
+        xh = torch.from_numpy(X[0]).pin_memory(); dxh = torch.from_numpy(X[1]).pin_memory()
+        Xh = (xh.numpy(), dxh.numpy(), X[2], X[3])
+        outh = torch.empty(m * 3 * m * 3, dtype=torch.float64).pin_memory()
+        e2e_ms = []
+        for i in range(1 + min(args.steps, 3)):
+            packing.clear_cache()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            K = kff_C(Xh, Xh, SIGMA, SIGMA0, ZETA, out=outh.numpy())
+            chk = float(K[0, 0])   # result is in host memory here
+            dt = time.perf_counter() - t0
+            if i > 0:
+                e2e_ms.append(dt * 1e3)
+        e2e = {"value": entries / (np.mean(e2e_ms) * 1e-3), "unit": "entries/s", "ms_per_step": float(np.mean(e2e_ms)),
+               "h2d_bytes_per_step": int(X[0].nbytes + X[1].nbytes + 2 * 4 * len(X[0])),
+               "d2h_bytes_per_step": int(outh.numel() * 8), "check": chk}
+        del outh
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = fp64_peak()
+    kern_ms = float(np.mean(step_ms))
+    achieved = algo_pairs * FLOP_PER_PAIR / (kern_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "kff_traffic_r01.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_step")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_flops_per_step": algo_pairs * FLOP_PER_PAIR,
+                "note": "FP64 tensor (DMMA) pipe; 868 flop per same-species row pair (SURVEY 8d), "
+                        "unique pairs of the symmetric build; device time of the block kernels per step"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=False, stdout=subprocess.DEVNULL)
+            cores = os.cpu_count() or 1
+            n_x1 = max(2, 3 * cores)   # ~0.25 core-s per x1 atom => ~10-20 s on all cores
+            rate, dt, kind, C = cpu_reference_rate(X, n_x1, cores)
+            # parity of the slab actually computed (max-normalised)
+            Kd = out.reshape(m * 3, m * 3)[: C.shape[0]].cpu().numpy()
+            err = float(np.abs(Kd - C).max() / np.abs(C).max())
+            cpu = {"value": rate, "unit": "entries/s", "cores": cores, "kind": kind, "seconds": dt,
+                   "sample": "K_FF slab: first %d of %d x1 atoms x all x2 atoms (%d entries), reference C++ "
+                             "threaded over x2 like its MPI split" % (n_x1, m, C.size),
+                   "max_norm_err_vs_gpu": err}
+        except Exception as exc:  # the baseline is reported, never required for the GPU number
+            cpu = {"value": None, "unit": "entries/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(exc)}
+
+    line = {"metric": "K_FF entries/s (fp64)", "value": value, "unit": "entries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(X, pairs), "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,49 @@
+"""GP algebra on the device (reference cspbo/gaussianprocess.py:105-127 fit, :138-141 predict):
+K + noise -> cuSOLVER Cholesky -> alpha, and the K*.alpha GEMV, through the C ABI."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import c_vp
+
+
+def _cuda(a):
+    import torch
+    if isinstance(a, torch.Tensor):
+        return a.to(device="cuda", dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def fit_alpha(K, y, n_energy, noise_e, f_coef, return_logdet=False, overwrite=False):
+    """alpha = (K + noise)^-1 y.  K: [N,N] numpy array or CUDA tensor (symmetric), y: [N].
+    Returns a numpy vector (or a CUDA tensor when K is one).  Raises CspboError(CSPBO_E_NOTPD) when
+    K + noise is not positive definite, like the LinAlgError of gaussianprocess.py:115-125."""
+    import torch
+    lib = _lib.load()
+    on_dev = isinstance(K, torch.Tensor) and K.is_cuda
+    Kd = _cuda(K)
+    if on_dev and not overwrite and Kd.data_ptr() == K.data_ptr():
+        Kd = Kd.clone()
+    N = Kd.shape[0]
+    yd = _cuda(y).reshape(-1).clone()
+    assert Kd.shape == (N, N) and yd.numel() == N
+    _lib.check(lib.cspbo_gp_add_noise(c_vp(Kd.data_ptr()), N, int(n_energy), float(noise_e), float(f_coef)))
+    logdet = ctypes.c_double(0.0)
+    _lib.check(lib.cspbo_gp_cholesky_solve(c_vp(Kd.data_ptr()), N, c_vp(yd.data_ptr()), 1,
+                                           ctypes.byref(logdet) if return_logdet else None))
+    alpha = yd if on_dev else yd.cpu().numpy()
+    return (alpha, logdet.value) if return_logdet else alpha
+
+
+def predict_mean(Kstar, alpha):
+    """K* . alpha (gaussianprocess.py:140,359)."""
+    import torch
+    lib = _lib.load()
+    on_dev = isinstance(Kstar, torch.Tensor) and Kstar.is_cuda
+    Kd, ad = _cuda(Kstar), _cuda(alpha).reshape(-1)
+    n, N = Kd.shape
+    assert ad.numel() == N
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    _lib.check(lib.cspbo_gp_predict(c_vp(Kd.data_ptr()), n, N, c_vp(ad.data_ptr()), c_vp(out.data_ptr())))
+    return out if on_dev else out.cpu().numpy()
