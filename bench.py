@@ -178,25 +178,25 @@ def run_ours(args):
     m = len(X[3])
     xd, dxd = torch.from_numpy(X[0]).cuda(), torch.from_numpy(X[1]).cuda()
     full = packing.Pack(xd, dxd, X[2], X[3])
+    sh = None
     if world == 1:
-        mine, sym, m_mine = full, True, m
-    else:
-        # strong scaling: rank r owns every world-th 8-atom row block of K_FF (complete rows)
-        blocks = np.arange((m + 7) // 8)
-        own = np.concatenate([np.arange(b * 8, min(m, b * 8 + 8)) for b in blocks[rank::world]])
-        off = np.concatenate(([0], np.cumsum(X[3])))
-        rows = np.concatenate([np.arange(off[g], off[g + 1]) for g in own])
-        mine = packing.Pack(torch.from_numpy(X[0][rows]).cuda(), torch.from_numpy(X[1][rows]).cuda(), X[2][rows],
-                            [X[3][g] for g in own])
-        sym, m_mine = False, len(own)
-    out = torch.empty((m_mine, 3, m * 3), dtype=torch.float64, device="cuda")
-    my_pairs = mine.pair_count(full)
-    algo_pairs = (my_pairs + len(X[0])) / 2 if sym else my_pairs
+        out = torch.empty((m, 3, m * 3), dtype=torch.float64, device="cuda")
+        algo_pairs = (pairs + len(X[0])) / 2      # unique same-species row pairs of the symmetric build
 
-    def step():
-        packing.build_block(_lib.DOT, _lib.KFF, mine, full, ZETA, scale=SIGMA * SIGMA * ZETA, symmetric=sym, out=out)
+        def step():
+            packing.build_block(_lib.DOT, _lib.KFF, full, full, ZETA, scale=SIGMA * SIGMA * ZETA, symmetric=True, out=out)
+    else:
+        # strong scaling: the symmetric build is sharded by block-cyclic row blocks; mirrored tiles go
+        # to the owner's HBM over NVLink peer memory inside the tile kernel (csp_bo_b200/distributed.py)
+        from csp_bo_b200.distributed import ShardedSymmetricBlock
+        sh = ShardedSymmetricBlock(full, _lib.KFF)
+        algo_pairs = (pairs + len(X[0])) / 2 / world
+
+        def step():
+            sh.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=False)
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -218,6 +218,10 @@ def run_ours(args):
     barrier()
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
+    tl = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+    launches = int(tl.item())
     total_ms = t_all0.elapsed_time(t_all1)
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -228,26 +232,71 @@ def run_ours(args):
     entries = 9.0 * m * m
     value = entries / (ms_per_step * 1e-3)
 
-    # ---- end-to-end through the public API: pinned host in, K_FF in pinned host memory out
-    e2e = None
+    # ---- end-to-end through the public API: pinned host descriptors in, K_FF rows in pinned host memory out
+    xh = torch.from_numpy(X[0]).pin_memory(); dxh = torch.from_numpy(X[1]).pin_memory()
+    Xh = (xh.numpy(), dxh.numpy(), X[2], X[3])
+    n_e2e = min(args.steps, 3)
     if world == 1:
-        xh = torch.from_numpy(X[0]).pin_memory(); dxh = torch.from_numpy(X[1]).pin_memory()
-        Xh = (xh.numpy(), dxh.numpy(), X[2], X[3])
         outh = torch.empty(m * 3 * m * 3, dtype=torch.float64).pin_memory()
-        e2e_ms = []
-        for i in range(1 + min(args.steps, 3)):
-            packing.clear_cache()
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            K = kff_C(Xh, Xh, SIGMA, SIGMA0, ZETA, out=outh.numpy())
-            chk = float(K[0, 0])   # result is in host memory here
-            dt = time.perf_counter() - t0
-            if i > 0:
-                e2e_ms.append(dt * 1e3)
-        e2e = {"value": entries / (np.mean(e2e_ms) * 1e-3), "unit": "entries/s", "ms_per_step": float(np.mean(e2e_ms)),
-               "h2d_bytes_per_step": int(X[0].nbytes + X[1].nbytes + 2 * 4 * len(X[0])),
-               "d2h_bytes_per_step": int(outh.numel() * 8), "check": chk}
-        del outh
+        d2h = int(outh.numel() * 8)
 
+        def e2e_step():
+            packing.clear_cache()
+            K = kff_C(Xh, Xh, SIGMA, SIGMA0, ZETA, out=outh.numpy())   # H2D + pack + build + D2H inside
+            return float(K[0, 0])
+    else:
+        outh = torch.empty(sh.local.shape, dtype=torch.float64).pin_memory()
+        d2h = int(outh.numel() * 8) * world
+
+        def e2e_step():
+            pk = packing.Pack(Xh[0], Xh[1], Xh[2], Xh[3])             # H2D of the replicated descriptors + pack
+            sh.pack = pk
+            sh.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
+            outh.copy_(sh.local, non_blocking=False)                  # this rank's complete rows -> host
+            sh.pack = full
+            return float(outh.view(-1)[0])
+    e2e_ms, chk = [], 0.0
+    for i in range(1 + n_e2e):
+        barrier(); t0 = time.perf_counter()
+        chk = e2e_step()
+        barrier(); dt = time.perf_counter() - t0
+        if i > 0:
+            e2e_ms.append(dt * 1e3)
+    te = torch.tensor([float(np.mean(e2e_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": entries / (float(te.item()) * 1e-3), "unit": "entries/s", "ms_per_step": float(te.item()),
+           "h2d_bytes_per_step": int(X[0].nbytes + X[1].nbytes + 2 * 4 * len(X[0])) * world,
+           "d2h_bytes_per_step": d2h, "check": chk,
+           "api": "kernels.dot_kernel.kff_C(host tuple, host tuple, out=pinned)" if world == 1 else
+                  "packing.Pack(host) + distributed.ShardedSymmetricBlock.build + row-block copy to pinned host"}
+    del outh
+
+    # ---- GP fit wall time: K_FF(X,X) + noise -> Cholesky -> alpha  (gaussianprocess.py:105-127, opt=False)
+    fit = None
+    try:
+        from csp_bo_b200 import gp
+        y = torch.from_numpy(np.random.default_rng(0).standard_normal(3 * m)).cuda()
+        fit_ms = []
+        for i in range(2):
+            barrier(); t0 = time.perf_counter()
+            if world == 1:
+                step(); Kfull = out.view(3 * m, 3 * m)
+            else:
+                sh.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
+                Kfull = sh.gather_full()        # NCCL all-gather of the row blocks, replicated Cholesky
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            alpha = gp.fit_alpha(Kfull, y, n_energy=0, noise_e=0.005, f_coef=30.0, overwrite=True)
+            torch.cuda.synchronize(); t2 = time.perf_counter()
+            fit_ms.append(((t2 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3))
+            del Kfull
+        fit = {"wall_ms": fit_ms[-1][0], "k_build_ms": fit_ms[-1][1], "cholesky_solve_ms": fit_ms[-1][2], "N": 3 * m,
+               "what": "K_FF + noise -> cuSOLVER potrf/potrs -> alpha; Cholesky replicated on every rank for N>1"}
+    except Exception as exc:
+        fit = {"error": str(exc)[:200]}
+
+    if sh is not None:
+        sh.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -277,6 +326,7 @@ def run_ours(args):
             n_x1 = max(2, 3 * cores)   # ~0.25 core-s per x1 atom => ~10-20 s on all cores
             rate, dt, kind, C = cpu_reference_rate(X, n_x1, cores)
             # parity of the slab actually computed (max-normalised)
+            step(); torch.cuda.synchronize()
             Kd = out.reshape(m * 3, m * 3)[: C.shape[0]].cpu().numpy()
             err = float(np.abs(Kd - C).max() / np.abs(C).max())
             cpu = {"value": rate, "unit": "entries/s", "cores": cores, "kind": kind, "seconds": dt,
@@ -290,7 +340,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(X, pairs), "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "fit": fit}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -61,12 +61,20 @@ SIGNATURES = {
     "cspbo_pack_bytes": [c_vp],
     "cspbo_pack_pair_count": [c_vp, c_vp],
     "cspbo_block_build": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_int],
+    "cspbo_dev_alloc": [c_ll, ctypes.POINTER(c_vp)],
+    "cspbo_dev_free": [c_vp],
+    "cspbo_ipc_export": [c_vp, c_vp],
+    "cspbo_ipc_open": [c_vp, ctypes.POINTER(c_vp)],
+    "cspbo_ipc_close": [c_vp],
+    "cspbo_sharded_rows": [c_vp, c_int, c_int],
+    "cspbo_pack_order": [c_vp, c_vp, c_ll],
+    "cspbo_block_build_sharded": [ctypes.POINTER(BlockDesc), c_vp, c_int, c_int, ctypes.POINTER(c_vp)],
     "cspbo_gp_add_noise": [c_vp, c_int, c_int, c_dbl, c_dbl],
     "cspbo_gp_cholesky_solve": [c_vp, c_int, c_vp, c_int, ctypes.POINTER(c_dbl)],
     "cspbo_gp_predict": [c_vp, c_int, c_int, c_vp, c_vp],
 }
 _RESTYPE = {"cspbo_last_error": ctypes.c_char_p, "cspbo_launch_count": c_ll, "cspbo_pack_bytes": c_ll,
-            "cspbo_pack_pair_count": c_ll}
+            "cspbo_pack_pair_count": c_ll, "cspbo_sharded_rows": c_ll}
 
 # reference-named shims (libdot_builder.py:5-9, librbf_builder.py:5-12)
 SHIM_SYMBOLS = {

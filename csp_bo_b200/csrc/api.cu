@@ -21,7 +21,7 @@ void set_error(const char *fmt, ...)
 
 int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
-                       cudaStream_t st);
+                       int accumulate, cudaStream_t st, int rank = 0, int nranks = 1, double *const *outs = nullptr);
 
 struct DevBuf {
     double *p = nullptr;
@@ -96,23 +96,20 @@ extern "C" int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack 
         CSPBO_CUDA(cudaMalloc(&tmp.p, (size_t)n_out * sizeof(double)));
         dout = tmp.p;
         if (accumulate) CSPBO_CUDA(cudaMemcpyAsync(dout, out, (size_t)n_out * sizeof(double), cudaMemcpyHostToDevice));
-        else CSPBO_CUDA(cudaMemsetAsync(dout, 0, (size_t)n_out * sizeof(double)));
         if (grad) {
             CSPBO_CUDA(cudaMalloc(&tmpg.p, (size_t)n_grad * sizeof(double)));
             dgrad = tmpg.p;
             if (accumulate) CSPBO_CUDA(cudaMemcpyAsync(dgrad, out_grad, (size_t)n_grad * sizeof(double), cudaMemcpyHostToDevice));
-            else CSPBO_CUDA(cudaMemsetAsync(dgrad, 0, (size_t)n_grad * sizeof(double)));
         }
-    } else if (!accumulate) {
-        CSPBO_CUDA(cudaMemsetAsync(dout, 0, (size_t)n_out * sizeof(double)));
-        if (grad) CSPBO_CUDA(cudaMemsetAsync(dgrad, 0, (size_t)n_grad * sizeof(double)));
     }
+    // every (group_i, group_j) output block is owned by exactly one warp, which writes it once:
+    // no zero-initialisation is needed in overwrite mode
 
     for (int pa = 0; pa < passesA; pa++)
         for (int pb = 0; pb < passesB; pb++) {
             // stress: the 9 derivative columns are processed as three independent triplets
             const long long off = (d.block == CSPBO_KFF) ? (long long)pa * 3 * sk : (long long)pb * 3 * sl;
-            int rc = build_block_device(d, a, b, pa * 3, pb * 3, dout + off, dgrad, si, sk, sj, sl, 0);
+            int rc = build_block_device(d, a, b, pa * 3, pb * 3, dout + off, dgrad, si, sk, sj, sl, accumulate, 0);
             if (rc) return rc;
         }
 
@@ -122,6 +119,88 @@ extern "C" int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack 
         CSPBO_CUDA(cudaStreamSynchronize(0));
     }
     return CSPBO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// sharded symmetric build + the IPC plumbing it needs (one process per GPU)
+// ------------------------------------------------------------------------------------------
+extern "C" int cspbo_dev_alloc(long long bytes, void **ptr)
+{
+    if (!ptr || bytes < 0) { set_error("dev_alloc: bad argument"); return CSPBO_E_ARG; }
+    *ptr = nullptr;
+    CSPBO_CUDA(cudaMalloc(ptr, (size_t)std::max<long long>(bytes, 8)));
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_dev_free(void *ptr)
+{
+    CSPBO_CUDA(cudaFree(ptr));
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_ipc_export(void *ptr, unsigned char *handle64)
+{
+    if (!ptr || !handle64) { set_error("ipc_export: null"); return CSPBO_E_ARG; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CSPBO_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle64, &h, 64);
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_ipc_open(const unsigned char *handle64, void **ptr)
+{
+    if (!ptr || !handle64) { set_error("ipc_open: null"); return CSPBO_E_ARG; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    *ptr = nullptr;
+    CSPBO_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_ipc_close(void *ptr)
+{
+    CSPBO_CUDA(cudaIpcCloseMemHandle(ptr));
+    return CSPBO_OK;
+}
+
+extern "C" long long cspbo_sharded_rows(const cspbo_pack *a, int rank, int nranks)
+{
+    if (!a || nranks < 1 || rank < 0 || rank >= nranks) return -1;
+    const long long mine = (a->n_blocks - rank + nranks - 1) / nranks;
+    return std::max<long long>(mine, 0) * 8;
+}
+
+extern "C" int cspbo_pack_order(const cspbo_pack *a, int *order, long long n)
+{
+    if (!a || !order) { set_error("pack_order: null"); return CSPBO_E_ARG; }
+    if (n < (long long)a->n_blocks * 8) { set_error("pack_order: buffer too small"); return CSPBO_E_ARG; }
+    for (long long i = 0; i < (long long)a->n_blocks * 8; i++) order[i] = a->h_slot_group[(size_t)i];
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_block_build_sharded(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
+                                         double *const *outs)
+{
+    if (!desc || !a || !outs) { set_error("block_build_sharded: null argument"); return CSPBO_E_ARG; }
+    if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) { set_error("block_build_sharded: bad rank %d/%d", rank, nranks); return CSPBO_E_ARG; }
+    for (int r = 0; r < nranks; r++)
+        if (!outs[r]) { set_error("block_build_sharded: outs[%d] is null", r); return CSPBO_E_ARG; }
+    cspbo_block_desc d = *desc;
+    if (d.block != CSPBO_KFF && d.block != CSPBO_KEE) { set_error("block_build_sharded: K_FF or K_EE only"); return CSPBO_E_ARG; }
+    if (d.stress || d.with_grad) { set_error("block_build_sharded: no stress / grad variants"); return CSPBO_E_ARG; }
+    if (d.family == CSPBO_RBF && !(d.l > 0.0)) { set_error("block_build_sharded: RBF needs l > 0"); return CSPBO_E_ARG; }
+    d.symmetric = 1;
+    const long long m = a->m;
+    long long si, sk, sj, sl;
+    if (d.block == CSPBO_KEE) {
+        if (a->nc != 0) { set_error("block_build_sharded: K_EE needs an energy pack"); return CSPBO_E_ARG; }
+        si = m; sk = 0; sj = 1; sl = 0;
+    } else {
+        if (a->nc < 3) { set_error("block_build_sharded: K_FF needs a force pack"); return CSPBO_E_ARG; }
+        si = 3 * m * 3; sk = m * 3; sj = 3; sl = 1;
+    }
+    return build_block_device(d, a, a, 0, 0, outs[rank], nullptr, si, sk, sj, sl, 0, 0, rank, nranks, outs);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -175,7 +254,7 @@ int compat_block(int family, int block, int n1, int n2, int n2_start, int n2_end
         DevBuf tmp;
         CSPBO_CUDA(cudaMalloc(&tmp.p, (size_t)n_out * sizeof(double)));
         CSPBO_CUDA(cudaMemcpyAsync(tmp.p, pout, (size_t)n_out * sizeof(double), cudaMemcpyHostToDevice));
-        rc = build_block_device(desc, A.p, B.p, 0, 0, tmp.p, tmp.p + 3, m2 * 6, 0, 6, 1, 0);
+        rc = build_block_device(desc, A.p, B.p, 0, 0, tmp.p, tmp.p + 3, m2 * 6, 0, 6, 1, 1, 0);
         if (rc) return rc;
         CSPBO_CUDA(cudaMemcpyAsync(pout, tmp.p, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost));
         CSPBO_CUDA(cudaStreamSynchronize(0));

@@ -27,8 +27,9 @@ extern std::atomic<long long> g_launches;
         }                                                                                    \
     } while (0)
 
-// Tile geometry.  A tile holds 8 row slots; slot r of every tile of a block belongs to the same
-// group (structure / force atom).  Each slot carries NV vectors (the unit descriptor u and,
+// Tile geometry.  Groups (structures / force atoms) are sorted by their per-species row counts and
+// cut into blocks of 8; a block owns, for every species e, T(block,e) = max_count tiles.  A tile holds
+// 8 row slots; slot r of every tile of a block belongs to group r of the block.  Each slot carries NV vectors (the unit descriptor u and,
 // for force packs, the nc projected+scaled derivative vectors) of 4*KS doubles, stored in
 // mma.m8n8k4 fragment order so that one 128-bit load per lane fetches a lane's operands for
 // two consecutive k-steps:
@@ -52,14 +53,14 @@ struct cspbo_pack {
     long long n_tiles = 0, n_blocks = 0;
     long long tile_doubles = 0;
     // host-side plan
-    std::vector<int> species;      // sorted species ids present in the packed rows
-    std::vector<int> blk0;         // first block of each species bucket (size ns+1)
-    std::vector<int> h_tile_start; // first tile of each block (size n_blocks+1)
+    std::vector<int> species;      // species ids present in the packed rows, most populous first
+    std::vector<int> h_tile_start; // first tile of (block, species): index block*ns + e (size n_blocks*ns+1)
+    std::vector<int> h_slot_group; // [n_blocks*8] group id of each slot, -1 = empty
     std::vector<long long> rows_per_species;
     // device-side tables
     double *d_tiles = nullptr;
     int *d_tile_start = nullptr;
-    int *d_slot_group = nullptr;     // [n_blocks*8] group id of each slot, -1 = empty
+    int *d_slot_group = nullptr;     // device copy of h_slot_group
     unsigned *d_tile_valid = nullptr;  // [n_tiles] bit r set <=> slot r holds a row with |x|>1e-8
     long long bytes = 0;
 };

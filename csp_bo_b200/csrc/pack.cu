@@ -6,11 +6,12 @@
 // per-pair quantity of the reference's d x d loop (dot_kernel.cpp:270-323) is one of the 16 dot
 // products [u_a; A^_a] . [u_b; A^_b]^T:
 //     c = u_a.u_b,  P_k = A^_a[:,k].u_b,  Q_l = u_a.A^_b[:,l],  T_kl = A^_a[:,k].A^_b[:,l]
-// Rows are bucketed by species (pairs of different species contribute nothing,
-// dot_kernel.cpp:255) and, inside a bucket, groups are sorted by row count and interleaved 8 at
-// a time so that slot r of every tile of a block is the same group: a thread's MMA accumulator
-// fragment then always belongs to one fixed (group_i, group_j) pair and the reference's
-// scatter-add `pout[(k+_i*3)*x2i+_j)*3+l] +=` becomes a register accumulation.
+// Groups are sorted once (lexicographically by their per-species row counts) and cut into blocks of
+// 8; inside a block the rows are bucketed by species (pairs of different species contribute
+// nothing, dot_kernel.cpp:255) and interleaved so that slot r of every tile of the block is group
+// r: a thread's MMA accumulator fragment then always belongs to one fixed (group_i, group_j) pair
+// and the reference's scatter-add `pout[(k+_i*3)*x2i+_j)*3+l] +=` becomes a register accumulation
+// that is written exactly once.
 #include <algorithm>
 #include <cstring>
 #include <numeric>
@@ -96,10 +97,10 @@ extern "C" int cspbo_pack_create(int n, int d, int nc, int m, int row_start, int
     long long *d_dest = nullptr;
     double *d_x = nullptr, *d_dx = nullptr;
     std::vector<long long> dest((size_t)std::max(n, 1), -1);
-    std::vector<int> slot_group;
 
     // ---- host plan -------------------------------------------------------------------
     {
+        // species, most populous first
         std::vector<int> sp;
         for (int r = row_start; r < row_end; r++) {
             if (inds[r] < 0 || inds[r] >= m) {
@@ -109,48 +110,72 @@ extern "C" int cspbo_pack_create(int n, int d, int nc, int m, int row_start, int
             sp.push_back(ele[r]);
         }
         std::sort(sp.begin(), sp.end());
-        sp.erase(std::unique(sp.begin(), sp.end()), sp.end());
-        p->species = sp;
-        const int ns = (int)sp.size();
-        p->blk0.assign(ns + 1, 0);
-        p->rows_per_species.assign(ns, 0);
-        p->h_tile_start.clear();
-        p->h_tile_start.push_back(0);
-        std::vector<int> count((size_t)std::max(m, 1));
-        std::vector<int> order;
-        std::vector<long long> first_dest((size_t)std::max(m, 1));  // dest of rank 0 of group g (current species)
-        std::vector<int> rank((size_t)std::max(m, 1));
+        std::vector<std::pair<long long, int>> hist;  // (-rows, species id)
+        for (size_t i = 0; i < sp.size();) {
+            size_t j = i;
+            while (j < sp.size() && sp[j] == sp[i]) j++;
+            hist.push_back({-(long long)(j - i), sp[i]});
+            i = j;
+        }
+        std::sort(hist.begin(), hist.end());
+        const int ns = (int)hist.size();
+        p->species.resize(ns);
+        p->rows_per_species.resize(ns);
+        for (int e = 0; e < ns; e++) { p->species[e] = hist[e].second; p->rows_per_species[e] = -hist[e].first; }
+        auto species_index = [&](int id) {
+            for (int e = 0; e < ns; e++) if (p->species[e] == id) return e;
+            return -1;
+        };
+        // per-group, per-species row counts
+        const int nsz = std::max(ns, 1);
+        std::vector<int> count((size_t)std::max(m, 1) * nsz, 0);
+        std::vector<int> erow((size_t)std::max(n, 1), -1);
+        for (int r = row_start; r < row_end; r++) {
+            erow[r] = species_index(ele[r]);
+            count[(size_t)inds[r] * nsz + erow[r]]++;
+        }
+        // one common group order: lexicographic on the count tuples, largest first, so that the 8
+        // groups of a block have (nearly) equal row counts in every species and tiles carry no padding
+        std::vector<int> order((size_t)m);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            const int *ca = &count[(size_t)a * nsz], *cb = &count[(size_t)b * nsz];
+            for (int e = 0; e < ns; e++)
+                if (ca[e] != cb[e]) return ca[e] > cb[e];
+            return false;
+        });
+        const int nb = (m + kSlots - 1) / kSlots;
+        p->n_blocks = nb;
+        p->h_slot_group.assign((size_t)std::max(nb, 1) * kSlots, -1);
+        p->h_tile_start.assign((size_t)nb * nsz + 1, 0);
+        std::vector<long long> first_dest((size_t)std::max(m, 1) * nsz, -1);
         long long tiles = 0;
-        for (int e = 0; e < ns; e++) {
-            std::fill(count.begin(), count.end(), 0);
-            for (int r = row_start; r < row_end; r++)
-                if (ele[r] == sp[e]) count[inds[r]]++;
-            order.clear();
-            for (int g = 0; g < m; g++)
-                if (count[g] > 0) { order.push_back(g); p->rows_per_species[e] += count[g]; }
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return count[a] > count[b]; });
-            const int nb = ((int)order.size() + kSlots - 1) / kSlots;
-            for (int b = 0; b < nb; b++) {
-                const int T = count[order[(size_t)b * kSlots]];
+        for (int b = 0; b < nb; b++) {
+            for (int s = 0; s < kSlots; s++) {
+                const size_t oi = (size_t)b * kSlots + s;
+                if (oi < (size_t)m) p->h_slot_group[oi] = order[oi];
+            }
+            for (int e = 0; e < ns; e++) {
+                int T = 0;
                 for (int s = 0; s < kSlots; s++) {
-                    const size_t oi = (size_t)b * kSlots + s;
-                    if (oi < order.size()) {
-                        slot_group.push_back(order[oi]);
-                        first_dest[order[oi]] = tiles * 8 + s;
-                    } else {
-                        slot_group.push_back(-1);
+                    const int g = p->h_slot_group[(size_t)b * kSlots + s];
+                    if (g >= 0) {
+                        T = std::max(T, count[(size_t)g * nsz + e]);
+                        first_dest[(size_t)g * nsz + e] = tiles * 8 + s;
                     }
                 }
+                p->h_tile_start[(size_t)b * nsz + e] = (int)tiles;
                 tiles += T;
-                p->h_tile_start.push_back((int)tiles);
             }
-            p->blk0[e + 1] = p->blk0[e] + nb;
-            std::fill(rank.begin(), rank.end(), 0);
-            for (int r = row_start; r < row_end; r++)
-                if (ele[r] == sp[e]) dest[r] = first_dest[inds[r]] + 8LL * (rank[inds[r]]++);
+        }
+        p->h_tile_start[(size_t)nb * nsz] = (int)tiles;
+        if (ns == 0) p->h_tile_start.assign((size_t)nb + 1, 0);
+        std::vector<int> rank((size_t)std::max(m, 1) * nsz, 0);
+        for (int r = row_start; r < row_end; r++) {
+            const size_t k = (size_t)inds[r] * nsz + erow[r];
+            dest[r] = first_dest[k] + 8LL * (rank[k]++);
         }
         p->n_tiles = tiles;
-        p->n_blocks = p->blk0[ns];
         if (tiles > 0x7fffffffLL / 8) { set_error("pack_create: too many tiles"); delete p; return CSPBO_E_ARG; }
     }
 
@@ -171,18 +196,18 @@ extern "C" int cspbo_pack_create(int n, int d, int nc, int m, int row_start, int
     {
         const size_t tb = (size_t)std::max<long long>(p->n_tiles, 1) * p->tile_doubles * sizeof(double);
         const size_t nbk = (size_t)std::max<long long>(p->n_blocks, 1);
+        const size_t nts = p->h_tile_start.size();
         PACK_CUDA(cudaMalloc(&p->d_tiles, tb));
         PACK_CUDA(cudaMemsetAsync(p->d_tiles, 0, tb));
-        PACK_CUDA(cudaMalloc(&p->d_tile_start, (nbk + 1) * sizeof(int)));
+        PACK_CUDA(cudaMalloc(&p->d_tile_start, nts * sizeof(int)));
         PACK_CUDA(cudaMalloc(&p->d_slot_group, nbk * 8 * sizeof(int)));
         PACK_CUDA(cudaMalloc(&p->d_tile_valid, (size_t)std::max<long long>(p->n_tiles, 1) * sizeof(unsigned)));
         PACK_CUDA(cudaMemsetAsync(p->d_tile_valid, 0, (size_t)std::max<long long>(p->n_tiles, 1) * sizeof(unsigned)));
-        p->bytes = (long long)(tb + (nbk + 1) * 4 + nbk * 32 + std::max<long long>(p->n_tiles, 1) * 4);
+        p->bytes = (long long)(tb + nts * 4 + nbk * 32 + std::max<long long>(p->n_tiles, 1) * 4);
         PACK_CUDA(cudaMemcpyAsync(p->d_tile_start, p->h_tile_start.data(), p->h_tile_start.size() * sizeof(int),
                                   cudaMemcpyHostToDevice));
-        if (!slot_group.empty())
-            PACK_CUDA(cudaMemcpyAsync(p->d_slot_group, slot_group.data(), slot_group.size() * sizeof(int),
-                                      cudaMemcpyHostToDevice));
+        PACK_CUDA(cudaMemcpyAsync(p->d_slot_group, p->h_slot_group.data(), p->h_slot_group.size() * sizeof(int),
+                                  cudaMemcpyHostToDevice));
     }
     if (n > 0 && p->n_tiles > 0) {
         PACK_CUDA(cudaMalloc(&d_dest, (size_t)n * sizeof(long long)));
@@ -204,7 +229,7 @@ extern "C" int cspbo_pack_create(int n, int d, int nc, int m, int row_start, int
         g_launches++;
         PACK_CUDA(cudaGetLastError());
     }
-    PACK_CUDA(cudaStreamSynchronize(0));  // dest / slot_group host buffers die with this scope
+    PACK_CUDA(cudaStreamSynchronize(0));  // dest host buffer dies with this scope
     cudaFree(d_dest); cudaFree(d_x); cudaFree(d_dx);
     *out = p;
     return CSPBO_OK;

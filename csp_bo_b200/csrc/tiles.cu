@@ -1,8 +1,8 @@
 // tiles.cu -- the covariance-block tile kernels (K_EE / K_EF / K_FF, Dot and RBF) for sm_100a.
 //
 // One templated kernel family replaces the 13 scalar loops of the reference
-// (cspbo/kernels/dot_kernel.cpp:4-506, rbf_kernel.cpp:4-822).  For a pair of packed 8-group
-// blocks (pack.cu) of one species, every 8x8 tile pair costs NV1*NV2*KS FP64 tensor-core
+// (cspbo/kernels/dot_kernel.cpp:4-506, rbf_kernel.cpp:4-822).  A warp owns one pair of packed 8-group
+// blocks (pack.cu) and walks their species buckets; every 8x8 tile pair costs NV1*NV2*KS FP64 tensor-core
 // instructions (DMMA.8x8x4, the only FP64 MMA shape sm_100a has natively) that produce, per
 // thread and for two (row a, row b) pairs, the full set of dot products
 //     H[0][0] = c = u_a.u_b      H[k][0] = P_k = A^_a[:,k].u_b
@@ -22,25 +22,36 @@
 
 namespace cspbo {
 
+constexpr int kMaxSpecies = 16;
+constexpr int kMaxRanks = 8;
+
 struct SideDev {
     const double *tiles;
-    const int *tile_start;
+    const int *tile_start;     // [nblk*ns + 1]: first tile of (block, species)
     const int *slot_group;
     const unsigned *tile_valid;
     int tile_doubles;  // NV*KS*32
     int voff;          // first derivative vector used is 1+voff
+    int ns;            // species buckets per block
 };
 
 struct TileParams {
     SideDev A, B;
-    int a_blk0, a_nblk, b_blk0, b_nblk;
+    int a_nblk, b_nblk;
+    int emap[kMaxSpecies];  // species bucket of A -> bucket of B holding the same species id, or -1
     int tbc;  // B tiles per shared-memory chunk
     int symmetric;
+    int accumulate;  // 1: out += result (reference `pout +=` semantics), 0: out = result
     double zeta, sigma2, sigma02, inv2l2, inv_l, inv_l3, tol;
     int use_tol;
     double scale, scale_grad;
     double *out, *out_grad;
     long long si, sk, sj, sl;  // out index = i*si + k*sk + j*sj + l*sl
+    // sharded symmetric build (one process per GPU): rank r owns the A blocks a with a % nranks == r
+    // and stores row block a at local block a / nranks of outs[r]; mirrored tiles are stored
+    // straight into the owner's buffer over NVLink peer memory (outs[] are IPC-mapped pointers).
+    int sharded, nranks, rank;
+    double *outs[kMaxRanks];
 };
 
 enum { MODE_KEE = 0, MODE_KEF = 1, MODE_KFF = 2 };
@@ -121,21 +132,14 @@ __global__ void __launch_bounds__(256) block_tile_kernel(const TileParams p)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int npg = (p.a_nblk + nwarps - 1) / nwarps;
+    const int a_mine = (p.a_nblk - p.rank + p.nranks - 1) / p.nranks;
+    const int npg = (a_mine + nwarps - 1) / nwarps;
     const int pg = blockIdx.x % npg;
     const int q = blockIdx.x / npg;
-    const int a_rel = pg * nwarps + warp;
-    const int b_rel = q;
-    bool active = a_rel < p.a_nblk;
+    const int a_blk = (pg * nwarps + warp) * p.nranks + p.rank;  // nranks == 1, rank == 0 unless sharded
+    const int b_blk = q;
     // symmetric build: only blocks with b >= a are computed (mirrored at write time)
-    if (p.symmetric && b_rel < a_rel) active = false;
-    const int a_blk = p.a_blk0 + (active ? a_rel : 0);
-    const int b_blk = p.b_blk0 + b_rel;
-
-    const int a_t0 = p.A.tile_start[a_blk];
-    const int Ta = active ? p.A.tile_start[a_blk + 1] - a_t0 : 0;
-    const int b_t0 = p.B.tile_start[b_blk];
-    const int Tb = p.B.tile_start[b_blk + 1] - b_t0;
+    const bool active = a_blk < p.a_nblk && !(p.symmetric && b_blk < a_blk);
 
     double *sB = smem;
     unsigned *sBvalid = reinterpret_cast<unsigned *>(smem + (size_t)p.tbc * p.B.tile_doubles);
@@ -155,6 +159,14 @@ __global__ void __launch_bounds__(256) block_tile_kernel(const TileParams p)
     const int ar = lane >> 2;        // a slot of this thread's accumulator rows
     const int bq = (lane & 3) * 2;   // first of its two b slots
 
+    for (int eA = 0; eA < p.A.ns; eA++) {
+    const int eB = p.emap[eA];
+    if (eB < 0) continue;
+    const int b_t0 = p.B.tile_start[b_blk * p.B.ns + eB];
+    const int Tb = p.B.tile_start[b_blk * p.B.ns + eB + 1] - b_t0;
+    if (Tb == 0) continue;
+    const int a_t0 = active ? p.A.tile_start[a_blk * p.A.ns + eA] : 0;
+    const int Ta = active ? p.A.tile_start[a_blk * p.A.ns + eA + 1] - a_t0 : 0;
     for (int c0 = 0; c0 < Tb; c0 += p.tbc) {
         const int nt = min(p.tbc, Tb - c0);
         __syncthreads();
@@ -252,10 +264,33 @@ __global__ void __launch_bounds__(256) block_tile_kernel(const TileParams p)
             }
         }
     }
+    }  // species
 
     if (!active) return;
     const int gi = p.A.slot_group[a_blk * 8 + ar];
     if (gi < 0) return;
+    if (p.sharded) {
+        // sharded symmetric build: rows are block-cyclic over ranks in packed order, columns keep the
+        // caller's group ids.  Own tile -> local HBM, mirrored tile -> peer HBM of the owner of b.
+        double *mine = p.outs[p.rank];
+        const long long lrow_i = (long long)(a_blk / p.nranks) * 8 + ar;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int gj = p.B.slot_group[b_blk * 8 + bq + e];
+            if (gj < 0) continue;
+            double *peer = p.outs[b_blk % p.nranks];
+            const long long lrow_j = (long long)(b_blk / p.nranks) * 8 + bq + e;
+#pragma unroll
+            for (int k = 0; k < NC1; k++)
+#pragma unroll
+                for (int l = 0; l < NC2; l++) {
+                    const double v = p.scale * acc[e][k][l];
+                    mine[lrow_i * p.si + k * p.sk + gj * p.sj + l * p.sl] = v;
+                    if (b_blk != a_blk) peer[lrow_j * p.si + l * p.sk + gi * p.sj + k * p.sl] = v;
+                }
+        }
+        return;
+    }
 #pragma unroll
     for (int e = 0; e < 2; e++) {
         const int gj = p.B.slot_group[b_blk * 8 + bq + e];
@@ -265,18 +300,30 @@ __global__ void __launch_bounds__(256) block_tile_kernel(const TileParams p)
 #pragma unroll
             for (int l = 0; l < NC2; l++) {
                 const long long o = gi * p.si + k * p.sk + gj * p.sj + l * p.sl;
-                p.out[o] += p.scale * acc[e][k][l];
-                if (GRAD) p.out_grad[o] += p.scale_grad * accg[e][k][l];
+                double v = p.scale * acc[e][k][l];
+                if (p.accumulate) v += p.out[o];
+                p.out[o] = v;
+                if (GRAD) {
+                    double g = p.scale_grad * accg[e][k][l];
+                    if (p.accumulate) g += p.out_grad[o];
+                    p.out_grad[o] = g;
+                }
             }
-        if (p.symmetric && b_rel != a_rel) {
+        if (p.symmetric && b_blk != a_blk) {
             // mirror: K[(j,l),(i,k)] = K[(i,k),(j,l)]   (only used for square K_EE / K_FF builds)
 #pragma unroll
             for (int k = 0; k < NC1; k++)
 #pragma unroll
                 for (int l = 0; l < NC2; l++) {
                     const long long o = gj * p.si + l * p.sk + gi * p.sj + k * p.sl;
-                    p.out[o] += p.scale * acc[e][k][l];
-                    if (GRAD) p.out_grad[o] += p.scale_grad * accg[e][k][l];
+                    double v = p.scale * acc[e][k][l];
+                    if (p.accumulate) v += p.out[o];
+                    p.out[o] = v;
+                    if (GRAD) {
+                        double g = p.scale_grad * accg[e][k][l];
+                        if (p.accumulate) g += p.out_grad[o];
+                        p.out_grad[o] = g;
+                    }
                 }
         }
     }
@@ -292,9 +339,11 @@ static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t
         CSPBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int npg = (p.a_nblk + nwarps - 1) / nwarps;
+    const int a_mine = (p.a_nblk - p.rank + p.nranks - 1) / p.nranks;
+    const int npg = (a_mine + nwarps - 1) / nwarps;
     const long long grid = (long long)npg * p.b_nblk;
     if (grid <= 0) return CSPBO_OK;
+    if (grid > 0x7fffffffLL) { set_error("block_build: grid too large"); return CSPBO_E_ARG; }
     kern<<<(unsigned)grid, nwarps * 32, smem, st>>>(p);
     g_launches++;
     CSPBO_CUDA(cudaGetLastError());
@@ -325,7 +374,7 @@ static int launch_ks(int mode, int fam, bool z2, const TileParams &p, int nwarps
 // Build one block between packs a and b into DEVICE memory `out` (accumulating).
 int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
-                       cudaStream_t st)
+                       int accumulate, cudaStream_t st, int rank, int nranks, double *const *outs)
 {
     if (a->ks != b->ks || a->d != b->d) {
         set_error("block_build: packs have different descriptor lengths (%d vs %d)", a->d, b->d);
@@ -335,8 +384,12 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     int fam = d.family == CSPBO_DOT ? FAM_DOT : (d.with_grad ? FAM_RBF_GRAD : FAM_RBF);
     const bool z2 = (d.zeta == 2.0);
     TileParams p;
-    p.A = {a->d_tiles, a->d_tile_start, a->d_slot_group, a->d_tile_valid, (int)a->tile_doubles, voffA};
-    p.B = {b->d_tiles, b->d_tile_start, b->d_slot_group, b->d_tile_valid, (int)b->tile_doubles, voffB};
+    p.A = {a->d_tiles, a->d_tile_start, a->d_slot_group, a->d_tile_valid, (int)a->tile_doubles, voffA, (int)a->species.size()};
+    p.B = {b->d_tiles, b->d_tile_start, b->d_slot_group, b->d_tile_valid, (int)b->tile_doubles, voffB, (int)b->species.size()};
+    if (a->species.size() > (size_t)kMaxSpecies || b->species.size() > (size_t)kMaxSpecies) {
+        set_error("block_build: more than %d species in one pack", kMaxSpecies);
+        return CSPBO_E_ARG;
+    }
     p.zeta = d.zeta; p.sigma2 = d.sigma2; p.sigma02 = d.sigma02;
     p.inv2l2 = d.family == CSPBO_RBF ? 1.0 / (2.0 * d.l * d.l) : 0.0;
     p.inv_l = d.family == CSPBO_RBF ? 1.0 / d.l : 0.0;
@@ -346,36 +399,39 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.out = out; p.out_grad = out_grad;
     p.si = si; p.sk = sk; p.sj = sj; p.sl = sl;
     p.symmetric = d.symmetric;
+    p.accumulate = accumulate;
+    p.sharded = outs != nullptr;
+    p.nranks = p.sharded ? nranks : 1;
+    p.rank = p.sharded ? rank : 0;
+    for (int r = 0; r < kMaxRanks; r++) p.outs[r] = (p.sharded && r < nranks) ? outs[r] : nullptr;
+    p.a_nblk = (int)a->n_blocks; p.b_nblk = (int)b->n_blocks;
+    if (p.a_nblk == 0 || p.b_nblk == 0) return CSPBO_OK;
+
+    int maxTb = 1;
+    for (int e = 0; e < kMaxSpecies; e++) p.emap[e] = -1;
+    const int nsB = (int)b->species.size();
+    for (size_t ea = 0; ea < a->species.size(); ea++)
+        for (size_t eb = 0; eb < b->species.size(); eb++)
+            if (b->species[eb] == a->species[ea]) {
+                p.emap[ea] = (int)eb;
+                for (int q = 0; q < p.b_nblk; q++)
+                    maxTb = std::max(maxTb, b->h_tile_start[(size_t)q * nsB + eb + 1] - b->h_tile_start[(size_t)q * nsB + eb]);
+            }
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-
-    for (size_t ea = 0; ea < a->species.size(); ea++) {
-        size_t eb = 0;
-        for (; eb < b->species.size(); eb++)
-            if (b->species[eb] == a->species[ea]) break;
-        if (eb == b->species.size()) continue;
-        p.a_blk0 = a->blk0[ea]; p.a_nblk = a->blk0[ea + 1] - a->blk0[ea];
-        p.b_blk0 = b->blk0[eb]; p.b_nblk = b->blk0[eb + 1] - b->blk0[eb];
-        if (p.a_nblk == 0 || p.b_nblk == 0) continue;
-        // warps per CTA: one A block per warp; shrink for small problems so the grid covers the SMs
-        int nwarps = 8;
-        while (nwarps > 1 && (long long)((p.a_nblk + nwarps - 1) / nwarps) * p.b_nblk < 2LL * sms) nwarps >>= 1;
-        // B tiles per shared-memory chunk: all tiles of the largest B block if they fit in ~96 KB
-        int maxTb = 0;
-        for (int q = p.b_blk0; q < p.b_blk0 + p.b_nblk; q++)
-            maxTb = std::max(maxTb, b->h_tile_start[q + 1] - b->h_tile_start[q]);
-        const size_t tile_bytes = (size_t)b->tile_doubles * sizeof(double);
-        int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, (96 * 1024) / tile_bytes));
-        p.tbc = tbc;
-        const size_t smem = (size_t)tbc * tile_bytes + (size_t)tbc * sizeof(unsigned) + 16;
-        int rc;
-        if (a->ks == 6) rc = launch_ks<6>(mode, fam, z2, p, nwarps, smem, st);
-        else rc = launch_ks<14>(mode, fam, z2, p, nwarps, smem, st);
-        if (rc) return rc;
-    }
-    return CSPBO_OK;
+    // warps per CTA: one A block per warp; shrink for small problems so the grid covers the SMs
+    int nwarps = 8;
+    const int a_mine = (p.a_nblk - p.rank + p.nranks - 1) / p.nranks;
+    while (nwarps > 1 && (long long)((a_mine + nwarps - 1) / nwarps) * p.b_nblk < 2LL * sms) nwarps >>= 1;
+    // B tiles per shared-memory chunk: a whole (block, species) run if it fits in ~96 KB
+    const size_t tile_bytes = (size_t)b->tile_doubles * sizeof(double);
+    const int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, (96 * 1024) / tile_bytes));
+    p.tbc = tbc;
+    const size_t smem = (size_t)tbc * tile_bytes + (size_t)tbc * sizeof(unsigned) + 16;
+    if (a->ks == 6) return launch_ks<6>(mode, fam, z2, p, nwarps, smem, st);
+    return launch_ks<14>(mode, fam, z2, p, nwarps, smem, st);
 }
 
 }  // namespace cspbo

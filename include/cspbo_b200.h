@@ -188,6 +188,26 @@ typedef struct {
 int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b,
                       double *out, double *out_grad, int mem, int accumulate);
 
+/* ---- sharded symmetric build: one process per GPU, K(X,X) distributed by row blocks ----------
+ * The groups of pack `a` are taken in PACKED order (cspbo_pack_order: position -> group id, -1 for the
+ * padding slots of the last block) and cut into blocks of 8; rank r owns blocks r, r+nranks, ...
+ * Its buffer outs[r] holds those row blocks contiguously: [cspbo_sharded_rows(a,r,nranks), 3, m*3]
+ * for K_FF ([rows, m] for K_EE); columns keep the caller's group order.  Every rank computes only
+ * the tiles (block a owned, block b >= a) and stores the mirrored tile directly into the owner's
+ * buffer through NVLink peer memory, so outs[] must hold, for every rank, a pointer valid in THIS
+ * process (own buffer from cspbo_dev_alloc, peers' through cspbo_ipc_open).  Replaces the reference's
+ * MPI split + Allreduce of the whole matrix (dot_kernel.py:188-247).  Callers must barrier across
+ * ranks before (buffers allocated) and after (peer stores landed) the call. */
+int cspbo_dev_alloc(long long bytes, void **ptr);            /* cudaMalloc: IPC-exportable */
+int cspbo_dev_free(void *ptr);
+int cspbo_ipc_export(void *ptr, unsigned char *handle64);    /* cudaIpcGetMemHandle (64 bytes) */
+int cspbo_ipc_open(const unsigned char *handle64, void **ptr);
+int cspbo_ipc_close(void *ptr);
+long long cspbo_sharded_rows(const cspbo_pack *a, int rank, int nranks);
+int cspbo_pack_order(const cspbo_pack *a, int *order, long long n);   /* n >= 8*ceil(m/8) */
+int cspbo_block_build_sharded(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
+                              double *const *outs);
+
 /* ------------------------------------------------------------------------------------------
  * (3) GP algebra on the device (all pointers are DEVICE pointers, column count = N)
  * ------------------------------------------------------------------------------------------ */
