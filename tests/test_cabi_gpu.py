@@ -1,0 +1,182 @@
+"""The C ABI called directly (ctypes, host pointers) against the oracle's C port on seeded random
+inputs that exercise the edge cases of the reference loops: several species, zero-norm rows
+(skipped, dot_kernel.cpp:25,37), groups that own no row, 1-row groups, the [n2_start,n2_end) slice
+(dot_kernel.cpp:245), non-zero initial pout (the functions accumulate), d not a multiple of 4,
+d = 50 (AgI.json), zeta in {1, 2, 2.5, 3}, and empty inputs."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from tests._cases import max_norm_err
+
+pytestmark = pytest.mark.gpu
+
+c_int, c_dbl, c_vp = ctypes.c_int, ctypes.c_double, ctypes.c_void_p
+
+
+def P(a):
+    return c_vp(a.ctypes.data)
+
+
+def make_side(rng, m, d, nc, species=(1, 8, 78), zero_rows=2, empty_groups=1, max_rows=9):
+    """Random stacked set with ragged groups; returns x, dxdr, ele, inds, m."""
+    counts = rng.integers(1, max_rows, size=m)
+    if empty_groups and m > 2:
+        counts[rng.integers(0, m, size=empty_groups)] = 0      # groups that own no row
+    n = int(counts.sum())
+    # power-spectrum descriptors are non-negative, so the cosine c stays positive (pow(c, zeta) real)
+    x = (np.abs(rng.standard_normal((n, d))) + 0.05) * rng.uniform(0.5, 50.0, size=(n, 1))
+    dx = rng.standard_normal((n, d, max(nc, 1))) * 3.0
+    if zero_rows and n > 4:
+        x[rng.integers(0, n, size=zero_rows)] = 0.0              # |x| = 0 rows are skipped
+    ele = rng.choice(species, size=n).astype(np.int32)
+    inds = np.repeat(np.arange(m, dtype=np.int32), counts)
+    return np.ascontiguousarray(x), np.ascontiguousarray(dx), ele, inds, m
+
+
+@pytest.fixture(scope="module")
+def libs(oracle_built):
+    from csp_bo_b200 import _lib
+    from oracle import cpu_reference as cr
+    lib = _lib.load()
+    port = cr.get_backend("port")
+    return lib, port, _lib
+
+
+def both(libs, family, name, args, out_shapes, init=0.0):
+    """Run cspbo_<family>_<name> and the oracle on identical zero/`init`-filled outputs."""
+    lib, port, _lib = libs
+    outs_g = [np.full(s, init) for s in out_shapes]
+    outs_o = [np.full(s, init) for s in out_shapes]
+    rc = getattr(lib, "cspbo_%s_%s" % (family, name))(*args, *[P(o) for o in outs_g])
+    assert rc == 0, lib.cspbo_last_error()
+    port.fn(family, name)(*args, *[P(o) for o in outs_o])
+    return outs_g, outs_o
+
+
+@pytest.mark.parametrize("d,zeta,seed", [(24, 2.0, 0), (24, 3.0, 1), (10, 2.5, 2), (50, 2.0, 3), (24, 1.0, 4)])
+def test_dot_entry_points(libs, d, zeta, seed):
+    rng = np.random.default_rng(seed)
+    x1, _, e1, g1, m1 = make_side(rng, 11, d, 0)
+    x2, dx2, e2, g2, m2 = make_side(rng, 13, d, 3)
+    xa, dxa, ea, ga, ma = make_side(rng, 9, d, 9)
+    n1, n2, na = len(x1), len(x2), len(xa)
+    I = c_int
+    g, o = both(libs, "dot", "kee_many", [I(n1), I(n1), I(d), I(m1), c_dbl(zeta), c_dbl(7.3), c_dbl(0.04),
+                                          P(x1), P(e1), P(g1), P(x1), P(e1), P(g1)], [(m1, m1)], init=0.25)
+    assert max_norm_err(g[0], o[0]) < 1e-12
+    g, o = both(libs, "dot", "kef_many", [I(n1), I(n2), I(d), I(m2), c_dbl(zeta), P(x1), P(e1), P(g1),
+                                          P(x2), P(dx2), P(e2), P(g2)], [(m1, m2, 3)])
+    assert max_norm_err(g[0], o[0]) < 1e-12
+    g, o = both(libs, "dot", "kef_many_stress", [I(n1), I(na), I(d), I(ma), c_dbl(zeta), P(x1), P(e1), P(g1),
+                                                 P(xa), P(dxa), P(ea), P(ga)], [(m1, ma, 9)])
+    assert max_norm_err(g[0], o[0]) < 1e-12
+    for (s, e) in ((0, n2), (n2 // 3, 2 * n2 // 3), (5, 5)):
+        g, o = both(libs, "dot", "kff_many", [I(n2), I(n2), I(s), I(e), I(d), I(m2), c_dbl(zeta),
+                                              P(x2), P(dx2), P(e2), P(g2), P(x2), P(dx2), P(e2), P(g2)],
+                    [(m2, 3, m2 * 3)], init=-1.5)
+        assert max_norm_err(g[0], o[0]) < 1e-12, (s, e)
+    g, o = both(libs, "dot", "kff_many_stress", [I(na), I(n2), I(0), I(n2), I(d), I(m2), c_dbl(zeta),
+                                                 P(xa), P(dxa), P(ea), P(ga), P(x2), P(dx2), P(e2), P(g2)],
+                [(ma, 9, m2 * 3)])
+    assert max_norm_err(g[0], o[0]) < 1e-12
+
+
+@pytest.mark.parametrize("d,zeta,l,seed", [(24, 2.0, 0.56, 10), (24, 3.0, 0.9, 11), (50, 2.0, 0.5, 12), (7, 2.5, 1.3, 13)])
+def test_rbf_entry_points(libs, d, zeta, l, seed):
+    rng = np.random.default_rng(seed)
+    x1, _, e1, g1, m1 = make_side(rng, 10, d, 0)
+    x2, dx2, e2, g2, m2 = make_side(rng, 12, d, 3)
+    xa, dxa, ea, ga, ma = make_side(rng, 8, d, 9)
+    n1, n2, na = len(x1), len(x2), len(xa)
+    I, s2, l2 = c_int, 39.0, l * l
+    g, o = both(libs, "rbf", "kee_many", [I(n1), I(n1), I(d), I(m1), c_dbl(zeta), c_dbl(s2), c_dbl(l2),
+                                          P(x1), P(e1), P(g1), P(x1), P(e1), P(g1)], [(m1, m1)])
+    assert max_norm_err(g[0], o[0]) < 1e-12
+    g, o = both(libs, "rbf", "kee_many_with_grad", [I(n1), I(n1), I(d), I(m1), c_dbl(zeta), c_dbl(s2), c_dbl(l2),
+                                                    P(x1), P(e1), P(g1), P(x1), P(e1), P(g1)], [(m1, m1), (m1, m1)], init=0.5)
+    assert max_norm_err(g[0], o[0]) < 1e-12 and max_norm_err(g[1], o[1]) < 1e-12
+    g, o = both(libs, "rbf", "kef_many", [I(n1), I(n2), I(d), I(m2), c_dbl(zeta), c_dbl(s2), c_dbl(l2),
+                                          P(x1), P(e1), P(g1), P(x2), P(dx2), P(e2), P(g2)], [(m1, m2, 3)])
+    assert max_norm_err(g[0], o[0]) < 1e-12
+    g, o = both(libs, "rbf", "kef_many_with_grad", [I(n1), I(n2), I(d), I(m2), c_dbl(zeta), c_dbl(s2), c_dbl(l),
+                                                    P(x1), P(e1), P(g1), P(x2), P(dx2), P(e2), P(g2)], [(m1, m2, 6)], init=2.0)
+    assert max_norm_err(g[0], o[0]) < 1e-12
+    g, o = both(libs, "rbf", "kef_many_stress", [I(n1), I(na), I(d), I(ma), c_dbl(zeta), c_dbl(s2), c_dbl(l2),
+                                                 P(x1), P(e1), P(g1), P(xa), P(dxa), P(ea), P(ga)], [(m1, ma, 9)])
+    assert max_norm_err(g[0], o[0]) < 1e-12
+    for tol in (1e-12, 0.0, -1.0):
+        g, o = both(libs, "rbf", "kff_many", [I(n2), I(n2), I(3), I(n2 - 2), I(d), I(m2), c_dbl(zeta), c_dbl(s2),
+                                              c_dbl(l2), c_dbl(tol), P(x2), P(dx2), P(e2), P(g2),
+                                              P(x2), P(dx2), P(e2), P(g2)], [(m2, 3, m2 * 3)], init=1.0)
+        assert max_norm_err(g[0], o[0]) < 1e-12, tol
+    g, o = both(libs, "rbf", "kff_many_with_grad", [I(n2), I(n2), I(0), I(n2), I(d), I(m2), c_dbl(zeta), c_dbl(s2),
+                                                    c_dbl(l), P(x2), P(dx2), P(e2), P(g2),
+                                                    P(x2), P(dx2), P(e2), P(g2)], [(m2, 3, m2 * 3), (m2, 3, m2 * 3)])
+    assert max_norm_err(g[0], o[0]) < 1e-12 and max_norm_err(g[1], o[1]) < 1e-12
+    g, o = both(libs, "rbf", "kff_many_stress", [I(na), I(n2), I(0), I(n2), I(d), I(m2), c_dbl(zeta), c_dbl(s2),
+                                                 c_dbl(l2), c_dbl(1e-12), P(xa), P(dxa), P(ea), P(ga),
+                                                 P(x2), P(dx2), P(e2), P(g2)], [(ma, 9, m2 * 3)])
+    assert max_norm_err(g[0], o[0]) < 1e-12
+
+
+def test_reference_named_shims(libs, fixtures):
+    """libdot_kernel_b200.so / librbf_kernel_b200.so: the exact names the reference's cffi binds."""
+    lib, port, _lib = libs
+    x, dx = fixtures["x2_x"], fixtures["x2_dxdr"]
+    ele = np.ascontiguousarray(fixtures["x2_ele"], dtype=np.int32)
+    inds = np.repeat(np.arange(27, dtype=np.int32), fixtures["x2_counts"])
+    n, d, m, I = len(x), 24, 27, c_int
+    for so, family, extra in (("libdot_kernel_b200.so", "dot", []),
+                              ("librbf_kernel_b200.so", "rbf", [c_dbl(39.0), c_dbl(0.3), c_dbl(1e-12)])):
+        shim = ctypes.CDLL(os.path.join(_lib.LIB_DIR, so))
+        shim.kff_many.restype = None
+        args = [I(n), I(n), I(0), I(n), I(d), I(m), c_dbl(2.0)] + extra + [P(x), P(dx), P(ele), P(inds), P(x), P(dx), P(ele), P(inds)]
+        got, want = np.zeros((m, 3, m * 3)), np.zeros((m, 3, m * 3))
+        shim.kff_many(*args, P(got))
+        port.fn(family, "kff_many")(*args, P(want))
+        assert max_norm_err(got, want) < 1e-12, so
+
+
+def test_empty_and_bad_arguments(libs):
+    lib, port, _lib = libs
+    x = np.ones((4, 24)); e = np.ones(4, dtype=np.int32); g = np.zeros(4, dtype=np.int32); out = np.zeros(4)
+    I = c_int
+    # n1 = 0: nothing to do, pout untouched
+    assert lib.cspbo_dot_kee_many(I(0), I(4), I(24), I(1), c_dbl(2.0), c_dbl(1.0), c_dbl(0.0),
+                                  P(x), P(e), P(g), P(x), P(e), P(g), P(out)) == 0
+    assert np.all(out == 0)
+    # unsupported descriptor length
+    xb = np.ones((4, 100))
+    assert lib.cspbo_dot_kee_many(I(4), I(4), I(100), I(1), c_dbl(2.0), c_dbl(1.0), c_dbl(0.0),
+                                  P(xb), P(e), P(g), P(xb), P(e), P(g), P(out)) == 2
+    assert b"unsupported" in lib.cspbo_last_error()
+    # group id outside [0, x2i)
+    gbad = np.array([0, 0, 0, 7], dtype=np.int32)
+    assert lib.cspbo_dot_kee_many(I(4), I(4), I(24), I(1), c_dbl(2.0), c_dbl(1.0), c_dbl(0.0),
+                                  P(x), P(e), P(g), P(x), P(e), P(gbad), P(out)) == 2
+
+
+def test_symmetric_and_general_builds_agree_at_scale():
+    """Size-independent properties at 5 001 force rows: the mirrored (symmetric) build equals the general
+    build, K_FF is symmetric, and K_FF + noise is positive definite (Cholesky succeeds)."""
+    import torch
+    from csp_bo_b200 import _lib, gp, synthetic
+    from csp_bo_b200.packing import Pack, build_block
+    X = synthetic.force_set(1667, seed=5)
+    p = Pack(X[0], X[1], X[2], X[3])
+    Ks, _ = build_block(_lib.DOT, _lib.KFF, p, p, 2.0, scale=688.0, symmetric=True, device=True)
+    Kg, _ = build_block(_lib.DOT, _lib.KFF, p, p, 2.0, scale=688.0, symmetric=False, device=True)
+    Ks, Kg = Ks.reshape(5001, 5001), Kg.reshape(5001, 5001)
+    den = float(Kg.abs().max())
+    assert float((Ks - Kg).abs().max()) / den < 1e-13
+    # mirrored off-diagonal blocks are bit-identical; the 8x8-group diagonal blocks compute (i,j) and
+    # (j,i) in different threads (different summation order), so allow rounding there
+    assert float((Ks - Ks.T).abs().max()) / den < 1e-13
+    assert float((Kg - Kg.T).abs().max()) / den < 1e-13
+    y = torch.ones(5001, dtype=torch.float64, device="cuda")
+    alpha = gp.fit_alpha(Ks, y, n_energy=0, noise_e=0.005, f_coef=30.0)
+    Kn = Ks + torch.eye(5001, dtype=torch.float64, device="cuda") * (30 * 0.005) ** 2
+    assert float((Kn @ alpha - y).abs().max()) < 1e-6
