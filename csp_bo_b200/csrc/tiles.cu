@@ -24,6 +24,15 @@ namespace cspbo {
 
 constexpr int kMaxSpecies = 16;
 constexpr int kMaxRanks = 8;
+// 3 CTAs x 4 warps per SM = 3 warps per scheduler: while one warp runs its chain-rule epilogue the
+// other two keep the FP64 tensor pipe fed (<= 170 registers/thread, <= 75 KB shared memory per CTA)
+constexpr int kMaxWarps = 4;
+constexpr int kMinCtas = 3;
+constexpr size_t kSmemChunk = 72 * 1024;
+// Rasterisation: A-block groups per strip.  Measured on B200 (20 001 force rows): strips of 1..64 are 3-6 %
+// slower than no strips (B block shared by all consecutive CTAs stays L2-hot, A tiles stream), so
+// the default is a single strip.
+constexpr int kStrip = 1 << 30;
 
 struct SideDev {
     const double *tiles;
@@ -40,6 +49,7 @@ struct TileParams {
     int a_nblk, b_nblk;
     int emap[kMaxSpecies];  // species bucket of A -> bucket of B holding the same species id, or -1
     int tbc;  // B tiles per shared-memory chunk
+    int strip;  // A-block groups per rasterisation strip
     int symmetric;
     int accumulate;  // 1: out += result (reference `pout +=` semantics), 0: out = result
     double zeta, sigma2, sigma02, inv2l2, inv_l, inv_l3, tol;
@@ -59,7 +69,7 @@ enum { FAM_DOT = 0, FAM_RBF = 1, FAM_RBF_GRAD = 2 };
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
@@ -119,7 +129,8 @@ __device__ __forceinline__ Weights pair_weights(double c, bool valid, const Tile
 }
 
 template <int MODE, int FAM, int KS, bool Z2>
-__global__ void __launch_bounds__(256) block_tile_kernel(const TileParams p)
+__global__ void __launch_bounds__(kMaxWarps * 32, (KS <= 6 && FAM != FAM_RBF_GRAD) ? kMinCtas : 2)
+block_tile_kernel(const TileParams p)
 {
     constexpr int NV1 = (MODE == MODE_KFF) ? 4 : 1;
     constexpr int NV2 = (MODE == MODE_KEE) ? 1 : 4;
@@ -134,8 +145,14 @@ __global__ void __launch_bounds__(256) block_tile_kernel(const TileParams p)
     const int nwarps = blockDim.x >> 5;
     const int a_mine = (p.a_nblk - p.rank + p.nranks - 1) / p.nranks;
     const int npg = (a_mine + nwarps - 1) / nwarps;
-    const int pg = blockIdx.x % npg;
-    const int q = blockIdx.x / npg;
+    // rasterisation: CTAs walk a strip of p.strip A-block groups across all B blocks (one strip = all
+    // A-block groups by default: consecutive CTAs share the B block, which stays L2-hot)
+    const int strip_ids = p.strip * p.b_nblk;
+    const int strip = blockIdx.x / strip_ids;
+    const int rem = blockIdx.x - strip * strip_ids;
+    const int strip_w = min(p.strip, npg - strip * p.strip);
+    const int q = rem / strip_w;
+    const int pg = strip * p.strip + (rem - q * strip_w);
     const int a_blk = (pg * nwarps + warp) * p.nranks + p.rank;  // nranks == 1, rank == 0 unless sharded
     const int b_blk = q;
     // symmetric build: only blocks with b >= a are computed (mirrored at write time)
@@ -206,15 +223,22 @@ __global__ void __launch_bounds__(256) block_tile_kernel(const TileParams p)
                 const double2 *bt = reinterpret_cast<const double2 *>(sB + (size_t)tb * p.B.tile_doubles);
 #pragma unroll
                 for (int h = 0; h < HALF; h++) {
+                    // one 128-bit LDS per B vector = operands of k-steps 2h and 2h+1; the 16 accumulators
+                    // of a k-step are independent, so consecutive DMMAs never wait on each other
+                    double2 b[NV2];
 #pragma unroll
                     for (int v2 = 0; v2 < NV2; v2++) {
                         const int tv = (v2 == 0) ? 0 : (p.B.voff + v2);
-                        const double2 b = bt[(tv * HALF + h) * 32 + lane];
-#pragma unroll
-                        for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h], b.x);
-#pragma unroll
-                        for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h + 1], b.y);
+                        b[v2] = bt[(tv * HALF + h) * 32 + lane];
                     }
+#pragma unroll
+                    for (int v2 = 0; v2 < NV2; v2++)
+#pragma unroll
+                        for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h], b[v2].x);
+#pragma unroll
+                    for (int v2 = 0; v2 < NV2; v2++)
+#pragma unroll
+                        for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h + 1], b[v2].y);
                 }
 
                 const unsigned vb = sBvalid[tb];
@@ -346,7 +370,14 @@ static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t
     if (grid > 0x7fffffffLL) { set_error("block_build: grid too large"); return CSPBO_E_ARG; }
     kern<<<(unsigned)grid, nwarps * 32, smem, st>>>(p);
     g_launches++;
-    CSPBO_CUDA(cudaGetLastError());
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("tile kernel launch failed: %s (grid %lld, block %d, smem %zu, tbc %d)", cudaGetErrorString(e), grid,
+                      nwarps * 32, smem, p.tbc);
+            return CSPBO_E_CUDA;
+        }
+    }
     return CSPBO_OK;
 }
 
@@ -422,13 +453,14 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // warps per CTA: one A block per warp; shrink for small problems so the grid covers the SMs
-    int nwarps = 8;
+    int nwarps = kMaxWarps;
     const int a_mine = (p.a_nblk - p.rank + p.nranks - 1) / p.nranks;
     while (nwarps > 1 && (long long)((a_mine + nwarps - 1) / nwarps) * p.b_nblk < 2LL * sms) nwarps >>= 1;
-    // B tiles per shared-memory chunk: a whole (block, species) run if it fits in ~96 KB
+    // B tiles per shared-memory chunk: a whole (block, species) run if it fits in 72 KB
     const size_t tile_bytes = (size_t)b->tile_doubles * sizeof(double);
-    const int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, (96 * 1024) / tile_bytes));
+    const int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, kSmemChunk / tile_bytes));
     p.tbc = tbc;
+    p.strip = kStrip;
     const size_t smem = (size_t)tbc * tile_bytes + (size_t)tbc * sizeof(unsigned) + 16;
     if (a->ks == 6) return launch_ks<6>(mode, fam, z2, p, nwarps, smem, st);
     return launch_ks<14>(mode, fam, z2, p, nwarps, smem, st);
