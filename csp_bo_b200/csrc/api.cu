@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "common.h"
 
@@ -21,7 +22,8 @@ void set_error(const char *fmt, ...)
 
 int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
-                       int accumulate, cudaStream_t st, int rank = 0, int nranks = 1, double *const *outs = nullptr);
+                       int accumulate, cudaStream_t st, int rank = 0, int nranks = 1, double *const *outs = nullptr,
+                       int a_begin = 0, int a_end = -1);
 
 struct DevBuf {
     double *p = nullptr;
@@ -104,6 +106,61 @@ extern "C" int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack 
     }
     // every (group_i, group_j) output block is owned by exactly one warp, which writes it once:
     // no zero-initialisation is needed in overwrite mode
+
+    // Host-bound K_FF: cut the A blocks into row slabs and copy every finished slab back on a second
+    // stream while the next one is being computed (a slab's rows are final once its own kernel has
+    // run: mirrored tiles only ever land in rows of the same or later slabs).
+    const bool pipelined = mem == CSPBO_MEM_HOST && d.block == CSPBO_KFF && a->n_blocks >= 64 &&
+                           (size_t)n_out * sizeof(double) >= ((size_t)64 << 20);
+    if (pipelined) {
+        const int nslab = 12;
+        const int nb = (int)a->n_blocks;
+        cudaStream_t cs = nullptr;
+        cudaEvent_t ev = nullptr;
+        CSPBO_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        CSPBO_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CSPBO_CUDA(cudaStreamSynchronize(0));   // upload of an accumulated-into pout has landed
+        int rc = CSPBO_OK;
+        std::vector<int> groups;
+        const long long rowlen = si, rowlen_g = 3LL * m2 * 3;
+        for (int s = 0; s < nslab && rc == CSPBO_OK; s++) {
+            const int b0 = (int)((long long)nb * s / nslab), b1 = (int)((long long)nb * (s + 1) / nslab);
+            if (b1 <= b0) continue;
+            for (int pa = 0; pa < passesA && rc == CSPBO_OK; pa++)
+                rc = build_block_device(d, a, b, pa * 3, 0, dout + (long long)pa * 3 * sk, dgrad, si, sk, sj, sl,
+                                        accumulate, 0, 0, 1, nullptr, b0, b1);
+            if (rc) break;
+            cudaEventRecord(ev, 0);
+            cudaStreamWaitEvent(cs, ev, 0);
+            groups.clear();
+            for (int blk = b0; blk < b1; blk++)
+                for (int r = 0; r < 8; r++) {
+                    const int g = a->h_slot_group[(size_t)blk * 8 + r];
+                    if (g >= 0) groups.push_back(g);
+                }
+            std::sort(groups.begin(), groups.end());
+            for (size_t i = 0; i < groups.size();) {   // merge runs of consecutive group ids into one copy
+                size_t j = i + 1;
+                while (j < groups.size() && groups[j] == groups[j - 1] + 1) j++;
+                const long long g0 = groups[i], cnt = (long long)(j - i);
+                cudaMemcpyAsync(out + g0 * rowlen, dout + g0 * rowlen, (size_t)(cnt * rowlen) * sizeof(double),
+                                cudaMemcpyDeviceToHost, cs);
+                if (grad)
+                    cudaMemcpyAsync(out_grad + g0 * rowlen_g, dgrad + g0 * rowlen_g,
+                                    (size_t)(cnt * rowlen_g) * sizeof(double), cudaMemcpyDeviceToHost, cs);
+                i = j;
+            }
+        }
+        cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(0), e3 = cudaGetLastError();
+        cudaEventDestroy(ev);
+        cudaStreamDestroy(cs);
+        if (rc) return rc;
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+            set_error("pipelined K_FF copy-back failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+            return CSPBO_E_CUDA;
+        }
+        return CSPBO_OK;
+    }
 
     for (int pa = 0; pa < passesA; pa++)
         for (int pb = 0; pb < passesB; pb++) {

@@ -47,6 +47,7 @@ struct SideDev {
 struct TileParams {
     SideDev A, B;
     int a_nblk, b_nblk;
+    int a_begin;  // first A block of this launch (row-slab pipelining of host-bound builds); a_nblk is the end
     int emap[kMaxSpecies];  // species bucket of A -> bucket of B holding the same species id, or -1
     int tbc;  // B tiles per shared-memory chunk
     int strip;  // A-block groups per rasterisation strip
@@ -143,7 +144,7 @@ block_tile_kernel(const TileParams p)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int a_mine = (p.a_nblk - p.rank + p.nranks - 1) / p.nranks;
+    const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
     const int npg = (a_mine + nwarps - 1) / nwarps;
     // rasterisation: CTAs walk a strip of p.strip A-block groups across all B blocks (one strip = all
     // A-block groups by default: consecutive CTAs share the B block, which stays L2-hot)
@@ -153,7 +154,7 @@ block_tile_kernel(const TileParams p)
     const int strip_w = min(p.strip, npg - strip * p.strip);
     const int q = rem / strip_w;
     const int pg = strip * p.strip + (rem - q * strip_w);
-    const int a_blk = (pg * nwarps + warp) * p.nranks + p.rank;  // nranks == 1, rank == 0 unless sharded
+    const int a_blk = p.a_begin + (pg * nwarps + warp) * p.nranks + p.rank;  // nranks == 1, rank == 0 unless sharded
     const int b_blk = q;
     // symmetric build: only blocks with b >= a are computed (mirrored at write time)
     const bool active = a_blk < p.a_nblk && !(p.symmetric && b_blk < a_blk);
@@ -363,7 +364,7 @@ static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t
         CSPBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int a_mine = (p.a_nblk - p.rank + p.nranks - 1) / p.nranks;
+    const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
     const int npg = (a_mine + nwarps - 1) / nwarps;
     const long long grid = (long long)npg * p.b_nblk;
     if (grid <= 0) return CSPBO_OK;
@@ -405,7 +406,7 @@ static int launch_ks(int mode, int fam, bool z2, const TileParams &p, int nwarps
 // Build one block between packs a and b into DEVICE memory `out` (accumulating).
 int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
-                       int accumulate, cudaStream_t st, int rank, int nranks, double *const *outs)
+                       int accumulate, cudaStream_t st, int rank, int nranks, double *const *outs, int a_begin, int a_end)
 {
     if (a->ks != b->ks || a->d != b->d) {
         set_error("block_build: packs have different descriptor lengths (%d vs %d)", a->d, b->d);
@@ -435,8 +436,10 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.nranks = p.sharded ? nranks : 1;
     p.rank = p.sharded ? rank : 0;
     for (int r = 0; r < kMaxRanks; r++) p.outs[r] = (p.sharded && r < nranks) ? outs[r] : nullptr;
-    p.a_nblk = (int)a->n_blocks; p.b_nblk = (int)b->n_blocks;
-    if (p.a_nblk == 0 || p.b_nblk == 0) return CSPBO_OK;
+    p.a_begin = std::max(a_begin, 0);
+    p.a_nblk = (a_end < 0) ? (int)a->n_blocks : std::min(a_end, (int)a->n_blocks);
+    p.b_nblk = (int)b->n_blocks;
+    if (p.a_nblk <= p.a_begin || p.b_nblk == 0) return CSPBO_OK;
 
     int maxTb = 1;
     for (int e = 0; e < kMaxSpecies; e++) p.emap[e] = -1;
@@ -454,14 +457,14 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // warps per CTA: one A block per warp; shrink for small problems so the grid covers the SMs
     int nwarps = kMaxWarps;
-    const int a_mine = (p.a_nblk - p.rank + p.nranks - 1) / p.nranks;
+    const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
     while (nwarps > 1 && (long long)((a_mine + nwarps - 1) / nwarps) * p.b_nblk < 2LL * sms) nwarps >>= 1;
     // B tiles per shared-memory chunk: a whole (block, species) run if it fits in 72 KB
     const size_t tile_bytes = (size_t)b->tile_doubles * sizeof(double);
     const int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, kSmemChunk / tile_bytes));
     p.tbc = tbc;
-    p.strip = kStrip;
     const size_t smem = (size_t)tbc * tile_bytes + (size_t)tbc * sizeof(unsigned) + 16;
+    p.strip = std::max(1, std::min(kStrip, (a_mine + nwarps - 1) / nwarps));
     if (a->ks == 6) return launch_ks<6>(mode, fam, z2, p, nwarps, smem, st);
     return launch_ks<14>(mode, fam, z2, p, nwarps, smem, st);
 }

@@ -180,3 +180,21 @@ def test_symmetric_and_general_builds_agree_at_scale():
     alpha = gp.fit_alpha(Ks, y, n_energy=0, noise_e=0.005, f_coef=30.0)
     Kn = Ks + torch.eye(5001, dtype=torch.float64, device="cuda") * (30 * 0.005) ** 2
     assert float((Kn @ alpha - y).abs().max()) < 1e-6
+
+
+def test_pipelined_host_copyback_equals_device_build():
+    """Host-bound K_FF builds above 64 MB are computed in row slabs whose copy-back overlaps the next
+    slab (api.cu); the result must be bit-identical to the one-shot device build, for the symmetric,
+    the general and the stress (9-row) variants."""
+    from csp_bo_b200 import _lib, synthetic
+    from csp_bo_b200.packing import Pack, build_block
+    X = synthetic.force_set(1100, seed=9)
+    Y = synthetic.force_set(1000, seed=10)
+    p, q = Pack(X[0], X[1], X[2], X[3]), Pack(Y[0], Y[1], Y[2], Y[3])
+    x9 = np.concatenate((X[1], 0.5 * X[1][:, :, [1, 2, 0]], -0.25 * X[1][:, :, [2, 0, 1]]), axis=2)
+    p9 = Pack(X[0], x9, X[2], X[3])
+    for a, b, kw in ((p, p, dict(symmetric=True)), (p, q, {}), (p9, q, dict(stress=True))):
+        dev, _ = build_block(_lib.RBF, _lib.KFF, a, b, 2.0, sigma2=39.0, l=0.56, tol=1e-10, use_tol=True, device=True, **kw)
+        host, _ = build_block(_lib.RBF, _lib.KFF, a, b, 2.0, sigma2=39.0, l=0.56, tol=1e-10, use_tol=True, **kw)
+        assert host.nbytes >= 64 << 20
+        assert np.array_equal(host, dev.cpu().numpy()), kw
