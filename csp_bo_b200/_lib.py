@@ -56,11 +56,14 @@ SIGNATURES = {
     "cspbo_rbf_kff_many_stress": [c_int, c_int, c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl, c_dbl] + _F + _F + [c_vp],
     "cspbo_pack_create": [c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int,
                           ctypes.POINTER(c_vp)],
+    "cspbo_pack_create_eps": [c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_dbl,
+                              ctypes.POINTER(c_vp)],
     "cspbo_pack_destroy": [c_vp],
     "cspbo_pack_groups": [c_vp],
     "cspbo_pack_bytes": [c_vp],
     "cspbo_pack_pair_count": [c_vp, c_vp],
     "cspbo_block_build": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_int],
+    "cspbo_block_diag": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_int],
     "cspbo_dev_alloc": [c_ll, ctypes.POINTER(c_vp)],
     "cspbo_dev_free": [c_vp],
     "cspbo_ipc_export": [c_vp, c_vp],

@@ -23,7 +23,7 @@ void set_error(const char *fmt, ...)
 int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
                        int accumulate, cudaStream_t st, int rank = 0, int nranks = 1, double *const *outs = nullptr,
-                       int a_begin = 0, int a_end = -1);
+                       int a_begin = 0, int a_end = -1, int diag = 0);
 
 struct DevBuf {
     double *p = nullptr;
@@ -173,6 +173,32 @@ extern "C" int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack 
     if (mem == CSPBO_MEM_HOST) {
         CSPBO_CUDA(cudaMemcpyAsync(out, dout, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost));
         if (grad) CSPBO_CUDA(cudaMemcpyAsync(out_grad, dgrad, (size_t)n_grad * sizeof(double), cudaMemcpyDeviceToHost));
+        CSPBO_CUDA(cudaStreamSynchronize(0));
+    }
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_block_diag(const cspbo_block_desc *desc, const cspbo_pack *a, double *out, int mem)
+{
+    if (!desc || !a || !out) { set_error("block_diag: null argument"); return CSPBO_E_ARG; }
+    cspbo_block_desc d = *desc;
+    if (d.block != CSPBO_KFF && d.block != CSPBO_KEE) { set_error("block_diag: K_EE or K_FF only"); return CSPBO_E_ARG; }
+    if (d.family == CSPBO_RBF && !(d.l > 0.0)) { set_error("block_diag: RBF needs l > 0"); return CSPBO_E_ARG; }
+    if ((d.block == CSPBO_KFF) != (a->nc >= 3)) { set_error("block_diag: pack kind does not match the block"); return CSPBO_E_ARG; }
+    d.symmetric = 0; d.stress = 0; d.with_grad = 0;
+    const long long n_out = (long long)a->m * (d.block == CSPBO_KFF ? 9 : 1);
+    if (n_out == 0) return CSPBO_OK;
+    double *dout = out;
+    DevBuf tmp;
+    if (mem == CSPBO_MEM_HOST) {
+        CSPBO_CUDA(cudaMalloc(&tmp.p, (size_t)n_out * sizeof(double)));
+        dout = tmp.p;
+    }
+    CSPBO_CUDA(cudaMemsetAsync(dout, 0, (size_t)n_out * sizeof(double)));
+    int rc = build_block_device(d, a, a, 0, 0, dout, nullptr, 0, 0, 0, 0, 0, 0, 0, 1, nullptr, 0, -1, 1);
+    if (rc) return rc;
+    if (mem == CSPBO_MEM_HOST) {
+        CSPBO_CUDA(cudaMemcpyAsync(out, dout, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost));
         CSPBO_CUDA(cudaStreamSynchronize(0));
     }
     return CSPBO_OK;

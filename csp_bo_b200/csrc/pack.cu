@@ -23,7 +23,7 @@ namespace cspbo {
 __global__ void pack_rows_kernel(int n, int d, int nc, int ks, int nv,
                                  const double *__restrict__ x, const double *__restrict__ dxdr,
                                  const long long *__restrict__ dest, double *__restrict__ tiles,
-                                 unsigned *__restrict__ tile_valid, long long tile_doubles)
+                                 unsigned *__restrict__ tile_valid, long long tile_doubles, double norm_shift)
 {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -41,8 +41,11 @@ __global__ void pack_rows_kernel(int n, int d, int nc, int ks, int nv,
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const double nrm = sqrt(ss);
-    if (!(nrm > 1e-8)) return;  // reference: rows with |x| <= eps are skipped (dot_kernel.cpp:25)
+    // norm_shift = 0: the C++ path (rows with |x| <= 1e-8 are skipped, dot_kernel.cpp:25);
+    // norm_shift = eps: the NumPy single-pair functions used by diag(), which add eps to every norm and
+    // skip nothing (Dot_mb.py:188-191,206,212)
+    const double nrm = sqrt(ss) + norm_shift;
+    if (norm_shift == 0.0 && !(nrm > 1e-8)) return;
     const double inv = 1.0 / nrm;
 
     double *t = tiles + tile * tile_doubles;
@@ -75,6 +78,13 @@ using namespace cspbo;
 extern "C" int cspbo_pack_create(int n, int d, int nc, int m, int row_start, int row_end,
                                  const double *x, const double *dxdr, const int *ele, const int *inds,
                                  int mem, cspbo_pack **out)
+{
+    return cspbo_pack_create_eps(n, d, nc, m, row_start, row_end, x, dxdr, ele, inds, mem, 0.0, out);
+}
+
+extern "C" int cspbo_pack_create_eps(int n, int d, int nc, int m, int row_start, int row_end,
+                                     const double *x, const double *dxdr, const int *ele, const int *inds,
+                                     int mem, double norm_shift, cspbo_pack **out)
 {
     if (!out) { set_error("pack_create: out is null"); return CSPBO_E_ARG; }
     *out = nullptr;
@@ -225,7 +235,7 @@ extern "C" int cspbo_pack_create(int n, int d, int nc, int m, int row_start, int
         }
         const int wpb = 8;
         pack_rows_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32>>>(n, d, nc, ks, p->nv, xs, dxs, d_dest,
-                                                                        p->d_tiles, p->d_tile_valid, p->tile_doubles);
+                                                                        p->d_tiles, p->d_tile_valid, p->tile_doubles, norm_shift);
         g_launches++;
         PACK_CUDA(cudaGetLastError());
     }

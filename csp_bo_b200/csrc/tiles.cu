@@ -52,6 +52,7 @@ struct TileParams {
     int tbc;  // B tiles per shared-memory chunk
     int strip;  // A-block groups per rasterisation strip
     int symmetric;
+    int diag;        // 1: one warp per block, b = a, only the (i,i) group pairs are stored: out[i, NC1, NC2]
     int accumulate;  // 1: out += result (reference `pout +=` semantics), 0: out = result
     double zeta, sigma2, sigma02, inv2l2, inv_l, inv_l3, tol;
     int use_tol;
@@ -155,7 +156,7 @@ block_tile_kernel(const TileParams p)
     const int q = rem / strip_w;
     const int pg = strip * p.strip + (rem - q * strip_w);
     const int a_blk = p.a_begin + (pg * nwarps + warp) * p.nranks + p.rank;  // nranks == 1, rank == 0 unless sharded
-    const int b_blk = q;
+    const int b_blk = p.diag ? a_blk : q;
     // symmetric build: only blocks with b >= a are computed (mirrored at write time)
     const bool active = a_blk < p.a_nblk && !(p.symmetric && b_blk < a_blk);
 
@@ -294,6 +295,17 @@ block_tile_kernel(const TileParams p)
     if (!active) return;
     const int gi = p.A.slot_group[a_blk * 8 + ar];
     if (gi < 0) return;
+    if (p.diag) {
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+            if (bq + e == ar) {
+#pragma unroll
+                for (int k = 0; k < NC1; k++)
+#pragma unroll
+                    for (int l = 0; l < NC2; l++) p.out[((long long)gi * NC1 + k) * NC2 + l] = p.scale * acc[e][k][l];
+            }
+        return;
+    }
     if (p.sharded) {
         // sharded symmetric build: rows are block-cyclic over ranks in packed order, columns keep the
         // caller's group ids.  Own tile -> local HBM, mirrored tile -> peer HBM of the owner of b.
@@ -406,7 +418,8 @@ static int launch_ks(int mode, int fam, bool z2, const TileParams &p, int nwarps
 // Build one block between packs a and b into DEVICE memory `out` (accumulating).
 int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
-                       int accumulate, cudaStream_t st, int rank, int nranks, double *const *outs, int a_begin, int a_end)
+                       int accumulate, cudaStream_t st, int rank, int nranks, double *const *outs, int a_begin, int a_end,
+                       int diag)
 {
     if (a->ks != b->ks || a->d != b->d) {
         set_error("block_build: packs have different descriptor lengths (%d vs %d)", a->d, b->d);
@@ -432,14 +445,15 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.si = si; p.sk = sk; p.sj = sj; p.sl = sl;
     p.symmetric = d.symmetric;
     p.accumulate = accumulate;
+    p.diag = diag;
     p.sharded = outs != nullptr;
     p.nranks = p.sharded ? nranks : 1;
     p.rank = p.sharded ? rank : 0;
     for (int r = 0; r < kMaxRanks; r++) p.outs[r] = (p.sharded && r < nranks) ? outs[r] : nullptr;
     p.a_begin = std::max(a_begin, 0);
     p.a_nblk = (a_end < 0) ? (int)a->n_blocks : std::min(a_end, (int)a->n_blocks);
-    p.b_nblk = (int)b->n_blocks;
-    if (p.a_nblk <= p.a_begin || p.b_nblk == 0) return CSPBO_OK;
+    p.b_nblk = diag ? 1 : (int)b->n_blocks;
+    if (p.a_nblk <= p.a_begin || b->n_blocks == 0) return CSPBO_OK;
 
     int maxTb = 1;
     for (int e = 0; e < kMaxSpecies; e++) p.emap[e] = -1;
@@ -448,7 +462,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
         for (size_t eb = 0; eb < b->species.size(); eb++)
             if (b->species[eb] == a->species[ea]) {
                 p.emap[ea] = (int)eb;
-                for (int q = 0; q < p.b_nblk; q++)
+                for (int q = 0; q < (int)b->n_blocks; q++)
                     maxTb = std::max(maxTb, b->h_tile_start[(size_t)q * nsB + eb + 1] - b->h_tile_start[(size_t)q * nsB + eb]);
             }
 
@@ -456,7 +470,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // warps per CTA: one A block per warp; shrink for small problems so the grid covers the SMs
-    int nwarps = kMaxWarps;
+    int nwarps = diag ? 1 : kMaxWarps;
     const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
     while (nwarps > 1 && (long long)((a_mine + nwarps - 1) / nwarps) * p.b_nblk < 2LL * sms) nwarps >>= 1;
     // B tiles per shared-memory chunk: a whole (block, species) run if it fits in 72 KB

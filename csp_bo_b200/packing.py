@@ -35,7 +35,7 @@ def group_ids(indices):
 class Pack:
     """Device-resident, tiled form of one stacked descriptor set."""
 
-    def __init__(self, x, dxdr, ele, indices, row_range=None):
+    def __init__(self, x, dxdr, ele, indices, row_range=None, norm_shift=0.0):
         lib = _lib.load()
         on_dev = _is_torch(x)
         if on_dev:
@@ -61,8 +61,9 @@ class Pack:
         self.m, self.n, self.d, self.nc = len(self.counts), n, d, nc
         r0, r1 = (0, n) if row_range is None else row_range
         h = c_vp()
-        _lib.check(lib.cspbo_pack_create(n, d, nc, self.m, int(r0), int(r1), _ptr(x), _ptr(dxdr), _ptr(ele), _ptr(inds),
-                                         MEM_DEVICE if on_dev else MEM_HOST, ctypes.byref(h)))
+        _lib.check(lib.cspbo_pack_create_eps(n, d, nc, self.m, int(r0), int(r1), _ptr(x), _ptr(dxdr), _ptr(ele),
+                                             _ptr(inds), MEM_DEVICE if on_dev else MEM_HOST, float(norm_shift),
+                                             ctypes.byref(h)))
         self._h = h
 
     @property
@@ -184,3 +185,12 @@ def build_block(family, block, a, b, zeta, sigma2=1.0, sigma02=0.0, l=1.0, tol=0
     _lib.check(lib.cspbo_block_build(ctypes.byref(desc), a.handle, b.handle, _ptr(out),
                                      _ptr(out_grad) if grad else None, mem, 0))
     return out, (out_grad if grad else None)
+
+
+def block_diag(family, block, a, zeta, sigma2=1.0, sigma02=0.0, l=1.0, scale=1.0):
+    """cspbo_block_diag: per-group self covariance, [m] (K_EE) or [m,3,3] (K_FF), as a numpy array."""
+    lib = _lib.load()
+    out = np.zeros((a.m,) if block == _lib.KEE else (a.m, 3, 3))
+    desc = BlockDesc(family, block, float(zeta), float(sigma2), float(sigma02), float(l), 0.0, 0, 0, 0, float(scale), 1.0, 0)
+    _lib.check(lib.cspbo_block_diag(ctypes.byref(desc), a.handle, _ptr(out), MEM_HOST))
+    return out

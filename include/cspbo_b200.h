@@ -151,6 +151,11 @@ typedef struct cspbo_pack cspbo_pack;   /* a stacked descriptor set, normalised 
 int cspbo_pack_create(int n, int d, int nc, int m, int row_start, int row_end,
                       const double *x, const double *dxdr, const int *ele, const int *inds,
                       int mem, cspbo_pack **out);
+/* Same, with `norm_shift` added to every row norm and no zero-norm skipping: norm_shift = 1e-8
+ * reproduces the eps-shifted NumPy formulas behind the kernels' diag() (Dot_mb.py:177-258). */
+int cspbo_pack_create_eps(int n, int d, int nc, int m, int row_start, int row_end,
+                          const double *x, const double *dxdr, const int *ele, const int *inds,
+                          int mem, double norm_shift, cspbo_pack **out);
 int cspbo_pack_destroy(cspbo_pack *p);
 int cspbo_pack_groups(const cspbo_pack *p);          /* m */
 long long cspbo_pack_bytes(const cspbo_pack *p);     /* HBM footprint */
@@ -187,6 +192,10 @@ typedef struct {
  * mem tells where out/out_grad live.  accumulate = 0 overwrites, 1 adds to the existing content. */
 int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b,
                       double *out, double *out_grad, int mem, int accumulate);
+
+/* Self covariance of every group of pack `a` (the diagonal blocks of K(a,a)): out[m] for K_EE,
+ * out[m,3,3] for K_FF.  Used by diag() for the predictive variance (Dot_mb.py:45-85). */
+int cspbo_block_diag(const cspbo_block_desc *desc, const cspbo_pack *a, double *out, int mem);
 
 /* ---- sharded symmetric build: one process per GPU, K(X,X) distributed by row blocks ----------
  * The groups of pack `a` are taken in PACKED order (cspbo_pack_order: position -> group id, -1 for the

@@ -431,6 +431,14 @@ class RefKernel:
                 build_covariance(None, None, C_se, C_sf))
 
 
+def _refkernel_diag(self, data):
+    """Dot_mb.diag / RBF_mb.diag (eps-shifted NumPy formulas), see kernel_diag below."""
+    return kernel_diag(self.family, self.para, self.zeta, data)
+
+
+RefKernel.diag = _refkernel_diag
+
+
 # ----------------------------------------------------------------------------- GP algebra
 def gp_fit(K, y, n_energy, noise_e, f_coef):
     """gaussianprocess.py:105-127: K + noise -> Cholesky -> alpha.  Returns (L, alpha)."""
@@ -443,3 +451,69 @@ def gp_fit(K, y, n_energy, noise_e, f_coef):
     L = cholesky(K, lower=True)
     alpha = cho_solve((L, True), np.asarray(y, dtype=np.float64).reshape(n, -1))
     return L, alpha
+
+
+# ----------------------------------------------------------------------------- diag (eps variants)
+def _single_pair_blocks(family, x1, x2, dx1, dx2, ele1, ele2, sigma2, p1, zeta, eps=1e-8):
+    """NumPy restatement of the reference's single-pair functions K_ee / K_ff used by diag()
+    (Dot_mb.py:177-258, RBF_mb.py:176-271): every norm carries +eps, nothing is skipped.
+    p1 = sigma0^2 (Dot) or l^2 (RBF).  Returns (kee scalar, kff[3,3] or None)."""
+    n1 = np.linalg.norm(x1, axis=1) + eps
+    n2 = np.linalg.norm(x2, axis=1) + eps
+    s = x1 @ x2.T
+    same = (np.asarray(ele1)[:, None] == np.asarray(ele2)[None, :])
+    d_ee = s / (eps + n1[:, None] * n2[None, :])
+    if family == "dot":
+        kee = (sigma2 * same * (d_ee ** zeta + p1)).sum() / (len(x1) * len(x2))
+    else:
+        kee = (sigma2 * np.exp(-(0.5 / p1) * (1 - d_ee ** zeta)) * same).sum() / (len(x1) * len(x2))
+    if dx1 is None:
+        return kee, None
+    n12 = n1[:, None] * n2[None, :]
+    d = s / n12 if family == "dot" else s / (eps + n12)
+    D2 = d ** (zeta - 2)
+    D1 = d * D2
+    dd1 = (x2[None, :, :] * n1[:, None, None] - s[:, :, None] * (x1 / n1[:, None])[:, None, :]) / (n1 ** 2)[:, None, None] / n2[None, :, None]
+    dd2 = (x1[:, None, :] * n2[None, :, None] - s[:, :, None] * (x2 / n2[:, None])[None, :, :]) / n1[:, None, None] / (n2 ** 2)[None, :, None]
+    eye = np.eye(x1.shape[1])
+    t33 = eye[None, :, :] - x2[:, :, None] * (x2 / (n2 ** 2)[:, None])[:, None, :]
+    x1n3, x2n3 = x1 / (n1 ** 3)[:, None], x2 / (n2 ** 3)[:, None]
+    out1 = (x1n3[:, None, :, None] * (x1[:, None, None, :] / n2[None, :, None, None])
+            - x1n3[:, None, :, None] * x2n3[None, :, None, :] * s[:, :, None, None])
+    d2d = t33[None, :, :, :] / n12[:, :, None, None] - out1
+    pq = dd1[:, :, :, None] * dd2[:, :, None, :]
+    d2D = zeta * (pq * (D2 * (zeta - 1))[:, :, None, None] + D1[:, :, None, None] * d2d)
+    if family == "dot":
+        M = d2D * (sigma2 * same)[:, :, None, None]
+    else:
+        k = sigma2 * np.exp(-(0.5 / p1) * (1 - d * D1)) * same
+        zd2 = -0.5 / p1 * zeta * zeta * D1 ** 2
+        M = (-d2D + zd2[:, :, None, None] * pq) * ((-0.5 / p1) * k)[:, :, None, None]
+    kff = np.einsum("apk,abpq,bql->kl", dx1, M, dx2)
+    return kee, kff
+
+
+def kernel_diag(family, para, zeta, data):
+    """Restates Dot_mb.diag / RBF_mb.diag (Dot_mb.py:45-85, RBF_mb.py:45-85)."""
+    sigma2 = para[0] ** 2
+    p1 = para[1] ** 2
+    out = []
+    if "energy" in data:
+        E = data["energy"]
+        if isinstance(E, tuple):
+            x, ele, counts = E
+            off = np.concatenate(([0], np.cumsum(counts)))
+            E = [(x[off[i]:off[i + 1]], ele[off[i]:off[i + 1]]) for i in range(len(counts))]
+        out.append(np.array([_single_pair_blocks(family, x, x, None, None, e, e, sigma2, p1, zeta)[0] for x, e in E]))
+    if "force" in data:
+        F = data["force"]
+        if isinstance(F, tuple):
+            x, dx, ele, counts = F
+            off = np.concatenate(([0], np.cumsum(counts)))
+            F = [(x[off[i]:off[i + 1]], dx[off[i]:off[i + 1]], ele[off[i]:off[i + 1]]) for i in range(len(counts))]
+        vals = []
+        for x, dx, e in F:
+            dx3 = np.asarray(dx)[:, :, :3]
+            vals.extend(np.diag(_single_pair_blocks(family, x, x, dx3, dx3, e, e, sigma2, p1, zeta)[1]))
+        out.append(np.array(vals))
+    return np.hstack(out)

@@ -85,6 +85,18 @@ def take_groups_e(energy, g0, g1):
     return (x[s:e], ele[s:e], list(counts[g0:g1]))
 
 
+def force_list(F):
+    x, dx, ele, counts = F
+    off = np.concatenate(([0], np.cumsum(counts)))
+    return [(x[off[i]:off[i + 1]], dx[off[i]:off[i + 1]], ele[off[i]:off[i + 1]]) for i in range(len(counts))]
+
+
+def energy_list(E):
+    x, ele, counts = E
+    off = np.concatenate(([0], np.cumsum(counts)))
+    return [(x[off[i]:off[i + 1]], ele[off[i]:off[i + 1]]) for i in range(len(counts))]
+
+
 def force_tuple(fx, name):
     return (fx[name + "_x"], fx[name + "_dxdr"], fx[name + "_ele"], list(fx[name + "_counts"]))
 
@@ -156,6 +168,8 @@ def golden_cases(fx, cr):
         out[fam + "_ktotal_grad_K"], out[fam + "_ktotal_grad_dK"] = K, dK
         K, Ks = k.k_total_with_stress(test9, train)
         out[fam + "_ktotal_stress_K"], out[fam + "_ktotal_stress_Ks"] = K, Ks
+        out[fam + "_diag"] = k.diag(test)           # tuple form
+        out[fam + "_diag_list"] = k.diag({"energy": energy_list(test["energy"]), "force": force_list(test9["force"])})
     return out
 
 

@@ -55,6 +55,26 @@ def main():
     fx = load_fixtures_from_reference()
     np.savez(os.path.join(HERE, "fixtures.npz"), **fx)
     out = golden_cases(fx, OracleImpl("ref"))
+    # diag(): the goldens come from the reference's OWN NumPy single-pair functions, exec'd from source
+    # (importing the package needs mpi4py/ase); the oracle's restatement must agree with them.
+    from tests._cases import energy_list, energy_tuple, force_list, force_tuple, stress_columns, take_groups, take_groups_e
+    big, ee2 = force_tuple(fx, "big"), energy_tuple(fx, "ee2")
+    tf = take_groups(big, 0, 12)
+    test = {"energy": take_groups_e(ee2, 4, 6), "force": tf}
+    test_l = {"energy": energy_list(test["energy"]),
+              "force": force_list((tf[0], stress_columns(tf[1]), tf[2], tf[3]))}
+    for fam, fname, cls, para in (("dot", "Dot_mb.py", "Dot_mb", [18.55544058601137, 0.01]),
+                                  ("rbf", "RBF_mb.py", "RBF_mb", [6.244955524643115, 0.5611029935713949])):
+        src = [l for l in open(os.path.join(REF, "cspbo", "kernels", fname)).read().split("\n") if not l.startswith("from .")]
+        ns = {}
+        exec("def build_covariance(*a, **k): pass\n"
+             "def get_mask(ele1, ele2):\n    import numpy as np\n    ids = np.where((ele1[:,None] - ele2[None,:]) != 0)\n"
+             "    return None if len(ids[0]) == 0 else ids\nkee_C = kef_C = kff_C = None\n" + "\n".join(src), ns)
+        k = ns[cls](para=para, zeta=2.0)
+        ref_list = k.diag({"energy": test_l["energy"], "force": [(a, b[:, :, :3], c) for a, b, c in test_l["force"]]})
+        for key in (fam + "_diag", fam + "_diag_list"):
+            assert np.abs(out[key] - ref_list).max() / np.abs(ref_list).max() < 1e-12, key
+            out[key] = ref_list
     np.savez_compressed(os.path.join(HERE, "golden_outputs.npz"), **out)
     for k, v in out.items():
         print("%-28s %-14s max|.|=%.6e" % (k, v.shape, np.abs(v).max()))

@@ -25,7 +25,9 @@ def test_compiled_reference_matches_goldens(oracle_built, fixtures, golden):
         pytest.skip("oracle/_ref not built (reference tree not mounted)")
     out = golden_cases(fixtures, OracleImpl("ref"))
     for k in golden:
-        assert max_norm_err(out[k], golden[k]) <= 1e-14, k
+        # diag goldens come from the reference's NumPy functions, the oracle restates them (1e-12);
+        # everything else is the same compiled C++ and must reproduce to rounding of the thread sum
+        assert max_norm_err(out[k], golden[k]) <= (1e-12 if "diag" in k else 1e-14), k
 
 
 def test_kff_symmetry_and_psd(golden):
