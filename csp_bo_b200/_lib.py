@@ -63,6 +63,7 @@ SIGNATURES = {
     "cspbo_pack_bytes": [c_vp],
     "cspbo_pack_pair_count": [c_vp, c_vp],
     "cspbo_block_build": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_vp, c_vp, c_int, c_int],
+    "cspbo_block_build_into": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_vp, c_ll, c_ll, c_ll],
     "cspbo_block_diag": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_int],
     "cspbo_dev_alloc": [c_ll, ctypes.POINTER(c_vp)],
     "cspbo_dev_free": [c_vp],
@@ -74,6 +75,8 @@ SIGNATURES = {
     "cspbo_block_build_sharded": [ctypes.POINTER(BlockDesc), c_vp, c_int, c_int, ctypes.POINTER(c_vp)],
     "cspbo_gp_add_noise": [c_vp, c_int, c_int, c_dbl, c_dbl],
     "cspbo_gp_cholesky_solve": [c_vp, c_int, c_vp, c_int, ctypes.POINTER(c_dbl)],
+    "cspbo_gp_cho_solve": [c_vp, c_int, c_vp, c_int],
+    "cspbo_gp_cholesky_inverse": [c_vp, c_int, c_vp],
     "cspbo_gp_predict": [c_vp, c_int, c_int, c_vp, c_vp],
 }
 _RESTYPE = {"cspbo_last_error": ctypes.c_char_p, "cspbo_launch_count": c_ll, "cspbo_pack_bytes": c_ll,

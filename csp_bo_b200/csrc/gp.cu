@@ -59,6 +59,14 @@ __global__ void logdet_kernel(const double *L, int N, double *out)
     }
 }
 
+// copy the column-major lower triangle (= row-major upper triangle) onto the other one
+__global__ void symmetrize_kernel(double *A, int N)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = idx / N, j = idx % N;
+    if (i < N && j > i) A[j * N + i] = A[i * N + j];   // row-major: lower(j,i) <- upper(i,j)
+}
+
 static std::mutex g_solver_mu;
 static cusolverDnHandle_t g_solver[64] = {nullptr};
 
@@ -146,6 +154,50 @@ extern "C" int cspbo_gp_predict(const double *Kstar, int n, int N, const double 
     if (n == 0) return CSPBO_OK;
     const int wpb = 8;
     predict_gemv_kernel<<<(n + wpb - 1) / wpb, wpb * 32>>>(Kstar, n, N, alpha, pred);
+    g_launches++;
+    CSPBO_CUDA(cudaGetLastError());
+    return CSPBO_OK;
+}
+
+
+extern "C" int cspbo_gp_cho_solve(const double *L, int N, double *B, int nrhs)
+{
+    if (!L || !B || N <= 0 || nrhs < 0) { set_error("gp_cho_solve: bad argument"); return CSPBO_E_ARG; }
+    if (nrhs == 0) return CSPBO_OK;
+    cusolverDnHandle_t h;
+    int rc = solver_handle(&h);
+    if (rc) return rc;
+    int *info = nullptr, hinfo = 0;
+    CSPBO_CUDA(cudaMalloc(&info, sizeof(int)));
+    cusolverStatus_t s = cusolverDnDpotrs(h, CUBLAS_FILL_MODE_LOWER, N, nrhs, L, N, B, N, info);
+    cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(info);
+    if (s != CUSOLVER_STATUS_SUCCESS || hinfo != 0) { set_error("potrs failed (status %d, info %d)", (int)s, hinfo); return CSPBO_E_SOLVER; }
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_gp_cholesky_inverse(const double *L, int N, double *Kinv)
+{
+    if (!L || !Kinv || N <= 0) { set_error("gp_cholesky_inverse: bad argument"); return CSPBO_E_ARG; }
+    cusolverDnHandle_t h;
+    int rc = solver_handle(&h);
+    if (rc) return rc;
+    CSPBO_CUDA(cudaMemcpyAsync(Kinv, L, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToDevice));
+    int lwork = 0;
+    cusolverStatus_t s = cusolverDnDpotri_bufferSize(h, CUBLAS_FILL_MODE_LOWER, N, Kinv, N, &lwork);
+    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potri_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
+    double *work = nullptr;
+    int *info = nullptr, hinfo = 0;
+    CSPBO_CUDA(cudaMalloc(&work, (size_t)std::max(lwork, 1) * sizeof(double)));
+    if (cudaMalloc(&info, sizeof(int)) != cudaSuccess) { cudaFree(work); set_error("cudaMalloc(info) failed"); return CSPBO_E_NOMEM; }
+    s = cusolverDnDpotri(h, CUBLAS_FILL_MODE_LOWER, N, Kinv, N, work, lwork, info);
+    cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(work);
+    cudaFree(info);
+    if (s != CUSOLVER_STATUS_SUCCESS || hinfo != 0) { set_error("potri failed (status %d, info %d)", (int)s, hinfo); return CSPBO_E_SOLVER; }
+    const long long total = (long long)N * N;
+    // potri filled the column-major lower triangle, i.e. the row-major UPPER one: mirror it
+    symmetrize_kernel<<<(unsigned)((total + 255) / 256), 256>>>(Kinv, N);
     g_launches++;
     CSPBO_CUDA(cudaGetLastError());
     return CSPBO_OK;

@@ -1,0 +1,334 @@
+"""GPU-resident Gaussian-process regressor: the fit / prediction / log-marginal-likelihood slice of the
+reference's `cspbo.gaussianprocess.GaussianProcess` (gaussianprocess.py:71-184, 325-390, 453-509) on top of
+the CUDA covariance kernels.  Same method names, arguments and return values; what is NOT carried
+over is everything that needs ase / pyxtal / the ASE database (save/load/export, add_structure,
+remove_train_pts, sparsify): those stay in the reference.
+
+Device residency: K is assembled block by block straight into one CUDA matrix
+(kernels/device.py), the noise is added and K is factorised in place by cuSOLVER
+(csrc/gp.cu), `alpha_` and the Cholesky factor stay in HBM, predictions are K*.alpha GEMVs on the
+device.  Only alpha-sized vectors and predictions cross PCIe.
+"""
+import warnings
+
+import numpy as np
+from scipy.optimize import minimize
+
+from . import _lib, gp
+from .kernels import device as kdev
+from .utilities import list_to_tuple
+
+# atomic numbers for descriptor.calculate() results that carry chemical symbols
+# (gaussianprocess.py:335 uses pyxtal's Element(ele).z)
+_SYMBOLS = ("X H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr "
+            "Rb Sr Y Zr Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe Cs Ba La Ce Pr Nd Pm Sm Eu Gd Tb Dy Ho Er Tm Yb Lu "
+            "Hf Ta W Re Os Ir Pt Au Hg Tl Pb Bi Po At Rn").split()
+_Z = {s: i for i, s in enumerate(_SYMBOLS)}
+
+
+class GaussianProcess():
+    """Gaussian-process regressor on energies and forces.
+
+    Args (as in the reference, gaussianprocess.py:26-29):
+        kernel: csp_bo_b200.kernels.Dot_mb | RBF_mb
+        descriptor: object with .calculate(struc) -> {'x','dxdr','rdxdr','seq','elements'} (only needed by
+                    predict_structure)
+        base_potential: optional object with .calculate(atoms) -> (E, F, S) offsets
+        f_coef: force noise = f_coef * energy noise
+        noise_e: [value, lower bound, upper bound]
+    """
+
+    def __init__(self, kernel, descriptor=None, base_potential=None, f_coef=5, noise_e=[5e-3, 2e-3, 1e-1]):
+        self.noise_e = noise_e[0]
+        self.f_coef = f_coef
+        self.noise_f = self.f_coef * self.noise_e
+        self.noise_bounds = noise_e[1:]
+        self.descriptor = descriptor
+        self.kernel = kernel
+        self.base_potential = base_potential
+        self.x = None
+        self.train_x = None
+        self.train_y = None
+        self.train_db = None
+        self.alpha_ = None
+        self.L_ = None            # CUDA tensor: cuSOLVER factor of K + noise (its lower triangle, column-major)
+        self._alpha_dev = None
+        self.N_energy = 0
+        self.N_forces = 0
+        self.N_energy_queue = 0
+        self.N_forces_queue = 0
+
+    def __str__(self):
+        s = "------Gaussian Process Regression------\n"
+        s += "Kernel: {:s}".format(str(self.kernel))
+        if hasattr(self, "train_x"):
+            s += " {:d} energy ({:.3f})".format(self.N_energy, self.noise_e)
+            s += " {:d} forces ({:.3f})\n".format(self.N_forces, self.noise_f)
+        return s
+
+    def __repr__(self):
+        return str(self)
+
+    # ------------------------------------------------------------------ training data
+    def set_train_pts(self, data, mode="w"):
+        """data: {'energy': [(x, E, ele)], 'force': [(x, dxdr, F, ele)], 'db': [...] (optional)}
+        (gaussianprocess.py:186-229)."""
+        if mode == "w" or self.train_x is None:
+            self.train_x = {'energy': [], 'force': []}
+            self.train_y = {'energy': [], 'force': []}
+            self.train_db = []
+            self.N_energy = self.N_forces = 0
+        N_E, N_F = 0, 0
+        for d in data.get("db", []):
+            (atoms, energy, force, energy_in, force_in) = d
+            e_id = N_E + 1 if energy_in else None
+            N_E += 1 if energy_in else 0
+            f_ids = [N_F + i for i in range(len(force_in))]
+            N_F += len(force_in)
+            self.train_db.append((atoms, energy, force, energy_in, force_in, e_id, f_ids))
+        if "db" not in data:
+            N_E, N_F = len(data.get("energy", [])), len(data.get("force", []))
+        if len(data.get("energy", [])) > 0:
+            self.add_train_pts_energy(data["energy"])
+        if len(data.get("force", [])) > 0:
+            self.add_train_pts_force(data["force"])
+        self.update_y_train()
+        self.N_energy += N_E
+        self.N_forces += N_F
+        self.N_energy_queue += N_E
+        self.N_forces_queue += N_F
+
+    def add_train_pts_energy(self, energy_data):
+        """energy_data: list of (X[n,d], E, ele)  (gaussianprocess.py:407-425)."""
+        (X, ELE, indices, E) = list_to_tuple(energy_data, include_value=True, mode='energy')
+        if len(self.train_x['energy']) == 3:
+            (_X, _ELE, _indices) = self.train_x['energy']
+            self.train_x['energy'] = (np.concatenate((_X, X), axis=0), np.concatenate((_ELE, ELE), axis=0),
+                                      list(_indices) + list(indices))
+            self.train_y['energy'] = list(self.train_y['energy']) + list(E)
+        else:
+            self.train_x['energy'] = (X, ELE, indices)
+            self.train_y['energy'] = list(E)
+
+    def add_train_pts_force(self, force_data):
+        """force_data: list of (X[n,d], dXdR[n,d,3], F[3], ele)  (gaussianprocess.py:427-451)."""
+        (X, dXdR, ELE, indices, F) = list_to_tuple(force_data, include_value=True)
+        if len(self.train_x['force']) == 4:
+            (_X, _dXdR, _ELE, _indices) = self.train_x['force']
+            self.train_x['force'] = (np.concatenate((_X, X), axis=0), np.concatenate((_dXdR, dXdR), axis=0),
+                                     np.concatenate((_ELE, ELE), axis=0), list(_indices) + list(indices))
+            self.train_y['force'] = list(self.train_y['force']) + list(F)
+        else:
+            self.train_x['force'] = (X, dXdR, ELE, indices)
+            self.train_y['force'] = list(F)
+
+    def update_y_train(self):
+        """Stack the targets: energies first, then forces atom-major (gaussianprocess.py:272-288)."""
+        E = np.asarray(self.train_y["energy"], dtype=np.float64).reshape(-1)
+        F = np.asarray(self.train_y["force"], dtype=np.float64).reshape(-1)
+        self.y_train = np.concatenate((E, F)).reshape(-1, 1)
+
+    def get_train_x(self):
+        return self.train_x
+
+    def _n_energy(self):
+        return len(self.train_x['energy'][-1]) if len(self.train_x['energy']) > 0 else 0
+
+    def _train_dict(self):
+        return {k: v for k, v in self.train_x.items() if len(v) > 0}
+
+    # ------------------------------------------------------------------ fit
+    def fit(self, TrainData=None, show=True, opt=True):
+        """gaussianprocess.py:71-131."""
+        if TrainData is not None:
+            self.set_train_pts(TrainData)
+        else:
+            self.update_y_train()
+        if show:
+            print(self)
+
+        def obj_func(params, eval_gradient=True):
+            if eval_gradient:
+                lml, grad = self.log_marginal_likelihood(params, eval_gradient=True, clone_kernel=False)
+                if show:
+                    print("Loss: {:12.3f} ".format(-lml) + " ".join("{:6.3f}".format(p) for p in params))
+                return (-lml, -grad)
+            return -self.log_marginal_likelihood(params, clone_kernel=False)
+
+        hyper_params = self.kernel.parameters() + [self.noise_e]
+        hyper_bounds = self.kernel.bounds + [self.noise_bounds]
+        if opt:
+            params, _ = self.optimize(obj_func, hyper_params, hyper_bounds)
+            self.kernel.update(params[:-1])
+            self.noise_e = params[-1]
+            self.noise_f = self.f_coef * params[-1]
+
+        K = kdev.k_total_device(self.kernel, self._train_dict())          # CUDA [N,N]
+        try:
+            alpha, logdet = gp.fit_alpha(K, self.y_train[:, 0], n_energy=self._n_energy(), noise_e=self.noise_e,
+                                         f_coef=self.f_coef, return_logdet=True, overwrite=True)
+        except _lib.CspboError as exc:
+            if exc.code == 5:    # CSPBO_E_NOTPD, the LinAlgError of gaussianprocess.py:118-125
+                raise np.linalg.LinAlgError("The kernel, %s, is not returning a positive definite matrix. Try gradually "
+                                            "increasing the noise." % self.kernel) from exc
+            raise
+        self.L_ = K                       # factorised in place
+        self._alpha_dev = alpha
+        self.alpha_ = alpha.cpu().numpy().reshape(-1, 1)
+        self._logdet = logdet
+        self.N_energy_queue = 0
+        self.N_forces_queue = 0
+        return self
+
+    def optimize(self, fun, theta0, bounds):
+        opt_res = minimize(fun, theta0, method="L-BFGS-B", bounds=bounds, jac=True,
+                           options={'maxiter': 10, 'ftol': 1e-2})
+        return opt_res.x, opt_res.fun
+
+    def log_marginal_likelihood(self, params, eval_gradient=False, clone_kernel=False):
+        """gaussianprocess.py:453-503, evaluated on the device."""
+        import torch
+        kernel = self.kernel
+        kernel.update(params[:-1])
+        data = self._train_dict()
+        if eval_gradient:
+            K, dKs = kdev.k_total_with_grad_device(kernel, data)
+        else:
+            K = kdev.k_total_device(kernel, data)
+        N, NE = K.shape[0], self._n_energy()
+        y = torch.from_numpy(np.ascontiguousarray(self.y_train[:, 0])).cuda()
+        try:
+            alpha, logdet = gp.fit_alpha(K, y, n_energy=NE, noise_e=params[-1], f_coef=self.f_coef,
+                                         return_logdet=True, overwrite=True)
+        except _lib.CspboError as exc:
+            if exc.code == 5:
+                return (-np.inf, np.zeros_like(params)) if eval_gradient else -np.inf
+            raise
+        MLL = float(-0.5 * torch.dot(y, alpha) - 0.5 * logdet - N / 2 * np.log(2 * np.pi))
+        if not eval_gradient:
+            return MLL
+        # 0.5 * tr((alpha alpha^T - K^-1) dK/dtheta), eq. 5.9 of GPML
+        Kinv = gp.cholesky_inverse(K)
+        W = torch.outer(alpha, alpha) - Kinv
+        llg = [0.5 * float((W * dK).sum()) for dK in dKs]
+        noise_diag = torch.full((N,), 2 * self.f_coef ** 2 * params[-1], dtype=torch.float64, device="cuda")
+        noise_diag[:NE] = 2 * params[-1]
+        llg.append(0.5 * float((torch.diagonal(W) * noise_diag).sum()))
+        return MLL, np.array(llg)
+
+    # ------------------------------------------------------------------ prediction
+    def predict(self, X, stress=False, total_E=False, return_std=False, return_cov=False):
+        """gaussianprocess.py:133-184."""
+        import torch
+        train = self._train_dict()
+        if stress:
+            K_trans, K_trans1 = kdev.k_total_with_stress_device(self.kernel, X, train)
+        else:
+            K_trans = kdev.k_total_device(self.kernel, X, train)
+        y_mean = gp.predict_mean(K_trans, self._alpha_dev).cpu().numpy()
+
+        Npts, N_atoms = 0, None
+        if 'energy' in X and len(X['energy']) > 0:
+            if isinstance(X["energy"], tuple):
+                N_atoms = np.array([x for x in X["energy"][-1]])
+            else:
+                N_atoms = np.array([len(x[0]) for x in X["energy"]])
+            Npts += len(N_atoms)
+        if 'force' in X and len(X['force']) > 0:
+            Npts += 3 * (len(X["force"][-1]) if isinstance(X["force"], tuple) else len(X["force"]))
+        factors = np.ones(Npts)
+        if total_E and N_atoms is not None:
+            factors[:len(N_atoms)] = N_atoms
+        y_mean *= factors
+
+        if return_cov:
+            v = gp.cho_solve(self.L_, K_trans.T.contiguous())
+            y_cov = kdev.k_total_device(self.kernel, X) - K_trans @ v
+            return y_mean, y_cov.cpu().numpy()
+        if return_std:
+            y_var = self._variance(X, K_trans)
+            if np.any(y_var < 0):
+                warnings.warn("Predicted variances smaller than 0. Setting those variances to 0.")
+            y_var[y_var < 0] = 0.0
+            return y_mean, np.sqrt(y_var) * factors
+        if stress:
+            return y_mean, gp.predict_mean(K_trans1, self._alpha_dev).cpu().numpy()
+        return y_mean
+
+    def _variance(self, data, K_trans):
+        """diag(k(X,X)) - diag(K* K^-1 K*^T)  (gaussianprocess.py:167-175,377-383) without forming K^-1."""
+        v = gp.cho_solve(self.L_, K_trans.T.contiguous())                  # [N, n*]
+        y_var = self.kernel.diag(data)
+        y_var = y_var - (K_trans * v.T).sum(dim=1).cpu().numpy()
+        return y_var
+
+    def validate_data(self, test_data=None, total_E=False, return_std=False):
+        """gaussianprocess.py:290-323."""
+        if test_data is None:
+            test_X_E = {"energy": self.train_x['energy']}
+            test_X_F = {"force": self.train_x['force']}
+            NE = self._n_energy()
+            E = self.y_train[:NE].flatten().copy()
+            F = self.y_train[NE:].flatten().copy()
+            natoms = list(self.train_x['energy'][-1]) if NE else []
+        else:
+            test_X_E = {"energy": [(d[0], d[2]) for d in test_data['energy']]}
+            test_X_F = {"force": [(d[0], d[1], d[3]) for d in test_data['force']]}
+            E = np.array([d[1] for d in test_data['energy']], dtype=np.float64)
+            F = np.array([d[2] for d in test_data['force']], dtype=np.float64).flatten()
+            natoms = [len(d[0]) for d in test_data['energy']]
+        if total_E:
+            for i in range(len(E)):
+                E[i] *= natoms[i]
+        E_Pred = E_std = F_Pred = F_std = None
+        if return_std:
+            if len(test_X_E['energy']) > 0:
+                E_Pred, E_std = self.predict(test_X_E, total_E=total_E, return_std=True)
+            if len(test_X_F['force']) > 0:
+                F_Pred, F_std = self.predict(test_X_F, return_std=True)
+            return E, E_Pred, E_std, F, F_Pred, F_std
+        if len(test_X_E['energy']) > 0:
+            E_Pred = self.predict(test_X_E, total_E=total_E)
+        if len(test_X_F['force']) > 0:
+            F_Pred = self.predict(test_X_F)
+        return E, E_Pred, F, F_Pred
+
+    def predict_structure(self, struc, stress=True, return_std=False, f_tol=1e-8):
+        """Energy, forces (and stress, std) of one structure from descriptor.calculate(struc)
+        (gaussianprocess.py:325-390)."""
+        d = self.descriptor.calculate(struc)
+        ele = np.array([e if isinstance(e, (int, np.integer)) else _Z[e] for e in d['elements']])
+        data = {"energy": [(d['x'], ele)], "force": []}
+        _n, l = d['x'].shape
+        n_atoms = len(struc)
+        for i in range(n_atoms):
+            ids = np.argwhere(d['seq'][:, 1] == i).flatten()
+            _i = d['seq'][ids, 0]
+            _x, _dxdr, ele0 = d['x'][_i, :], d['dxdr'][ids], ele[_i]
+            if stress:
+                _rdxdr = d['rdxdr'][ids].reshape([len(ids), l, 9])[:, :, [0, 4, 8, 1, 2, 5]]
+                data["force"].append((_x, np.concatenate((_dxdr, _rdxdr), axis=2), ele0))
+            else:
+                data["force"].append((_x, _dxdr, ele0))
+        train = self._train_dict()
+        if stress:
+            K_trans, K_trans1 = kdev.k_total_with_stress_device(self.kernel, data, train, f_tol)
+        else:
+            K_trans = kdev.k_total_device(self.kernel, data, train, f_tol)
+        y_mean = gp.predict_mean(K_trans, self._alpha_dev).cpu().numpy()
+        y_mean[0] *= n_atoms
+        E = y_mean[0]
+        F = y_mean[1:].reshape([n_atoms, 3])
+        S = gp.predict_mean(K_trans1, self._alpha_dev).cpu().numpy().reshape([n_atoms, 6]) if stress else None
+        if self.base_potential is not None:
+            energy_off, force_off, stress_off = self.base_potential.calculate(struc)
+            E += energy_off
+            F += force_off
+            if stress:
+                S += stress_off
+        if return_std:
+            y_var = self._variance(data, K_trans)
+            y_var[y_var < 0] = 0.0
+            y_std = np.sqrt(y_var)
+            return E, F, S, y_std[0], y_std[1:].reshape([n_atoms, 3])
+        return E, F, S

@@ -47,3 +47,25 @@ def predict_mean(Kstar, alpha):
     out = torch.empty(n, dtype=torch.float64, device="cuda")
     _lib.check(lib.cspbo_gp_predict(c_vp(Kd.data_ptr()), n, N, c_vp(ad.data_ptr()), c_vp(out.data_ptr())))
     return out if on_dev else out.cpu().numpy()
+
+
+def cho_solve(L, Bt):
+    """(L L^T)^-1 B for the factor left in K by fit_alpha(..., overwrite=True).
+    Bt: CUDA tensor [N, nrhs] (any layout); returns a CUDA tensor [N, nrhs]."""
+    import torch
+    lib = _lib.load()
+    N = L.shape[0]
+    assert Bt.shape[0] == N
+    X = Bt.T.contiguous().clone()          # row-major [nrhs, N] == column-major [N, nrhs]
+    _lib.check(lib.cspbo_gp_cho_solve(c_vp(L.data_ptr()), N, c_vp(X.data_ptr()), int(X.shape[0])))
+    return X.T
+
+
+def cholesky_inverse(L):
+    """K^-1 from the in-place factor (cuSOLVER potri), CUDA tensor [N,N]."""
+    import torch
+    lib = _lib.load()
+    N = L.shape[0]
+    out = torch.empty_like(L)
+    _lib.check(lib.cspbo_gp_cholesky_inverse(c_vp(L.data_ptr()), N, c_vp(out.data_ptr())))
+    return out

@@ -193,6 +193,12 @@ typedef struct {
 int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b,
                       double *out, double *out_grad, int mem, int accumulate);
 
+/* Build a plain block (no stress / grad) straight into a row-major DEVICE matrix K with leading
+ * dimension ldk at offset (row0, col0): K_EE -> [m1, m2], K_EF -> [m1, 3*m2], K_FF -> [3*m1, 3*m2].
+ * This is how [[K_EE, K_EF], [K_FE, K_FF]] (base.py:13-14) is assembled without host round trips. */
+int cspbo_block_build_into(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b,
+                           double *K, long long ldk, long long row0, long long col0);
+
 /* Self covariance of every group of pack `a` (the diagonal blocks of K(a,a)): out[m] for K_EE,
  * out[m,3,3] for K_FF.  Used by diag() for the predictive variance (Dot_mb.py:45-85). */
 int cspbo_block_diag(const cspbo_block_desc *desc, const cspbo_pack *a, double *out, int mem);
@@ -225,6 +231,12 @@ int cspbo_gp_add_noise(double *K, int N, int n_energy, double noise_e, double f_
 /* In-place lower Cholesky of the symmetric K (cuSOLVER potrf) followed by alpha = K^-1 y (potrs);
  * y[N, nrhs] column-major == row-major for nrhs = 1.   gaussianprocess.py:116,127 */
 int cspbo_gp_cholesky_solve(double *K, int N, double *y_inout, int nrhs, double *logdet);
+/* Solve (L L^T) X = B with the factor left in K by cspbo_gp_cholesky_solve.  B is [N, nrhs]
+ * column-major, i.e. a row-major [nrhs, N] matrix such as K* itself; overwritten with X.
+ * gaussianprocess.py:166 (cho_solve) and the K^-1 K*^T of :174,:382 */
+int cspbo_gp_cho_solve(const double *L, int N, double *B, int nrhs);
+/* Kinv = (L L^T)^-1 (cuSOLVER potri), full symmetric matrix.  gaussianprocess.py:497 */
+int cspbo_gp_cholesky_inverse(const double *L, int N, double *Kinv);
 /* pred[n] = Kstar[n, N] . alpha[N]    gaussianprocess.py:140,359 */
 int cspbo_gp_predict(const double *Kstar, int n, int N, const double *alpha, double *pred);
 

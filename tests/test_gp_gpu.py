@@ -1,0 +1,147 @@
+"""GPU GaussianProcess (fit / predict / LML / predict_structure on the device) against the CPU
+restatement of the reference's gaussianprocess.py (oracle/gp_reference.py).  Tolerance of
+BASELINE.json's north_star: 1e-8 on predicted energies / forces (max-normalised)."""
+import numpy as np
+import pytest
+
+from tests._cases import (energy_tuple, force_list, energy_list, force_tuple, max_norm_err, stress_columns,
+                          take_groups, take_groups_e)
+
+pytestmark = pytest.mark.gpu
+
+PRED_TOL = 1e-8
+KERNELS = [("dot", [18.55544058601137, 0.01], [[1e-2, 5e+1], [1e-2, 1e+1]]),
+           ("rbf", [6.244955524643115, 0.5611029935713949], [[1e-2, 5e+1], [1e-1, 1e+1]])]
+
+
+def make_kernel(fam, para, bounds):
+    from csp_bo_b200.kernels import Dot_mb, RBF_mb
+    return (Dot_mb if fam == "dot" else RBF_mb)(para=list(para), bounds=bounds, zeta=2)
+
+
+@pytest.fixture(scope="module")
+def problem(fixtures, oracle_built):
+    big, x2, ee2 = force_tuple(fixtures, "big"), force_tuple(fixtures, "x2"), energy_tuple(fixtures, "ee2")
+    train_x = {"energy": take_groups_e(ee2, 0, 4), "force": x2}
+    rng = np.random.default_rng(42)
+    y = np.concatenate((rng.normal(-3.0, 0.05, 4), rng.normal(0.0, 0.8, 81)))
+    test = {"energy": take_groups_e(ee2, 4, 6), "force": take_groups(big, 0, 12)}
+    return train_x, y, test
+
+
+def train_lists(train_x, y):
+    """the reference's TrainData format: energy (x, E, ele), force (x, dxdr, F, ele)"""
+    E = [(x, float(y[i]), ele) for i, (x, ele) in enumerate(energy_list(train_x["energy"]))]
+    ne = len(E)
+    F = [(x, dx, y[ne + 3 * i: ne + 3 * i + 3], ele) for i, (x, dx, ele) in enumerate(force_list(train_x["force"]))]
+    return {"energy": E, "force": F}
+
+
+@pytest.mark.parametrize("fam,para,bounds", KERNELS)
+def test_fit_and_predict(problem, fam, para, bounds):
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from oracle.gp_reference import RefGaussianProcess
+    train_x, y, test = problem
+    ref = RefGaussianProcess(fam, para, 2.0, bounds, f_coef=30, noise_e=(0.005, 0.002, 0.1))
+    ref.set_train(train_x, y)
+    ref.fit(opt=False)
+    model = GaussianProcess(make_kernel(fam, para, bounds), f_coef=30, noise_e=[0.005, 0.002, 0.1])
+    model.fit(train_lists(train_x, y), show=False, opt=False)
+    assert model.N_energy == 4 and model.N_forces == 27
+    assert max_norm_err(model.alpha_, ref.alpha_) < PRED_TOL
+    for X in (test, {"energy": energy_list(test["energy"]), "force": force_list(test["force"])},
+              {"force": test["force"]}, {"energy": test["energy"]}):
+        assert max_norm_err(model.predict(X), ref.predict(X)) < PRED_TOL
+    assert max_norm_err(model.predict(test, total_E=True), ref.predict(test, total_E=True)) < PRED_TOL
+    m, s = model.predict(test, return_std=True)
+    mr, sr = ref.predict(test, return_std=True)
+    assert max_norm_err(m, mr) < PRED_TOL
+    # the variance diag(k) - diag(K* K^-1 K*^T) cancels ~5 digits and K is ill conditioned (noise 2.5e-5 on
+    # entries of O(100)): both implementations carry ~1e-8 * |diag| of conditioning noise, so compare there
+    dscale = np.abs(model.kernel.diag(test)).max()
+    assert np.abs(s ** 2 - sr ** 2).max() <= 1e-8 * dscale
+    m, c = model.predict(test, return_cov=True)
+    mr, cr_ = ref.predict(test, return_cov=True)
+    assert max_norm_err(c, cr_) < 1e-7
+    # validate_data on the training set = predictions of the stored training tuples
+    E, E_pred, F, F_pred = model.validate_data()
+    assert np.allclose(E, y[:4]) and np.allclose(F, y[4:])
+    assert max_norm_err(E_pred, ref.predict({"energy": train_x["energy"]})) < PRED_TOL
+    assert max_norm_err(F_pred, ref.predict({"force": train_x["force"]})) < PRED_TOL
+
+
+@pytest.mark.parametrize("fam,para,bounds", KERNELS)
+def test_log_marginal_likelihood_and_gradient(problem, fam, para, bounds):
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from oracle.gp_reference import RefGaussianProcess
+    train_x, y, _ = problem
+    ref = RefGaussianProcess(fam, para, 2.0, bounds, f_coef=30, noise_e=(0.005, 0.002, 0.1))
+    ref.set_train(train_x, y)
+    model = GaussianProcess(make_kernel(fam, para, bounds), f_coef=30, noise_e=[0.005, 0.002, 0.1])
+    model.set_train_pts(train_lists(train_x, y))
+    for params in (list(para) + [0.005], [para[0] * 0.7, para[1] * 1.3, 0.02]):
+        lml, grad = model.log_marginal_likelihood(np.array(params), eval_gradient=True)
+        lml_r, grad_r = ref.log_marginal_likelihood(np.array(params), eval_gradient=True)
+        assert abs(lml - lml_r) <= 1e-8 * abs(lml_r)
+        assert max_norm_err(grad, grad_r) < 1e-7
+        assert abs(model.log_marginal_likelihood(np.array(params)) - lml_r) <= 1e-8 * abs(lml_r)
+
+
+def test_fit_with_hyperparameter_optimisation(problem):
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from oracle.gp_reference import RefGaussianProcess
+    fam, para, bounds = KERNELS[1]
+    train_x, y, test = problem
+    ref = RefGaussianProcess(fam, para, 2.0, bounds, f_coef=30, noise_e=(0.005, 0.002, 0.1))
+    ref.set_train(train_x, y)
+    ref.fit(opt=True)
+    model = GaussianProcess(make_kernel(fam, para, bounds), f_coef=30, noise_e=[0.005, 0.002, 0.1])
+    model.fit(train_lists(train_x, y), show=False, opt=True)
+    got = np.array(model.kernel.parameters() + [model.noise_e])
+    want = np.array(list(ref.kernel.para) + [ref.noise_e])
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-8), (got, want)
+    assert max_norm_err(model.predict(test), ref.predict(test)) < 1e-5
+
+
+class FakeDescriptor:
+    """Stands in for cspbo.SO3: returns the dictionary predict_structure consumes (SO3.py:187-291)."""
+
+    def __init__(self, fixtures, n_atoms=6, seed=3):
+        rng = np.random.default_rng(seed)
+        x, ele = fixtures["ee2_x"], fixtures["ee2_ele"]
+        rows = rng.choice(len(x), n_atoms, replace=False)
+        self.x = x[rows]
+        self.z = ele[rows]
+        pairs = [(i, j) for i in range(n_atoms) for j in range(n_atoms) if rng.random() < 0.7 or i == j]
+        self.seq = np.array(pairs)
+        scale = np.linalg.norm(self.x, axis=1)[self.seq[:, 0]]
+        self.dxdr = rng.standard_normal((len(pairs), x.shape[1], 3)) * scale[:, None, None] * 0.3
+        self.rdxdr = rng.standard_normal((len(pairs), x.shape[1], 3, 3)) * scale[:, None, None, None] * 0.3
+        sym = {1: "H", 8: "O", 78: "Pt"}
+        self.elements = [sym[int(z)] for z in self.z]
+
+    def calculate(self, struc):
+        return {"x": self.x, "dxdr": self.dxdr, "rdxdr": self.rdxdr, "seq": self.seq, "elements": self.elements}
+
+
+@pytest.mark.parametrize("fam,para,bounds", KERNELS)
+@pytest.mark.parametrize("stress", [True, False])
+def test_predict_structure(problem, fixtures, fam, para, bounds, stress):
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from oracle.gp_reference import RefGaussianProcess
+    train_x, y, _ = problem
+    desc = FakeDescriptor(fixtures)
+    ref = RefGaussianProcess(fam, para, 2.0, bounds, f_coef=30, noise_e=(0.005, 0.002, 0.1))
+    ref.set_train(train_x, y)
+    ref.fit(opt=False)
+    model = GaussianProcess(make_kernel(fam, para, bounds), descriptor=desc, f_coef=30, noise_e=[0.005, 0.002, 0.1])
+    model.fit(train_lists(train_x, y), show=False, opt=False)
+    struc = list(range(6))          # only len(struc) is used
+    got = model.predict_structure(struc, stress=stress, return_std=True)
+    want = ref.predict_structure(desc.calculate(None), 6, desc.z, stress=stress, return_std=True)
+    assert abs(got[0] - want[0]) <= PRED_TOL * max(1.0, abs(want[0]))
+    assert max_norm_err(got[1], want[1]) < PRED_TOL
+    if stress:
+        assert max_norm_err(got[2], want[2]) < PRED_TOL
+    dscale = 2e2
+    assert abs(got[3] ** 2 - want[3] ** 2) <= 1e-8 * dscale and np.abs(got[4] ** 2 - want[4] ** 2).max() <= 1e-8 * dscale
