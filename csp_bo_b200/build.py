@@ -47,6 +47,9 @@ def build(force=False, verbose_ptxas=False):
         if force or _stale(obj, [src] + HEADERS):
             cmd = [NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I", INC, "-I", SRC,
                                    "-c", src, "-o", obj]
+            if os.environ.get("CSPBO_TUNE"):      # e.g. CSPBO_TUNE="6,2,48": warps per CTA, CTAs per SM, KB per stage
+                w, c, kb = os.environ["CSPBO_TUNE"].split(",")
+                cmd += ["-DCSPBO_WARPS=" + w, "-DCSPBO_CTAS=" + c, "-DCSPBO_STAGE_KB=" + kb]
             if verbose_ptxas:
                 cmd += ["-Xptxas", "-v"]
             _run(cmd)

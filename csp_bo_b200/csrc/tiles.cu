@@ -26,9 +26,14 @@ constexpr int kMaxSpecies = 16;
 constexpr int kMaxRanks = 8;
 // 3 CTAs x 4 warps per SM = 3 warps per scheduler: while one warp runs its chain-rule epilogue the
 // other two keep the FP64 tensor pipe fed (<= 170 registers/thread, <= 75 KB shared memory per CTA)
-constexpr int kMaxWarps = 4;
-constexpr int kMinCtas = 3;
-constexpr size_t kSmemChunk = 72 * 1024;
+#ifndef CSPBO_WARPS
+#define CSPBO_WARPS 4
+#define CSPBO_CTAS 3
+#define CSPBO_STAGE_KB 36
+#endif
+constexpr int kMaxWarps = CSPBO_WARPS;
+constexpr int kMinCtas = CSPBO_CTAS;
+constexpr size_t kSmemChunk = CSPBO_STAGE_KB * 1024;   // per stage; two stages are double-buffered
 // Rasterisation: A-block groups per strip.  Measured on B200 (20 001 force rows): strips of 1..64 are 3-6 %
 // slower than no strips (B block shared by all consecutive CTAs stays L2-hot, A tiles stream), so
 // the default is a single strip.
@@ -75,6 +80,66 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+
+
+// ---- 1-D bulk TMA (cp.async.bulk, SASS UBLKCP) + mbarrier helpers -----------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Wait for the phase with the given parity; a bounded spin turns a lost transaction into a trap
+// instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; spin++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (spin > (1u << 26)) __trap();
+    }
+}
+
+// Walks the (species, chunk) runs of one B block: every run is a contiguous piece of the packed
+// tile array, at most p.tbc tiles long, so one bulk copy fetches it.
+struct ChunkIter {
+    int eA, c0, b_t0, Tb;
+    __device__ __forceinline__ void next_species(const TileParams &p, int b_blk)
+    {
+        for (++eA; eA < p.A.ns; ++eA) {
+            const int eB = p.emap[eA];
+            if (eB < 0) continue;
+            b_t0 = p.B.tile_start[b_blk * p.B.ns + eB];
+            Tb = p.B.tile_start[b_blk * p.B.ns + eB + 1] - b_t0;
+            c0 = 0;
+            if (Tb > 0) return;
+        }
+    }
+    __device__ __forceinline__ void start(const TileParams &p, int b_blk) { eA = -1; c0 = 0; b_t0 = 0; Tb = 0; next_species(p, b_blk); }
+    __device__ __forceinline__ bool done(const TileParams &p) const { return eA >= p.A.ns; }
+    __device__ __forceinline__ void next(const TileParams &p, int b_blk)
+    {
+        c0 += p.tbc;
+        if (c0 >= Tb) next_species(p, b_blk);
+    }
+    __device__ __forceinline__ int nt(const TileParams &p) const { return min(p.tbc, Tb - c0); }
+};
 
 // Per-pair scalar weights of the chain rule.
 struct Weights {
@@ -131,7 +196,7 @@ __device__ __forceinline__ Weights pair_weights(double c, bool valid, const Tile
 }
 
 template <int MODE, int FAM, int KS, bool Z2>
-__global__ void __launch_bounds__(kMaxWarps * 32, (KS <= 6 && FAM != FAM_RBF_GRAD) ? kMinCtas : 2)
+__global__ void __launch_bounds__(kMaxWarps * 32, (KS <= 6 && FAM != FAM_RBF_GRAD) ? kMinCtas : (kMinCtas > 1 ? 2 : 1))
 block_tile_kernel(const TileParams p)
 {
     constexpr int NV1 = (MODE == MODE_KFF) ? 4 : 1;
@@ -160,8 +225,15 @@ block_tile_kernel(const TileParams p)
     // symmetric build: only blocks with b >= a are computed (mirrored at write time)
     const bool active = a_blk < p.a_nblk && !(p.symmetric && b_blk < a_blk);
 
-    double *sB = smem;
-    unsigned *sBvalid = reinterpret_cast<unsigned *>(smem + (size_t)p.tbc * p.B.tile_doubles);
+    // two stage buffers of p.tbc tiles, filled by 1-D bulk TMA copies that complete on an mbarrier
+    const int stage_doubles = p.tbc * p.B.tile_doubles;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + 2 * (size_t)stage_doubles);
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     double acc[2][NC1][NC2];
     double accg[2][GRAD ? NC1 : 1][GRAD ? NC2 : 1];
@@ -178,25 +250,28 @@ block_tile_kernel(const TileParams p)
     const int ar = lane >> 2;        // a slot of this thread's accumulator rows
     const int bq = (lane & 3) * 2;   // first of its two b slots
 
-    for (int eA = 0; eA < p.A.ns; eA++) {
-    const int eB = p.emap[eA];
-    if (eB < 0) continue;
-    const int b_t0 = p.B.tile_start[b_blk * p.B.ns + eB];
-    const int Tb = p.B.tile_start[b_blk * p.B.ns + eB + 1] - b_t0;
-    if (Tb == 0) continue;
-    const int a_t0 = active ? p.A.tile_start[a_blk * p.A.ns + eA] : 0;
-    const int Ta = active ? p.A.tile_start[a_blk * p.A.ns + eA + 1] - a_t0 : 0;
-    for (int c0 = 0; c0 < Tb; c0 += p.tbc) {
-        const int nt = min(p.tbc, Tb - c0);
-        __syncthreads();
-        {   // cooperative, coalesced 128-bit copy of nt consecutive B tiles
-            const double2 *src = reinterpret_cast<const double2 *>(p.B.tiles + (size_t)(b_t0 + c0) * p.B.tile_doubles);
-            double2 *dst = reinterpret_cast<double2 *>(sB);
-            const int n2 = nt * (p.B.tile_doubles >> 1);
-            for (int i = threadIdx.x; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
-            for (int i = threadIdx.x; i < nt; i += blockDim.x) sBvalid[i] = p.B.tile_valid[b_t0 + c0 + i];
-        }
-        __syncthreads();
+    ChunkIter cur;
+    cur.start(p, b_blk);
+    auto issue = [&](const ChunkIter &c, int st) {
+        const unsigned bytes = (unsigned)(c.nt(p) * p.B.tile_doubles * (int)sizeof(double));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this stage are done
+        mbar_expect_tx(&full[st], bytes);
+        tma_bulk_g2s(smem + (size_t)st * stage_doubles, p.B.tiles + (size_t)(c.b_t0 + c.c0) * p.B.tile_doubles, bytes, &full[st]);
+    };
+    if (!cur.done(p) && threadIdx.x == 0) issue(cur, 0);
+    for (int it = 0; !cur.done(p); it++) {
+        ChunkIter nxt = cur;
+        nxt.next(p, b_blk);
+        const int st = it & 1;
+        // prefetch the next run into the other stage (its last readers passed the barrier below)
+        if (!nxt.done(p) && threadIdx.x == 0) issue(nxt, st ^ 1);
+        const int eA = cur.eA;
+        const int nt = cur.nt(p);
+        const int b_tile0 = cur.b_t0 + cur.c0;
+        const int a_t0 = active ? p.A.tile_start[a_blk * p.A.ns + eA] : 0;
+        const int Ta = active ? p.A.tile_start[a_blk * p.A.ns + eA + 1] - a_t0 : 0;
+        const double *sB = smem + (size_t)st * stage_doubles;
+        mbar_wait(&full[st], (unsigned)(it >> 1) & 1u);
 
         for (int ta = 0; ta < Ta; ta++) {
             // A fragments of this slab: registers for the whole sweep over the chunk
@@ -243,7 +318,7 @@ block_tile_kernel(const TileParams p)
                         for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h + 1], b[v2].y);
                 }
 
-                const unsigned vb = sBvalid[tb];
+                const unsigned vb = __ldg(p.B.tile_valid + b_tile0 + tb);
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const bool ok = a_ok && ((vb >> (bq + e)) & 1u);
@@ -289,8 +364,9 @@ block_tile_kernel(const TileParams p)
                 }
             }
         }
+        __syncthreads();   // every warp is done with stage st before it is refilled two runs later
+        cur = nxt;
     }
-    }  // species
 
     if (!active) return;
     const int gi = p.A.slot_group[a_blk * 8 + ar];
@@ -473,11 +549,11 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     int nwarps = diag ? 1 : kMaxWarps;
     const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
     while (nwarps > 1 && (long long)((a_mine + nwarps - 1) / nwarps) * p.b_nblk < 2LL * sms) nwarps >>= 1;
-    // B tiles per shared-memory chunk: a whole (block, species) run if it fits in 72 KB
+    // B tiles per stage: a whole (block, species) run if it fits in 36 KB
     const size_t tile_bytes = (size_t)b->tile_doubles * sizeof(double);
     const int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, kSmemChunk / tile_bytes));
     p.tbc = tbc;
-    const size_t smem = (size_t)tbc * tile_bytes + (size_t)tbc * sizeof(unsigned) + 16;
+    const size_t smem = 2 * (size_t)tbc * tile_bytes + 2 * sizeof(unsigned long long);
     p.strip = std::max(1, std::min(kStrip, (a_mine + nwarps - 1) / nwarps));
     if (a->ks == 6) return launch_ks<6>(mode, fam, z2, p, nwarps, smem, st);
     return launch_ks<14>(mode, fam, z2, p, nwarps, smem, st);
