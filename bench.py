@@ -267,7 +267,7 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": entries / (float(te.item()) * 1e-3), "unit": "entries/s", "ms_per_step": float(te.item()),
            "h2d_bytes_per_step": int(X[0].nbytes + X[1].nbytes + 2 * 4 * len(X[0])) * world,
-           "d2h_bytes_per_step": d2h, "check": chk,
+           "d2h_bytes_per_step": d2h, "check": chk, "ms_all": [round(v, 2) for v in e2e_ms],
            "api": "kernels.dot_kernel.kff_C(host tuple, host tuple, out=pinned)" if world == 1 else
                   "packing.Pack(host) + distributed.ShardedSymmetricBlock.build + row-block copy to pinned host"}
     del outh

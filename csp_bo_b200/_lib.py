@@ -41,6 +41,7 @@ SIGNATURES = {
     "cspbo_set_device": [c_int],
     "cspbo_device_count": [ctypes.POINTER(c_int)],
     "cspbo_synchronize": [],
+    "cspbo_release_scratch": [],
     "cspbo_dot_kee_many": [c_int, c_int, c_int, c_int, c_dbl, c_dbl, c_dbl] + _E + _E + [c_vp],
     "cspbo_dot_kef_many": [c_int, c_int, c_int, c_int, c_dbl] + _E + _F + [c_vp],
     "cspbo_dot_kef_many_stress": [c_int, c_int, c_int, c_int, c_dbl] + _E + _F + [c_vp],
@@ -58,6 +59,8 @@ SIGNATURES = {
                           ctypes.POINTER(c_vp)],
     "cspbo_pack_create_eps": [c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_dbl,
                               ctypes.POINTER(c_vp)],
+    "cspbo_pack_create_ex": [c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_dbl, c_int,
+                             ctypes.POINTER(c_vp)],
     "cspbo_pack_destroy": [c_vp],
     "cspbo_pack_groups": [c_vp],
     "cspbo_pack_bytes": [c_vp],

@@ -30,6 +30,37 @@ struct DevBuf {
     ~DevBuf() { cudaFree(p); }
 };
 
+static std::mutex g_scratch_mu;
+static void *g_scratch[64][SCRATCH_SLOTS] = {};
+static size_t g_scratch_size[64][SCRATCH_SLOTS] = {};
+
+int scratch_get(int slot, size_t bytes, void **ptr)
+{
+    int dev = 0;
+    CSPBO_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || slot < 0 || slot >= SCRATCH_SLOTS) { set_error("scratch_get: bad device/slot"); return CSPBO_E_ARG; }
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    if (g_scratch_size[dev][slot] < bytes) {
+        if (g_scratch[dev][slot]) {
+            CSPBO_CUDA(cudaDeviceSynchronize());   // nobody may still be using the old buffer
+            cudaFree(g_scratch[dev][slot]);
+            g_scratch[dev][slot] = nullptr;
+            g_scratch_size[dev][slot] = 0;
+        }
+        const size_t want = bytes + bytes / 8;   // a little headroom against regrowth
+        cudaError_t e = cudaMalloc(&g_scratch[dev][slot], want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&g_scratch[dev][slot], bytes);
+            if (e != cudaSuccess) { cudaGetLastError(); set_error("scratch_get: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return CSPBO_E_NOMEM; }
+            g_scratch_size[dev][slot] = bytes;
+        } else {
+            g_scratch_size[dev][slot] = want;
+        }
+    }
+    *ptr = g_scratch[dev][slot];
+    return CSPBO_OK;
+}
+
 }  // namespace cspbo
 
 using namespace cspbo;
@@ -49,6 +80,86 @@ extern "C" int cspbo_device_count(int *count)
     if (!count) { set_error("device_count: null"); return CSPBO_E_ARG; }
     *count = 0;
     CSPBO_CUDA(cudaGetDeviceCount(count));
+    return CSPBO_OK;
+}
+
+namespace cspbo {
+struct CachedBlock { void *ptr; size_t size; int dev; };
+static std::vector<CachedBlock> g_free_blocks;               // released, reusable
+static std::vector<CachedBlock> g_live_blocks;               // handed out
+static const size_t kCacheLimit = (size_t)2 << 30;
+
+int dev_alloc_cached(size_t bytes, void **ptr)
+{
+    int dev = 0;
+    CSPBO_CUDA(cudaGetDevice(&dev));
+    bytes = std::max<size_t>(bytes, 256);
+    {
+        std::lock_guard<std::mutex> lk(g_scratch_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_free_blocks.size(); i++) {
+            const CachedBlock &b = g_free_blocks[i];
+            if (b.dev == dev && b.size >= bytes && b.size <= 2 * bytes + 4096 &&
+                (best < 0 || b.size < g_free_blocks[(size_t)best].size))
+                best = (int)i;
+        }
+        if (best >= 0) {
+            CachedBlock b = g_free_blocks[(size_t)best];
+            g_free_blocks.erase(g_free_blocks.begin() + best);
+            g_live_blocks.push_back(b);
+            *ptr = b.ptr;
+            return CSPBO_OK;
+        }
+    }
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cspbo_release_scratch();          // give cached memory back and retry once
+        e = cudaMalloc(&q, bytes);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); return CSPBO_E_NOMEM; }
+    }
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    g_live_blocks.push_back({q, bytes, dev});
+    *ptr = q;
+    return CSPBO_OK;
+}
+
+void dev_free_cached(void *ptr)
+{
+    if (!ptr) return;
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    for (size_t i = 0; i < g_live_blocks.size(); i++)
+        if (g_live_blocks[i].ptr == ptr) {
+            CachedBlock b = g_live_blocks[i];
+            g_live_blocks.erase(g_live_blocks.begin() + (long)i);
+            size_t held = 0;
+            for (const CachedBlock &f : g_free_blocks) held += (f.dev == b.dev) ? f.size : 0;
+            if (held + b.size <= kCacheLimit) g_free_blocks.push_back(b);
+            else cudaFree(b.ptr);
+            return;
+        }
+    cudaFree(ptr);
+}
+}  // namespace cspbo
+
+extern "C" int cspbo_release_scratch(void)
+{
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    for (const CachedBlock &b : g_free_blocks) cudaFree(b.ptr);
+    g_free_blocks.clear();
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int dev = 0; dev < 64; dev++)
+        for (int s = 0; s < SCRATCH_SLOTS; s++)
+            if (g_scratch[dev][s]) {
+                cudaSetDevice(dev);
+                cudaFree(g_scratch[dev][s]);
+                g_scratch[dev][s] = nullptr;
+                g_scratch_size[dev][s] = 0;
+            }
+    cudaSetDevice(cur);
     return CSPBO_OK;
 }
 
@@ -93,14 +204,16 @@ extern "C" int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack 
     if (n_out == 0) return CSPBO_OK;
 
     double *dout = out, *dgrad = out_grad;
-    DevBuf tmp, tmpg;
     if (mem == CSPBO_MEM_HOST) {
-        CSPBO_CUDA(cudaMalloc(&tmp.p, (size_t)n_out * sizeof(double)));
-        dout = tmp.p;
+        void *sp = nullptr;
+        int rcs = scratch_get(SCRATCH_OUT, (size_t)n_out * sizeof(double), &sp);
+        if (rcs) return rcs;
+        dout = static_cast<double *>(sp);
         if (accumulate) CSPBO_CUDA(cudaMemcpyAsync(dout, out, (size_t)n_out * sizeof(double), cudaMemcpyHostToDevice));
         if (grad) {
-            CSPBO_CUDA(cudaMalloc(&tmpg.p, (size_t)n_grad * sizeof(double)));
-            dgrad = tmpg.p;
+            rcs = scratch_get(SCRATCH_GRAD, (size_t)n_grad * sizeof(double), &sp);
+            if (rcs) return rcs;
+            dgrad = static_cast<double *>(sp);
             if (accumulate) CSPBO_CUDA(cudaMemcpyAsync(dgrad, out_grad, (size_t)n_grad * sizeof(double), cudaMemcpyHostToDevice));
         }
     }
@@ -113,7 +226,8 @@ extern "C" int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack 
     const bool pipelined = mem == CSPBO_MEM_HOST && d.block == CSPBO_KFF && a->n_blocks >= 64 &&
                            (size_t)n_out * sizeof(double) >= ((size_t)64 << 20);
     if (pipelined) {
-        const int nslab = 12;
+        const bool classes = a->row_classes > 1;
+        const int nslab = classes ? a->row_classes : 12;
         const int nb = (int)a->n_blocks;
         cudaStream_t cs = nullptr;
         cudaEvent_t ev = nullptr;
@@ -124,7 +238,8 @@ extern "C" int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack 
         std::vector<int> groups;
         const long long rowlen = si, rowlen_g = 3LL * m2 * 3;
         for (int s = 0; s < nslab && rc == CSPBO_OK; s++) {
-            const int b0 = (int)((long long)nb * s / nslab), b1 = (int)((long long)nb * (s + 1) / nslab);
+            const int b0 = classes ? a->h_class_blk0[(size_t)s] : (int)((long long)nb * s / nslab);
+            const int b1 = classes ? a->h_class_blk0[(size_t)s + 1] : (int)((long long)nb * (s + 1) / nslab);
             if (b1 <= b0) continue;
             for (int pa = 0; pa < passesA && rc == CSPBO_OK; pa++)
                 rc = build_block_device(d, a, b, pa * 3, 0, dout + (long long)pa * 3 * sk, dgrad, si, sk, sj, sl,
@@ -132,6 +247,20 @@ extern "C" int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack 
             if (rc) break;
             cudaEventRecord(ev, 0);
             cudaStreamWaitEvent(cs, ev, 0);
+            if (classes) {
+                // rows of class s are the groups s, s+S, s+2S, ...: one strided copy
+                const long long cnt = (m1 - s + nslab - 1) / nslab;
+                if (cnt > 0) {
+                    cudaMemcpy2DAsync(out + (long long)s * rowlen, (size_t)nslab * rowlen * sizeof(double),
+                                      dout + (long long)s * rowlen, (size_t)nslab * rowlen * sizeof(double),
+                                      (size_t)rowlen * sizeof(double), (size_t)cnt, cudaMemcpyDeviceToHost, cs);
+                    if (grad)
+                        cudaMemcpy2DAsync(out_grad + (long long)s * rowlen_g, (size_t)nslab * rowlen_g * sizeof(double),
+                                          dgrad + (long long)s * rowlen_g, (size_t)nslab * rowlen_g * sizeof(double),
+                                          (size_t)rowlen_g * sizeof(double), (size_t)cnt, cudaMemcpyDeviceToHost, cs);
+                }
+                continue;
+            }
             groups.clear();
             for (int blk = b0; blk < b1; blk++)
                 for (int r = 0; r < 8; r++) {

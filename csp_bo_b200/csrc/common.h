@@ -36,6 +36,18 @@ extern std::atomic<long long> g_launches;
 //     index(v, f, slot) = ((v*(KS/2) + f/8)*32 + slot*4 + f%4)*2 + (f/4)%2
 constexpr int kSlots = 8;
 
+// Grow-only device scratch buffers, cached per (device, slot) so that host-pointer calls do not
+// cudaMalloc / cudaFree gigabytes on every call (measured: 2 ms typical, but outliers of 0.2-2 s).
+// Not thread safe across concurrent builds in one process; cspbo_release_scratch() frees them.
+enum { SCRATCH_OUT = 0, SCRATCH_GRAD = 1, SCRATCH_X = 2, SCRATCH_DX = 3, SCRATCH_DEST = 4, SCRATCH_SLOTS = 5 };
+int scratch_get(int slot, size_t bytes, void **ptr);
+
+// Small caching allocator for the pack's device arrays: blocks released by cspbo_pack_destroy are kept
+// (up to 2 GiB per device) and handed out again, so re-packing the same training set every call
+// does not pay cudaMalloc / cudaFree (which synchronise and occasionally take >100 ms).
+int dev_alloc_cached(size_t bytes, void **ptr);
+void dev_free_cached(void *ptr);
+
 inline int ksteps_for(int d)
 {
     if (d <= 0) return -1;
@@ -57,6 +69,8 @@ struct cspbo_pack {
     std::vector<int> h_tile_start; // first tile of (block, species): index block*ns + e (size n_blocks*ns+1)
     std::vector<int> h_slot_group; // [n_blocks*8] group id of each slot, -1 = empty
     std::vector<long long> rows_per_species;
+    int row_classes = 1;            // groups were split by g % row_classes before blocking
+    std::vector<int> h_class_blk0;  // first block of each row class (size row_classes+1)
     // device-side tables
     double *d_tiles = nullptr;
     int *d_tile_start = nullptr;

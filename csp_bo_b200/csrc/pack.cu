@@ -79,12 +79,19 @@ extern "C" int cspbo_pack_create(int n, int d, int nc, int m, int row_start, int
                                  const double *x, const double *dxdr, const int *ele, const int *inds,
                                  int mem, cspbo_pack **out)
 {
-    return cspbo_pack_create_eps(n, d, nc, m, row_start, row_end, x, dxdr, ele, inds, mem, 0.0, out);
+    return cspbo_pack_create_ex(n, d, nc, m, row_start, row_end, x, dxdr, ele, inds, mem, 0.0, 1, out);
 }
 
 extern "C" int cspbo_pack_create_eps(int n, int d, int nc, int m, int row_start, int row_end,
                                      const double *x, const double *dxdr, const int *ele, const int *inds,
                                      int mem, double norm_shift, cspbo_pack **out)
+{
+    return cspbo_pack_create_ex(n, d, nc, m, row_start, row_end, x, dxdr, ele, inds, mem, norm_shift, 1, out);
+}
+
+extern "C" int cspbo_pack_create_ex(int n, int d, int nc, int m, int row_start, int row_end,
+                                    const double *x, const double *dxdr, const int *ele, const int *inds,
+                                    int mem, double norm_shift, int row_classes, cspbo_pack **out)
 {
     if (!out) { set_error("pack_create: out is null"); return CSPBO_E_ARG; }
     *out = nullptr;
@@ -146,25 +153,38 @@ extern "C" int cspbo_pack_create_eps(int n, int d, int nc, int m, int row_start,
         }
         // one common group order: lexicographic on the count tuples, largest first, so that the 8
         // groups of a block have (nearly) equal row counts in every species and tiles carry no padding
-        std::vector<int> order((size_t)m);
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        auto by_counts = [&](int a, int b) {
             const int *ca = &count[(size_t)a * nsz], *cb = &count[(size_t)b * nsz];
             for (int e = 0; e < ns; e++)
                 if (ca[e] != cb[e]) return ca[e] > cb[e];
             return false;
-        });
-        const int nb = (m + kSlots - 1) / kSlots;
+        };
+        // row classes (host-bound builds): groups are first split by g % row_classes and blocks never
+        // straddle a class, so the rows of one class sit at a uniform pitch in the caller's matrix and
+        // a finished class is copied back with ONE strided (2-D) copy (api.cu, pipelined path)
+        const int ncls = std::max(1, std::min(row_classes, std::max(m, 1)));
+        std::vector<int> slots;
+        slots.reserve((size_t)m + 8 * (size_t)ncls);
+        p->row_classes = ncls;
+        p->h_class_blk0.assign((size_t)ncls + 1, 0);
+        std::vector<int> order;
+        for (int c = 0; c < ncls; c++) {
+            order.clear();
+            for (int g = c; g < m; g += ncls) order.push_back(g);
+            std::stable_sort(order.begin(), order.end(), by_counts);
+            p->h_class_blk0[(size_t)c] = (int)(slots.size() / kSlots);
+            slots.insert(slots.end(), order.begin(), order.end());
+            while (slots.size() % kSlots) slots.push_back(-1);
+        }
+        const int nb = (int)(slots.size() / kSlots);
+        p->h_class_blk0[(size_t)ncls] = nb;
         p->n_blocks = nb;
         p->h_slot_group.assign((size_t)std::max(nb, 1) * kSlots, -1);
+        std::copy(slots.begin(), slots.end(), p->h_slot_group.begin());
         p->h_tile_start.assign((size_t)nb * nsz + 1, 0);
         std::vector<long long> first_dest((size_t)std::max(m, 1) * nsz, -1);
         long long tiles = 0;
         for (int b = 0; b < nb; b++) {
-            for (int s = 0; s < kSlots; s++) {
-                const size_t oi = (size_t)b * kSlots + s;
-                if (oi < (size_t)m) p->h_slot_group[oi] = order[oi];
-            }
             for (int e = 0; e < ns; e++) {
                 int T = 0;
                 for (int s = 0; s < kSlots; s++) {
@@ -207,11 +227,11 @@ extern "C" int cspbo_pack_create_eps(int n, int d, int nc, int m, int row_start,
         const size_t tb = (size_t)std::max<long long>(p->n_tiles, 1) * p->tile_doubles * sizeof(double);
         const size_t nbk = (size_t)std::max<long long>(p->n_blocks, 1);
         const size_t nts = p->h_tile_start.size();
-        PACK_CUDA(cudaMalloc(&p->d_tiles, tb));
+        if ((rc = dev_alloc_cached(tb, (void **)&p->d_tiles)) != CSPBO_OK) goto fail;
         PACK_CUDA(cudaMemsetAsync(p->d_tiles, 0, tb));
-        PACK_CUDA(cudaMalloc(&p->d_tile_start, nts * sizeof(int)));
-        PACK_CUDA(cudaMalloc(&p->d_slot_group, nbk * 8 * sizeof(int)));
-        PACK_CUDA(cudaMalloc(&p->d_tile_valid, (size_t)std::max<long long>(p->n_tiles, 1) * sizeof(unsigned)));
+        if ((rc = dev_alloc_cached(nts * sizeof(int), (void **)&p->d_tile_start)) != CSPBO_OK) goto fail;
+        if ((rc = dev_alloc_cached(nbk * 8 * sizeof(int), (void **)&p->d_slot_group)) != CSPBO_OK) goto fail;
+        if ((rc = dev_alloc_cached((size_t)std::max<long long>(p->n_tiles, 1) * sizeof(unsigned), (void **)&p->d_tile_valid)) != CSPBO_OK) goto fail;
         PACK_CUDA(cudaMemsetAsync(p->d_tile_valid, 0, (size_t)std::max<long long>(p->n_tiles, 1) * sizeof(unsigned)));
         p->bytes = (long long)(tb + nts * 4 + nbk * 32 + std::max<long long>(p->n_tiles, 1) * 4);
         PACK_CUDA(cudaMemcpyAsync(p->d_tile_start, p->h_tile_start.data(), p->h_tile_start.size() * sizeof(int),
@@ -220,15 +240,15 @@ extern "C" int cspbo_pack_create_eps(int n, int d, int nc, int m, int row_start,
                                   cudaMemcpyHostToDevice));
     }
     if (n > 0 && p->n_tiles > 0) {
-        PACK_CUDA(cudaMalloc(&d_dest, (size_t)n * sizeof(long long)));
+        if ((rc = scratch_get(SCRATCH_DEST, (size_t)n * sizeof(long long), (void **)&d_dest)) != CSPBO_OK) goto fail;
         PACK_CUDA(cudaMemcpyAsync(d_dest, dest.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
         const double *xs = x, *dxs = dxdr;
         if (mem == CSPBO_MEM_HOST) {
-            PACK_CUDA(cudaMalloc(&d_x, (size_t)n * d * sizeof(double)));
+            if ((rc = scratch_get(SCRATCH_X, (size_t)n * d * sizeof(double), (void **)&d_x)) != CSPBO_OK) goto fail;
             PACK_CUDA(cudaMemcpyAsync(d_x, x, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice));
             xs = d_x;
             if (nc > 0) {
-                PACK_CUDA(cudaMalloc(&d_dx, (size_t)n * d * nc * sizeof(double)));
+                if ((rc = scratch_get(SCRATCH_DX, (size_t)n * d * nc * sizeof(double), (void **)&d_dx)) != CSPBO_OK) goto fail;
                 PACK_CUDA(cudaMemcpyAsync(d_dx, dxdr, (size_t)n * d * nc * sizeof(double), cudaMemcpyHostToDevice));
                 dxs = d_dx;
             }
@@ -239,12 +259,10 @@ extern "C" int cspbo_pack_create_eps(int n, int d, int nc, int m, int row_start,
         g_launches++;
         PACK_CUDA(cudaGetLastError());
     }
-    PACK_CUDA(cudaStreamSynchronize(0));  // dest host buffer dies with this scope
-    cudaFree(d_dest); cudaFree(d_x); cudaFree(d_dx);
+    PACK_CUDA(cudaStreamSynchronize(0));  // dest host buffer dies with this scope; scratch is reusable again
     *out = p;
     return CSPBO_OK;
 fail:
-    cudaFree(d_dest); cudaFree(d_x); cudaFree(d_dx);
     cspbo_pack_destroy(p);
     return rc;
 #undef PACK_CUDA
@@ -253,10 +271,10 @@ fail:
 extern "C" int cspbo_pack_destroy(cspbo_pack *p)
 {
     if (!p) return CSPBO_OK;
-    cudaFree(p->d_tiles);
-    cudaFree(p->d_tile_start);
-    cudaFree(p->d_slot_group);
-    cudaFree(p->d_tile_valid);
+    dev_free_cached(p->d_tiles);
+    dev_free_cached(p->d_tile_start);
+    dev_free_cached(p->d_slot_group);
+    dev_free_cached(p->d_tile_valid);
     delete p;
     return CSPBO_OK;
 }

@@ -8,7 +8,7 @@ row split + Allreduce (dot_kernel.py:188-247) is replaced by the GPU grid.
 import numpy as np
 
 from .. import _lib
-from ..packing import build_block, pack_energy, pack_force
+from ..packing import HOST_ROW_CLASSES, build_block, pack_energy, pack_force
 from ..utilities import list_to_tuple
 
 
@@ -62,7 +62,11 @@ def kff_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False, stress=False, out
 
     `out` (extension): optional preallocated (pinned) float64 buffer of m1*nc1*m2*3 elements."""
     X1, X2 = _force(X1, stress), _force(X2)
-    a = pack_force(X1)
+    # host-bound result above 64 MB: pack side 1 in row classes so finished classes stream back while
+    # the next one is computed (cspbo_block_build, pipelined path)
+    on_dev = out is not None and type(out).__module__.startswith('torch') and out.is_cuda
+    big = (not on_dev) and 72.0 * len(X1[3]) * len(X2[3]) * (3 if stress else 1) >= (64 << 20) and len(X1[3]) >= 512
+    a = pack_force(X1, row_classes=HOST_ROW_CLASSES if big else 1)
     same = (X1 is X2) or (X1[0] is X2[0] and X1[1] is X2[1])
     b = a if same else pack_force(X2)
     m1, m2 = a.m, b.m

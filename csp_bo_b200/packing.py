@@ -35,7 +35,7 @@ def group_ids(indices):
 class Pack:
     """Device-resident, tiled form of one stacked descriptor set."""
 
-    def __init__(self, x, dxdr, ele, indices, row_range=None, norm_shift=0.0):
+    def __init__(self, x, dxdr, ele, indices, row_range=None, norm_shift=0.0, row_classes=1):
         lib = _lib.load()
         on_dev = _is_torch(x)
         if on_dev:
@@ -61,9 +61,10 @@ class Pack:
         self.m, self.n, self.d, self.nc = len(self.counts), n, d, nc
         r0, r1 = (0, n) if row_range is None else row_range
         h = c_vp()
-        _lib.check(lib.cspbo_pack_create_eps(n, d, nc, self.m, int(r0), int(r1), _ptr(x), _ptr(dxdr), _ptr(ele),
-                                             _ptr(inds), MEM_DEVICE if on_dev else MEM_HOST, float(norm_shift),
-                                             ctypes.byref(h)))
+        _lib.check(lib.cspbo_pack_create_ex(n, d, nc, self.m, int(r0), int(r1), _ptr(x), _ptr(dxdr), _ptr(ele),
+                                            _ptr(inds), MEM_DEVICE if on_dev else MEM_HOST, float(norm_shift),
+                                            int(row_classes), ctypes.byref(h)))
+        self.row_classes = int(row_classes)
         self._h = h
 
     @property
@@ -125,13 +126,16 @@ def pack_energy(X, cache=True):
     return p
 
 
-def pack_force(X, cache=True, row_range=None):
+HOST_ROW_CLASSES = 6     # row classes of packs that feed large host-bound K_FF builds (see cspbo_pack_create_ex)
+
+
+def pack_force(X, cache=True, row_range=None, row_classes=1):
     x, dxdr, ele, indices = X
-    key = _fingerprint((x, dxdr, ele), ("F", tuple(np.asarray(indices).tolist()[:4]), len(indices), row_range))
+    key = _fingerprint((x, dxdr, ele), ("F", tuple(np.asarray(indices).tolist()[:4]), len(indices), row_range, row_classes))
     if cache and key in _CACHE:
         _CACHE.move_to_end(key)
         return _CACHE[key]
-    p = Pack(x, dxdr, ele, indices, row_range=row_range)
+    p = Pack(x, dxdr, ele, indices, row_range=row_range, row_classes=row_classes)
     if cache:
         _CACHE[key] = p
         while len(_CACHE) > _CACHE_MAX:

@@ -60,6 +60,8 @@ long long cspbo_launch_count(void);
 int cspbo_set_device(int device);
 int cspbo_device_count(int *count);
 int cspbo_synchronize(void);
+/* free the cached device scratch buffers used by host-pointer calls (staging of x / dxdr / outputs) */
+int cspbo_release_scratch(void);
 
 /* ------------------------------------------------------------------------------------------
  * (1) reference-compatible entry points.  Host pointers.  pout is accumulated into.
@@ -156,6 +158,12 @@ int cspbo_pack_create(int n, int d, int nc, int m, int row_start, int row_end,
 int cspbo_pack_create_eps(int n, int d, int nc, int m, int row_start, int row_end,
                           const double *x, const double *dxdr, const int *ele, const int *inds,
                           int mem, double norm_shift, cspbo_pack **out);
+/* Full form.  row_classes > 1 splits the groups by (group id % row_classes) before blocking, which
+ * lets a host-bound K_FF build copy each finished class back with one strided copy while the next
+ * class is being computed (cspbo_block_build with mem = CSPBO_MEM_HOST).  1 = plain layout. */
+int cspbo_pack_create_ex(int n, int d, int nc, int m, int row_start, int row_end,
+                         const double *x, const double *dxdr, const int *ele, const int *inds,
+                         int mem, double norm_shift, int row_classes, cspbo_pack **out);
 int cspbo_pack_destroy(cspbo_pack *p);
 int cspbo_pack_groups(const cspbo_pack *p);          /* m */
 long long cspbo_pack_bytes(const cspbo_pack *p);     /* HBM footprint */

@@ -193,7 +193,10 @@ def test_pipelined_host_copyback_equals_device_build():
     p, q = Pack(X[0], X[1], X[2], X[3]), Pack(Y[0], Y[1], Y[2], Y[3])
     x9 = np.concatenate((X[1], 0.5 * X[1][:, :, [1, 2, 0]], -0.25 * X[1][:, :, [2, 0, 1]]), axis=2)
     p9 = Pack(X[0], x9, X[2], X[3])
-    for a, b, kw in ((p, p, dict(symmetric=True)), (p, q, {}), (p9, q, dict(stress=True))):
+    pc = Pack(X[0], X[1], X[2], X[3], row_classes=12)      # class-strided copy-back (one 2-D copy per class)
+    pc9 = Pack(X[0], x9, X[2], X[3], row_classes=5)
+    for a, b, kw in ((p, p, dict(symmetric=True)), (p, q, {}), (p9, q, dict(stress=True)),
+                     (pc, pc, dict(symmetric=True)), (pc, q, {}), (pc9, q, dict(stress=True))):
         dev, _ = build_block(_lib.RBF, _lib.KFF, a, b, 2.0, sigma2=39.0, l=0.56, tol=1e-10, use_tol=True, device=True, **kw)
         host, _ = build_block(_lib.RBF, _lib.KFF, a, b, 2.0, sigma2=39.0, l=0.56, tol=1e-10, use_tol=True, **kw)
         assert host.nbytes >= 64 << 20

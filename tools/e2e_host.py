@@ -18,3 +18,9 @@ def full():
     packing.clear_cache(); kff_C(Xh, Xh, 18.55, 0.01, 2.0, out=o)
 print("kff_C e2e    ", [t(full) for _ in range(6)])
 print("build->pinned", [t(lambda: build_block(_lib.DOT, _lib.KFF, p, p, 2.0, scale=3.0, symmetric=True, out=o)) for _ in range(4)])
+pc = Pack(Xh[0], Xh[1], Xh[2], Xh[3], row_classes=6)
+outd = torch.empty((m, 3, m * 3), dtype=torch.float64, device="cuda")
+print("device build, plain pack  ", [t(lambda: build_block(_lib.DOT, _lib.KFF, p, p, 2.0, scale=3.0, symmetric=True, out=outd)) for _ in range(3)])
+print("device build, 6-class pack", [t(lambda: build_block(_lib.DOT, _lib.KFF, pc, pc, 2.0, scale=3.0, symmetric=True, out=outd)) for _ in range(3)])
+print("host build, 6-class pack  ", [t(lambda: build_block(_lib.DOT, _lib.KFF, pc, pc, 2.0, scale=3.0, symmetric=True, out=o)) for _ in range(3)])
+print("pack only (pinned host)    ", [t(lambda: Pack(Xh[0], Xh[1], Xh[2], Xh[3], row_classes=6)) for _ in range(3)])
