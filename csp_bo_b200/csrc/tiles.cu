@@ -17,6 +17,8 @@
 // (row a in group i, row b in group j) is a plain register accumulation; each thread owns the
 // 3x3 (or 1x3, 1x1) output blocks of two fixed group pairs and writes them once.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.h"
 
@@ -57,6 +59,7 @@ struct TileParams {
     int tbc;  // B tiles per shared-memory chunk
     int strip;  // A-block groups per rasterisation strip
     int symmetric;
+    int stream_out;  // 1: outputs are stored with the evict-first (streaming) policy
     int diag;        // 1: one warp per block, b = a, only the (i,i) group pairs are stored: out[i, NC1, NC2]
     int accumulate;  // 1: out += result (reference `pout +=` semantics), 0: out = result
     double zeta, sigma2, sigma02, inv2l2, inv_l, inv_l3, tol;
@@ -415,7 +418,7 @@ block_tile_kernel(const TileParams p)
                 const long long o = gi * p.si + k * p.sk + gj * p.sj + l * p.sl;
                 double v = p.scale * acc[e][k][l];
                 if (p.accumulate) v += p.out[o];
-                p.out[o] = v;
+                if (p.stream_out) __stcs(p.out + o, v); else p.out[o] = v;
                 if (GRAD) {
                     double g = p.scale_grad * accg[e][k][l];
                     if (p.accumulate) g += p.out_grad[o];
@@ -431,7 +434,7 @@ block_tile_kernel(const TileParams p)
                     const long long o = gj * p.si + l * p.sk + gi * p.sj + k * p.sl;
                     double v = p.scale * acc[e][k][l];
                     if (p.accumulate) v += p.out[o];
-                    p.out[o] = v;
+                    if (p.stream_out) __stcs(p.out + o, v); else p.out[o] = v;
                     if (GRAD) {
                         double g = p.scale_grad * accg[e][k][l];
                         if (p.accumulate) g += p.out_grad[o];
@@ -522,6 +525,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.symmetric = d.symmetric;
     p.accumulate = accumulate;
     p.diag = diag;
+    p.stream_out = 0;   // streaming stores measured neutral (time and DRAM traffic)
     p.sharded = outs != nullptr;
     p.nranks = p.sharded ? nranks : 1;
     p.rank = p.sharded ? rank : 0;
@@ -555,8 +559,45 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.tbc = tbc;
     const size_t smem = 2 * (size_t)tbc * tile_bytes + 2 * sizeof(unsigned long long);
     p.strip = std::max(1, std::min(kStrip, (a_mine + nwarps - 1) / nwarps));
-    if (a->ks == 6) return launch_ks<6>(mode, fam, z2, p, nwarps, smem, st);
-    return launch_ks<14>(mode, fam, z2, p, nwarps, smem, st);
+    // Keep the packed tiles L2-resident while the write-once output streams through: an access-policy
+    // window (persisting on hit, streaming on miss) over the B tiles.  Measured at 20 001 force rows:
+    // DRAM reads 20.5 -> 9.5 GB per build at unchanged run time (profiles/).
+    bool window = false;
+    {
+        static int persist_of[64], window_of[64];
+        static bool probed[64] = {};
+        const int di = (dev >= 0 && dev < 64) ? dev : 0;
+        int &max_persist = persist_of[di], &max_window = window_of[di];
+        if (!probed[di]) {
+            probed[di] = true;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+            if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            cudaGetLastError();
+        }
+        const size_t tile_bytes_all = (size_t)b->n_tiles * b->tile_doubles * sizeof(double);
+        if (max_persist > 0 && max_window > 0 && tile_bytes_all >= ((size_t)8 << 20)) {
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            av.accessPolicyWindow.base_ptr = (void *)b->d_tiles;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(tile_bytes_all, (size_t)max_window);
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+            cudaGetLastError();
+        }
+    }
+    const int rc_launch = (a->ks == 6) ? launch_ks<6>(mode, fam, z2, p, nwarps, smem, st)
+                                       : launch_ks<14>(mode, fam, z2, p, nwarps, smem, st);
+    if (window) {   // the window is captured at launch; do not leak it onto later work of this stream
+        cudaStreamAttrValue av;
+        memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
+    return rc_launch;
 }
 
 }  // namespace cspbo
