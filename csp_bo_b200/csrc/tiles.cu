@@ -59,6 +59,8 @@ struct TileParams {
     int tbc;  // B tiles per shared-memory chunk
     int strip;  // A-block groups per rasterisation strip
     int symmetric;
+    int split;       // 1: the warps of a CTA share ONE A block and split its tiles (small problems: 4x more
+                     //    parallelism, 4x shorter critical path); partial sums are reduced through shared memory
     int stream_out;  // 1: outputs are stored with the evict-first (streaming) policy
     int diag;        // 1: one warp per block, b = a, only the (i,i) group pairs are stored: out[i, NC1, NC2]
     int accumulate;  // 1: out += result (reference `pout +=` semantics), 0: out = result
@@ -214,7 +216,8 @@ block_tile_kernel(const TileParams p)
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
     const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
-    const int npg = (a_mine + nwarps - 1) / nwarps;
+    const int a_units = p.split ? 1 : nwarps;     // A blocks per CTA
+    const int npg = (a_mine + a_units - 1) / a_units;
     // rasterisation: CTAs walk a strip of p.strip A-block groups across all B blocks (one strip = all
     // A-block groups by default: consecutive CTAs share the B block, which stays L2-hot)
     const int strip_ids = p.strip * p.b_nblk;
@@ -223,7 +226,7 @@ block_tile_kernel(const TileParams p)
     const int strip_w = min(p.strip, npg - strip * p.strip);
     const int q = rem / strip_w;
     const int pg = strip * p.strip + (rem - q * strip_w);
-    const int a_blk = p.a_begin + (pg * nwarps + warp) * p.nranks + p.rank;  // nranks == 1, rank == 0 unless sharded
+    const int a_blk = p.a_begin + (pg * a_units + (p.split ? 0 : warp)) * p.nranks + p.rank;  // nranks == 1, rank == 0 unless sharded
     const int b_blk = p.diag ? a_blk : q;
     // symmetric build: only blocks with b >= a are computed (mirrored at write time)
     const bool active = a_blk < p.a_nblk && !(p.symmetric && b_blk < a_blk);
@@ -276,7 +279,7 @@ block_tile_kernel(const TileParams p)
         const double *sB = smem + (size_t)st * stage_doubles;
         mbar_wait(&full[st], (unsigned)(it >> 1) & 1u);
 
-        for (int ta = 0; ta < Ta; ta++) {
+        for (int ta = p.split ? warp : 0; ta < Ta; ta += p.split ? nwarps : 1) {
             // A fragments of this slab: registers for the whole sweep over the chunk
             double a[NV1][KS];
             const double2 *at = reinterpret_cast<const double2 *>(p.A.tiles + (size_t)(a_t0 + ta) * p.A.tile_doubles);
@@ -371,6 +374,39 @@ block_tile_kernel(const TileParams p)
         cur = nxt;
     }
 
+    if (p.split && nwarps > 1) {
+        // all warps worked on the same (a_blk, b_blk): sum their partial accumulators in warp 0.
+        // (the stage buffers are free: every warp passed the last __syncthreads of the run loop)
+        constexpr int NACC = 2 * NC1 * NC2 * (GRAD ? 2 : 1);
+        double *red = smem + ((size_t)(warp > 0 ? warp - 1 : 0) * 32 + lane) * NACC;
+        if (warp > 0) {
+            int n = 0;
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+#pragma unroll
+                for (int k = 0; k < NC1; k++)
+#pragma unroll
+                    for (int l = 0; l < NC2; l++) {
+                        red[n++] = acc[e][k][l];
+                        if (GRAD) red[n++] = accg[e][k][l];
+                    }
+        }
+        __syncthreads();
+        if (warp > 0) return;
+        for (int w = 1; w < nwarps; w++) {
+            const double *r = smem + ((size_t)(w - 1) * 32 + lane) * NACC;
+            int n = 0;
+#pragma unroll
+            for (int e = 0; e < 2; e++)
+#pragma unroll
+                for (int k = 0; k < NC1; k++)
+#pragma unroll
+                    for (int l = 0; l < NC2; l++) {
+                        acc[e][k][l] += r[n++];
+                        if (GRAD) accg[e][k][l] += r[n++];
+                    }
+        }
+    }
     if (!active) return;
     const int gi = p.A.slot_group[a_blk * 8 + ar];
     if (gi < 0) return;
@@ -456,7 +492,7 @@ static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t
         configured = smem;
     }
     const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
-    const int npg = (a_mine + nwarps - 1) / nwarps;
+    const int npg = p.split ? a_mine : (a_mine + nwarps - 1) / nwarps;
     const long long grid = (long long)npg * p.b_nblk;
     if (grid <= 0) return CSPBO_OK;
     if (grid > 0x7fffffffLL) { set_error("block_build: grid too large"); return CSPBO_E_ARG; }
@@ -550,15 +586,18 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // warps per CTA: one A block per warp; shrink for small problems so the grid covers the SMs
-    int nwarps = diag ? 1 : kMaxWarps;
+    int nwarps = kMaxWarps;
     const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
-    while (nwarps > 1 && (long long)((a_mine + nwarps - 1) / nwarps) * p.b_nblk < 2LL * sms) nwarps >>= 1;
+    // Small problems (fewer than ~2 warps per scheduler in the one-block-per-warp mapping): let the 4 warps
+    // of a CTA split the tiles of ONE A block instead, which quarters the critical path of a K* build
+    p.split = (diag || (long long)a_mine * p.b_nblk < 32LL * sms) ? 1 : 0;
     // B tiles per stage: a whole (block, species) run if it fits in 36 KB
     const size_t tile_bytes = (size_t)b->tile_doubles * sizeof(double);
     const int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, kSmemChunk / tile_bytes));
     p.tbc = tbc;
-    const size_t smem = 2 * (size_t)tbc * tile_bytes + 2 * sizeof(unsigned long long);
-    p.strip = std::max(1, std::min(kStrip, (a_mine + nwarps - 1) / nwarps));
+    const size_t smem = std::max<size_t>(2 * (size_t)tbc * tile_bytes, (size_t)(kMaxWarps - 1) * 32 * 36 * sizeof(double)) +
+                        2 * sizeof(unsigned long long);
+    p.strip = std::max(1, std::min(kStrip, p.split ? a_mine : (a_mine + nwarps - 1) / nwarps));
     // Keep the packed tiles L2-resident while the write-once output streams through: an access-policy
     // window (persisting on hit, streaming on miss) over the B tiles.  Measured at 20 001 force rows:
     // DRAM reads 20.5 -> 9.5 GB per build at unchanged run time (profiles/).

@@ -19,11 +19,10 @@ def list_to_tuple(data, stress=False, include_value=False, mode='force'):
     values = [fd[-2] for fd in data] if include_value else None
     if mode == 'force':
         length = 9 if stress else 3
-        dXdR = np.zeros([X.shape[0], X.shape[1], length])
-        count = 0
-        for fd, shp in zip(data, indices):
-            dXdR[count:count + shp, :, :] = fd[1]
-            count += shp
+        dXdR = np.concatenate([np.asarray(fd[1], dtype=np.float64) for fd in data], axis=0)
+        if dXdR.shape[1:] != (X.shape[1], length):
+            raise ValueError("dxdr blocks must have shape [n, %d, %d] (stress=%s), got %s"
+                             % (X.shape[1], length, stress, dXdR.shape))
         return (X, dXdR, ELE, indices, values) if include_value else (X, dXdR, ELE, indices)
     return (X, ELE, indices, values) if include_value else (X, ELE, indices)
 
