@@ -315,23 +315,22 @@ extern "C" int cspbo_block_build_into(const cspbo_block_desc *desc, const cspbo_
     if (d.family != CSPBO_DOT && d.family != CSPBO_RBF) { set_error("block_build_into: bad family"); return CSPBO_E_ARG; }
     if (d.stress || d.with_grad) { set_error("block_build_into: plain blocks only (no stress / grad)"); return CSPBO_E_ARG; }
     if (d.family == CSPBO_RBF && !(d.l > 0.0)) { set_error("block_build_into: RBF needs l > 0"); return CSPBO_E_ARG; }
-    long long si, sk, sj, sl, rows, cols;
+    long long si, sk, sj, sl, cols;
     if (d.block == CSPBO_KEE) {
         if (a->nc != 0 || b->nc != 0) { set_error("block_build_into: K_EE needs two energy packs"); return CSPBO_E_ARG; }
-        si = ldk; sk = 0; sj = 1; sl = 0; rows = a->m; cols = b->m;
+        si = ldk; sk = 0; sj = 1; sl = 0; cols = b->m;
     } else if (d.block == CSPBO_KEF) {
         if (a->nc != 0 || b->nc < 3) { set_error("block_build_into: K_EF needs (energy, force) packs"); return CSPBO_E_ARG; }
-        si = ldk; sk = 0; sj = 3; sl = 1; rows = a->m; cols = 3LL * b->m;
+        si = ldk; sk = 0; sj = 3; sl = 1; cols = 3LL * b->m;
     } else if (d.block == CSPBO_KFF) {
         if (a->nc < 3 || b->nc < 3) { set_error("block_build_into: K_FF needs two force packs"); return CSPBO_E_ARG; }
-        si = 3 * ldk; sk = ldk; sj = 3; sl = 1; rows = 3LL * a->m; cols = 3LL * b->m;
+        si = 3 * ldk; sk = ldk; sj = 3; sl = 1; cols = 3LL * b->m;
     } else { set_error("block_build_into: bad block"); return CSPBO_E_ARG; }
     if (row0 < 0 || col0 < 0 || col0 + cols > ldk) { set_error("block_build_into: block does not fit (ldk %lld)", ldk); return CSPBO_E_ARG; }
     if (d.symmetric && (a != b || d.block == CSPBO_KEF || row0 != col0)) {
         set_error("block_build_into: symmetric needs a == b on the diagonal of K");
         return CSPBO_E_ARG;
     }
-    (void)rows;
     return build_block_device(d, a, b, 0, 0, K + row0 * ldk + col0, nullptr, si, sk, sj, sl, 0, 0);
 }
 

@@ -1,8 +1,8 @@
 """GPU-resident Gaussian-process regressor: the fit / prediction / log-marginal-likelihood slice of the
 reference's `cspbo.gaussianprocess.GaussianProcess` (gaussianprocess.py:71-184, 325-390, 453-509) on top of
-the CUDA covariance kernels.  Same method names, arguments and return values; what is NOT carried
-over is everything that needs ase / pyxtal / the ASE database (save/load/export, add_structure,
-remove_train_pts, sparsify): those stay in the reference.
+the CUDA covariance kernels, plus remove_train_pts / sparsify / CUR (:230-270, :754-790).  Same method
+names, arguments and return values; what is NOT carried over is everything that needs ase / pyxtal /
+the ASE database (save/load/export_ase_db, add_structure): those stay in the reference.
 
 Device residency: K is assembled block by block straight into one CUDA matrix
 (kernels/device.py), the noise is added and K is factorised in place by cuSOLVER
@@ -16,7 +16,7 @@ from scipy.optimize import minimize
 
 from . import _lib, gp
 from .kernels import device as kdev
-from .utilities import list_to_tuple
+from .utilities import list_to_tuple, tuple_to_list
 
 # atomic numbers for descriptor.calculate() results that carry chemical symbols
 # (gaussianprocess.py:335 uses pyxtal's Element(ele).z)
@@ -136,6 +136,46 @@ class GaussianProcess():
 
     def _train_dict(self):
         return {k: v for k, v in self.train_x.items() if len(v) > 0}
+
+    def remove_train_pts(self, e_ids, f_ids):
+        """Drop the energy points `e_ids` and force points `f_ids` and refit (gaussianprocess.py:230-270;
+        the ASE-database bookkeeping of the reference is kept only as far as train_db entries exist)."""
+        data = {"energy": [], "force": []}
+        energy_data = tuple_to_list(self.train_x['energy'], mode='energy') if len(self.train_x['energy']) else []
+        force_data = tuple_to_list(self.train_x['force']) if len(self.train_x['force']) else []
+        for i, (X, ele) in enumerate(energy_data):
+            if i not in e_ids:
+                data['energy'].append((X, self.train_y['energy'][i], ele))
+        for i, (X, dxdr, ele) in enumerate(force_data):
+            if i not in f_ids:
+                data["force"].append((X, dxdr, self.train_y['force'][i], ele))
+        if self.train_db:
+            data["db"] = []
+            for (atoms, energy, force, energy_in, force_in, e_id, _f_ids) in self.train_db:
+                if e_id in e_ids:
+                    energy_in = False
+                _force_in = [force_in[i] for i, f_id in enumerate(_f_ids) if f_id not in f_ids]
+                if energy_in or len(_force_in) > 0:
+                    data['db'].append((atoms, energy, force, energy_in, _force_in))
+        self.set_train_pts(data)
+        self.fit(show=False, opt=False)
+
+    def sparsify(self, e_tol=1e-10, f_tol=1e-10):
+        """Remove training points that the CUR decomposition marks as redundant
+        (gaussianprocess.py:754-772)."""
+        K = kdev.k_total_device(self.kernel, self._train_dict())
+        N_e = self._n_energy()
+        N_f = len(self.train_x["force"][-1]) if len(self.train_x["force"]) else 0
+        pts_e = CUR(K[:N_e, :N_e], e_tol) if N_e else np.array([], dtype=int)
+        pts = CUR(K[N_e:, N_e:], f_tol) if N_f else np.array([], dtype=int)
+        pts_f = []
+        if N_f > 1:
+            sel = set(int(v) for v in pts)
+            pts_f = [i for i in range(N_f) if {3 * i, 3 * i + 1, 3 * i + 2} <= sel]
+        print("{:d} energy and {:d} force points will be removed".format(len(pts_e), len(pts_f)))
+        if len(pts_e) + len(pts_f) > 0:
+            self.remove_train_pts(list(int(v) for v in pts_e), pts_f)
+        return list(int(v) for v in pts_e), pts_f
 
     # ------------------------------------------------------------------ fit
     def fit(self, TrainData=None, show=True, opt=True):
@@ -332,3 +372,17 @@ class GaussianProcess():
             y_std = np.sqrt(y_var)
             return E, F, S, y_std[0], y_std[1:].reshape([n_atoms, 3])
         return E, F, S
+
+
+def CUR(K, l_tol=1e-10):
+    """CUR selection of Appendix D, Jinnouchi et al., PRB 014105 (2019), as in gaussianprocess.py:775-790:
+    leverage scores omega_j = sum over eigenvectors with eigenvalue < l_tol of U[j,eta]^2; returns the
+    indices of the N_low largest scores.  K: CUDA tensor or numpy array; eigh runs on the device."""
+    import torch
+    Kd = K if isinstance(K, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(K, dtype=np.float64)).cuda()
+    L, U = torch.linalg.eigh(Kd)
+    low = L < l_tol
+    n_low = int(low.sum())
+    omega = (U[:, low] ** 2).sum(dim=1)
+    ids = torch.argsort(-omega, stable=True)
+    return ids[:n_low].cpu().numpy()

@@ -50,7 +50,7 @@ extern "C" {
 #define CSPBO_E_NOTPD       5
 #define CSPBO_E_NODEVICE    6   /* no CUDA device: there is NO CPU fallback */
 
-#define CSPBO_MAX_D         64  /* largest descriptor length the tile kernels are compiled for */
+#define CSPBO_MAX_D         56  /* largest descriptor length the tile kernels are compiled for (k-steps 6 or 14) */
 
 const char *cspbo_last_error(void);
 int cspbo_version(void);

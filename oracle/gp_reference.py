@@ -135,3 +135,12 @@ class RefGaussianProcess:
             sd = np.sqrt(y_var)
             return E, F, S, sd[0], sd[1:].reshape([n_atoms, 3])
         return E, F, S
+
+
+def CUR(K, l_tol=1e-10):
+    """gaussianprocess.py:775-790 (the O(N^2) double loop written as a masked sum)."""
+    L, U = np.linalg.eigh(K)
+    low = L < l_tol
+    omega = (U[:, low] ** 2).sum(axis=1)
+    ids = np.argsort(-1 * omega, kind="stable")
+    return ids[:int(low.sum())], omega

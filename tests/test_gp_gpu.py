@@ -145,3 +145,29 @@ def test_predict_structure(problem, fixtures, fam, para, bounds, stress):
         assert max_norm_err(got[2], want[2]) < PRED_TOL
     dscale = 2e2
     assert abs(got[3] ** 2 - want[3] ** 2) <= 1e-8 * dscale and np.abs(got[4] ** 2 - want[4] ** 2).max() <= 1e-8 * dscale
+
+
+def test_cur_and_sparsify(problem, fixtures):
+    """A training set with duplicated force atoms has exact null directions: CUR must flag them
+    (leverage scores equal to the NumPy restatement) and sparsify must drop whole duplicated atoms."""
+    import torch
+    from csp_bo_b200.gaussianprocess import CUR, GaussianProcess
+    from oracle import gp_reference as gr
+    train_x, y, _ = problem
+    fam, para, bounds = KERNELS[0]
+    F = force_list(train_x["force"])
+    dup = F[:20] + F[:5]                       # atoms 0..4 appear twice
+    ydup = np.concatenate((y[4:4 + 60], y[4:4 + 15]))
+    data = {"energy": [], "force": [(x, dx, ydup[3 * i:3 * i + 3], ele) for i, (x, dx, ele) in enumerate(dup)]}
+    model = GaussianProcess(make_kernel(fam, para, bounds), f_coef=30, noise_e=[0.005, 0.002, 0.1])
+    model.fit(data, show=False, opt=False)
+    K = model.kernel.k_total({"force": model.train_x["force"]})
+    ids_ref, omega_ref = gr.CUR(K, 1e-6)
+    ids = CUR(torch.from_numpy(K).cuda(), 1e-6)
+    assert len(ids) == len(ids_ref) >= 15
+    L, U = np.linalg.eigh(K)
+    omega = (U[:, L < 1e-6] ** 2).sum(axis=1)
+    assert np.allclose(np.sort(omega[ids]), np.sort(omega_ref[ids_ref]), atol=1e-8)
+    removed_e, removed_f = model.sparsify(e_tol=1e-6, f_tol=1e-6)
+    assert removed_e == [] and len(removed_f) >= 1 and all(i < 25 for i in removed_f)
+    assert model.N_forces == 25 - len(removed_f) and model.alpha_.shape == (3 * model.N_forces, 1)
