@@ -1,0 +1,618 @@
+// so3.cu -- SO(3) power-spectrum descriptor and its Cartesian derivatives on the GPU: the producer of the
+// hot path's inputs {x, dxdr, rdxdr, seq} (reference cspbo/SO3.py:187-291 calculate, :317-376 neighbour
+// list, :463-505 radial basis + quadrature, :581-695 compute_dcs).  SURVEY.md 8(f) row 2.
+//
+//   host   neighbour pairs (brute force over periodic images, same pair set as ase's
+//          NeighborList(cutoffs=rcut/2, bothways=True, self_interaction=False)), `seq` slots, the
+//          orthonormalised radial basis W (SO3.py:463-479) and the Gauss-Chebyshev tables
+//   K1     one warp per (centre, neighbour) pair: radial integrals I_nl(R) = sum_q G[n,q] i_l(2 a R r_q) and
+//          dI/dR, spherical harmonics Y_lm (l <= lmax+1) and their gradients, then the expansion
+//          coefficients c_nlm and dc_nlm/dr
+//   K2     one block per centre: c_tot = sum of its pairs; power spectrum x = sum_m c_tot conj(c_tot)
+//   K3     one warp per seq slot (i,j): dP of every pair (periodic images) of the slot, summed in a
+//          fixed order -> dxdr[slot], stress terms -r_j (x) dP
+//   K4     one block per centre: the (i,i) slot, dxdr[ii] = -sum_{j != i} dxdr[ij]; stress += r_i (x) sum dP
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "common.h"
+
+namespace cspbo {
+
+constexpr int SO3_MAXN = 6;    // nmax
+constexpr int SO3_MAXL = 7;    // lmax + 1 (harmonics are needed one order higher for the gradients)
+constexpr int SO3_MAXQ = 160;  // quadrature nodes (nmax+lmax+1)*10
+
+struct So3Params {
+    int nmax, lmax, nq, cutoff, nlm;   // nlm = (lmax+1)^2 valid (l,m) per radial index
+    double rcut, alpha;
+};
+
+__constant__ double c_rq[SO3_MAXQ];
+__constant__ double c_G[SO3_MAXN * SO3_MAXQ];
+__constant__ double c_norm[SO3_MAXL + 1];
+
+__device__ __forceinline__ int lm_index(int l, int m) { return l * l + l + m; }   // (l,m) -> 0..(L+1)^2-1
+
+// modified spherical Bessel functions of the first kind i_0..i_lmax(x)
+__device__ void sph_in(double x, int lmax, double *il)
+{
+    if (x < 4.0) {
+        // power series: i_l = x^l/(2l+1)!! * sum_k (x^2/2)^k / (k! (2l+3)(2l+5)...(2l+2k+1))
+        const double t = 0.5 * x * x;
+        double pref = 1.0;
+        for (int l = 0; l <= lmax; l++) {
+            if (l > 0) pref *= x / (2.0 * l + 1.0);
+            double term = 1.0, sum = 1.0;
+            for (int k = 1; k < 40; k++) {
+                term *= t / (k * (2.0 * l + 2.0 * k + 1.0));
+                sum += term;
+                if (term < 1e-18 * sum) break;
+            }
+            il[l] = pref * sum;
+        }
+    } else {
+        const double ex = exp(x), emx = 1.0 / ex;
+        const double sh = 0.5 * (ex - emx), ch = 0.5 * (ex + emx);
+        il[0] = sh / x;
+        if (lmax >= 1) il[1] = (x * ch - sh) / (x * x);
+        for (int l = 1; l < lmax; l++) il[l + 1] = il[l - 1] - (2.0 * l + 1.0) / x * il[l];
+    }
+}
+
+__device__ __forceinline__ double cutoff_fn(int kind, double R, double rc, bool deriv)
+{
+    const double x = R / rc;
+    switch (kind) {
+        case 0:  // cosine (SO3.py:378-385)
+            return deriv ? -0.5 * M_PI / rc * sin(M_PI * x) : 0.5 * (cos(M_PI * x) + 1.0);
+        case 1: {  // tanh (:387-395)
+            const double th = tanh(1.0 - x), t2 = th * th;
+            return deriv ? -(3.0 / rc) * t2 * (1.0 - t2) : t2 * th;
+        }
+        case 2:  // poly1 (:397-408)
+            return deriv ? (6.0 / (rc * rc)) * R * (x - 1.0) : x * x * (2.0 * x - 3.0) + 1.0;
+        case 3:  // poly2 (:410-419)
+            return deriv ? (-30.0 / rc) * (x * x * (x - 1.0) * (x - 1.0)) : x * x * x * (x * (15.0 - 6.0 * x) - 10.0) + 1.0;
+        case 4: {  // poly3 (:421-430)
+            const double a = x * (x - 1.0);
+            return deriv ? (140.0 / rc) * (a * a * a) : x * x * x * x * (x * (x * (20.0 * x - 70.0) + 84.0) - 35.0) + 1.0;
+        }
+        case 5: {  // poly4 (:432-441)
+            const double a = x * (x - 1.0);
+            return deriv ? (-630.0 / rc) * (a * a * a * a)
+                         : x * x * x * x * x * (x * (x * (x * (315.0 - 70.0 * x) - 540.0) + 420.0) - 126.0) + 1.0;
+        }
+        default:  // unity (:457-461): value 1, "derivative" 1 as in the reference
+            return 1.0;
+    }
+}
+
+struct cplx { double re, im; };
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+
+// K1 ------------------------------------------------------------------------------------------
+// per-warp shared scratch: I[n][l], dI[n][l] (radial), Y[(L+2)^2], dY[(L+1)^2][3]
+__global__ void __launch_bounds__(128) so3_pair_kernel(So3Params P, int n_pairs, const double *__restrict__ rel,
+                                                       const double *__restrict__ wts, double2 *__restrict__ C,
+                                                       double2 *__restrict__ dC)
+{
+    __shared__ double sI[4][SO3_MAXN][SO3_MAXL], sdI[4][SO3_MAXN][SO3_MAXL];
+    __shared__ cplx sY[4][(SO3_MAXL + 1) * (SO3_MAXL + 1)];
+    __shared__ cplx sdY[4][SO3_MAXL * SO3_MAXL][3];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int pair = blockIdx.x * 4 + w;
+    if (pair >= n_pairs) return;
+    const double rx = rel[3 * pair], ry = rel[3 * pair + 1], rz = rel[3 * pair + 2];
+    const double R = sqrt(rx * rx + ry * ry + rz * rz);
+    const double ux = rx / R, uy = ry / R, uz = rz / R;
+    const int L = P.lmax + 1;
+
+    // radial integrals: lane -> (n, l)
+    for (int e = lane; e < P.nmax * L; e += 32) {
+        const int n = e / L, l = e % L;
+        double acc = 0.0, dacc = 0.0;
+        double il[SO3_MAXL + 2];
+        for (int q = 0; q < P.nq; q++) {
+            const double x = 2.0 * P.alpha * R * c_rq[q];
+            sph_in(x, l + 1, il);
+            // i_l'(x) = i_{l+1}(x) + (l/x) i_l(x)
+            const double dil = il[l + 1] + (l > 0 ? (double)l / x * il[l] : 0.0);
+            const double g = c_G[n * SO3_MAXQ + q];
+            acc += g * il[l];
+            dacc += g * dil * (2.0 * P.alpha * c_rq[q]);
+        }
+        sI[w][n][l] = acc;
+        sdI[w][n][l] = dacc;
+    }
+    // spherical harmonics Y_l^m, l <= lmax+1: lane -> (l, m >= 0)
+    {
+        const int LY = P.lmax + 1;   // highest order needed
+        const int ny = (LY + 1) * (LY + 2) / 2;
+        for (int e = lane; e < ny; e += 32) {
+            int l = 0, m = e;
+            while (m > l) { m -= l + 1; l++; }   // e -> (l, m) with 0 <= m <= l
+            // Q_l^m = P_l^m / sin^m(theta) by upward recurrence in l from Q_m^m = (-1)^m (2m-1)!!
+            double qmm = 1.0;
+            for (int k = 1; k <= m; k++) qmm *= -(2.0 * k - 1.0);
+            double q0 = qmm, q1 = uz * (2.0 * m + 1.0) * qmm, ql = (l == m) ? q0 : q1;
+            for (int ll = m + 2; ll <= l; ll++) {
+                ql = ((2.0 * ll - 1.0) * uz * q1 - (ll + m - 1.0) * q0) / (ll - m);
+                q0 = q1; q1 = ql;
+            }
+            // normalisation sqrt((2l+1)/(4 pi) (l-m)!/(l+m)!)
+            double ratio = 1.0;
+            for (int k = l - m + 1; k <= l + m; k++) ratio /= k;
+            const double nrm = sqrt((2.0 * l + 1.0) / (4.0 * M_PI) * ratio);
+            // (sin(theta) e^{i phi})^m = ((x + i y)/R)^m
+            cplx z = {1.0, 0.0};
+            const cplx b = {ux, uy};
+            for (int k = 0; k < m; k++) z = cmul(z, b);
+            const cplx y = {nrm * ql * z.re, nrm * ql * z.im};
+            sY[w][lm_index(l, m)] = y;
+            if (m > 0) {
+                const double sg = (m & 1) ? -1.0 : 1.0;
+                sY[w][lm_index(l, -m)] = {sg * y.re, -sg * y.im};
+            }
+        }
+    }
+    __syncwarp();
+    // gradients of Y_l^m for l <= lmax (SO3.py:645-672): spherical covariant components from Y_{l+-1}
+    for (int e = lane; e < L * L; e += 32) {
+        int l = (int)floor(sqrt((double)e));
+        while (l * l > e) l--;
+        while ((l + 1) * (l + 1) <= e) l++;
+        const int m = e - l * l - l;
+        cplx g0 = {0, 0}, gp = {0, 0}, gm = {0, 0};
+        if (l >= 1) {
+            const double invR = 1.0 / R;
+            auto Yv = [&](int ll, int mm) -> cplx {
+                if (mm < -ll || mm > ll) return cplx{0.0, 0.0};
+                return sY[w][lm_index(ll, mm)];
+            };
+            double c;
+            cplx t;
+            c = -sqrt(((l + 1.0) * (l + 1.0) - m * m) / (2.0 * l + 1.0) / (2.0 * l + 3.0)) * l * invR;
+            t = Yv(l + 1, m); g0 = {c * t.re, c * t.im};
+            if (abs(m) <= l - 1) {
+                c = sqrt(((double)l * l - m * m) / (2.0 * l - 1.0) / (2.0 * l + 1.0)) * (l + 1.0) * invR;
+                t = Yv(l - 1, m); g0.re += c * t.re; g0.im += c * t.im;
+            }
+            c = -sqrt((l + m + 1.0) * (l + m + 2.0) / 2.0 / (2.0 * l + 1.0) / (2.0 * l + 3.0)) * l * invR;
+            t = Yv(l + 1, m + 1); gp = {c * t.re, c * t.im};
+            if (abs(m + 1) <= l - 1) {
+                c = sqrt((l - m - 1.0) * (l - m) / 2.0 / (2.0 * l - 1.0) / (2.0 * l + 1.0)) * (l + 1.0) * invR;
+                t = Yv(l - 1, m + 1); gp.re -= c * t.re; gp.im -= c * t.im;
+            }
+            c = -sqrt((l - m + 1.0) * (l - m + 2.0) / 2.0 / (2.0 * l + 1.0) / (2.0 * l + 3.0)) * l * invR;
+            t = Yv(l + 1, m - 1); gm = {c * t.re, c * t.im};
+            if (abs(m - 1) <= l - 1) {
+                c = sqrt((l + m - 1.0) * (l + m) / 2.0 / (2.0 * l - 1.0) / (2.0 * l + 1.0)) * (l + 1.0) * invR;
+                t = Yv(l - 1, m - 1); gm.re -= c * t.re; gm.im -= c * t.im;
+            }
+        }
+        const double s = 0.70710678118654752440;
+        sdY[w][e][0] = {s * (gm.re - gp.re), s * (gm.im - gp.im)};          // 1/sqrt2 (xm - xp)
+        sdY[w][e][1] = {-s * (gm.im + gp.im), s * (gm.re + gp.re)};         // i/sqrt2 (xm + xp)
+        sdY[w][e][2] = g0;
+    }
+    __syncwarp();
+    // coefficients: lane -> (n, l, m)
+    const double ex = 4.0 * M_PI * exp(-P.alpha * R * R);
+    const double dexR = -2.0 * P.alpha * R * ex;
+    const double fc = cutoff_fn(P.cutoff, R, P.rcut, false), dfcR = cutoff_fn(P.cutoff, R, P.rcut, true);
+    const double wt = wts[pair];
+    const double u[3] = {ux, uy, uz};
+    const int nlm = P.nlm;
+    for (int e = lane; e < P.nmax * nlm; e += 32) {
+        const int n = e / nlm, lm = e % nlm;
+        int l = (int)floor(sqrt((double)lm));
+        while (l * l > lm) l--;
+        while ((l + 1) * (l + 1) <= lm) l++;
+        const double I = sI[w][n][l], dI = sdI[w][n][l];
+        const cplx Y = sY[w][lm];
+        const double sc = wt * c_norm[l];
+        const cplx YI = {Y.re * I, Y.im * I};
+        const cplx c0 = {ex * YI.re, ex * YI.im};                        // before the cutoff
+        C[(size_t)pair * P.nmax * nlm + e] = make_double2(sc * fc * c0.re, sc * fc * c0.im);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const cplx dY = sdY[w][lm][k];
+            // d/dr_k [ ex * I * Y ] = dex u_k I Y + ex (dY_k I + Y dI u_k)
+            double gr = dexR * u[k] * YI.re + ex * (dY.re * I + Y.re * dI * u[k]);
+            double gi = dexR * u[k] * YI.im + ex * (dY.im * I + Y.im * dI * u[k]);
+            gr = gr * fc + dfcR * u[k] * c0.re;
+            gi = gi * fc + dfcR * u[k] * c0.im;
+            dC[((size_t)pair * P.nmax * nlm + e) * 3 + k] = make_double2(sc * gr, sc * gi);
+        }
+    }
+}
+
+// K2 ------------------------------------------------------------------------------------------
+__global__ void so3_center_kernel(So3Params P, const int *__restrict__ pair_start, const double2 *__restrict__ C,
+                                  double2 *__restrict__ ctot, double *__restrict__ x, int ncoefs)
+{
+    extern __shared__ double2 sct[];
+    const int i = blockIdx.x;
+    const int ne = P.nmax * P.nlm;
+    for (int e = threadIdx.x; e < ne; e += blockDim.x) {
+        double re = 0.0, im = 0.0;
+        for (int p = pair_start[i]; p < pair_start[i + 1]; p++) {
+            const double2 c = C[(size_t)p * ne + e];
+            re += c.x; im += c.y;
+        }
+        sct[e] = make_double2(re, im);
+        ctot[(size_t)i * ne + e] = make_double2(re, im);
+    }
+    __syncthreads();
+    const int L = P.lmax + 1;
+    // x[i, tril(n,n')*L + l] = sum_m Re(ctot[n,l,m] conj(ctot[n',l,m]))   (SO3.py:231,265)
+    for (int c = threadIdx.x; c < ncoefs; c += blockDim.x) {
+        const int t = c / L, l = c % L;
+        int n = 0, rem = t;
+        while (rem > n) { rem -= n + 1; n++; }
+        const int n2 = rem;
+        double acc = 0.0;
+        for (int m = -l; m <= l; m++) {
+            const double2 a = sct[n * P.nlm + lm_index(l, m)], b = sct[n2 * P.nlm + lm_index(l, m)];
+            acc += a.x * b.x + a.y * b.y;
+        }
+        x[(size_t)i * ncoefs + c] = acc;
+    }
+}
+
+// K3 ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) so3_slot_kernel(So3Params P, int n_slots, const int *__restrict__ slot_start,
+                                                       const int *__restrict__ slot_pairs, const int *__restrict__ slot_center,
+                                                       const double *__restrict__ Rj, const double2 *__restrict__ dC,
+                                                       const double2 *__restrict__ ctot, double *__restrict__ dxdr,
+                                                       double *__restrict__ rdxdr, double stress_scale, int ncoefs)
+{
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (slot >= n_slots) return;
+    const int i = slot_center[slot];
+    const int ne = P.nmax * P.nlm, L = P.lmax + 1;
+    const double2 *ct = ctot + (size_t)i * ne;
+    for (int e = lane; e < ncoefs * 3; e += 32) {
+        const int c = e / 3, k = e % 3;
+        const int t = c / L, l = c % L;
+        int n = 0, rem = t;
+        while (rem > n) { rem -= n + 1; n++; }
+        const int n2 = rem;
+        double sum = 0.0, st[3] = {0.0, 0.0, 0.0};
+        for (int q = slot_start[slot]; q < slot_start[slot + 1]; q++) {
+            const int p = slot_pairs[q];
+            const double2 *d = dC + (size_t)p * ne * 3;
+            double acc = 0.0;
+            for (int m = -l; m <= l; m++) {
+                const int lm = lm_index(l, m);
+                const double2 a = d[(n * P.nlm + lm) * 3 + k], b = ct[n2 * P.nlm + lm];
+                const double2 a2 = d[(n2 * P.nlm + lm) * 3 + k], b2 = ct[n * P.nlm + lm];
+                acc += a.x * b.x + a.y * b.y + a2.x * b2.x + a2.y * b2.y;   // Re(dc conj(ct)) + transpose
+            }
+            sum += acc;
+            if (rdxdr) {
+#pragma unroll
+                for (int a = 0; a < 3; a++) st[a] -= Rj[3 * p + a] * acc;   // pstress -= r_j (x) dP  (SO3.py:257)
+            }
+        }
+        dxdr[((size_t)slot * ncoefs + c) * 3 + k] = sum;
+        if (rdxdr) {
+#pragma unroll
+            for (int a = 0; a < 3; a++) rdxdr[(((size_t)slot * ncoefs + c) * 3 + a) * 3 + k] = stress_scale * st[a];
+        }
+    }
+}
+
+// K4 ------------------------------------------------------------------------------------------
+__global__ void so3_self_kernel(int n_atoms, const int *__restrict__ seq_start, const int *__restrict__ self_slot,
+                                const double *__restrict__ pos, double *__restrict__ dxdr, double *__restrict__ rdxdr,
+                                double stress_scale, int ncoefs)
+{
+    const int i = blockIdx.x;
+    const int ii = self_slot[i];
+    for (int e = threadIdx.x; e < ncoefs * 3; e += blockDim.x) {
+        double S = 0.0;
+        for (int s = seq_start[i]; s < seq_start[i + 1]; s++) S += dxdr[(size_t)s * ncoefs * 3 + e];
+        // dplist[ii] -= sum over all slots of i (SO3.py:270); pstress[ii] += r_i (x) sum_w dP_w (:271-272)
+        dxdr[(size_t)ii * ncoefs * 3 + e] -= S;
+        if (rdxdr) {
+            const int c = e / 3, k = e % 3;
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+                rdxdr[(((size_t)ii * ncoefs + c) * 3 + a) * 3 + k] += stress_scale * pos[3 * i + a] * S;
+        }
+    }
+}
+
+// ---- host: radial basis tables ----------------------------------------------------------------
+static void invert(std::vector<double> &a, int n)
+{
+    std::vector<double> inv((size_t)n * n, 0.0);
+    for (int i = 0; i < n; i++) inv[(size_t)i * n + i] = 1.0;
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        for (int r = c + 1; r < n; r++) if (fabs(a[(size_t)r * n + c]) > fabs(a[(size_t)piv * n + c])) piv = r;
+        for (int k = 0; k < n; k++) { std::swap(a[(size_t)c * n + k], a[(size_t)piv * n + k]); std::swap(inv[(size_t)c * n + k], inv[(size_t)piv * n + k]); }
+        const double d = a[(size_t)c * n + c];
+        for (int k = 0; k < n; k++) { a[(size_t)c * n + k] /= d; inv[(size_t)c * n + k] /= d; }
+        for (int r = 0; r < n; r++) if (r != c) {
+            const double f = a[(size_t)r * n + c];
+            for (int k = 0; k < n; k++) { a[(size_t)r * n + k] -= f * a[(size_t)c * n + k]; inv[(size_t)r * n + k] -= f * inv[(size_t)c * n + k]; }
+        }
+    }
+    a = inv;
+}
+
+// symmetric square root by cyclic Jacobi (the reference takes V sqrt(D) V^-1 of eig(sinv), SO3.py:475-478)
+static void sym_sqrt(std::vector<double> &a, int n)
+{
+    std::vector<double> V((size_t)n * n, 0.0);
+    for (int i = 0; i < n; i++) V[(size_t)i * n + i] = 1.0;
+    for (int sweep = 0; sweep < 100; sweep++) {
+        double off = 0.0;
+        for (int p = 0; p < n; p++) for (int q = p + 1; q < n; q++) off += a[(size_t)p * n + q] * a[(size_t)p * n + q];
+        if (off < 1e-300) break;
+        for (int p = 0; p < n; p++)
+            for (int q = p + 1; q < n; q++) {
+                const double apq = a[(size_t)p * n + q];
+                if (fabs(apq) < 1e-300) continue;
+                const double theta = (a[(size_t)q * n + q] - a[(size_t)p * n + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; k++) {
+                    const double akp = a[(size_t)k * n + p], akq = a[(size_t)k * n + q];
+                    a[(size_t)k * n + p] = c * akp - s * akq; a[(size_t)k * n + q] = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; k++) {
+                    const double apk = a[(size_t)p * n + k], aqk = a[(size_t)q * n + k];
+                    a[(size_t)p * n + k] = c * apk - s * aqk; a[(size_t)q * n + k] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; k++) {
+                    const double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
+                    V[(size_t)k * n + p] = c * vkp - s * vkq; V[(size_t)k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    std::vector<double> out((size_t)n * n, 0.0);
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) {
+        double acc = 0.0;
+        for (int k = 0; k < n; k++) acc += V[(size_t)i * n + k] * sqrt(std::max(a[(size_t)k * n + k], 0.0)) * V[(size_t)j * n + k];
+        out[(size_t)i * n + j] = acc;
+    }
+    a = out;
+}
+
+}  // namespace cspbo
+
+using namespace cspbo;
+
+struct cspbo_so3 {
+    So3Params P;
+    int weight_on = 0;
+    std::vector<double> h_rq, h_G, h_norm;
+    // results of the last compute (device) + host seq
+    int n_atoms = 0, n_pairs = 0, n_seq = 0, ncoefs = 0, stress = 0;
+    std::vector<long long> h_seq;
+    double *d_x = nullptr, *d_dxdr = nullptr, *d_rdxdr = nullptr;
+};
+
+extern "C" int cspbo_so3_create(int nmax, int lmax, double rcut, double alpha, int cutoff, int weight_on, cspbo_so3 **out)
+{
+    if (!out) { set_error("so3_create: null"); return CSPBO_E_ARG; }
+    *out = nullptr;
+    if (nmax < 1 || nmax > SO3_MAXN || lmax < 0 || lmax + 1 > SO3_MAXL || !(rcut > 0) || !(alpha > 0) || cutoff < 0 || cutoff > 6) {
+        set_error("so3_create: unsupported parameters (nmax<=%d, lmax<=%d)", SO3_MAXN, SO3_MAXL - 1);
+        return CSPBO_E_ARG;
+    }
+    const int nq = (nmax + lmax + 1) * 10;
+    if (nq > SO3_MAXQ) { set_error("so3_create: too many quadrature nodes"); return CSPBO_E_ARG; }
+    cspbo_so3 *h = new (std::nothrow) cspbo_so3();
+    if (!h) { set_error("so3_create: allocation failed"); return CSPBO_E_NOMEM; }
+    h->P = {nmax, lmax, nq, cutoff, (lmax + 1) * (lmax + 1), rcut, alpha};
+    h->weight_on = weight_on;
+    // W (SO3.py:463-479)
+    std::vector<double> w((size_t)nmax * nmax);
+    for (int a = 1; a <= nmax; a++) {
+        const double t1 = (2.0 * a + 5) * (2.0 * a + 6) * (2.0 * a + 7);
+        for (int b = 1; b <= a; b++) {
+            const double t2 = (2.0 * b + 5) * (2.0 * b + 6) * (2.0 * b + 7);
+            w[(size_t)(a - 1) * nmax + b - 1] = w[(size_t)(b - 1) * nmax + a - 1] =
+                sqrt(t1 * t2) / (5.0 + a + b) / (6.0 + a + b) / (7.0 + a + b);
+        }
+    }
+    invert(w, nmax);
+    sym_sqrt(w, nmax);
+    // quadrature (SO3.py:497-505) and G (SO3.py:600-626)
+    h->h_rq.assign(SO3_MAXQ, 0.0);
+    h->h_G.assign((size_t)SO3_MAXN * SO3_MAXQ, 0.0);
+    const double weight = M_PI / nq * rcut / 2.0;
+    for (int q = 0; q < nq; q++) {
+        const double xq = cos((2.0 * (q + 1) - 1.0) * M_PI / 2.0 / nq);
+        const double r = rcut / 2.0 * (xq + 1.0);
+        h->h_rq[(size_t)q] = r;
+        for (int n = 1; n <= nmax; n++) {
+            double g = 0.0;
+            for (int a = 1; a <= nmax; a++) {
+                const double phi = pow(rcut - r, a + 2.0) / sqrt(2.0 * pow(rcut, 2.0 * a + 7.0) / (2.0 * a + 5) / (2.0 * a + 6) / (2.0 * a + 7));
+                g += w[(size_t)(n - 1) * nmax + a - 1] * phi;
+            }
+            h->h_G[(size_t)(n - 1) * SO3_MAXQ + q] = g * weight * r * r * exp(-alpha * r * r) * sqrt(1.0 - xq * xq);
+        }
+    }
+    h->h_norm.assign(SO3_MAXL + 1, 0.0);
+    for (int l = 0; l <= lmax; l++) h->h_norm[(size_t)l] = sqrt(2.0 * sqrt(2.0) * M_PI / sqrt(2.0 * l + 1.0));
+    *out = h;
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_so3_destroy(cspbo_so3 *h)
+{
+    if (!h) return CSPBO_OK;
+    dev_free_cached(h->d_x); dev_free_cached(h->d_dxdr); dev_free_cached(h->d_rdxdr);
+    delete h;
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_so3_compute(cspbo_so3 *h, int n_atoms, const double *pos, const int *numbers, const double *cell,
+                                 const int *pbc, int stress, int *n_seq_out, int *n_coefs_out)
+{
+    if (!h || !pos || !numbers || !cell || !pbc || n_atoms < 0) { set_error("so3_compute: bad argument"); return CSPBO_E_ARG; }
+    const So3Params P = h->P;
+    const int L = P.lmax + 1, ncoefs = P.nmax * (P.nmax + 1) / 2 * L;
+    // ---- neighbour pairs (SO3.py:317-359): |r_j + offset.cell - r_i| < rcut, zero-offset self excluded
+    double inv[9];
+    {
+        const double *c = cell;
+        const double det = c[0] * (c[4] * c[8] - c[5] * c[7]) - c[1] * (c[3] * c[8] - c[5] * c[6]) + c[2] * (c[3] * c[7] - c[4] * c[6]);
+        if (fabs(det) < 1e-300) { set_error("so3_compute: singular cell"); return CSPBO_E_ARG; }
+        inv[0] = (c[4] * c[8] - c[5] * c[7]) / det; inv[1] = (c[2] * c[7] - c[1] * c[8]) / det; inv[2] = (c[1] * c[5] - c[2] * c[4]) / det;
+        inv[3] = (c[5] * c[6] - c[3] * c[8]) / det; inv[4] = (c[0] * c[8] - c[2] * c[6]) / det; inv[5] = (c[2] * c[3] - c[0] * c[5]) / det;
+        inv[6] = (c[3] * c[7] - c[4] * c[6]) / det; inv[7] = (c[1] * c[6] - c[0] * c[7]) / det; inv[8] = (c[0] * c[4] - c[1] * c[3]) / det;
+    }
+    int nimg[3];
+    for (int k = 0; k < 3; k++) {
+        // height of the cell along reciprocal direction k = 1 / |column k of inv|
+        const double nrm = sqrt(inv[k] * inv[k] + inv[3 + k] * inv[3 + k] + inv[6 + k] * inv[6 + k]);
+        double fmin = 1e300, fmax = -1e300;
+        for (int a = 0; a < n_atoms; a++) {
+            const double f = pos[3 * a] * inv[k] + pos[3 * a + 1] * inv[3 + k] + pos[3 * a + 2] * inv[6 + k];
+            fmin = std::min(fmin, f); fmax = std::max(fmax, f);
+        }
+        const int span = n_atoms ? (int)ceil(fmax - fmin) : 0;
+        nimg[k] = pbc[k] ? (int)ceil(P.rcut * nrm) + span : 0;
+    }
+    struct Pair { int i, j; int o[3]; double rel[3]; };
+    std::vector<Pair> pairs;
+    const double rc2 = P.rcut * P.rcut;
+    for (int i = 0; i < n_atoms; i++)
+        for (int j = 0; j < n_atoms; j++)
+            for (int a = -nimg[0]; a <= nimg[0]; a++)
+                for (int b = -nimg[1]; b <= nimg[1]; b++)
+                    for (int c = -nimg[2]; c <= nimg[2]; c++) {
+                        double r[3];
+                        for (int k = 0; k < 3; k++)
+                            r[k] = pos[3 * j + k] + a * cell[k] + b * cell[3 + k] + c * cell[6 + k] - pos[3 * i + k];
+                        const double d2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+                        if (d2 < rc2 && d2 > 1e-24) pairs.push_back({i, j, {a, b, c}, {r[0], r[1], r[2]}});
+                    }
+    // loop order above is already (i, j, offset): the deterministic summation order of K2 / K3
+    const int np = (int)pairs.size();
+    // ---- seq slots (SO3.py:361-372): for every centre its neighbour ids plus itself, sorted
+    std::vector<int> pair_start((size_t)n_atoms + 1, 0), seq_start((size_t)n_atoms + 1, 0), self_slot((size_t)std::max(n_atoms, 1), 0);
+    std::vector<int> slot_start, slot_pairs, slot_center, pair_slot((size_t)std::max(np, 1));
+    h->h_seq.clear();
+    {
+        int p = 0;
+        for (int i = 0; i < n_atoms; i++) {
+            pair_start[(size_t)i] = p;
+            const int p0 = p;
+            while (p < np && pairs[(size_t)p].i == i) p++;
+            // distinct neighbour ids (pairs are sorted by j inside i) merged with i itself, ascending
+            std::vector<int> js;
+            for (int q = p0; q < p; q++)
+                if (js.empty() || js.back() != pairs[(size_t)q].j) js.push_back(pairs[(size_t)q].j);
+            if (!std::binary_search(js.begin(), js.end(), i)) js.insert(std::lower_bound(js.begin(), js.end(), i), i);
+            seq_start[(size_t)i] = (int)slot_center.size();
+            int q = p0;
+            for (int j : js) {
+                const int slot = (int)slot_center.size();
+                slot_center.push_back(i);
+                slot_start.push_back((int)slot_pairs.size());
+                h->h_seq.push_back(i); h->h_seq.push_back(j);
+                if (j == i) self_slot[(size_t)i] = slot;
+                while (q < p && pairs[(size_t)q].j == j) { slot_pairs.push_back(q); pair_slot[(size_t)q] = slot; q++; }
+            }
+        }
+        pair_start[(size_t)n_atoms] = np;
+        seq_start[(size_t)n_atoms] = (int)slot_center.size();
+        slot_start.push_back((int)slot_pairs.size());
+    }
+    const int nseq = (int)slot_center.size();
+    h->n_atoms = n_atoms; h->n_pairs = np; h->n_seq = nseq; h->ncoefs = ncoefs; h->stress = stress;
+    if (n_seq_out) *n_seq_out = nseq;
+    if (n_coefs_out) *n_coefs_out = ncoefs;
+
+    // ---- device buffers ------------------------------------------------------------------
+    dev_free_cached(h->d_x); dev_free_cached(h->d_dxdr); dev_free_cached(h->d_rdxdr);
+    h->d_x = h->d_dxdr = h->d_rdxdr = nullptr;
+    if (n_atoms == 0) return CSPBO_OK;
+    int rc;
+    const size_t ne = (size_t)P.nmax * P.nlm;
+    if ((rc = dev_alloc_cached((size_t)n_atoms * ncoefs * 8, (void **)&h->d_x))) return rc;
+    if ((rc = dev_alloc_cached((size_t)nseq * ncoefs * 3 * 8, (void **)&h->d_dxdr))) return rc;
+    if (stress && (rc = dev_alloc_cached((size_t)nseq * ncoefs * 9 * 8, (void **)&h->d_rdxdr))) return rc;
+    double *d_rel = nullptr, *d_wt = nullptr, *d_Rj = nullptr, *d_pos = nullptr;
+    double2 *d_C = nullptr, *d_dC = nullptr, *d_ct = nullptr;
+    int *d_ps = nullptr, *d_ss = nullptr, *d_sp = nullptr, *d_sc = nullptr, *d_seqs = nullptr, *d_self = nullptr;
+    std::vector<void *> tmp;
+    auto A = [&](size_t bytes, void **p) { int r = dev_alloc_cached(bytes, p); if (!r) tmp.push_back(*p); return r; };
+    auto cleanup = [&]() { for (void *p : tmp) dev_free_cached(p); };
+#define SO3_TRY(expr) do { int r__ = (expr); if (r__) { cleanup(); return r__; } } while (0)
+#define SO3_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); cleanup(); return CSPBO_E_CUDA; } } while (0)
+    const size_t npz = (size_t)std::max(np, 1);
+    SO3_TRY(A(npz * 3 * 8, (void **)&d_rel)); SO3_TRY(A(npz * 8, (void **)&d_wt)); SO3_TRY(A(npz * 3 * 8, (void **)&d_Rj));
+    SO3_TRY(A((size_t)n_atoms * 3 * 8, (void **)&d_pos));
+    SO3_TRY(A(npz * ne * 16, (void **)&d_C)); SO3_TRY(A(npz * ne * 3 * 16, (void **)&d_dC)); SO3_TRY(A((size_t)n_atoms * ne * 16, (void **)&d_ct));
+    SO3_TRY(A(((size_t)n_atoms + 1) * 4, (void **)&d_ps)); SO3_TRY(A(((size_t)nseq + 1) * 4, (void **)&d_ss));
+    SO3_TRY(A(npz * 4, (void **)&d_sp)); SO3_TRY(A((size_t)nseq * 4, (void **)&d_sc));
+    SO3_TRY(A(((size_t)n_atoms + 1) * 4, (void **)&d_seqs)); SO3_TRY(A((size_t)n_atoms * 4, (void **)&d_self));
+    std::vector<double> rel(npz * 3), wt(npz), Rj(npz * 3);
+    for (int p = 0; p < np; p++) {
+        const Pair &pr = pairs[(size_t)p];
+        for (int k = 0; k < 3; k++) { rel[(size_t)p * 3 + k] = pr.rel[k]; Rj[(size_t)p * 3 + k] = pr.rel[k] + pos[3 * pr.i + k]; }
+        double f = 1.0;
+        if (h->weight_on && numbers[pr.j] != numbers[pr.i]) f = -1.0;     // SO3.py:350-354
+        wt[(size_t)p] = f * numbers[pr.j];
+    }
+    SO3_CUDA(cudaMemcpyToSymbol(c_rq, h->h_rq.data(), SO3_MAXQ * 8));
+    SO3_CUDA(cudaMemcpyToSymbol(c_G, h->h_G.data(), (size_t)SO3_MAXN * SO3_MAXQ * 8));
+    SO3_CUDA(cudaMemcpyToSymbol(c_norm, h->h_norm.data(), (SO3_MAXL + 1) * 8));
+    SO3_CUDA(cudaMemcpyAsync(d_rel, rel.data(), npz * 3 * 8, cudaMemcpyHostToDevice));
+    SO3_CUDA(cudaMemcpyAsync(d_wt, wt.data(), npz * 8, cudaMemcpyHostToDevice));
+    SO3_CUDA(cudaMemcpyAsync(d_Rj, Rj.data(), npz * 3 * 8, cudaMemcpyHostToDevice));
+    SO3_CUDA(cudaMemcpyAsync(d_pos, pos, (size_t)n_atoms * 3 * 8, cudaMemcpyHostToDevice));
+    SO3_CUDA(cudaMemcpyAsync(d_ps, pair_start.data(), ((size_t)n_atoms + 1) * 4, cudaMemcpyHostToDevice));
+    SO3_CUDA(cudaMemcpyAsync(d_ss, slot_start.data(), ((size_t)nseq + 1) * 4, cudaMemcpyHostToDevice));
+    if (np) SO3_CUDA(cudaMemcpyAsync(d_sp, slot_pairs.data(), (size_t)np * 4, cudaMemcpyHostToDevice));
+    SO3_CUDA(cudaMemcpyAsync(d_sc, slot_center.data(), (size_t)nseq * 4, cudaMemcpyHostToDevice));
+    SO3_CUDA(cudaMemcpyAsync(d_seqs, seq_start.data(), ((size_t)n_atoms + 1) * 4, cudaMemcpyHostToDevice));
+    SO3_CUDA(cudaMemcpyAsync(d_self, self_slot.data(), (size_t)n_atoms * 4, cudaMemcpyHostToDevice));
+    double vol = fabs(cell[0] * (cell[4] * cell[8] - cell[5] * cell[7]) - cell[1] * (cell[3] * cell[8] - cell[5] * cell[6]) +
+                      cell[2] * (cell[3] * cell[7] - cell[4] * cell[6]));
+    const double sscale = -1.0 / vol;                                         // rdxdr = -pstress / volume (SO3.py:279-280)
+    if (np) {
+        so3_pair_kernel<<<(np + 3) / 4, 128>>>(P, np, d_rel, d_wt, d_C, d_dC);
+        g_launches++;
+    }
+    so3_center_kernel<<<n_atoms, 128, ne * 16>>>(P, d_ps, d_C, d_ct, h->d_x, ncoefs);
+    g_launches++;
+    so3_slot_kernel<<<(nseq + 3) / 4, 128>>>(P, nseq, d_ss, d_sp, d_sc, d_Rj, d_dC, d_ct, h->d_dxdr, stress ? h->d_rdxdr : nullptr,
+                                            sscale, ncoefs);
+    g_launches++;
+    so3_self_kernel<<<n_atoms, 128>>>(n_atoms, d_seqs, d_self, d_pos, h->d_dxdr, stress ? h->d_rdxdr : nullptr, sscale, ncoefs);
+    g_launches++;
+    SO3_CUDA(cudaGetLastError());
+    SO3_CUDA(cudaStreamSynchronize(0));
+    cleanup();
+    return CSPBO_OK;
+#undef SO3_TRY
+#undef SO3_CUDA
+}
+
+extern "C" int cspbo_so3_fetch(const cspbo_so3 *h, double *x, double *dxdr, double *rdxdr, long long *seq)
+{
+    if (!h) { set_error("so3_fetch: null handle"); return CSPBO_E_ARG; }
+    if (seq) memcpy(seq, h->h_seq.data(), h->h_seq.size() * sizeof(long long));
+    if (h->n_atoms == 0) return CSPBO_OK;
+    if (x) CSPBO_CUDA(cudaMemcpy(x, h->d_x, (size_t)h->n_atoms * h->ncoefs * 8, cudaMemcpyDeviceToHost));
+    if (dxdr) CSPBO_CUDA(cudaMemcpy(dxdr, h->d_dxdr, (size_t)h->n_seq * h->ncoefs * 3 * 8, cudaMemcpyDeviceToHost));
+    if (rdxdr) {
+        if (!h->stress) { set_error("so3_fetch: stress terms were not computed"); return CSPBO_E_ARG; }
+        CSPBO_CUDA(cudaMemcpy(rdxdr, h->d_rdxdr, (size_t)h->n_seq * h->ncoefs * 9 * 8, cudaMemcpyDeviceToHost));
+    }
+    return CSPBO_OK;
+}

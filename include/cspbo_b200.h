@@ -248,6 +248,23 @@ int cspbo_gp_cholesky_inverse(const double *L, int N, double *Kinv);
 /* pred[n] = Kstar[n, N] . alpha[N]    gaussianprocess.py:140,359 */
 int cspbo_gp_predict(const double *Kstar, int n, int N, const double *alpha, double *pred);
 
+/* ------------------------------------------------------------------------------------------
+ * (4) SO(3) power-spectrum descriptor on the device: produces the inputs of layers (1)-(3)
+ *     (reference cspbo/SO3.py: calculate :187-291, neighbour list :317-376, compute_dcs :581-695).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct cspbo_so3 cspbo_so3;
+/* cutoff: 0 cosine, 1 tanh, 2 poly1, 3 poly2, 4 poly3, 5 poly4, 6 unity (SO3.py:378-461);
+ * weight_on: neighbours of another species count negative (SO3.py:350-354). nmax <= 6, lmax <= 6. */
+int cspbo_so3_create(int nmax, int lmax, double rcut, double alpha, int cutoff, int weight_on, cspbo_so3 **out);
+int cspbo_so3_destroy(cspbo_so3 *h);
+/* One structure: positions[n,3], atomic numbers[n], cell[3,3] (rows = lattice vectors), pbc[3] (HOST).
+ * Returns the number of (centre, neighbour) slots of `seq` and the descriptor length. */
+int cspbo_so3_compute(cspbo_so3 *h, int n_atoms, const double *positions, const int *numbers, const double *cell,
+                      const int *pbc, int stress, int *n_seq, int *n_coefs);
+/* Copy the results of the last compute to HOST buffers: x[n,nc], dxdr[n_seq,nc,3], rdxdr[n_seq,nc,3,3]
+ * (NULL to skip; needs stress=1), seq[n_seq,2] (int64). */
+int cspbo_so3_fetch(const cspbo_so3 *h, double *x, double *dxdr, double *rdxdr, long long *seq);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,100 @@
+"""SO(3) descriptor: the NumPy restatement (oracle/so3_reference.py) is pinned on the CPU against
+goldens produced by the reference's own cspbo/SO3.py source (tests/golden/so3_ref_harness.py), and the
+CUDA implementation is checked against both on the GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from tests._cases import max_norm_err
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "so3_golden.npz")
+CASES = ["si8", "ptho12", "cu2_small_cell"]
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return dict(np.load(GOLD))
+
+
+def structure(gold, name):
+    from oracle.so3_reference import Structure
+    prm = gold[name + "_prm"]
+    st = Structure(gold[name + "_pos"], gold[name + "_num"], gold[name + "_cell"])
+    return st, dict(nmax=int(prm[0]), lmax=int(prm[1]), rcut=float(prm[2]), alpha=float(prm[3]))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_restatement_matches_reference_goldens(gold, name):
+    from oracle import so3_reference as so
+    st, prm = structure(gold, name)
+    d = so.so3_calculate(st, stress=True, **prm)
+    assert np.array_equal(d["seq"], gold[name + "_seq"])
+    for k in ("x", "dxdr", "rdxdr"):
+        assert max_norm_err(d[k], gold[name + "_" + k]) < 1e-12, (name, k)
+
+
+def test_oracle_gradient_is_consistent_with_finite_differences(gold):
+    """dxdr[(i,j)] is d x_i / d r_j: move atom j, watch x_i."""
+    from oracle import so3_reference as so
+    st, prm = structure(gold, "si8")
+    d0 = so.so3_calculate(st, stress=False, **prm)
+    h = 1e-5
+    j, k = 3, 1
+    pos = st.positions.copy()
+    pos[j, k] += h
+    dp = so.so3_calculate(so.Structure(pos, st.numbers, st.cell), stress=False, **prm)
+    pos[j, k] -= 2 * h
+    dm = so.so3_calculate(so.Structure(pos, st.numbers, st.cell), stress=False, **prm)
+    fd = (dp["x"] - dm["x"]) / (2 * h)
+    for s, (i, jj) in enumerate(d0["seq"]):
+        if jj == j:
+            assert np.abs(fd[i] - d0["dxdr"][s, :, k]).max() < 1e-6 * max(1.0, np.abs(d0["dxdr"]).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_descriptor_matches_reference_goldens(gold, name):
+    from csp_bo_b200.SO3 import SO3
+    st, prm = structure(gold, name)
+    d = SO3(derivative=True, stress=True, **prm).calculate(st)
+    assert np.array_equal(d["seq"], gold[name + "_seq"])
+    assert d["elements"] == list(st.symbols)
+    for k in ("x", "dxdr", "rdxdr"):
+        assert max_norm_err(d[k], gold[name + "_" + k]) < 1e-10, (name, k)
+    # derivative=False / stress=False branches (SO3.py:282-291)
+    d2 = SO3(derivative=True, stress=False, **prm).calculate(st)
+    assert d2["rdxdr"] is None and np.array_equal(d2["dxdr"], d["dxdr"])
+    d3 = SO3(derivative=False, **prm).calculate(st)
+    assert d3["dxdr"] is None and np.array_equal(d3["x"], d["x"])
+
+
+@pytest.mark.gpu
+def test_gpu_descriptor_options(gold):
+    from csp_bo_b200.SO3 import SO3
+    st, prm = structure(gold, "ptho12")
+    d = SO3(derivative=True, stress=True, weight_on=True, **prm).calculate(st)
+    for k in ("x", "dxdr", "rdxdr"):
+        assert max_norm_err(d[k], gold["ptho12_won_" + k]) < 1e-10, k
+    for cut in ("tanh", "poly2"):
+        d = SO3(derivative=True, stress=True, cutoff_function=cut, **prm).calculate(st)
+        for k in ("x", "dxdr"):
+            assert max_norm_err(d[k], gold["ptho12_%s_%s" % (cut, k)]) < 1e-10, (cut, k)
+
+
+@pytest.mark.gpu
+def test_gpu_descriptor_larger_cell_vs_oracle():
+    """192-atom Pt/H/O-like cell (the README workload's size) against the NumPy oracle."""
+    from csp_bo_b200.SO3 import SO3
+    from oracle import so3_reference as so
+    rng = np.random.default_rng(5)
+    g = np.array([(i, j, k) for i in range(4) for j in range(6) for k in range(8)], dtype=float)
+    cell = np.diag([4 * 2.6, 6 * 2.6, 8 * 2.6])
+    pos = g * 2.6 + rng.normal(0, 0.25, g.shape)
+    num = rng.choice([1, 8, 78], size=len(pos), p=[0.5, 0.3, 0.2])
+    st = so.Structure(pos, num, cell)
+    ref = so.so3_calculate(st, nmax=3, lmax=3, rcut=3.5, alpha=2.0, stress=True)
+    d = SO3(nmax=3, lmax=3, rcut=3.5, alpha=2.0, derivative=True, stress=True).calculate(st)
+    assert np.array_equal(d["seq"], ref["seq"])
+    for k in ("x", "dxdr", "rdxdr"):
+        assert max_norm_err(d[k], ref[k]) < 1e-10, k
