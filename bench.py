@@ -295,6 +295,16 @@ def run_ours(args):
     except Exception as exc:
         fit = {"error": str(exc)[:200]}
 
+    # ---- one MD / validation step (config 1 of BASELINE.json): SO3 descriptor of a 192-atom Pt/H/O structure
+    # + K* against a 16-energy + 409-force model + K*.alpha, through GaussianProcess.predict_structure.
+    # The reference's README quotes 35.767 s for 10 such structures (README.md:28).
+    md = None
+    if world == 1:
+        try:
+            md = md_step_leg()
+        except Exception as exc:
+            md = {"error": str(exc)[:200]}
+
     if sh is not None:
         sh.close()
     if rank != 0:
@@ -340,10 +350,56 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(X, pairs), "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "fit": fit}
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "fit": fit, "md_step": md}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def md_step_leg():
+    import torch
+    from csp_bo_b200 import synthetic
+    from csp_bo_b200.SO3 import SO3
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from csp_bo_b200.kernels import Dot_mb
+    from csp_bo_b200.utilities import tuple_to_list
+
+    class Struct:                      # the few ase.Atoms members the descriptor reads
+        def __init__(self, pos, num, cell):
+            self.positions, self.numbers, self._cell, self.pbc = pos, num, cell, np.array([True] * 3)
+            self.symbols = [{1: "H", 8: "O", 78: "Pt"}[int(z)] for z in num]
+
+        def get_cell(self):
+            return self._cell
+
+        def __len__(self):
+            return len(self.positions)
+
+    rng = np.random.default_rng(5)
+    g = np.array([(i, j, k) for i in range(4) for j in range(6) for k in range(8)], dtype=float)
+    st = Struct(g * 2.6 + rng.normal(0, 0.25, g.shape), rng.choice([1, 8, 78], size=192, p=[0.5, 0.3, 0.2]),
+                np.diag([4 * 2.6, 6 * 2.6, 8 * 2.6]))
+    trainE, trainF = synthetic.energy_set(16, seed=1), synthetic.force_set(409, seed=2)
+    E = [(x, float(rng.normal()), ele) for x, ele in tuple_to_list(trainE, mode='energy')]
+    F = [(x, dx, rng.normal(size=3), ele) for x, dx, ele in tuple_to_list(trainF)]
+    desc = SO3(nmax=3, lmax=3, rcut=3.5, alpha=2.0, derivative=True, stress=True)
+    model = GaussianProcess(Dot_mb(para=[SIGMA, SIGMA0], zeta=2), descriptor=desc, f_coef=30, noise_e=[0.005, 0.002, 0.1])
+    model.fit({"energy": E, "force": F}, show=False, opt=False)
+    out = {}
+    for stress in (False, True):
+        ts = []
+        for _ in range(6):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            model.predict_structure(st, stress=stress)
+            torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+        out["predict_structure_ms_stress_%d" % int(stress)] = float(np.median(ts[1:]))
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter(); desc.calculate(st); ts.append((time.perf_counter() - t0) * 1e3)
+    out["so3_descriptor_ms"] = float(np.median(ts[1:]))
+    out["what"] = ("192-atom Pt/H/O structure, SO3(nmax=3,lmax=3,rcut=3.5) + K*[577(+1152 stress) x 1243] + K*.alpha; "
+                   "reference README.md:28: 35.767 s for 10 structures")
+    return out
 
 
 def main():

@@ -473,32 +473,36 @@ extern "C" int cspbo_so3_compute(cspbo_so3 *h, int n_atoms, const double *pos, c
         inv[3] = (c[5] * c[6] - c[3] * c[8]) / det; inv[4] = (c[0] * c[8] - c[2] * c[6]) / det; inv[5] = (c[2] * c[3] - c[0] * c[5]) / det;
         inv[6] = (c[3] * c[7] - c[4] * c[6]) / det; inv[7] = (c[1] * c[6] - c[0] * c[7]) / det; inv[8] = (c[0] * c[4] - c[1] * c[3]) / det;
     }
-    int nimg[3];
-    for (int k = 0; k < 3; k++) {
-        // height of the cell along reciprocal direction k = 1 / |column k of inv|
-        const double nrm = sqrt(inv[k] * inv[k] + inv[3 + k] * inv[3 + k] + inv[6 + k] * inv[6 + k]);
-        double fmin = 1e300, fmax = -1e300;
-        for (int a = 0; a < n_atoms; a++) {
-            const double f = pos[3 * a] * inv[k] + pos[3 * a + 1] * inv[3 + k] + pos[3 * a + 2] * inv[6 + k];
-            fmin = std::min(fmin, f); fmax = std::max(fmax, f);
-        }
-        const int span = n_atoms ? (int)ceil(fmax - fmin) : 0;
-        nimg[k] = pbc[k] ? (int)ceil(P.rcut * nrm) + span : 0;
-    }
+    // fractional coordinates and the cell heights along the reciprocal directions
+    double hgt[3];
+    for (int k = 0; k < 3; k++) hgt[k] = 1.0 / sqrt(inv[k] * inv[k] + inv[3 + k] * inv[3 + k] + inv[6 + k] * inv[6 + k]);
+    std::vector<double> frac((size_t)std::max(n_atoms, 1) * 3);
+    for (int a = 0; a < n_atoms; a++)
+        for (int k = 0; k < 3; k++)
+            frac[(size_t)a * 3 + k] = pos[3 * a] * inv[k] + pos[3 * a + 1] * inv[3 + k] + pos[3 * a + 2] * inv[6 + k];
     struct Pair { int i, j; int o[3]; double rel[3]; };
     std::vector<Pair> pairs;
     const double rc2 = P.rcut * P.rcut;
     for (int i = 0; i < n_atoms; i++)
-        for (int j = 0; j < n_atoms; j++)
-            for (int a = -nimg[0]; a <= nimg[0]; a++)
-                for (int b = -nimg[1]; b <= nimg[1]; b++)
-                    for (int c = -nimg[2]; c <= nimg[2]; c++) {
+        for (int j = 0; j < n_atoms; j++) {
+            // an image offset o can only be in range if |f_j + o - f_i| * height <= rcut along every axis
+            int lo[3], hi[3];
+            for (int k = 0; k < 3; k++) {
+                if (!pbc[k]) { lo[k] = hi[k] = 0; continue; }
+                const double df = frac[(size_t)i * 3 + k] - frac[(size_t)j * 3 + k], w = P.rcut / hgt[k];
+                lo[k] = (int)ceil(df - w - 1e-9);
+                hi[k] = (int)floor(df + w + 1e-9);
+            }
+            for (int a = lo[0]; a <= hi[0]; a++)
+                for (int b = lo[1]; b <= hi[1]; b++)
+                    for (int c = lo[2]; c <= hi[2]; c++) {
                         double r[3];
                         for (int k = 0; k < 3; k++)
                             r[k] = pos[3 * j + k] + a * cell[k] + b * cell[3 + k] + c * cell[6 + k] - pos[3 * i + k];
                         const double d2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
                         if (d2 < rc2 && d2 > 1e-24) pairs.push_back({i, j, {a, b, c}, {r[0], r[1], r[2]}});
                     }
+        }
     // loop order above is already (i, j, offset): the deterministic summation order of K2 / K3
     const int np = (int)pairs.size();
     // ---- seq slots (SO3.py:361-372): for every centre its neighbour ids plus itself, sorted

@@ -98,3 +98,57 @@ def test_gpu_descriptor_larger_cell_vs_oracle():
     assert np.array_equal(d["seq"], ref["seq"])
     for k in ("x", "dxdr", "rdxdr"):
         assert max_norm_err(d[k], ref[k]) < 1e-10, k
+
+
+@pytest.mark.gpu
+def test_full_pipeline_descriptor_to_forces(oracle_built):
+    """Structures -> SO3 (GPU) -> training tuples -> GaussianProcess.fit -> predict_structure, against the
+    same chain on the CPU oracle (NumPy SO3 + reference C++ kernels + SciPy)."""
+    from csp_bo_b200.SO3 import SO3
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from csp_bo_b200.kernels import RBF_mb
+    from oracle import so3_reference as so
+    from oracle.gp_reference import RefGaussianProcess
+    rng = np.random.default_rng(11)
+    prm = dict(nmax=3, lmax=3, rcut=3.5, alpha=2.0)
+    sym = {"H": 1, "O": 8, "Pt": 78, "Si": 14, "Cu": 29}
+
+    def make(seed):
+        r = np.random.default_rng(seed)
+        g = np.array([(i, j, k) for i in range(2) for j in range(2) for k in range(3)], dtype=float)
+        return so.Structure(g * 2.5 + r.normal(0, 0.2, g.shape), r.choice([1, 8, 78], size=12), np.diag([5.0, 5.0, 7.5]))
+
+    def tuples(d, ele, E, F):
+        energy = [(d['x'], E / len(ele), ele)]
+        force = []
+        for i in range(len(ele)):
+            ids = np.argwhere(d['seq'][:, 1] == i).flatten()
+            _i = d['seq'][ids, 0]
+            force.append((d['x'][_i, :], d['dxdr'][ids], F[i], ele[_i]))
+        return energy, force
+
+    desc = SO3(derivative=True, stress=True, **prm)
+    data_g, data_o = {"energy": [], "force": []}, {"energy": [], "force": []}
+    for s in range(3):
+        st = make(s)
+        E, F = float(rng.normal(-30, 1)), rng.normal(0, 0.5, (12, 3))
+        for data, d in ((data_g, desc.calculate(st)), (data_o, so.so3_calculate(st, stress=True, **prm))):
+            e, f = tuples(d, st.numbers, E, F)
+            data["energy"] += e
+            data["force"] += f[:6]
+    para, bounds = [6.244955524643115, 0.5611029935713949], [[1e-2, 5e+1], [1e-1, 1e+1]]
+    model = GaussianProcess(RBF_mb(para=list(para), bounds=bounds, zeta=2), descriptor=desc, f_coef=30, noise_e=[0.005, 0.002, 0.1])
+    model.fit(data_g, show=False, opt=False)
+    # oracle chain
+    from csp_bo_b200.utilities import list_to_tuple
+    y = np.concatenate(([e[1] for e in data_o["energy"]], np.concatenate([f[2] for f in data_o["force"]])))
+    train_x = {"energy": list_to_tuple([(e[0], e[2]) for e in data_o["energy"]], mode="energy"),
+               "force": list_to_tuple([(f[0], f[1], f[3]) for f in data_o["force"]])}
+    ref = RefGaussianProcess("rbf", para, 2.0, bounds, f_coef=30, noise_e=(0.005, 0.002, 0.1))
+    ref.set_train(train_x, y)
+    ref.fit(opt=False)
+    test = make(99)
+    E, F, S = model.predict_structure(test, stress=True)
+    Er, Fr, Sr = ref.predict_structure(so.so3_calculate(test, stress=True, **prm), 12, test.numbers, stress=True)
+    assert abs(E - Er) <= 1e-8 * max(1.0, abs(Er))
+    assert max_norm_err(F, Fr) < 1e-8 and max_norm_err(S, Sr) < 1e-8
