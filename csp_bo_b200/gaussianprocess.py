@@ -9,6 +9,7 @@ Device residency: K is assembled block by block straight into one CUDA matrix
 (csrc/gp.cu), `alpha_` and the Cholesky factor stay in HBM, predictions are K*.alpha GEMVs on the
 device.  Only alpha-sized vectors and predictions cross PCIe.
 """
+import json
 import warnings
 
 import numpy as np
@@ -255,6 +256,71 @@ class GaussianProcess():
         noise_diag[:NE] = 2 * params[-1]
         llg.append(0.5 * float((torch.diagonal(W) * noise_diag).sum()))
         return MLL, np.array(llg)
+
+    # ------------------------------------------------------------------ model files
+    def save_dict(self, db_filename):
+        """gaussianprocess.py:539-551."""
+        dict0 = {"noise": {"energy": self.noise_e, "f_coef": self.f_coef, "bounds": self.noise_bounds},
+                 "kernel": self.kernel.save_dict(), "descriptor": self.descriptor.save_dict(),
+                 "db_filename": db_filename}
+        if self.base_potential is not None:
+            dict0["base_potential"] = self.base_potential.save_dict()
+        return dict0
+
+    def load(self, filename, N_max=None, opt=False, device='cuda', db_rows=None):
+        """Load a model JSON written by the reference (gaussianprocess.py:525-537), recompute the descriptors
+        of its ASE database on the GPU and refit.  `db_rows` (list from asedb.read_rows / rows_from_npz_dict)
+        overrides the db file named in the JSON."""
+        with open(filename, "r") as fp:
+            dict0 = json.load(fp)
+        self.load_from_dict(dict0, N_max=N_max, device=device, db_rows=db_rows)
+        self.fit(show=False, opt=opt)
+        print("load the GP model from ", filename)
+
+    def load_from_dict(self, dict0, N_max=None, device='cuda', db_rows=None):
+        """gaussianprocess.py:553-592."""
+        from .kernels import Dot_mb, RBF_mb
+        from .SO3 import SO3
+        name = dict0["kernel"]["name"]
+        if name == "RBF_mb":
+            self.kernel = RBF_mb()
+        elif name == "Dot_mb":
+            self.kernel = Dot_mb()
+        else:
+            raise NotImplementedError("unknow kernel {:s}".format(name))
+        self.kernel.load_from_dict(dict0["kernel"])
+        if dict0["descriptor"]["_type"] == "SO3":
+            self.descriptor = SO3()
+            self.descriptor.load_from_dict(dict0["descriptor"])
+        else:
+            raise NotImplementedError("unknow descriptors {:s}".format(str(dict0["descriptor"].get("_type"))))
+        if "base_potential" in dict0:
+            raise NotImplementedError("base potentials (LJ) live in the reference's calculator.py")
+        self.kernel.device = device
+        self.noise_e = dict0["noise"]["energy"]
+        self.f_coef = dict0["noise"]["f_coef"]
+        self.noise_bounds = dict0["noise"]["bounds"]
+        self.noise_f = self.f_coef * self.noise_e
+        self.extract_db(dict0["db_filename"] if db_rows is None else db_rows, N_max)
+
+    def extract_db(self, db, N_max=None):
+        """Descriptors of every structure of an ASE database (path) or of a list of rows, keeping the
+        energies / forces flagged energy_in / force_in (gaussianprocess.py:627-671)."""
+        from . import asedb
+        rows = asedb.read_rows(db, limit=N_max) if isinstance(db, str) else (db if N_max is None else db[:N_max])
+        pts_to_add = {"energy": [], "force": [], "db": []}
+        for row in rows:
+            atoms, energy, force = row["atoms"], row["energy"], row["force"].copy()
+            d = self.descriptor.calculate(atoms)
+            ele = np.array([e if isinstance(e, (int, np.integer)) else _Z[e] for e in d['elements']])
+            if row["energy_in"]:
+                pts_to_add["energy"].append((d['x'], energy / len(atoms), ele))
+            for fid in row["force_in"]:
+                ids = np.argwhere(d['seq'][:, 1] == fid).flatten()
+                _i = d['seq'][ids, 0]
+                pts_to_add["force"].append((d['x'][_i, :], d['dxdr'][ids], force[fid], ele[_i]))
+            pts_to_add["db"].append((atoms, energy, force, row["energy_in"], row["force_in"]))
+        self.set_train_pts(pts_to_add, "w")
 
     # ------------------------------------------------------------------ prediction
     def predict(self, X, stress=False, total_E=False, return_std=False, return_cov=False):

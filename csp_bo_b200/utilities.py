@@ -41,3 +41,54 @@ def tuple_to_list(data, mode='force'):
             out.append((X[c:c + ind], ELE[c:c + ind]))
             c += ind
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# metrics printed by the reference's example scripts (cspbo/utilities.py:44-90)
+def rmse(true, predicted):
+    true, predicted = np.asarray(true), np.asarray(predicted)
+    return float(np.sqrt(np.sum((true - predicted) ** 2) / len(true)))
+
+
+def mae(true, predicted):
+    true, predicted = np.asarray(true), np.asarray(predicted)
+    return float(np.sum(np.abs(true - predicted)) / len(true))
+
+
+def r2(true, predicted):
+    true, predicted = np.asarray(true), np.asarray(predicted)
+    t_bar = np.sum(true) / len(true)
+    square_error = np.sum((true - predicted) ** 2)
+    true_variance = np.sum((true - t_bar) ** 2)
+    return float(1 - square_error / true_variance)
+
+
+def metric_single(y_train, y_train_pred, header, show_max=False):
+    """Prints and returns the label of cspbo/utilities.py:80-90, e.g. 'Train Energy [ 16]: R2 0.9480 MAE ...'."""
+    r2_train, mae_train, rmse_train = r2(y_train, y_train_pred), mae(y_train, y_train_pred), rmse(y_train, y_train_pred)
+    str1 = "{:s} [{:4d}]: ".format(header, len(y_train))
+    str1 += "R2 {:6.4f} MAE {:6.3f} RMSE {:6.3f}".format(r2_train, mae_train, rmse_train)
+    if show_max:
+        str1 += " Max {:6.3f}".format(float(np.max(np.abs(np.asarray(y_train) - np.asarray(y_train_pred)))))
+    print(str1)
+    return str1
+
+
+def convert_train_data(data, des, N_force=100000):
+    """[(structure, energy, forces)] -> {'energy', 'force', 'db'} training dictionary through the descriptor
+    `des` (cspbo/utilities.py:104-136; every atom contributes a force point until N_force is reached)."""
+    from .gaussianprocess import _Z
+    energy_data, force_data, db_data = [], [], []
+    for (struc, energy, forces) in data:
+        d = des.calculate(struc)
+        ele = np.array([e if isinstance(e, (int, np.integer)) else _Z[e] for e in d['elements']])
+        f_ids = []
+        for i in range(len(struc)):
+            if len(force_data) < N_force:
+                ids = np.argwhere(d['seq'][:, 1] == i).flatten()
+                _i = d['seq'][ids, 0]
+                force_data.append((d['x'][_i, :], d['dxdr'][ids], forces[i], ele[_i]))
+                f_ids.append(i)
+        energy_data.append((d['x'], energy / len(struc), ele))
+        db_data.append((struc, energy, forces, True, f_ids))
+    return {"energy": energy_data, "force": force_data, "db": db_data}
