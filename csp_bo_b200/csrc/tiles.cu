@@ -590,7 +590,10 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
     // Small problems (fewer than ~2 warps per scheduler in the one-block-per-warp mapping): let the 4 warps
     // of a CTA split the tiles of ONE A block instead, which quarters the critical path of a K* build
-    p.split = (diag || (long long)a_mine * p.b_nblk < 32LL * sms) ? 1 : 0;
+    // (decided on the whole A side, not on the row slab of a pipelined host-bound build, so that every
+    // way of building the same block sums in the same order and gives bit-identical results)
+    const long long a_all = ((long long)a->n_blocks + p.nranks - 1) / p.nranks;
+    p.split = (diag || a_all * p.b_nblk < 32LL * sms) ? 1 : 0;
     // B tiles per stage: a whole (block, species) run if it fits in 36 KB
     const size_t tile_bytes = (size_t)b->tile_doubles * sizeof(double);
     const int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, kSmemChunk / tile_bytes));

@@ -404,18 +404,20 @@ class GaussianProcess():
         (gaussianprocess.py:325-390)."""
         d = self.descriptor.calculate(struc)
         ele = np.array([e if isinstance(e, (int, np.integer)) else _Z[e] for e in d['elements']])
-        data = {"energy": [(d['x'], ele)], "force": []}
         _n, l = d['x'].shape
         n_atoms = len(struc)
-        for i in range(n_atoms):
-            ids = np.argwhere(d['seq'][:, 1] == i).flatten()
-            _i = d['seq'][ids, 0]
-            _x, _dxdr, ele0 = d['x'][_i, :], d['dxdr'][ids], ele[_i]
-            if stress:
-                _rdxdr = d['rdxdr'][ids].reshape([len(ids), l, 9])[:, :, [0, 4, 8, 1, 2, 5]]
-                data["force"].append((_x, np.concatenate((_dxdr, _rdxdr), axis=2), ele0))
-            else:
-                data["force"].append((_x, _dxdr, ele0))
+        # the reference gathers, per atom i, the seq rows with seq[:,1] == i in ascending order
+        # (gaussianprocess.py:341-351); a stable sort on that column gives the same stacked tuple at once
+        seq = np.asarray(d['seq'])
+        order = np.argsort(seq[:, 1], kind='stable')
+        centres = seq[order, 0]
+        counts = np.bincount(seq[:, 1], minlength=n_atoms)
+        dX = d['dxdr'][order]
+        if stress:
+            rd = d['rdxdr'][order].reshape([len(order), l, 9])[:, :, [0, 4, 8, 1, 2, 5]]
+            dX = np.concatenate((dX, rd), axis=2)
+        data = {"energy": (np.ascontiguousarray(d['x']), ele, [len(ele)]),
+                "force": (np.ascontiguousarray(d['x'][centres]), np.ascontiguousarray(dX), ele[centres], [int(c) for c in counts])}
         train = self._train_dict()
         if stress:
             K_trans, K_trans1 = kdev.k_total_with_stress_device(self.kernel, data, train, f_tol)
