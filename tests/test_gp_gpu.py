@@ -171,3 +171,20 @@ def test_cur_and_sparsify(problem, fixtures):
     removed_e, removed_f = model.sparsify(e_tol=1e-6, f_tol=1e-6)
     assert removed_e == [] and len(removed_f) >= 1 and all(i < 25 for i in removed_f)
     assert model.N_forces == 25 - len(removed_f) and model.alpha_.shape == (3 * model.N_forces, 1)
+
+
+@pytest.mark.parametrize("n,N", [(1, 1), (3, 7), (5, 64), (17, 2047), (9, 2048), (33, 2049), (7, 4097), (64, 6145), (2, 20001)])
+def test_predict_gemv_shapes(n, N):
+    """K*.alpha (gaussianprocess.py:140,359) through cspbo_gp_predict: odd / even N (rows of an odd-N
+    matrix alternate between 16-byte aligned and not), one and several column chunks, offset views."""
+    import torch
+    from csp_bo_b200 import gp
+    g = torch.Generator(device="cpu").manual_seed(n * 100003 + N)
+    Ks = torch.randn((n, N), dtype=torch.float64, generator=g)
+    al = torch.randn(N, dtype=torch.float64, generator=g)
+    ref = (Ks.numpy() @ al.numpy())
+    got = gp.predict_mean(Ks.cuda(), al.cuda()).cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max()) * np.sqrt(N)
+    # deterministic: chunk partial sums are added in a fixed order
+    again = gp.predict_mean(Ks.cuda(), al.cuda()).cpu().numpy()
+    assert np.array_equal(got, again)
