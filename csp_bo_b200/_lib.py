@@ -76,6 +76,8 @@ SIGNATURES = {
     "cspbo_sharded_rows": [c_vp, c_int, c_int],
     "cspbo_pack_order": [c_vp, c_vp, c_ll],
     "cspbo_block_build_sharded": [ctypes.POINTER(BlockDesc), c_vp, c_int, c_int, ctypes.POINTER(c_vp)],
+    "cspbo_sharded_rows_ex": [c_vp, c_int, c_int, c_int, c_int],
+    "cspbo_block_build_sharded_ex": [ctypes.POINTER(BlockDesc), c_vp, c_int, c_int, ctypes.POINTER(c_vp), c_int, c_int, c_int],
     "cspbo_so3_create": [c_int, c_int, c_dbl, c_dbl, c_int, c_int, ctypes.POINTER(c_vp)],
     "cspbo_so3_destroy": [c_vp],
     "cspbo_so3_compute": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
@@ -85,9 +87,11 @@ SIGNATURES = {
     "cspbo_gp_cho_solve": [c_vp, c_int, c_vp, c_int],
     "cspbo_gp_cholesky_inverse": [c_vp, c_int, c_vp],
     "cspbo_gp_predict": [c_vp, c_int, c_int, c_vp, c_vp],
+    "cspbo_gp_panel_factor": [c_vp, c_ll, c_ll, c_int, c_ll, c_vp, c_vp],
+    "cspbo_gp_panel_update": [c_vp, c_ll, c_int, c_vp, c_ll, c_ll, c_int, c_ll, c_vp],
 }
 _RESTYPE = {"cspbo_last_error": ctypes.c_char_p, "cspbo_launch_count": c_ll, "cspbo_pack_bytes": c_ll,
-            "cspbo_pack_pair_count": c_ll, "cspbo_sharded_rows": c_ll}
+            "cspbo_pack_pair_count": c_ll, "cspbo_sharded_rows": c_ll, "cspbo_sharded_rows_ex": c_ll}
 
 # reference-named shims (libdot_builder.py:5-9, librbf_builder.py:5-12)
 SHIM_SYMBOLS = {

@@ -23,7 +23,9 @@ void set_error(const char *fmt, ...)
 int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
                        int accumulate, cudaStream_t st, int rank = 0, int nranks = 1, double *const *outs = nullptr,
-                       int a_begin = 0, int a_end = -1, int diag = 0);
+                       int a_begin = 0, int a_end = -1, int diag = 0, int sb_blocks = 1, int zigzag = 0,
+                       int packed_cols = 0);
+int sharded_superblocks(int n_blocks, int rank, int nranks, int sb_blocks, int zigzag);
 
 struct DevBuf {
     double *p = nullptr;
@@ -405,9 +407,13 @@ extern "C" int cspbo_ipc_close(void *ptr)
 
 extern "C" long long cspbo_sharded_rows(const cspbo_pack *a, int rank, int nranks)
 {
-    if (!a || nranks < 1 || rank < 0 || rank >= nranks) return -1;
-    const long long mine = (a->n_blocks - rank + nranks - 1) / nranks;
-    return std::max<long long>(mine, 0) * 8;
+    return cspbo_sharded_rows_ex(a, rank, nranks, 1, 0);
+}
+
+extern "C" long long cspbo_sharded_rows_ex(const cspbo_pack *a, int rank, int nranks, int sb_blocks, int zigzag)
+{
+    if (!a || nranks < 1 || rank < 0 || rank >= nranks || sb_blocks < 1) return -1;
+    return (long long)sharded_superblocks((int)a->n_blocks, rank, nranks, sb_blocks, zigzag) * sb_blocks * 8;
 }
 
 extern "C" int cspbo_pack_order(const cspbo_pack *a, int *order, long long n)
@@ -421,7 +427,15 @@ extern "C" int cspbo_pack_order(const cspbo_pack *a, int *order, long long n)
 extern "C" int cspbo_block_build_sharded(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
                                          double *const *outs)
 {
+    return cspbo_block_build_sharded_ex(desc, a, rank, nranks, outs, 1, 0, 0);
+}
+
+extern "C" int cspbo_block_build_sharded_ex(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
+                                            double *const *outs, int sb_blocks, int zigzag, int packed_cols)
+{
     if (!desc || !a || !outs) { set_error("block_build_sharded: null argument"); return CSPBO_E_ARG; }
+    if (sb_blocks < 1) { set_error("block_build_sharded: sb_blocks must be >= 1"); return CSPBO_E_ARG; }
+    if (packed_cols && a->row_classes != 1) { set_error("block_build_sharded: packed_cols needs a pack with row_classes = 1"); return CSPBO_E_ARG; }
     if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) { set_error("block_build_sharded: bad rank %d/%d", rank, nranks); return CSPBO_E_ARG; }
     for (int r = 0; r < nranks; r++)
         if (!outs[r]) { set_error("block_build_sharded: outs[%d] is null", r); return CSPBO_E_ARG; }
@@ -439,7 +453,8 @@ extern "C" int cspbo_block_build_sharded(const cspbo_block_desc *desc, const csp
         if (a->nc < 3) { set_error("block_build_sharded: K_FF needs a force pack"); return CSPBO_E_ARG; }
         si = 3 * m * 3; sk = m * 3; sj = 3; sl = 1;
     }
-    return build_block_device(d, a, a, 0, 0, outs[rank], nullptr, si, sk, sj, sl, 0, 0, rank, nranks, outs);
+    return build_block_device(d, a, a, 0, 0, outs[rank], nullptr, si, sk, sj, sl, 0, 0, rank, nranks, outs, 0, -1, 0,
+                              sb_blocks, zigzag, packed_cols);
 }
 
 // ------------------------------------------------------------------------------------------

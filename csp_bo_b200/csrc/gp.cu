@@ -2,6 +2,7 @@
 // (reference cspbo/gaussianprocess.py:105-127 fit, :138-141 / :359-366 prediction).
 //   noise add + K*.alpha GEMV : hand-written HBM-bound kernels
 //   Cholesky factorisation / solve : cuSOLVER potrf / potrs (as BASELINE.json's north_star asks)
+#include <cublas_v2.h>
 #include <cusolverDn.h>
 
 #include <mutex>
@@ -248,5 +249,94 @@ extern "C" int cspbo_gp_cholesky_inverse(const double *L, int N, double *Kinv)
     symmetrize_kernel<<<(unsigned)((total + 255) / 256), 256>>>(Kinv, N);
     g_launches++;
     CSPBO_CUDA(cudaGetLastError());
+    return CSPBO_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Panel operations of the sharded (one process per GPU) Cholesky: K = U^T U, rows of U live where the
+// rows of K live (csp_bo_b200/distributed.py: ShardedCholesky).  Row-major addressing; every call is
+// asynchronous on the caller's stream, positive-definiteness is reported through a device-side info word
+// so that the panel pipeline never synchronises with the host.
+// ------------------------------------------------------------------------------------------
+namespace cspbo {
+
+struct StreamHandles {
+    cudaStream_t stream;
+    int device;
+    cublasHandle_t blas;
+    cusolverDnHandle_t solver;
+    double *work;
+    int lwork;
+};
+static StreamHandles g_sh[16];
+static int g_nsh = 0;
+
+static int stream_handles(cudaStream_t st, StreamHandles **out)
+{
+    int dev = 0;
+    CSPBO_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_solver_mu);
+    for (int i = 0; i < g_nsh; i++)
+        if (g_sh[i].stream == st && g_sh[i].device == dev) { *out = &g_sh[i]; return CSPBO_OK; }
+    if (g_nsh >= 16) { set_error("too many distinct streams use the panel operations"); return CSPBO_E_ARG; }
+    StreamHandles h = {st, dev, nullptr, nullptr, nullptr, 0};
+    if (cublasCreate(&h.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return CSPBO_E_SOLVER; }
+    if (cusolverDnCreate(&h.solver) != CUSOLVER_STATUS_SUCCESS) { cublasDestroy(h.blas); set_error("cusolverDnCreate failed"); return CSPBO_E_SOLVER; }
+    cublasSetStream(h.blas, st);
+    cusolverDnSetStream(h.solver, st);
+    g_sh[g_nsh] = h;
+    *out = &g_sh[g_nsh++];
+    return CSPBO_OK;
+}
+
+}  // namespace cspbo
+
+extern "C" int cspbo_gp_panel_factor(double *rows, long long ld, long long col0, int h, long long ncols, int *info_dev,
+                                     void *stream)
+{
+    if (!rows || !info_dev || h <= 0 || col0 < 0 || col0 + h > ncols || ncols > ld) { set_error("gp_panel_factor: bad argument"); return CSPBO_E_ARG; }
+    StreamHandles *sh;
+    int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
+    if (rc) return rc;
+    // row-major upper factor of the symmetric diagonal block == column-major lower factor
+    double *D = rows + col0;
+    int lwork = 0;
+    cusolverStatus_t s = cusolverDnDpotrf_bufferSize(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, &lwork);
+    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
+    if (lwork > sh->lwork) {
+        if (sh->work) { CSPBO_CUDA(cudaStreamSynchronize(sh->stream)); cudaFree(sh->work); sh->work = nullptr; sh->lwork = 0; }
+        CSPBO_CUDA(cudaMalloc(&sh->work, (size_t)lwork * sizeof(double)));
+        sh->lwork = lwork;
+    }
+    s = cusolverDnDpotrf(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, sh->work, sh->lwork, info_dev);
+    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf failed (status %d)", (int)s); return CSPBO_E_SOLVER; }
+    const long long rest = ncols - col0 - h;
+    if (rest > 0) {
+        // U[s, rest] = U_ss^-T K[s, rest]; column-major: B (rest x h) <- B L_ss^-T
+        const double one = 1.0;
+        cublasStatus_t b = cublasDtrsm(sh->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+                                       (int)rest, h, &one, D, (int)ld, D + h, (int)ld);
+        if (b != CUBLAS_STATUS_SUCCESS) { set_error("trsm failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
+    }
+    g_launches++;
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_gp_panel_update(const double *panel, long long ldp, int h, double *rows, long long ld, long long col0,
+                                     int nb, long long ncols, void *stream)
+{
+    if (!panel || !rows || h <= 0 || nb <= 0 || col0 < 0 || col0 + nb > ncols || ncols > ld || ncols > ldp) { set_error("gp_panel_update: bad argument"); return CSPBO_E_ARG; }
+    StreamHandles *sh;
+    int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
+    if (rc) return rc;
+    // rows[0:nb, col0:ncols] -= panel[0:h, col0:col0+nb]^T panel[0:h, col0:ncols]
+    // column-major: C (nt x nb) -= B (nt x h) A^T, A = the first nb rows of B
+    const double minus = -1.0, one = 1.0;
+    const long long nt = ncols - col0;
+    cublasStatus_t b = cublasDgemm(sh->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)nt, nb, h, &minus, panel + col0, (int)ldp,
+                                   panel + col0, (int)ldp, &one, rows + col0, (int)ld);
+    if (b != CUBLAS_STATUS_SUCCESS) { set_error("gemm failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
+    g_launches++;
     return CSPBO_OK;
 }

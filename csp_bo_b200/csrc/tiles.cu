@@ -72,9 +72,21 @@ struct TileParams {
     // sharded symmetric build (one process per GPU): rank r owns the A blocks a with a % nranks == r
     // and stores row block a at local block a / nranks of outs[r]; mirrored tiles are stored
     // straight into the owner's buffer over NVLink peer memory (outs[] are IPC-mapped pointers).
+    // sb_blocks (G) consecutive blocks form a superblock, the unit of ownership: superblock s belongs to
+    // rank s % nranks, or with zigzag to the mirrored rank on odd cycles (balances the triangular work
+    // when G is large), and is the (s / nranks)-th superblock of its owner's buffer.  packed_cols: columns are
+    // stored in packed order too (position b_blk*8+slot instead of the caller's group id), which makes the
+    // distributed matrix the symmetric permutation P K P^T that the sharded Cholesky factorises in place.
     int sharded, nranks, rank;
+    int sb_blocks, zigzag, packed_cols, a_slots;   // a_slots: blocks (incl. a ragged tail) this rank enumerates
     double *outs[kMaxRanks];
 };
+
+__device__ __host__ __forceinline__ int sb_owner(int sb, int nranks, int zigzag)
+{
+    const int cyc = sb / nranks, pos = sb - cyc * nranks;
+    return (zigzag && (cyc & 1)) ? nranks - 1 - pos : pos;
+}
 
 enum { MODE_KEE = 0, MODE_KEF = 1, MODE_KFF = 2 };
 enum { FAM_DOT = 0, FAM_RBF = 1, FAM_RBF_GRAD = 2 };
@@ -215,7 +227,7 @@ block_tile_kernel(const TileParams p)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
+    const int a_mine = p.sharded ? p.a_slots : (p.a_nblk - p.a_begin);
     const int a_units = p.split ? 1 : nwarps;     // A blocks per CTA
     const int npg = (a_mine + a_units - 1) / a_units;
     // rasterisation: CTAs walk a strip of p.strip A-block groups across all B blocks (one strip = all
@@ -226,7 +238,13 @@ block_tile_kernel(const TileParams p)
     const int strip_w = min(p.strip, npg - strip * p.strip);
     const int q = rem / strip_w;
     const int pg = strip * p.strip + (rem - q * strip_w);
-    const int a_blk = p.a_begin + (pg * a_units + (p.split ? 0 : warp)) * p.nranks + p.rank;  // nranks == 1, rank == 0 unless sharded
+    const int a_idx = pg * a_units + (p.split ? 0 : warp);
+    int a_blk = p.a_begin + a_idx;
+    if (p.sharded) {   // a_idx-th block of this rank's buffer -> global block id
+        const int cyc = a_idx / p.sb_blocks, within = a_idx - cyc * p.sb_blocks;
+        const int pos = (p.zigzag && (cyc & 1)) ? p.nranks - 1 - p.rank : p.rank;
+        a_blk = (cyc * p.nranks + pos) * p.sb_blocks + within;
+    }
     const int b_blk = p.diag ? a_blk : q;
     // symmetric build: only blocks with b >= a are computed (mirrored at write time)
     const bool active = a_blk < p.a_nblk && !(p.symmetric && b_blk < a_blk);
@@ -425,20 +443,23 @@ block_tile_kernel(const TileParams p)
         // sharded symmetric build: rows are block-cyclic over ranks in packed order, columns keep the
         // caller's group ids.  Own tile -> local HBM, mirrored tile -> peer HBM of the owner of b.
         double *mine = p.outs[p.rank];
-        const long long lrow_i = (long long)(a_blk / p.nranks) * 8 + ar;
+        const int sa = a_blk / p.sb_blocks, sb = b_blk / p.sb_blocks;
+        const long long lrow_i = ((long long)(sa / p.nranks) * p.sb_blocks + (a_blk - sa * p.sb_blocks)) * 8 + ar;
+        const long long ci = p.packed_cols ? (long long)a_blk * 8 + ar : gi;
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const int gj = p.B.slot_group[b_blk * 8 + bq + e];
             if (gj < 0) continue;
-            double *peer = p.outs[b_blk % p.nranks];
-            const long long lrow_j = (long long)(b_blk / p.nranks) * 8 + bq + e;
+            double *peer = p.outs[sb_owner(sb, p.nranks, p.zigzag)];
+            const long long lrow_j = ((long long)(sb / p.nranks) * p.sb_blocks + (b_blk - sb * p.sb_blocks)) * 8 + bq + e;
+            const long long cj = p.packed_cols ? (long long)b_blk * 8 + bq + e : gj;
 #pragma unroll
             for (int k = 0; k < NC1; k++)
 #pragma unroll
                 for (int l = 0; l < NC2; l++) {
                     const double v = p.scale * acc[e][k][l];
-                    mine[lrow_i * p.si + k * p.sk + gj * p.sj + l * p.sl] = v;
-                    if (b_blk != a_blk) peer[lrow_j * p.si + l * p.sk + gi * p.sj + k * p.sl] = v;
+                    mine[lrow_i * p.si + k * p.sk + cj * p.sj + l * p.sl] = v;
+                    if (b_blk != a_blk) peer[lrow_j * p.si + l * p.sk + ci * p.sj + k * p.sl] = v;
                 }
         }
         return;
@@ -491,7 +512,7 @@ static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t
         CSPBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
+    const int a_mine = p.sharded ? p.a_slots : (p.a_nblk - p.a_begin);
     const int npg = p.split ? a_mine : (a_mine + nwarps - 1) / nwarps;
     const long long grid = (long long)npg * p.b_nblk;
     if (grid <= 0) return CSPBO_OK;
@@ -530,11 +551,20 @@ static int launch_ks(int mode, int fam, bool z2, const TileParams &p, int nwarps
     }
 }
 
+// Number of superblocks (a ragged last one included) owned by `rank`.
+int sharded_superblocks(int n_blocks, int rank, int nranks, int sb_blocks, int zigzag)
+{
+    const int nsb = (n_blocks + sb_blocks - 1) / sb_blocks;
+    int mine = 0;
+    for (int s = 0; s < nsb; s++) mine += sb_owner(s, nranks, zigzag) == rank;
+    return mine;
+}
+
 // Build one block between packs a and b into DEVICE memory `out` (accumulating).
 int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
                        int accumulate, cudaStream_t st, int rank, int nranks, double *const *outs, int a_begin, int a_end,
-                       int diag)
+                       int diag, int sb_blocks, int zigzag, int packed_cols)
 {
     if (a->ks != b->ks || a->d != b->d) {
         set_error("block_build: packs have different descriptor lengths (%d vs %d)", a->d, b->d);
@@ -566,8 +596,12 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.nranks = p.sharded ? nranks : 1;
     p.rank = p.sharded ? rank : 0;
     for (int r = 0; r < kMaxRanks; r++) p.outs[r] = (p.sharded && r < nranks) ? outs[r] : nullptr;
-    p.a_begin = std::max(a_begin, 0);
-    p.a_nblk = (a_end < 0) ? (int)a->n_blocks : std::min(a_end, (int)a->n_blocks);
+    p.sb_blocks = std::max(sb_blocks, 1);
+    p.zigzag = zigzag ? 1 : 0;
+    p.packed_cols = packed_cols ? 1 : 0;
+    p.a_begin = p.sharded ? 0 : std::max(a_begin, 0);
+    p.a_nblk = (a_end < 0 || p.sharded) ? (int)a->n_blocks : std::min(a_end, (int)a->n_blocks);
+    p.a_slots = p.sharded ? sharded_superblocks((int)a->n_blocks, p.rank, p.nranks, p.sb_blocks, p.zigzag) * p.sb_blocks : 0;
     p.b_nblk = diag ? 1 : (int)b->n_blocks;
     if (p.a_nblk <= p.a_begin || b->n_blocks == 0) return CSPBO_OK;
 
@@ -587,7 +621,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // warps per CTA: one A block per warp; shrink for small problems so the grid covers the SMs
     int nwarps = kMaxWarps;
-    const int a_mine = (p.a_nblk - p.a_begin - p.rank + p.nranks - 1) / p.nranks;
+    const int a_mine = p.sharded ? p.a_slots : (p.a_nblk - p.a_begin);
     // Small problems (fewer than ~2 warps per scheduler in the one-block-per-warp mapping): let the 4 warps
     // of a CTA split the tiles of ONE A block instead, which quarters the critical path of a K* build
     // (decided on the whole A side, not on the row slab of a pipelined host-bound build, so that every

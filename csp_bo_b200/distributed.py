@@ -20,27 +20,44 @@ from ._lib import BlockDesc, c_vp
 
 
 # ----------------------------------------------------------------------------- pure host logic
-def owned_blocks(n_blocks, rank, world):
-    """Block ids owned by `rank` (block-cyclic)."""
-    return list(range(rank, n_blocks, world))
+def superblock_owner(s, world, zigzag=False):
+    """Owner of superblock s: s % world, mirrored on odd cycles when zigzag (balances triangular work)."""
+    cyc, pos = divmod(s, world)
+    return world - 1 - pos if (zigzag and cyc & 1) else pos
 
 
-def sharded_rows(n_blocks, rank, world):
-    """Number of group rows (incl. padding slots) in `rank`'s buffer."""
-    return 8 * len(owned_blocks(n_blocks, rank, world))
+def owned_superblocks(n_blocks, rank, world, sb_blocks=1, zigzag=False):
+    nsb = (n_blocks + sb_blocks - 1) // sb_blocks
+    return [s for s in range(nsb) if superblock_owner(s, world, zigzag) == rank]
 
 
-def local_positions(n_blocks, rank, world):
-    """Packed positions (block*8+slot) of the rows of `rank`'s buffer, in buffer order."""
-    blocks = np.asarray(owned_blocks(n_blocks, rank, world), dtype=np.int64)
-    return (blocks[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+def owned_blocks(n_blocks, rank, world, sb_blocks=1, zigzag=False):
+    """Block ids owned by `rank`, in the order of its buffer (block-cyclic by superblocks of `sb_blocks`)."""
+    return [b for s in owned_superblocks(n_blocks, rank, world, sb_blocks, zigzag)
+            for b in range(s * sb_blocks, min((s + 1) * sb_blocks, n_blocks))]
 
 
-def assemble_full(parts, order, m, ncomp=3):
+def sharded_rows(n_blocks, rank, world, sb_blocks=1, zigzag=False):
+    """Number of group rows (incl. padding slots and the ragged tail of the last superblock) in `rank`'s buffer."""
+    return 8 * sb_blocks * len(owned_superblocks(n_blocks, rank, world, sb_blocks, zigzag))
+
+
+def local_positions(n_blocks, rank, world, sb_blocks=1, zigzag=False):
+    """Packed positions (block*8+slot) of the rows of `rank`'s buffer, in buffer order; -1 for the rows
+    of blocks past the end of a ragged last superblock."""
+    pos = []
+    for s in owned_superblocks(n_blocks, rank, world, sb_blocks, zigzag):
+        for b in range(s * sb_blocks, (s + 1) * sb_blocks):
+            pos.extend(range(b * 8, b * 8 + 8) if b < n_blocks else [-1] * 8)
+    return np.asarray(pos, dtype=np.int64)
+
+
+def assemble_full(parts, order, m, ncomp=3, sb_blocks=1, zigzag=False, packed_cols=False):
     """Rebuild the dense matrix in the caller's group order from per-rank row blocks.
 
     parts[r]: array [sharded_rows(r), ncomp, m*ncomp] (K_FF) or [sharded_rows(r), m] (K_EE, ncomp=1)
     order:    packed position -> group id (-1 = padding slot), length 8*n_blocks
+    packed_cols: the columns of `parts` are in packed order too and are un-permuted as well.
     Works on numpy arrays and torch tensors (CPU or CUDA)."""
     world = len(parts)
     n_blocks = len(order) // 8
@@ -52,8 +69,8 @@ def assemble_full(parts, order, m, ncomp=3):
     else:
         full = np.empty((m,) + tuple(parts[0].shape[1:]), dtype=parts[0].dtype)
     for r in range(world):
-        pos = local_positions(n_blocks, r, world)
-        g = order[pos]
+        pos = local_positions(n_blocks, r, world, sb_blocks, zigzag)
+        g = np.where(pos >= 0, order[np.maximum(pos, 0)], -1)
         keep = np.nonzero(g >= 0)[0]
         if len(keep) == 0:
             continue
@@ -64,22 +81,32 @@ def assemble_full(parts, order, m, ncomp=3):
             full[idx] = parts[r][src]
         else:
             full[g[keep]] = parts[r][keep]
+    if packed_cols:
+        # column (p, l) of `full` belongs to group order[p]: gather so that column (g, l) comes first
+        inv = np.empty(m, dtype=np.int64)
+        inv[order[:m]] = np.arange(m)
+        if is_torch:
+            import torch
+            invt = torch.as_tensor(inv, device=full.device, dtype=torch.long)
+            full = full.reshape(full.shape[:-1] + (m, ncomp)).index_select(full.dim() - 1, invt).reshape(full.shape)
+        else:
+            full = full.reshape(full.shape[:-1] + (m, ncomp))[..., inv, :].reshape(full.shape)
     if ncomp == 1:
         return full.reshape(m, m)
     return full.reshape(m * ncomp, m * ncomp)
 
 
-def gather_row_blocks(local, n_blocks, rank, world, group=None):
+def gather_row_blocks(local, n_blocks, rank, world, group=None, sb_blocks=1, zigzag=False):
     """all_gather of the (unequal) per-rank row blocks; device-agnostic (NCCL on CUDA tensors, gloo on
     CPU tensors).  Returns the list of per-rank arrays, trimmed to their true row counts."""
     import torch
     import torch.distributed as dist
-    max_rows = 8 * ((n_blocks + world - 1) // world)
+    max_rows = max(sharded_rows(n_blocks, r, world, sb_blocks, zigzag) for r in range(world))
     pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=group)
-    return [p[: sharded_rows(n_blocks, r, world)] for r, p in enumerate(parts)]
+    return [p[: sharded_rows(n_blocks, r, world, sb_blocks, zigzag)] for r, p in enumerate(parts)]
 
 
 # ----------------------------------------------------------------------------- device side
@@ -94,19 +121,23 @@ class _RawCuda:
 class ShardedSymmetricBlock:
     """K_FF(X,X) or K_EE(X,X) of one packed training set, distributed over the ranks of `group`."""
 
-    def __init__(self, pack, block=_lib.KFF, group=None):
+    def __init__(self, pack, block=_lib.KFF, group=None, sb_blocks=1, zigzag=False, packed_cols=False):
+        """sb_blocks / zigzag / packed_cols: the ownership and column order of cspbo_block_build_sharded_ex
+        (include/cspbo_b200.h); the defaults are the plain block-cyclic layout, ShardedCholesky.from_block
+        needs packed_cols=True and wide superblocks (the panels of the factorisation)."""
         import torch
         import torch.distributed as dist
         self.lib = _lib.load()
         self.pack, self.block, self.group = pack, block, group
+        self.sb_blocks, self.zigzag, self.packed_cols = int(sb_blocks), bool(zigzag), bool(packed_cols)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.m = pack.m
         self.n_blocks = (self.m + 7) // 8
         self.ncomp = 3 if block == _lib.KFF else 1
         self.row_shape = (3, self.m * 3) if block == _lib.KFF else (self.m,)
-        self.rows = int(self.lib.cspbo_sharded_rows(pack.handle, self.rank, self.world))
-        assert self.rows == sharded_rows(self.n_blocks, self.rank, self.world)
+        self.rows = int(self.lib.cspbo_sharded_rows_ex(pack.handle, self.rank, self.world, self.sb_blocks, int(self.zigzag)))
+        assert self.rows == sharded_rows(self.n_blocks, self.rank, self.world, self.sb_blocks, self.zigzag)
         order = np.empty(self.n_blocks * 8, dtype=np.int32)
         _lib.check(self.lib.cspbo_pack_order(pack.handle, c_vp(order.ctypes.data), len(order)))
         self.order = order
@@ -147,8 +178,8 @@ class ShardedSymmetricBlock:
             self._barrier()
         desc = BlockDesc(family, self.block, float(zeta), float(sigma2), float(sigma02), float(l), float(tol),
                          int(bool(use_tol)), 0, 0, float(scale), 1.0, 1)
-        _lib.check(self.lib.cspbo_block_build_sharded(ctypes.byref(desc), self.pack.handle, self.rank, self.world,
-                                                      self._ptrs))
+        _lib.check(self.lib.cspbo_block_build_sharded_ex(ctypes.byref(desc), self.pack.handle, self.rank, self.world,
+                                                         self._ptrs, self.sb_blocks, int(self.zigzag), int(self.packed_cols)))
         if sync:
             self._barrier()
         return self.local
@@ -158,10 +189,11 @@ class ShardedSymmetricBlock:
         matrix in the caller's group order on every rank, e.g. for a replicated Cholesky."""
         import torch
         import torch.distributed as dist
+        lay = dict(sb_blocks=self.sb_blocks, zigzag=self.zigzag)
         if self.world == 1:
-            return assemble_full([self.local], self.order, self.m, self.ncomp)
-        parts = gather_row_blocks(self.local, self.n_blocks, self.rank, self.world, self.group)
-        return assemble_full(parts, self.order, self.m, self.ncomp)
+            return assemble_full([self.local], self.order, self.m, self.ncomp, packed_cols=self.packed_cols, **lay)
+        parts = gather_row_blocks(self.local, self.n_blocks, self.rank, self.world, self.group, **lay)
+        return assemble_full(parts, self.order, self.m, self.ncomp, packed_cols=self.packed_cols, **lay)
 
     def close(self):
         import torch
@@ -184,3 +216,182 @@ class ShardedSymmetricBlock:
                 self.close()
         except Exception:
             pass
+
+
+# ----------------------------------------------------------------------------- sharded Cholesky
+class _DeviceOps:
+    """Panel operations on the GPU through the C ABI (cuSOLVER potrf + cuBLAS trsm / gemm on explicit
+    streams, csrc/gp.cu).  The only implementation the product has; tests/test_distributed_cpu.py injects a
+    torch-CPU twin to exercise the rank choreography over gloo without a GPU."""
+    cuda = True
+
+    def __init__(self):
+        self.lib = _lib.load()
+
+    def panel_factor(self, rows, col0, h, ncols, info, stream):
+        _lib.check(self.lib.cspbo_gp_panel_factor(c_vp(rows.data_ptr()), rows.stride(0), int(col0), int(h), int(ncols),
+                                                  c_vp(info.data_ptr()), c_vp(stream)))
+
+    def panel_update(self, panel, h, rows, col0, nb, ncols, stream):
+        _lib.check(self.lib.cspbo_gp_panel_update(c_vp(panel.data_ptr()), panel.stride(0), int(h), c_vp(rows.data_ptr()),
+                                                  rows.stride(0), int(col0), int(nb), int(ncols), c_vp(stream)))
+
+
+class ShardedCholesky:
+    """In-place Cholesky K = U^T U of a symmetric matrix whose rows are distributed over the ranks by
+    superblocks (panels) of `nbw` rows -- exactly what ShardedSymmetricBlock(..., packed_cols=True) leaves in
+    HBM -- followed by the solves for alpha.  Replaces the reference's replicated scipy `cholesky` /
+    `cho_solve` (gaussianprocess.py:116,127: every MPI rank factorises the whole K redundantly).
+
+    Right-looking with one panel of look-ahead, one process per GPU:
+      step s: the owner factorises its panel rows (cuSOLVER potrf of the nbw x nbw diagonal block + cuBLAS
+      trsm of the rest of the rows) on a high-priority panel stream and broadcasts them (NCCL over NVLink,
+      the only data-path collective); the owner of panel s+1 updates just that panel first and goes on
+      to factorise it while every rank applies panel s to the rest of its own rows (cuBLAS dgemm, one per
+      owned superblock, triangular: only columns right of the diagonal block) on the update stream.
+    Every rank keeps the broadcast rows, so after the factorisation U is replicated ([N,N], upper
+    triangle valid) and the O(N^2) solves, the predictive variance and the LML run locally.
+    """
+
+    def __init__(self, local2d, N, nbw, rank, world, zigzag=False, group=None, ops=None):
+        import torch
+        self.torch = torch
+        self.local, self.N, self.nbw = local2d, int(N), int(nbw)
+        self.rank, self.world, self.zigzag, self.group = rank, world, bool(zigzag), group
+        self.ops = ops if ops is not None else _DeviceOps()
+        self.S = (self.N + self.nbw - 1) // self.nbw
+        self.cuda = bool(getattr(self.ops, "cuda", False))
+        dev = local2d.device
+        self.U = torch.empty((self.N, self.N), dtype=torch.float64, device=dev)
+        self.info = torch.zeros(max(self.S, 1), dtype=torch.int32, device=dev)
+        if self.cuda:
+            lo, hi = torch.cuda.Stream.priority_range()
+            self.s_panel = torch.cuda.Stream(priority=hi)
+            self.s_update = torch.cuda.Stream(priority=lo)
+        self._src = [torch.distributed.get_global_rank(group, r) if (group is not None and world > 1) else r
+                     for r in range(world)]
+
+    @classmethod
+    def from_block(cls, sh, ops=None):
+        """Factorise the matrix a ShardedSymmetricBlock(packed_cols=True) has built, in place."""
+        if not sh.packed_cols:
+            raise ValueError("ShardedCholesky needs a block built with packed_cols=True")
+        N = sh.m * sh.ncomp
+        return cls(sh.local.reshape(-1, N), N, 8 * sh.sb_blocks * sh.ncomp, sh.rank, sh.world, sh.zigzag, sh.group, ops)
+
+    def _owner(self, s):
+        return superblock_owner(s, self.world, self.zigzag)
+
+    def add_noise(self, noise2):
+        """K[i,i] += noise2 on the rows this rank owns (gaussianprocess.py:109-113)."""
+        for s in range(self.S):
+            if self._owner(s) != self.rank:
+                continue
+            r0, l0 = s * self.nbw, (s // self.world) * self.nbw
+            h = min(self.nbw, self.N - r0)
+            self.local[l0:l0 + h, r0:r0 + h].diagonal().add_(float(noise2))
+
+    def factor(self):
+        torch, ops = self.torch, self.ops
+        N, nbw, S, W, me = self.N, self.nbw, self.S, self.world, self.rank
+        U, loc = self.U, self.local
+        sp = self.s_panel.cuda_stream if self.cuda else None
+        su = self.s_update.cuda_stream if self.cuda else None
+        if self.cuda:
+            cur = torch.cuda.current_stream()
+            self.s_panel.wait_stream(cur)
+            self.s_update.wait_stream(cur)
+        e_bulk = {}
+        mine = [s for s in range(S) if self._owner(s) == me]
+
+        class _Null:
+            def __enter__(self): return self
+            def __exit__(self, *a): return False
+        on_panel = (lambda: torch.cuda.stream(self.s_panel)) if self.cuda else _Null
+        on_update = (lambda: torch.cuda.stream(self.s_update)) if self.cuda else _Null
+
+        for s in range(S):
+            o = self._owner(s)
+            r0 = s * nbw
+            h = min(nbw, N - r0)
+            with on_panel():
+                if me == o:
+                    l0 = (s // W) * nbw
+                    if self.cuda and s >= 2:
+                        self.s_panel.wait_event(e_bulk[s - 2])   # panels <= s-2 applied in bulk; s-1 by the look-ahead
+                    ops.panel_factor(loc[l0:l0 + h], r0, h, N, self.info[s:s + 1], sp)
+                    U[r0:r0 + h].copy_(loc[l0:l0 + h], non_blocking=True)
+                if W > 1:
+                    torch.distributed.broadcast(U[r0:r0 + h], src=self._src[o], group=self.group)
+                if self.cuda:
+                    e_bcast = torch.cuda.Event()
+                    e_bcast.record(self.s_panel)
+                # look-ahead: the next panel gets panel s first, on the panel stream
+                ahead = s + 1 < S and self._owner(s + 1) == me
+                if ahead:
+                    if self.cuda and s >= 1:
+                        self.s_panel.wait_event(e_bulk[s - 1])
+                    t = s + 1
+                    l0, c0 = (t // W) * nbw, t * nbw
+                    ht = min(nbw, N - c0)
+                    ops.panel_update(U[r0:r0 + h], h, loc[l0:l0 + ht], c0, ht, N, sp)
+            with on_update():
+                if self.cuda:
+                    self.s_update.wait_event(e_bcast)
+                for t in mine:
+                    if t <= s or (ahead and t == s + 1):
+                        continue
+                    l0, c0 = (t // W) * nbw, t * nbw
+                    ht = min(nbw, N - c0)
+                    ops.panel_update(U[r0:r0 + h], h, loc[l0:l0 + ht], c0, ht, N, su)
+                if self.cuda:
+                    e_bulk[s] = torch.cuda.Event()
+                    e_bulk[s].record(self.s_update)
+                    e_bulk.pop(s - 3, None)
+        if self.cuda:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(self.s_panel)
+            cur.wait_stream(self.s_update)
+        return self
+
+    def check(self):
+        """Raise CspboError(CSPBO_E_NOTPD) if a diagonal block was not positive definite (one host sync)."""
+        bad = self.torch.nonzero(self.info > 0)
+        if self.world > 1:
+            flag = self.torch.tensor([float(bad.numel() > 0)], dtype=self.torch.float64, device=self.local.device)
+            self.torch.distributed.all_reduce(flag, op=self.torch.distributed.ReduceOp.MAX, group=self.group)
+            failed = flag.item() > 0
+        else:
+            failed = bad.numel() > 0
+        if failed:
+            raise _lib.CspboError(5, "K is not positive definite (sharded Cholesky, panel %s)"
+                                  % (int(bad[0]) if bad.numel() else "on another rank"))
+
+    def logdet(self):
+        return float(2.0 * self.torch.log(self.U.diagonal()).sum())
+
+    def solve(self, B):
+        """(U^T U)^-1 B with the replicated factor; B: [N] or [N, nrhs] in the matrix's (packed) order."""
+        from . import gp
+        Bt = B.reshape(self.N, -1)
+        if not self.cuda:
+            return self.ops.solve(self.U, Bt).reshape(B.shape)
+        return gp.cho_solve(self.U, Bt).reshape(B.shape)
+
+
+def fit_alpha_sharded(sh, y, noise2, ops=None, return_solver=False):
+    """alpha = (K + noise2*I)^-1 y for the K a ShardedSymmetricBlock(packed_cols=True) has just built.
+    y and alpha are in the caller's row order (group-major, ncomp rows per group); every rank gets alpha."""
+    import torch
+    chol = ShardedCholesky.from_block(sh, ops=ops)
+    chol.add_noise(noise2)
+    chol.factor()
+    chol.check()
+    order = torch.as_tensor(np.asarray(sh.order[: sh.m], dtype=np.int64), device=chol.U.device)
+    yt = torch.as_tensor(np.asarray(y, dtype=np.float64) if not isinstance(y, torch.Tensor) else y,
+                         dtype=torch.float64, device=chol.U.device).reshape(sh.m, sh.ncomp)
+    ap = chol.solve(yt[order].reshape(-1))
+    alpha = torch.empty_like(yt)
+    alpha[order] = ap.reshape(sh.m, sh.ncomp)
+    alpha = alpha.reshape(-1)
+    return (alpha, chol) if return_solver else alpha

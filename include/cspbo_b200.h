@@ -230,6 +230,15 @@ long long cspbo_sharded_rows(const cspbo_pack *a, int rank, int nranks);
 int cspbo_pack_order(const cspbo_pack *a, int *order, long long n);   /* n >= 8*ceil(m/8) */
 int cspbo_block_build_sharded(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
                               double *const *outs);
+/* Generalised ownership for the sharded Cholesky: sb_blocks consecutive 8-group blocks form a superblock
+ * (the panel of the factorisation), superblock s belongs to rank s % nranks -- with zigzag != 0 to rank
+ * nranks-1 - s % nranks on odd cycles s / nranks, which balances the triangular work for wide panels --
+ * and is the (s / nranks)-th superblock of its owner's buffer.  packed_cols != 0 stores the columns in
+ * packed order as well (column of group slot p is p, padding slots are the last ones), i.e. the
+ * distributed matrix is P K P^T with P = cspbo_pack_order.  (1, 0, 0) is cspbo_block_build_sharded. */
+long long cspbo_sharded_rows_ex(const cspbo_pack *a, int rank, int nranks, int sb_blocks, int zigzag);
+int cspbo_block_build_sharded_ex(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
+                                 double *const *outs, int sb_blocks, int zigzag, int packed_cols);
 
 /* ------------------------------------------------------------------------------------------
  * (3) GP algebra on the device (all pointers are DEVICE pointers, column count = N)
@@ -245,6 +254,18 @@ int cspbo_gp_cholesky_solve(double *K, int N, double *y_inout, int nrhs, double 
 int cspbo_gp_cho_solve(const double *L, int N, double *B, int nrhs);
 /* Kinv = (L L^T)^-1 (cuSOLVER potri), full symmetric matrix.  gaussianprocess.py:497 */
 int cspbo_gp_cholesky_inverse(const double *L, int N, double *Kinv);
+/* Panel operations of the sharded Cholesky K = U^T U (row-major; rows of U live where the rows of K live;
+ * csp_bo_b200/distributed.py).  Both are asynchronous on `stream` (a cudaStream_t).
+ * panel_factor: `rows` = the first of h consecutive matrix rows (leading dimension ld) whose diagonal block
+ *   sits at columns [col0, col0+h): factorise it in place (cuSOLVER potrf; *info_dev > 0 <=> not positive
+ *   definite, device memory, never read by the call) and solve the rest of the panel, columns [col0+h, ncols).
+ * panel_update: rows[0:nb, col0:ncols] -= panel[0:h, col0:col0+nb]^T . panel[0:h, col0:ncols]  (cuBLAS dgemm),
+ *   the trailing update of the nb matrix rows whose diagonal block starts at column col0.
+ * Distributed restatement of the single scipy `cholesky` of gaussianprocess.py:116. */
+int cspbo_gp_panel_factor(double *rows, long long ld, long long col0, int h, long long ncols, int *info_dev,
+                          void *stream);
+int cspbo_gp_panel_update(const double *panel, long long ldp, int h, double *rows, long long ld, long long col0,
+                          int nb, long long ncols, void *stream);
 /* pred[n] = Kstar[n, N] . alpha[N]    gaussianprocess.py:140,359 */
 int cspbo_gp_predict(const double *Kstar, int n, int N, const double *alpha, double *pred);
 

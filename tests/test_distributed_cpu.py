@@ -56,3 +56,117 @@ def test_gloo_world2_gather_and_unpermute(m, golden):
         port = 29500 + (os.getpid() % 2000)
         mp.spawn(_worker, args=(world, port, np.ascontiguousarray(K), order, m, out), nprocs=world, join=True)
         assert len(out) == world and all(v == 0.0 for v in out.values()), dict(out)
+
+
+# ------------------------------------------------------------------------------------------
+# sharded Cholesky: the rank choreography (ownership, look-ahead, broadcasts, triangular updates) with a
+# torch-CPU twin of the device panel operations, world 1 in-process and world 2 over gloo
+class TorchOps:
+    """CPU twin of distributed._DeviceOps (csrc/gp.cu panel_factor / panel_update), test-only."""
+    cuda = False
+
+    def panel_factor(self, rows, col0, h, ncols, info, stream):
+        D = rows[:h, col0:col0 + h]
+        Uss, inf = torch.linalg.cholesky_ex(D, upper=True)
+        info.copy_(inf.to(info.dtype).reshape(1))
+        D.copy_(torch.triu(Uss) + torch.tril(D, -1))
+        if col0 + h < ncols:
+            R = rows[:h, col0 + h:ncols]
+            R.copy_(torch.linalg.solve_triangular(Uss.T, R, upper=False))
+
+    def panel_update(self, panel, h, rows, col0, nb, ncols, stream):
+        rows[:nb, col0:ncols] -= panel[:h, col0:col0 + nb].T @ panel[:h, col0:ncols]
+
+    def solve(self, U, B):
+        Ut = torch.triu(U)
+        return torch.cholesky_solve(B, Ut, upper=True)
+
+
+def _spd(N, seed):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((N, N))
+    return A @ A.T / N + np.eye(N)
+
+
+def _rows_of(K, N, nbw, rank, world, zigzag):
+    S = (N + nbw - 1) // nbw
+    mine = [s for s in range(S) if D.superblock_owner(s, world, zigzag) == rank]
+    local = torch.zeros((len(mine) * nbw, N), dtype=torch.float64)
+    for i, s in enumerate(mine):
+        h = min(nbw, N - s * nbw)
+        local[i * nbw:i * nbw + h] = torch.from_numpy(K[s * nbw:s * nbw + h])
+    return local
+
+
+@pytest.mark.parametrize("N,nbw,zigzag", [(24, 24, False), (100, 24, True), (193, 48, True), (96, 48, False)])
+def test_sharded_cholesky_world1(N, nbw, zigzag):
+    K = _spd(N, N)
+    ch = D.ShardedCholesky(_rows_of(K, N, nbw, 0, 1, zigzag), N, nbw, 0, 1, zigzag, ops=TorchOps())
+    ch.add_noise(0.25)
+    ch.factor().check()
+    ref = np.linalg.cholesky(K + 0.25 * np.eye(N)).T
+    assert np.abs(np.triu(ch.U.numpy()) - ref).max() < 1e-12
+    y = np.random.default_rng(1).standard_normal(N)
+    assert np.abs(ch.solve(torch.from_numpy(y)).numpy() - np.linalg.solve(K + 0.25 * np.eye(N), y)).max() < 1e-10
+    assert abs(ch.logdet() - np.linalg.slogdet(K + 0.25 * np.eye(N))[1]) < 1e-10
+
+
+def test_sharded_cholesky_not_positive_definite():
+    K = _spd(60, 3)
+    K[30, 30] = -5.0
+    ch = D.ShardedCholesky(_rows_of(K, 60, 24, 0, 1, False), 60, 24, 0, 1, ops=TorchOps())
+    from csp_bo_b200._lib import CspboError
+    with pytest.raises(CspboError):
+        ch.factor().check()
+
+
+def _chol_worker(rank, world, port, K, N, nbw, zigzag, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ch = D.ShardedCholesky(_rows_of(K, N, nbw, rank, world, zigzag), N, nbw, rank, world, zigzag, ops=TorchOps())
+        ch.add_noise(0.5)
+        ch.factor().check()
+        ref = np.linalg.cholesky(K + 0.5 * np.eye(N)).T
+        y = np.random.default_rng(7).standard_normal(N)
+        a = ch.solve(torch.from_numpy(y)).numpy()
+        out[rank] = (float(np.abs(np.triu(ch.U.numpy()) - ref).max()),
+                     float(np.abs(a - np.linalg.solve(K + 0.5 * np.eye(N), y)).max()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("N,nbw,zigzag", [(100, 24, True), (170, 24, False)])
+def test_sharded_cholesky_gloo_world2(N, nbw, zigzag):
+    K = _spd(N, 11)
+    world = 2
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        port = 31500 + (os.getpid() % 2000) + N
+        mp.spawn(_chol_worker, args=(world, port, K, N, nbw, zigzag, out), nprocs=world, join=True)
+        assert len(out) == world and all(v[0] < 1e-12 and v[1] < 1e-10 for v in out.values()), dict(out)
+
+
+def test_layout_roundtrip_superblocks_packed_cols():
+    """assemble_full undoes every (sb_blocks, zigzag, packed_cols) layout of cspbo_block_build_sharded_ex."""
+    m = 61
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((3 * m, 3 * m)); K = A + A.T
+    nb = (m + 7) // 8
+    order = np.full(nb * 8, -1, dtype=np.int64)
+    order[:m] = rng.permutation(m)
+    K4 = K.reshape(m, 3, m, 3)
+    for world in (1, 2, 3):
+        for G in (1, 2, 4):
+            for zz in (False, True):
+                for packed in (False, True):
+                    parts = []
+                    for r in range(world):
+                        pos = D.local_positions(nb, r, world, G, zz)
+                        g = np.where(pos >= 0, order[np.maximum(pos, 0)], -1)
+                        loc = np.zeros((len(pos), 3, m, 3))
+                        src = K4[g[g >= 0]]
+                        loc[g >= 0] = src[:, :, order[:m], :] if packed else src
+                        parts.append(loc.reshape(len(pos), 3, m * 3))
+                    full = D.assemble_full(parts, order, m, 3, G, zz, packed)
+                    assert np.array_equal(full, K), (world, G, zz, packed)

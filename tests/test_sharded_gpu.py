@@ -58,3 +58,84 @@ def test_sharded_two_gpus_peer_stores():
         out = mgr.dict()
         mp.spawn(_rank_main, args=(2, 29611, out), nprocs=2, join=True)
         assert len(out) == 2 and all(v < 1e-12 for v in out.values()), dict(out)
+
+
+@pytest.mark.parametrize("sb_blocks,zigzag", [(1, False), (2, True), (4, True)])
+def test_sharded_layouts_world1(fixtures, golden, sb_blocks, zigzag):
+    """superblock ownership + packed column order of cspbo_block_build_sharded_ex (the layout the sharded
+    Cholesky factorises in place) reproduce the golden K_FF after un-permuting."""
+    from csp_bo_b200 import _lib
+    from csp_bo_b200.distributed import ShardedSymmetricBlock
+    from csp_bo_b200.packing import Pack
+    x2 = force_tuple(fixtures, "x2")
+    p = Pack(x2[0], x2[1], x2[2], x2[3])
+    for packed in (False, True):
+        sh = ShardedSymmetricBlock(p, _lib.KFF, sb_blocks=sb_blocks, zigzag=zigzag, packed_cols=packed)
+        sh.build(_lib.DOT, 2.0, scale=28.835 ** 2 * 2.0)
+        K = sh.gather_full().cpu().numpy()
+        assert max_norm_err(K, golden["dot_kff_x2x2"]) < 1e-10
+        sh.close()
+
+
+@pytest.mark.parametrize("n_atoms,sb_blocks", [(27, 1), (300, 4), (301, 8)])
+def test_sharded_cholesky_world1_matches_cusolver(n_atoms, sb_blocks):
+    """fit through the sharded path (packed-order build -> panel Cholesky with look-ahead -> solve) against the
+    dense single-call cuSOLVER fit of the same K; 1e-8 is the north_star tolerance on predictions."""
+    import torch
+    from csp_bo_b200 import _lib, gp, synthetic
+    from csp_bo_b200.distributed import ShardedSymmetricBlock, fit_alpha_sharded
+    from csp_bo_b200.packing import Pack, build_block
+    X = synthetic.force_set(n_atoms, seed=3)
+    p = Pack(X[0], X[1], X[2], X[3])
+    s2 = 18.555440586011372 ** 2 * 2.0
+    Kd, _ = build_block(_lib.DOT, _lib.KFF, p, p, 2.0, scale=s2, symmetric=True, device=True)
+    N = 3 * n_atoms
+    y = torch.from_numpy(np.random.default_rng(0).standard_normal(N)).cuda()
+    nf2 = (30.0 * 0.005) ** 2
+    ref, logdet = gp.fit_alpha(Kd.reshape(N, N).clone(), y, n_energy=0, noise_e=0.005, f_coef=30.0, return_logdet=True)
+    sh = ShardedSymmetricBlock(p, _lib.KFF, sb_blocks=sb_blocks, zigzag=True, packed_cols=True)
+    sh.build(_lib.DOT, 2.0, scale=s2)
+    alpha, chol = fit_alpha_sharded(sh, y, nf2, return_solver=True)
+    Ktest = Kd.reshape(N, N)[: min(N, 64)]
+    pr, pa = Ktest @ ref, Ktest @ alpha
+    assert float((pr - pa).abs().max() / pr.abs().max()) < 1e-8
+    assert abs(chol.logdet() - logdet) < 1e-8 * abs(logdet)
+    sh.close()
+
+
+def _chol_rank_main(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from csp_bo_b200 import _lib, gp, synthetic
+    from csp_bo_b200.distributed import ShardedSymmetricBlock, fit_alpha_sharded
+    from csp_bo_b200.packing import Pack, build_block
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    _lib.check(_lib.load().cspbo_set_device(rank))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        X = synthetic.force_set(500, seed=12)
+        p = Pack(X[0], X[1], X[2], X[3])
+        N = 1500
+        Kd, _ = build_block(_lib.DOT, _lib.KFF, p, p, 2.0, scale=700.0, symmetric=True, device=True)
+        y = torch.from_numpy(np.random.default_rng(0).standard_normal(N)).cuda()
+        ref = gp.fit_alpha(Kd.reshape(N, N).clone(), y, n_energy=0, noise_e=0.005, f_coef=30.0)
+        sh = ShardedSymmetricBlock(p, _lib.KFF, sb_blocks=4, zigzag=True, packed_cols=True)
+        sh.build(_lib.DOT, 2.0, scale=700.0)
+        alpha = fit_alpha_sharded(sh, y, (30.0 * 0.005) ** 2)
+        pr, pa = Kd.reshape(N, N)[:64] @ ref, Kd.reshape(N, N)[:64] @ alpha
+        out[rank] = float((pr - pa).abs().max() / pr.abs().max())
+        sh.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_cholesky_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_chol_rank_main, args=(2, 29631, out), nprocs=2, join=True)
+        assert len(out) == 2 and all(v < 1e-8 for v in out.values()), dict(out)
