@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 N_ATOMS = 6667
 SIGMA, SIGMA0, ZETA = 18.555440586011372, 0.01, 2.0
 FLOP_PER_PAIR = 32 * 24 + 100     # F_FF(d) = 2*16*d + 100 at d = 24
+FIT_SB_BLOCKS = 16                # panel width of the sharded Cholesky fit leg: 16 blocks x 8 atoms x 3 = 384 rows
 FP64_PEAK_FALLBACK = 37.03        # TFLOP/s, DMMA.8x8x4 issue-bound peak measured on this pool (profiles/fp64_peak_r01.json)
 
 
@@ -273,27 +274,46 @@ def run_ours(args):
     del outh
 
     # ---- GP fit wall time: K_FF(X,X) + noise -> Cholesky -> alpha  (gaussianprocess.py:105-127, opt=False)
+    # N = 1: dense build + one cuSOLVER potrf/potrs.  N > 1: the build is sharded by row panels in packed
+    # order and factorised in place by the sharded Cholesky (panel potrf/trsm on the owner, NCCL broadcast of the
+    # panel rows, trailing dgemm updates on every rank's own rows; csp_bo_b200/distributed.py)
     fit = None
     try:
         from csp_bo_b200 import gp
         y = torch.from_numpy(np.random.default_rng(0).standard_normal(3 * m)).cuda()
         fit_ms = []
-        for i in range(2):
-            barrier(); t0 = time.perf_counter()
-            if world == 1:
+        nf2 = (30.0 * 0.005) ** 2
+        if world == 1:
+            for i in range(2):
+                barrier(); t0 = time.perf_counter()
                 step(); Kfull = out.view(3 * m, 3 * m)
-            else:
-                sh.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
-                Kfull = sh.gather_full()        # NCCL all-gather of the row blocks, replicated Cholesky
-            torch.cuda.synchronize(); t1 = time.perf_counter()
-            alpha = gp.fit_alpha(Kfull, y, n_energy=0, noise_e=0.005, f_coef=30.0, overwrite=True)
-            torch.cuda.synchronize(); t2 = time.perf_counter()
-            fit_ms.append(((t2 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3))
-            del Kfull
-        fit = {"wall_ms": fit_ms[-1][0], "k_build_ms": fit_ms[-1][1], "cholesky_solve_ms": fit_ms[-1][2], "N": 3 * m,
-               "what": "K_FF + noise -> cuSOLVER potrf/potrs -> alpha; Cholesky replicated on every rank for N>1"}
+                torch.cuda.synchronize(); t1 = time.perf_counter()
+                alpha = gp.fit_alpha(Kfull, y, n_energy=0, noise_e=0.005, f_coef=30.0, overwrite=True)
+                torch.cuda.synchronize(); t2 = time.perf_counter()
+                fit_ms.append(((t2 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3))
+                del Kfull
+            how = "K_FF + noise -> cuSOLVER potrf/potrs -> alpha"
+        else:
+            from csp_bo_b200.distributed import ShardedSymmetricBlock, fit_alpha_sharded
+            shf = ShardedSymmetricBlock(full, _lib.KFF, sb_blocks=FIT_SB_BLOCKS, zigzag=True, packed_cols=True)
+            for i in range(3):
+                barrier(); t0 = time.perf_counter()
+                shf.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
+                torch.cuda.synchronize(); t1 = time.perf_counter()
+                alpha = fit_alpha_sharded(shf, y, nf2)
+                barrier(); t2 = time.perf_counter()
+                fit_ms.append(((t2 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3))
+            shf.close()
+            how = ("K_FF sharded by %d-row panels (packed order, zigzag owners) -> sharded Cholesky (owner potrf/trsm, "
+                   "NCCL panel broadcast, per-rank dgemm updates, look-ahead 1) -> potrs on the replicated factor" % (24 * FIT_SB_BLOCKS))
+        best = min(fit_ms[1:], key=lambda v: v[0])
+        tl = torch.tensor(list(best), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        fit = {"wall_ms": float(tl[0]), "k_build_ms": float(tl[1]), "cholesky_solve_ms": float(tl[2]), "N": 3 * m, "what": how,
+               "alpha_check": float(alpha.abs().sum())}
     except Exception as exc:
-        fit = {"error": str(exc)[:200]}
+        fit = {"error": str(exc)[:300]}
 
     # ---- one MD / validation step (config 1 of BASELINE.json): SO3 descriptor of a 192-atom Pt/H/O structure
     # + K* against a 16-energy + 409-force model + K*.alpha, through GaussianProcess.predict_structure.

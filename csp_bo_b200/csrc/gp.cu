@@ -279,7 +279,13 @@ static int stream_handles(cudaStream_t st, StreamHandles **out)
     std::lock_guard<std::mutex> lk(g_solver_mu);
     for (int i = 0; i < g_nsh; i++)
         if (g_sh[i].stream == st && g_sh[i].device == dev) { *out = &g_sh[i]; return CSPBO_OK; }
-    if (g_nsh >= 16) { set_error("too many distinct streams use the panel operations"); return CSPBO_E_ARG; }
+    if (g_nsh >= 16) {   // evict the oldest entry (its stream is most likely gone with its owner)
+        cublasDestroy(g_sh[0].blas);
+        cusolverDnDestroy(g_sh[0].solver);
+        cudaFree(g_sh[0].work);
+        for (int i = 1; i < g_nsh; i++) g_sh[i - 1] = g_sh[i];
+        g_nsh--;
+    }
     StreamHandles h = {st, dev, nullptr, nullptr, nullptr, 0};
     if (cublasCreate(&h.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return CSPBO_E_SOLVER; }
     if (cusolverDnCreate(&h.solver) != CUSOLVER_STATUS_SUCCESS) { cublasDestroy(h.blas); set_error("cusolverDnCreate failed"); return CSPBO_E_SOLVER; }

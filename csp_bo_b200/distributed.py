@@ -237,6 +237,19 @@ class _DeviceOps:
                                                   rows.stride(0), int(col0), int(nb), int(ncols), c_vp(stream)))
 
 
+_STREAMS = {}
+
+
+def _panel_streams():
+    """(panel, update) CUDA streams of the current device, shared by every ShardedCholesky of the process."""
+    import torch
+    dev = torch.cuda.current_device()
+    if dev not in _STREAMS:
+        lo, hi = torch.cuda.Stream.priority_range()
+        _STREAMS[dev] = (torch.cuda.Stream(priority=hi), torch.cuda.Stream(priority=lo))
+    return _STREAMS[dev]
+
+
 class ShardedCholesky:
     """In-place Cholesky K = U^T U of a symmetric matrix whose rows are distributed over the ranks by
     superblocks (panels) of `nbw` rows -- exactly what ShardedSymmetricBlock(..., packed_cols=True) leaves in
@@ -260,14 +273,13 @@ class ShardedCholesky:
         self.rank, self.world, self.zigzag, self.group = rank, world, bool(zigzag), group
         self.ops = ops if ops is not None else _DeviceOps()
         self.S = (self.N + self.nbw - 1) // self.nbw
+        self.max_chunk = 4      # neighbouring superblocks updated by one dgemm (world 1 only)
         self.cuda = bool(getattr(self.ops, "cuda", False))
         dev = local2d.device
         self.U = torch.empty((self.N, self.N), dtype=torch.float64, device=dev)
         self.info = torch.zeros(max(self.S, 1), dtype=torch.int32, device=dev)
         if self.cuda:
-            lo, hi = torch.cuda.Stream.priority_range()
-            self.s_panel = torch.cuda.Stream(priority=hi)
-            self.s_update = torch.cuda.Stream(priority=lo)
+            self.s_panel, self.s_update = _panel_streams()
         self._src = [torch.distributed.get_global_rank(group, r) if (group is not None and world > 1) else r
                      for r in range(world)]
 
@@ -338,12 +350,20 @@ class ShardedCholesky:
             with on_update():
                 if self.cuda:
                     self.s_update.wait_event(e_bcast)
-                for t in mine:
-                    if t <= s or (ahead and t == s + 1):
-                        continue
+                todo = [t for t in mine if t > s and not (ahead and t == s + 1)]
+                i = 0
+                while i < len(todo):
+                    # superblocks that are neighbours in the matrix AND in this rank's buffer (world 1) share one
+                    # dgemm: the few extra nbw x nbw blocks left of their diagonals are never read again
+                    j = i + 1
+                    while j < len(todo) and j - i < self.max_chunk and todo[j] == todo[j - 1] + 1 and \
+                            todo[j] // W == todo[j - 1] // W + 1:
+                        j += 1
+                    t = todo[i]
                     l0, c0 = (t // W) * nbw, t * nbw
-                    ht = min(nbw, N - c0)
+                    ht = min((todo[j - 1] + 1) * nbw, N) - c0
                     ops.panel_update(U[r0:r0 + h], h, loc[l0:l0 + ht], c0, ht, N, su)
+                    i = j
                 if self.cuda:
                     e_bulk[s] = torch.cuda.Event()
                     e_bulk[s].record(self.s_update)
