@@ -268,7 +268,16 @@ struct StreamHandles {
     cusolverDnHandle_t solver;
     double *work;
     int lwork;
+    double *inv;     // [hcap x hcap] inverse of the current diagonal factor
+    double *eye;     // [hcap x hcap] identity
+    int hcap;
 };
+
+__global__ void set_identity_kernel(double *A, int h)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < h * h) A[i] = (i / h == i % h) ? 1.0 : 0.0;
+}
 static StreamHandles g_sh[16];
 static int g_nsh = 0;
 
@@ -283,10 +292,12 @@ static int stream_handles(cudaStream_t st, StreamHandles **out)
         cublasDestroy(g_sh[0].blas);
         cusolverDnDestroy(g_sh[0].solver);
         cudaFree(g_sh[0].work);
+        cudaFree(g_sh[0].inv);
+        cudaFree(g_sh[0].eye);
         for (int i = 1; i < g_nsh; i++) g_sh[i - 1] = g_sh[i];
         g_nsh--;
     }
-    StreamHandles h = {st, dev, nullptr, nullptr, nullptr, 0};
+    StreamHandles h = {st, dev, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0};
     if (cublasCreate(&h.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return CSPBO_E_SOLVER; }
     if (cusolverDnCreate(&h.solver) != CUSOLVER_STATUS_SUCCESS) { cublasDestroy(h.blas); set_error("cusolverDnCreate failed"); return CSPBO_E_SOLVER; }
     cublasSetStream(h.blas, st);
@@ -344,5 +355,63 @@ extern "C" int cspbo_gp_panel_update(const double *panel, long long ldp, int h, 
                                    panel + col0, (int)ldp, &one, rows + col0, (int)ld);
     if (b != CUBLAS_STATUS_SUCCESS) { set_error("gemm failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
     g_launches++;
+    return CSPBO_OK;
+}
+
+
+extern "C" int cspbo_gp_stream_sm_target(void *stream, int sm_count)
+{
+    StreamHandles *sh;
+    int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
+    if (rc) return rc;
+    if (cublasSetSmCountTarget(sh->blas, sm_count) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetSmCountTarget(%d) failed", sm_count); return CSPBO_E_SOLVER; }
+    return CSPBO_OK;
+}
+
+extern "C" int cspbo_gp_panel_factor_to(double *rows, long long ld, long long col0, int h, long long ncols, double *out,
+                                        long long ldo, int *info_dev, void *stream)
+{
+    if (!rows || !out || !info_dev || h <= 0 || col0 < 0 || col0 + h > ncols || ncols > ld || ncols > ldo) { set_error("gp_panel_factor_to: bad argument"); return CSPBO_E_ARG; }
+    StreamHandles *sh;
+    int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
+    if (rc) return rc;
+    double *D = rows + col0;
+    int lwork = 0;
+    cusolverStatus_t s = cusolverDnDpotrf_bufferSize(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, &lwork);
+    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
+    if (lwork > sh->lwork || h > sh->hcap) {
+        CSPBO_CUDA(cudaStreamSynchronize(sh->stream));
+        if (lwork > sh->lwork) {
+            cudaFree(sh->work); sh->work = nullptr; sh->lwork = 0;
+            CSPBO_CUDA(cudaMalloc(&sh->work, (size_t)lwork * sizeof(double)));
+            sh->lwork = lwork;
+        }
+        if (h > sh->hcap) {
+            cudaFree(sh->inv); cudaFree(sh->eye); sh->inv = sh->eye = nullptr; sh->hcap = 0;
+            CSPBO_CUDA(cudaMalloc(&sh->inv, (size_t)h * h * sizeof(double)));
+            CSPBO_CUDA(cudaMalloc(&sh->eye, (size_t)h * h * sizeof(double)));
+            sh->hcap = h;
+        }
+    }
+    s = cusolverDnDpotrf(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, sh->work, sh->lwork, info_dev);
+    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf failed (status %d)", (int)s); return CSPBO_E_SOLVER; }
+    // the factored diagonal block travels as it is (its strict other triangle is never read)
+    CSPBO_CUDA(cudaMemcpy2DAsync(out + col0, (size_t)ldo * sizeof(double), D, (size_t)ld * sizeof(double), (size_t)h * sizeof(double),
+                                 (size_t)h, cudaMemcpyDeviceToDevice, sh->stream));
+    const long long rest = ncols - col0 - h;
+    if (rest > 0) {
+        // rest of the panel through the explicit inverse of the h x h factor: one small triangular solve
+        // against the identity and one wide trmm (tensor-pipe bound) instead of a wide, latency-bound trsm:
+        //   column-major: OUT (rest x h) = B (rest x h) . (L_ss^-1)^T
+        const double one = 1.0;
+        set_identity_kernel<<<(h * h + 255) / 256, 256, 0, sh->stream>>>(sh->inv, h);
+        cublasStatus_t b = cublasDtrsm(sh->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, h, h,
+                                       &one, D, (int)ld, sh->inv, h);
+        if (b != CUBLAS_STATUS_SUCCESS) { set_error("trsm(identity) failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
+        b = cublasDtrmm(sh->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)rest, h, &one,
+                        sh->inv, h, D + h, (int)ld, out + col0 + h, (int)ldo);
+        if (b != CUBLAS_STATUS_SUCCESS) { set_error("trmm failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
+    }
+    g_launches += 2;
     return CSPBO_OK;
 }

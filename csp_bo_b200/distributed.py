@@ -12,6 +12,7 @@ no collective has moved the matrix.  NCCL is used for the plumbing only (handle 
 the optional gather of the row blocks for a replicated Cholesky, the alpha broadcast).
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -232,6 +233,18 @@ class _DeviceOps:
         _lib.check(self.lib.cspbo_gp_panel_factor(c_vp(rows.data_ptr()), rows.stride(0), int(col0), int(h), int(ncols),
                                                   c_vp(info.data_ptr()), c_vp(stream)))
 
+    def panel_factor_to(self, rows, col0, h, ncols, out, info, stream):
+        """factorise the panel held in `rows` and leave the finished rows in `out` (the replicated factor)."""
+        if os.environ.get("CSPBO_CHOL_TRSM"):       # tuning knob: plain trsm instead of inverse + trmm
+            self.panel_factor(rows, col0, h, ncols, info, stream)
+            out.copy_(rows, non_blocking=True)
+            return
+        _lib.check(self.lib.cspbo_gp_panel_factor_to(c_vp(rows.data_ptr()), rows.stride(0), int(col0), int(h), int(ncols),
+                                                     c_vp(out.data_ptr()), out.stride(0), c_vp(info.data_ptr()), c_vp(stream)))
+
+    def sm_target(self, stream, count):
+        _lib.check(self.lib.cspbo_gp_stream_sm_target(c_vp(stream), int(count)))
+
     def panel_update(self, panel, h, rows, col0, nb, ncols, stream):
         _lib.check(self.lib.cspbo_gp_panel_update(c_vp(panel.data_ptr()), panel.stride(0), int(h), c_vp(rows.data_ptr()),
                                                   rows.stride(0), int(col0), int(nb), int(ncols), c_vp(stream)))
@@ -274,6 +287,7 @@ class ShardedCholesky:
         self.ops = ops if ops is not None else _DeviceOps()
         self.S = (self.N + self.nbw - 1) // self.nbw
         self.max_chunk = 4      # neighbouring superblocks updated by one dgemm (world 1 only)
+        self.bulk_sms = int(os.environ.get("CSPBO_BULK_SMS", "0"))
         self.cuda = bool(getattr(self.ops, "cuda", False))
         dev = local2d.device
         self.U = torch.empty((self.N, self.N), dtype=torch.float64, device=dev)
@@ -315,6 +329,8 @@ class ShardedCholesky:
             self.s_update.wait_stream(cur)
         e_bulk = {}
         mine = [s for s in range(S) if self._owner(s) == me]
+        if self.cuda and self.bulk_sms:
+            ops.sm_target(su, self.bulk_sms)    # leave a few SMs to the latency-critical panel stream
 
         class _Null:
             def __enter__(self): return self
@@ -331,8 +347,7 @@ class ShardedCholesky:
                     l0 = (s // W) * nbw
                     if self.cuda and s >= 2:
                         self.s_panel.wait_event(e_bulk[s - 2])   # panels <= s-2 applied in bulk; s-1 by the look-ahead
-                    ops.panel_factor(loc[l0:l0 + h], r0, h, N, self.info[s:s + 1], sp)
-                    U[r0:r0 + h].copy_(loc[l0:l0 + h], non_blocking=True)
+                    ops.panel_factor_to(loc[l0:l0 + h], r0, h, N, U[r0:r0 + h], self.info[s:s + 1], sp)
                 if W > 1:
                     torch.distributed.broadcast(U[r0:r0 + h], src=self._src[o], group=self.group)
                 if self.cuda:

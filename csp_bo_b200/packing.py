@@ -6,6 +6,7 @@ A `Pack` is a stacked "energy" tuple (X, ELE, indices) or "force" tuple (X, dXdR
 the reference wrappers (cspbo/kernels/dot_kernel.py:207-216).
 """
 import ctypes
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -126,7 +127,7 @@ def pack_energy(X, cache=True):
     return p
 
 
-HOST_ROW_CLASSES = 6     # row classes of packs that feed large host-bound K_FF builds (see cspbo_pack_create_ex)
+HOST_ROW_CLASSES = int(os.environ.get("CSPBO_HOST_ROW_CLASSES", "6"))     # row classes of packs that feed large host-bound K_FF builds (see cspbo_pack_create_ex)
 
 
 def pack_force(X, cache=True, row_range=None, row_classes=1):

@@ -266,6 +266,15 @@ int cspbo_gp_panel_factor(double *rows, long long ld, long long col0, int h, lon
                           void *stream);
 int cspbo_gp_panel_update(const double *panel, long long ldp, int h, double *rows, long long ld, long long col0,
                           int nb, long long ncols, void *stream);
+/* panel_factor_to: like panel_factor, but the finished panel rows are written to `out` (leading dimension ldo, same
+ * column positions) -- the replicated factor the owner broadcasts from -- and the rest of the panel is obtained through
+ * the explicit inverse of the h x h diagonal factor (small trsm against the identity + one wide trmm) instead of a
+ * wide, latency-bound trsm.  Only the diagonal block of `rows` is modified. */
+int cspbo_gp_panel_factor_to(double *rows, long long ld, long long col0, int h, long long ncols, double *out,
+                             long long ldo, int *info_dev, void *stream);
+/* limit the cuBLAS kernels issued on `stream` by the panel operations to sm_count SMs (0 = all): keeps a few SMs
+ * free for the latency-critical panel stream while the bulk updates run (cublasSetSmCountTarget). */
+int cspbo_gp_stream_sm_target(void *stream, int sm_count);
 /* pred[n] = Kstar[n, N] . alpha[N]    gaussianprocess.py:140,359 */
 int cspbo_gp_predict(const double *Kstar, int n, int N, const double *alpha, double *pred);
 

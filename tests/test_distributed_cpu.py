@@ -74,6 +74,10 @@ class TorchOps:
             R = rows[:h, col0 + h:ncols]
             R.copy_(torch.linalg.solve_triangular(Uss.T, R, upper=False))
 
+    def panel_factor_to(self, rows, col0, h, ncols, out, info, stream):
+        self.panel_factor(rows, col0, h, ncols, info, stream)
+        out.copy_(rows)
+
     def panel_update(self, panel, h, rows, col0, nb, ncols, stream):
         rows[:nb, col0:ncols] -= panel[:h, col0:col0 + nb].T @ panel[:h, col0:ncols]
 
