@@ -5,6 +5,7 @@
 #include <cublas_v2.h>
 #include <cusolverDn.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -18,14 +19,13 @@ __global__ void add_noise_kernel(double *K, int N, int n_energy, double ne2, dou
 }
 
 // pred[r] = sum_j Kstar[r, j] alpha[j].  HBM-bound: every K* byte is read exactly once, 2 flop per 8 bytes.
-// One warp owns one (row, column chunk) piece of kGemvChunk columns and keeps kGemvUnroll 128-bit streaming
+// One warp owns one (row, column chunk) piece of CHUNK columns and keeps UNROLL 128-bit streaming
 // loads per lane in flight (Little: ~6.5 MB must be in flight chip-wide); chunks give a row of a small-n
 // K* (one MD step: n = 577) enough warps to cover all 148 SMs.  Partial sums go to partial[chunk][row]
 // and are added in chunk order by gemv_reduce_kernel, so the result is deterministic (no atomics).
-constexpr int kGemvChunk = 2048;
-constexpr int kGemvUnroll = 4;
 constexpr int kGemvWarps = 8;
 
+template <int UNROLL, int CHUNK>
 __global__ void __launch_bounds__(kGemvWarps * 32)
 predict_gemv_kernel(const double *__restrict__ Ks, int n, int N, const double *__restrict__ alpha,
                     double *__restrict__ out, int nchunks)
@@ -33,39 +33,42 @@ predict_gemv_kernel(const double *__restrict__ Ks, int n, int N, const double *_
     const int lane = threadIdx.x & 31;
     const long long piece = (long long)blockIdx.x * kGemvWarps + (threadIdx.x >> 5);
     if (piece >= (long long)n * nchunks) return;
-    // consecutive warps take consecutive chunks of the same row: a CTA streams one contiguous 128 KB run
+    // consecutive warps take consecutive chunks of the same row: a CTA streams one contiguous run
     const int row = (int)(piece / nchunks), chunk = (int)(piece - (long long)row * nchunks);
-    const int c0 = chunk * kGemvChunk;
-    const int len = min(kGemvChunk, N - c0);
+    const int c0 = chunk * CHUNK;
+    const int len = min(CHUNK, N - c0);
     const double *kr = Ks + (long long)row * N + c0;
     const double *ar = alpha + c0;
-    double acc[kGemvUnroll];
+    double acc[UNROLL];
 #pragma unroll
-    for (int u = 0; u < kGemvUnroll; u++) acc[u] = 0.0;
+    for (int u = 0; u < UNROLL; u++) acc[u] = 0.0;
     // peel to 16-byte alignment of the K* row piece (rows of an odd-N matrix alternate)
     const int head = (int)((reinterpret_cast<size_t>(kr) >> 3) & 1) && len > 0 ? 1 : 0;
     if (head && lane == 0) acc[0] = kr[0] * __ldg(ar);
     const int body = (len - head) >> 1;   // double2 elements
     const double2 *k2 = reinterpret_cast<const double2 *>(kr + head);
     const double *a1 = ar + head;
+    auto ldk = [](const double2 *q) { return __ldcs(q); };   // streaming: every K* byte is used once
     int j = lane;
-    for (; j + (kGemvUnroll - 1) * 32 < body; j += kGemvUnroll * 32) {
-        double2 kv[kGemvUnroll];
+    for (; j + (UNROLL - 1) * 32 < body; j += UNROLL * 32) {
+        double2 kv[UNROLL];
 #pragma unroll
-        for (int u = 0; u < kGemvUnroll; u++) kv[u] = __ldcs(k2 + j + u * 32);
+        for (int u = 0; u < UNROLL; u++) kv[u] = ldk(k2 + j + u * 32);
 #pragma unroll
-        for (int u = 0; u < kGemvUnroll; u++) {
+        for (int u = 0; u < UNROLL; u++) {
             acc[u] = fma(kv[u].x, __ldg(a1 + 2 * (j + u * 32)), acc[u]);
             acc[u] = fma(kv[u].y, __ldg(a1 + 2 * (j + u * 32) + 1), acc[u]);
         }
     }
     for (; j < body; j += 32) {
-        const double2 kv = __ldcs(k2 + j);
+        const double2 kv = ldk(k2 + j);
         acc[0] = fma(kv.x, __ldg(a1 + 2 * j), acc[0]);
         acc[0] = fma(kv.y, __ldg(a1 + 2 * j + 1), acc[0]);
     }
     if (((len - head) & 1) && lane == 0) acc[1] = fma(kr[len - 1], __ldg(ar + len - 1), acc[1]);
-    double s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) s += acc[u];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) out[(long long)chunk * n + row] = s;
@@ -190,16 +193,22 @@ extern "C" int cspbo_gp_predict(const double *Kstar, int n, int N, const double 
 {
     if (n < 0 || N < 0 || (n > 0 && (!Kstar || !pred)) || (N > 0 && !alpha)) { set_error("gp_predict: bad argument"); return CSPBO_E_ARG; }
     if (n == 0) return CSPBO_OK;
-    const int nchunks = (N + kGemvChunk - 1) / kGemvChunk;
+    // 8 x 128-bit loads in flight per lane; 4096-column chunks unless that leaves the 148 SMs short of warps.
+    // Measured on B200 (tools/gemv_probe.py): 4 loads/2048 -> 4.6 TB/s, 8/2048 -> 5.6, 8/4096 -> 5.75 (20001^2), 6.5 TB/s at 40002^2
+    typedef void (*kern_t)(const double *, int, int, const double *, double *, int);
+    const bool small = (long long)n * ((N + 4095) / 4096) < 148LL * 8 * 4;
+    kern_t kern = small ? predict_gemv_kernel<8, 2048> : predict_gemv_kernel<8, 4096>;
+    const int chunk = small ? 2048 : 4096;
+    const int nchunks = (N + chunk - 1) / chunk;
     const long long pieces = (long long)n * nchunks;
     const unsigned grid = (unsigned)((pieces + kGemvWarps - 1) / kGemvWarps);
     if (nchunks <= 1) {
-        predict_gemv_kernel<<<grid, kGemvWarps * 32>>>(Kstar, n, N, alpha, pred, 1);
+        kern<<<grid, kGemvWarps * 32>>>(Kstar, n, N, alpha, pred, 1);
     } else {
         void *partial = nullptr;
         int rc = scratch_get(SCRATCH_GEMV, (size_t)pieces * sizeof(double), &partial);
         if (rc) return rc;
-        predict_gemv_kernel<<<grid, kGemvWarps * 32>>>(Kstar, n, N, alpha, static_cast<double *>(partial), nchunks);
+        kern<<<grid, kGemvWarps * 32>>>(Kstar, n, N, alpha, static_cast<double *>(partial), nchunks);
         g_launches++;
         gemv_reduce_kernel<<<(n + 255) / 256, 256>>>(static_cast<const double *>(partial), n, nchunks, pred);
     }

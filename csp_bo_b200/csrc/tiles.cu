@@ -185,6 +185,8 @@ __device__ __forceinline__ Weights pair_weights(double c, bool valid, const Tile
         else if (MODE == MODE_KEF) { w.w1 = z * cm1; w.w2 = 0.0; }
         else { w.w1 = cz + p.sigma02; w.w2 = 0.0; }  // sigma2 applied through p.scale
     } else {
+                // (a 256-entry-table exp with a degree-4 polynomial, 9 instead of 17 FP64 instructions, was measured
+        // SLOWER here: K_EE RBF 18.3 -> 21.1 ms; the dependent L1 lookup is not hidden at 3 warps per scheduler)
         const double K = p.sigma2 * exp(-(1.0 - cz) * p.inv2l2);
         const double dKdD = K * p.inv2l2;
         const double gl = (cz - 1.0) * p.inv_l3 + 2.0 * p.inv_l;  // (D-1)/l^3 + 2/l
@@ -630,9 +632,17 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.split = (diag || a_all * p.b_nblk < 32LL * sms) ? 1 : 0;
     // B tiles per stage: a whole (block, species) run if it fits in 36 KB
     const size_t tile_bytes = (size_t)b->tile_doubles * sizeof(double);
-    const int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, kSmemChunk / tile_bytes));
+    size_t stage_bytes = kSmemChunk;
+    {
+        static const char *kb_ee = getenv("CSPBO_STAGE_KB_EE"), *kb_ef = getenv("CSPBO_STAGE_KB_EF");
+        if (mode == MODE_KEE && kb_ee) stage_bytes = (size_t)atoi(kb_ee) * 1024;
+        if (mode == MODE_KEF && kb_ef) stage_bytes = (size_t)atoi(kb_ef) * 1024;
+    }
+    const int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, stage_bytes / tile_bytes));
     p.tbc = tbc;
-    const size_t smem = std::max<size_t>(2 * (size_t)tbc * tile_bytes, (size_t)(kMaxWarps - 1) * 32 * 36 * sizeof(double)) +
+    // the stage buffers double as the scratch of the split-mode reduction (NACC accumulators per thread of 3 warps)
+    const int nacc = 2 * (mode == MODE_KFF ? 9 : (mode == MODE_KEF ? 3 : 1)) * (fam == FAM_RBF_GRAD ? 2 : 1);
+    const size_t smem = std::max<size_t>(2 * (size_t)tbc * tile_bytes, (size_t)(kMaxWarps - 1) * 32 * nacc * sizeof(double)) +
                         2 * sizeof(unsigned long long);
     p.strip = std::max(1, std::min(kStrip, p.split ? a_mine : (a_mine + nwarps - 1) / nwarps));
     // Keep the packed tiles L2-resident while the write-once output streams through: an access-policy
