@@ -338,18 +338,31 @@ class ShardedCholesky:
         on_panel = (lambda: torch.cuda.stream(self.s_panel)) if self.cuda else _Null
         on_update = (lambda: torch.cuda.stream(self.s_update)) if self.cuda else _Null
 
+        trace = self.trace = [] if (self.cuda and os.environ.get("CSPBO_CHOL_TRACE")) else None
+
+        def mark():
+            if trace is None:
+                return None
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(self.s_panel)
+            return e
+
         for s in range(S):
             o = self._owner(s)
             r0 = s * nbw
             h = min(nbw, N - r0)
             with on_panel():
+                t0 = mark()
                 if me == o:
                     l0 = (s // W) * nbw
                     if self.cuda and s >= 2:
                         self.s_panel.wait_event(e_bulk[s - 2])   # panels <= s-2 applied in bulk; s-1 by the look-ahead
+                    t0 = mark()
                     ops.panel_factor_to(loc[l0:l0 + h], r0, h, N, U[r0:r0 + h], self.info[s:s + 1], sp)
+                t1 = mark()
                 if W > 1:
                     torch.distributed.broadcast(U[r0:r0 + h], src=self._src[o], group=self.group)
+                t2 = mark()
                 if self.cuda:
                     e_bcast = torch.cuda.Event()
                     e_bcast.record(self.s_panel)
@@ -361,7 +374,14 @@ class ShardedCholesky:
                     t = s + 1
                     l0, c0 = (t // W) * nbw, t * nbw
                     ht = min(nbw, N - c0)
+                    t3 = mark()
                     ops.panel_update(U[r0:r0 + h], h, loc[l0:l0 + ht], c0, ht, N, sp)
+                    if trace is not None:
+                        trace.append(("lookahead", s, t3, mark()))
+                if trace is not None:
+                    if me == o:
+                        trace.append(("factor", s, t0, t1))
+                    trace.append(("bcast_owner" if me == o else "bcast_wait", s, t1, t2))
             with on_update():
                 if self.cuda:
                     self.s_update.wait_event(e_bcast)
@@ -388,6 +408,13 @@ class ShardedCholesky:
             cur.wait_stream(self.s_panel)
             cur.wait_stream(self.s_update)
         return self
+
+    def trace_summary(self):
+        """Per-phase device time on the panel stream (CSPBO_CHOL_TRACE=1), ms summed over panels."""
+        out = {}
+        for name, s, a, b in (self.trace or []):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
 
     def check(self):
         """Raise CspboError(CSPBO_E_NOTPD) if a diagonal block was not positive definite (one host sync)."""

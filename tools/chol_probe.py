@@ -61,6 +61,8 @@ for G in sbs:
         ap = chol.solve(y.reshape(sh.m, 3)[order].reshape(-1))
         alpha = torch.empty((sh.m, 3), dtype=torch.float64, device="cuda"); alpha[order] = ap.reshape(sh.m, 3)
         sync(); t4 = time.perf_counter()
+        if os.environ.get("CSPBO_CHOL_TRACE") and it == 2:
+            print(json.dumps(dict(rank=rank, G=G, trace={k: round(v, 2) for k, v in chol.trace_summary().items()})), flush=True)
         rec.append(dict(build=(t1 - t0) * 1e3, alloc_noise=(t2 - t1) * 1e3, factor=(t3 - t2) * 1e3, solve=(t4 - t3) * 1e3, total=(t4 - t0) * 1e3))
         del chol
     err = float(((Ktest @ ref) - (Ktest @ alpha.reshape(-1))).abs().max() / (Ktest @ ref).abs().max()) if ref is not None else None
