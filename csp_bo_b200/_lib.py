@@ -87,9 +87,9 @@ SIGNATURES = {
     "cspbo_gp_cho_solve": [c_vp, c_int, c_vp, c_int],
     "cspbo_gp_cholesky_inverse": [c_vp, c_int, c_vp],
     "cspbo_gp_predict": [c_vp, c_int, c_int, c_vp, c_vp],
-    "cspbo_gp_panel_factor": [c_vp, c_ll, c_ll, c_int, c_ll, c_vp, c_vp],
-    "cspbo_gp_panel_update": [c_vp, c_ll, c_int, c_vp, c_ll, c_ll, c_int, c_ll, c_vp],
-    "cspbo_gp_panel_factor_to": [c_vp, c_ll, c_ll, c_int, c_ll, c_vp, c_ll, c_vp, c_vp],
+    "cspbo_gp_chol_diag": [c_vp, c_ll, c_int, c_vp, c_vp, c_vp],
+    "cspbo_gp_chol_apply_inv": [c_vp, c_int, c_vp, c_ll, c_ll, c_vp, c_ll, c_vp],
+    "cspbo_gp_chol_update": [c_vp, c_ll, c_int, c_ll, c_vp, c_ll, c_vp, c_ll, c_int, c_vp],
     "cspbo_gp_stream_sm_target": [c_vp, c_int],
 }
 _RESTYPE = {"cspbo_last_error": ctypes.c_char_p, "cspbo_launch_count": c_ll, "cspbo_pack_bytes": c_ll,

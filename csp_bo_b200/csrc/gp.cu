@@ -277,9 +277,6 @@ struct StreamHandles {
     cusolverDnHandle_t solver;
     double *work;
     int lwork;
-    double *inv;     // [hcap x hcap] inverse of the current diagonal factor
-    double *eye;     // [hcap x hcap] identity
-    int hcap;
 };
 
 __global__ void set_identity_kernel(double *A, int h)
@@ -301,12 +298,10 @@ static int stream_handles(cudaStream_t st, StreamHandles **out)
         cublasDestroy(g_sh[0].blas);
         cusolverDnDestroy(g_sh[0].solver);
         cudaFree(g_sh[0].work);
-        cudaFree(g_sh[0].inv);
-        cudaFree(g_sh[0].eye);
         for (int i = 1; i < g_nsh; i++) g_sh[i - 1] = g_sh[i];
         g_nsh--;
     }
-    StreamHandles h = {st, dev, nullptr, nullptr, nullptr, 0, nullptr, nullptr, 0};
+    StreamHandles h = {st, dev, nullptr, nullptr, nullptr, 0};
     if (cublasCreate(&h.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return CSPBO_E_SOLVER; }
     if (cusolverDnCreate(&h.solver) != CUSOLVER_STATUS_SUCCESS) { cublasDestroy(h.blas); set_error("cusolverDnCreate failed"); return CSPBO_E_SOLVER; }
     cublasSetStream(h.blas, st);
@@ -318,55 +313,67 @@ static int stream_handles(cudaStream_t st, StreamHandles **out)
 
 }  // namespace cspbo
 
-extern "C" int cspbo_gp_panel_factor(double *rows, long long ld, long long col0, int h, long long ncols, int *info_dev,
-                                     void *stream)
+// D: h x h symmetric diagonal block (row-major, leading dimension ld) -> its factor in place (row-major upper ==
+// column-major lower, cuSOLVER potrf) and inv[h*h] = the inverse of that factor (trsm against the identity).
+extern "C" int cspbo_gp_chol_diag(double *D, long long ld, int h, double *inv, int *info_dev, void *stream)
 {
-    if (!rows || !info_dev || h <= 0 || col0 < 0 || col0 + h > ncols || ncols > ld) { set_error("gp_panel_factor: bad argument"); return CSPBO_E_ARG; }
+    if (!D || !inv || !info_dev || h <= 0 || ld < h) { set_error("gp_chol_diag: bad argument"); return CSPBO_E_ARG; }
     StreamHandles *sh;
     int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
     if (rc) return rc;
-    // row-major upper factor of the symmetric diagonal block == column-major lower factor
-    double *D = rows + col0;
     int lwork = 0;
     cusolverStatus_t s = cusolverDnDpotrf_bufferSize(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, &lwork);
     if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
     if (lwork > sh->lwork) {
-        if (sh->work) { CSPBO_CUDA(cudaStreamSynchronize(sh->stream)); cudaFree(sh->work); sh->work = nullptr; sh->lwork = 0; }
+        CSPBO_CUDA(cudaStreamSynchronize(sh->stream));
+        cudaFree(sh->work); sh->work = nullptr; sh->lwork = 0;
         CSPBO_CUDA(cudaMalloc(&sh->work, (size_t)lwork * sizeof(double)));
         sh->lwork = lwork;
     }
     s = cusolverDnDpotrf(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, sh->work, sh->lwork, info_dev);
     if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf failed (status %d)", (int)s); return CSPBO_E_SOLVER; }
-    const long long rest = ncols - col0 - h;
-    if (rest > 0) {
-        // U[s, rest] = U_ss^-T K[s, rest]; column-major: B (rest x h) <- B L_ss^-T
-        const double one = 1.0;
-        cublasStatus_t b = cublasDtrsm(sh->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
-                                       (int)rest, h, &one, D, (int)ld, D + h, (int)ld);
-        if (b != CUBLAS_STATUS_SUCCESS) { set_error("trsm failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
-    }
+    const double one = 1.0;
+    set_identity_kernel<<<(h * h + 255) / 256, 256, 0, sh->stream>>>(inv, h);
+    cublasStatus_t b = cublasDtrsm(sh->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, h, h, &one,
+                                   D, (int)ld, inv, h);
+    if (b != CUBLAS_STATUS_SUCCESS) { set_error("trsm(identity) failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
+    g_launches += 2;
+    return CSPBO_OK;
+}
+
+// dst[h, w] = U_ss^-T src[h, w] (row-major views with leading dimensions ldb / ldc): the panel rows right of the
+// diagonal block, through the explicit inverse (one wide, tensor-pipe bound trmm instead of a latency-bound trsm).
+extern "C" int cspbo_gp_chol_apply_inv(const double *inv, int h, const double *src, long long ldb, long long w, double *dst,
+                                       long long ldc, void *stream)
+{
+    if (!inv || !src || !dst || h <= 0 || w < 0 || ldb < w || ldc < w) { set_error("gp_chol_apply_inv: bad argument"); return CSPBO_E_ARG; }
+    if (w == 0) return CSPBO_OK;
+    StreamHandles *sh;
+    int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
+    if (rc) return rc;
+    const double one = 1.0;   // column-major: DST (w x h) = SRC (w x h) . (L_ss^-1)^T
+    cublasStatus_t b = cublasDtrmm(sh->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)w, h, &one,
+                                   inv, h, src, (int)ldb, dst, (int)ldc);
+    if (b != CUBLAS_STATUS_SUCCESS) { set_error("trmm failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
     g_launches++;
     return CSPBO_OK;
 }
 
-extern "C" int cspbo_gp_panel_update(const double *panel, long long ldp, int h, double *rows, long long ld, long long col0,
-                                     int nb, long long ncols, void *stream)
+// C[nb, w] -= A[h, nb]^T . B[h, w]  (row-major views): every trailing update of the factorisation.
+extern "C" int cspbo_gp_chol_update(double *C, long long ldc, int nb, long long w, const double *A, long long lda, const double *B,
+                                    long long ldb, int h, void *stream)
 {
-    if (!panel || !rows || h <= 0 || nb <= 0 || col0 < 0 || col0 + nb > ncols || ncols > ld || ncols > ldp) { set_error("gp_panel_update: bad argument"); return CSPBO_E_ARG; }
+    if (!C || !A || !B || h <= 0 || nb < 0 || w < 0 || ldc < w || lda < nb || ldb < w) { set_error("gp_chol_update: bad argument"); return CSPBO_E_ARG; }
+    if (nb == 0 || w == 0) return CSPBO_OK;
     StreamHandles *sh;
     int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
     if (rc) return rc;
-    // rows[0:nb, col0:ncols] -= panel[0:h, col0:col0+nb]^T panel[0:h, col0:ncols]
-    // column-major: C (nt x nb) -= B (nt x h) A^T, A = the first nb rows of B
-    const double minus = -1.0, one = 1.0;
-    const long long nt = ncols - col0;
-    cublasStatus_t b = cublasDgemm(sh->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)nt, nb, h, &minus, panel + col0, (int)ldp,
-                                   panel + col0, (int)ldp, &one, rows + col0, (int)ld);
+    const double minus = -1.0, one = 1.0;   // column-major: C (w x nb) -= B (w x h) . A (nb x h)^T
+    cublasStatus_t b = cublasDgemm(sh->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)w, nb, h, &minus, B, (int)ldb, A, (int)lda, &one, C, (int)ldc);
     if (b != CUBLAS_STATUS_SUCCESS) { set_error("gemm failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
     g_launches++;
     return CSPBO_OK;
 }
-
 
 extern "C" int cspbo_gp_stream_sm_target(void *stream, int sm_count)
 {
@@ -374,53 +381,5 @@ extern "C" int cspbo_gp_stream_sm_target(void *stream, int sm_count)
     int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
     if (rc) return rc;
     if (cublasSetSmCountTarget(sh->blas, sm_count) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetSmCountTarget(%d) failed", sm_count); return CSPBO_E_SOLVER; }
-    return CSPBO_OK;
-}
-
-extern "C" int cspbo_gp_panel_factor_to(double *rows, long long ld, long long col0, int h, long long ncols, double *out,
-                                        long long ldo, int *info_dev, void *stream)
-{
-    if (!rows || !out || !info_dev || h <= 0 || col0 < 0 || col0 + h > ncols || ncols > ld || ncols > ldo) { set_error("gp_panel_factor_to: bad argument"); return CSPBO_E_ARG; }
-    StreamHandles *sh;
-    int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
-    if (rc) return rc;
-    double *D = rows + col0;
-    int lwork = 0;
-    cusolverStatus_t s = cusolverDnDpotrf_bufferSize(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, &lwork);
-    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
-    if (lwork > sh->lwork || h > sh->hcap) {
-        CSPBO_CUDA(cudaStreamSynchronize(sh->stream));
-        if (lwork > sh->lwork) {
-            cudaFree(sh->work); sh->work = nullptr; sh->lwork = 0;
-            CSPBO_CUDA(cudaMalloc(&sh->work, (size_t)lwork * sizeof(double)));
-            sh->lwork = lwork;
-        }
-        if (h > sh->hcap) {
-            cudaFree(sh->inv); cudaFree(sh->eye); sh->inv = sh->eye = nullptr; sh->hcap = 0;
-            CSPBO_CUDA(cudaMalloc(&sh->inv, (size_t)h * h * sizeof(double)));
-            CSPBO_CUDA(cudaMalloc(&sh->eye, (size_t)h * h * sizeof(double)));
-            sh->hcap = h;
-        }
-    }
-    s = cusolverDnDpotrf(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, sh->work, sh->lwork, info_dev);
-    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf failed (status %d)", (int)s); return CSPBO_E_SOLVER; }
-    // the factored diagonal block travels as it is (its strict other triangle is never read)
-    CSPBO_CUDA(cudaMemcpy2DAsync(out + col0, (size_t)ldo * sizeof(double), D, (size_t)ld * sizeof(double), (size_t)h * sizeof(double),
-                                 (size_t)h, cudaMemcpyDeviceToDevice, sh->stream));
-    const long long rest = ncols - col0 - h;
-    if (rest > 0) {
-        // rest of the panel through the explicit inverse of the h x h factor: one small triangular solve
-        // against the identity and one wide trmm (tensor-pipe bound) instead of a wide, latency-bound trsm:
-        //   column-major: OUT (rest x h) = B (rest x h) . (L_ss^-1)^T
-        const double one = 1.0;
-        set_identity_kernel<<<(h * h + 255) / 256, 256, 0, sh->stream>>>(sh->inv, h);
-        cublasStatus_t b = cublasDtrsm(sh->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, h, h,
-                                       &one, D, (int)ld, sh->inv, h);
-        if (b != CUBLAS_STATUS_SUCCESS) { set_error("trsm(identity) failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
-        b = cublasDtrmm(sh->blas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, (int)rest, h, &one,
-                        sh->inv, h, D + h, (int)ld, out + col0 + h, (int)ldo);
-        if (b != CUBLAS_STATUS_SUCCESS) { set_error("trmm failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
-    }
-    g_launches += 2;
     return CSPBO_OK;
 }

@@ -220,47 +220,68 @@ class ShardedSymmetricBlock:
 
 
 # ----------------------------------------------------------------------------- sharded Cholesky
+def _view(t):
+    """(pointer, leading dimension) of a 2-D row-major view with unit column stride."""
+    assert t.dim() == 2 and (t.shape[1] <= 1 or t.stride(1) == 1), "row-major view expected"
+    return c_vp(t.data_ptr()), int(t.stride(0))
+
+
 class _DeviceOps:
-    """Panel operations on the GPU through the C ABI (cuSOLVER potrf + cuBLAS trsm / gemm on explicit
-    streams, csrc/gp.cu).  The only implementation the product has; tests/test_distributed_cpu.py injects a
-    torch-CPU twin to exercise the rank choreography over gloo without a GPU."""
+    """Building blocks of the factorisation on the GPU through the C ABI (cuSOLVER potrf, cuBLAS trsm / trmm / dgemm
+    on explicit streams, csrc/gp.cu).  The only implementation the product has; tests/test_distributed_cpu.py
+    injects a torch-CPU twin to exercise the rank choreography over gloo without a GPU."""
     cuda = True
 
     def __init__(self):
         self.lib = _lib.load()
 
-    def panel_factor(self, rows, col0, h, ncols, info, stream):
-        _lib.check(self.lib.cspbo_gp_panel_factor(c_vp(rows.data_ptr()), rows.stride(0), int(col0), int(h), int(ncols),
-                                                  c_vp(info.data_ptr()), c_vp(stream)))
+    def diag(self, D, inv, info, stream):
+        """D[h,h] -> its upper factor in place; inv[h,h] (contiguous) = inverse of the factor."""
+        dp, ld = _view(D)
+        _lib.check(self.lib.cspbo_gp_chol_diag(dp, ld, int(D.shape[0]), c_vp(inv.data_ptr()), c_vp(info.data_ptr()), c_vp(stream)))
 
-    def panel_factor_to(self, rows, col0, h, ncols, out, info, stream):
-        """factorise the panel held in `rows` and leave the finished rows in `out` (the replicated factor)."""
-        if os.environ.get("CSPBO_CHOL_TRSM"):       # tuning knob: plain trsm instead of inverse + trmm
-            self.panel_factor(rows, col0, h, ncols, info, stream)
-            out.copy_(rows, non_blocking=True)
-            return
-        _lib.check(self.lib.cspbo_gp_panel_factor_to(c_vp(rows.data_ptr()), rows.stride(0), int(col0), int(h), int(ncols),
-                                                     c_vp(out.data_ptr()), out.stride(0), c_vp(info.data_ptr()), c_vp(stream)))
+    def apply_inv(self, inv, src, dst, stream):
+        """dst[h,w] = U_ss^-T src[h,w]"""
+        sp, lds = _view(src)
+        dp, ldd = _view(dst)
+        _lib.check(self.lib.cspbo_gp_chol_apply_inv(c_vp(inv.data_ptr()), int(src.shape[0]), sp, lds, int(src.shape[1]), dp, ldd,
+                                                    c_vp(stream)))
+
+    def update(self, C, A, B, stream):
+        """C[nb,w] -= A[h,nb]^T B[h,w]"""
+        cp, ldc = _view(C)
+        ap, lda = _view(A)
+        bp, ldb = _view(B)
+        _lib.check(self.lib.cspbo_gp_chol_update(cp, ldc, int(C.shape[0]), int(C.shape[1]), ap, lda, bp, ldb, int(A.shape[0]),
+                                                 c_vp(stream)))
 
     def sm_target(self, stream, count):
         _lib.check(self.lib.cspbo_gp_stream_sm_target(c_vp(stream), int(count)))
 
-    def panel_update(self, panel, h, rows, col0, nb, ncols, stream):
-        _lib.check(self.lib.cspbo_gp_panel_update(c_vp(panel.data_ptr()), panel.stride(0), int(h), c_vp(rows.data_ptr()),
-                                                  rows.stride(0), int(col0), int(nb), int(ncols), c_vp(stream)))
-
 
 _STREAMS = {}
+_NARROW_GROUPS = {}
 
 
-def _panel_streams():
-    """(panel, update) CUDA streams of the current device, shared by every ShardedCholesky of the process."""
+def _chol_streams():
+    """(diagonal, panel, update) CUDA streams of the current device, shared by every ShardedCholesky of the process."""
     import torch
     dev = torch.cuda.current_device()
     if dev not in _STREAMS:
         lo, hi = torch.cuda.Stream.priority_range()
-        _STREAMS[dev] = (torch.cuda.Stream(priority=hi), torch.cuda.Stream(priority=lo))
+        _STREAMS[dev] = (torch.cuda.Stream(priority=hi), torch.cuda.Stream(priority=min(hi + 1, lo)), torch.cuda.Stream(priority=lo))
     return _STREAMS[dev]
+
+
+def _narrow_group(group, world):
+    """A second communicator over the same ranks: the small diagonal-chain broadcasts must not queue behind the
+    wide panel broadcasts on one NCCL stream."""
+    import torch.distributed as dist
+    key = id(group)
+    if key not in _NARROW_GROUPS:
+        ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+        _NARROW_GROUPS[key] = dist.new_group(ranks=ranks)
+    return _NARROW_GROUPS[key]
 
 
 class ShardedCholesky:
@@ -269,15 +290,22 @@ class ShardedCholesky:
     HBM -- followed by the solves for alpha.  Replaces the reference's replicated scipy `cholesky` /
     `cho_solve` (gaussianprocess.py:116,127: every MPI rank factorises the whole K redundantly).
 
-    Right-looking with one panel of look-ahead, one process per GPU:
-      step s: the owner factorises its panel rows (cuSOLVER potrf of the nbw x nbw diagonal block + cuBLAS
-      trsm of the rest of the rows) on a high-priority panel stream and broadcasts them (NCCL over NVLink,
-      the only data-path collective); the owner of panel s+1 updates just that panel first and goes on
-      to factorise it while every rank applies panel s to the rest of its own rows (cuBLAS dgemm, one per
-      owned superblock, triangular: only columns right of the diagonal block) on the update stream.
-    Every rank keeps the broadcast rows, so after the factorisation U is replicated ([N,N], upper
-    triangle valid) and the O(N^2) solves, the predictive variance and the LML run locally.
+    Right-looking, one process per GPU, three streams per rank.  The only sequential chain of a blocked Cholesky
+    is diagonal block -> diagonal block, so it is kept as short as the data dependencies allow:
+
+      diagonal stream (panel s, owner): potrf of the nbw x nbw diagonal block + its explicit inverse, then only
+          the next TWO blocks of the panel rows ("narrow piece", trmm with the inverse); these few MB are broadcast on
+          their own communicator and the owner of panel s+1 applies them to its diagonal block and the block
+          right of it, which is all the next potrf and the next narrow piece need.
+      panel stream: the rest of the panel rows (wide trmm), their broadcast (NCCL over NVLink: the only bulk
+          collective), and the look-ahead update of the remaining columns of panel s+1.
+      update stream: every rank applies panel s to its own superblocks t >= s+2 (one dgemm per owned superblock,
+          triangular: only the columns from the diagonal block on).
+
+    Every rank keeps the broadcast rows, so after the factorisation U is replicated ([N,N], upper triangle valid)
+    and the O(N^2) solves, the predictive variance and the LML run locally.
     """
+    RING = 4
 
     def __init__(self, local2d, N, nbw, rank, world, zigzag=False, group=None, ops=None):
         import torch
@@ -292,10 +320,14 @@ class ShardedCholesky:
         dev = local2d.device
         self.U = torch.empty((self.N, self.N), dtype=torch.float64, device=dev)
         self.info = torch.zeros(max(self.S, 1), dtype=torch.int32, device=dev)
+        self.inv = torch.zeros((self.RING, self.nbw * self.nbw), dtype=torch.float64, device=dev)
+        self.stage = torch.zeros((self.RING, self.nbw * 3 * self.nbw), dtype=torch.float64, device=dev)
         if self.cuda:
-            self.s_panel, self.s_update = _panel_streams()
+            self.s_diag, self.s_panel, self.s_update = _chol_streams()
         self._src = [torch.distributed.get_global_rank(group, r) if (group is not None and world > 1) else r
                      for r in range(world)]
+        self.g_narrow = _narrow_group(group, world) if world > 1 else None
+        self.trace = None
 
     @classmethod
     def from_block(cls, sh, ops=None):
@@ -318,101 +350,146 @@ class ShardedCholesky:
             self.local[l0:l0 + h, r0:r0 + h].diagonal().add_(float(noise2))
 
     def factor(self):
-        torch, ops = self.torch, self.ops
-        N, nbw, S, W, me = self.N, self.nbw, self.S, self.world, self.rank
-        U, loc = self.U, self.local
-        sp = self.s_panel.cuda_stream if self.cuda else None
-        su = self.s_update.cuda_stream if self.cuda else None
-        if self.cuda:
+        torch, ops, dist = self.torch, self.ops, self.torch.distributed
+        N, nbw, S, W, me, R = self.N, self.nbw, self.S, self.world, self.rank, self.RING
+        U, loc, cuda = self.U, self.local, self.cuda
+        sd = self.s_diag.cuda_stream if cuda else None
+        sp = self.s_panel.cuda_stream if cuda else None
+        su = self.s_update.cuda_stream if cuda else None
+        if cuda:
             cur = torch.cuda.current_stream()
-            self.s_panel.wait_stream(cur)
-            self.s_update.wait_stream(cur)
-        e_bulk = {}
-        mine = [s for s in range(S) if self._owner(s) == me]
-        if self.cuda and self.bulk_sms:
-            ops.sm_target(su, self.bulk_sms)    # leave a few SMs to the latency-critical panel stream
+            for st in (self.s_diag, self.s_panel, self.s_update):
+                st.wait_stream(cur)
+            if self.bulk_sms:
+                ops.sm_target(su, self.bulk_sms)
 
         class _Null:
             def __enter__(self): return self
             def __exit__(self, *a): return False
-        on_panel = (lambda: torch.cuda.stream(self.s_panel)) if self.cuda else _Null
-        on_update = (lambda: torch.cuda.stream(self.s_update)) if self.cuda else _Null
+        on = (lambda st: torch.cuda.stream(st)) if cuda else (lambda st: _Null())
+        SD, SP, SU = (self.s_diag, self.s_panel, self.s_update) if cuda else (None, None, None)
 
-        trace = self.trace = [] if (self.cuda and os.environ.get("CSPBO_CHOL_TRACE")) else None
+        def record(st):
+            if not cuda:
+                return None
+            e = torch.cuda.Event()
+            e.record(st)
+            return e
 
-        def mark():
+        def wait(st, ev):
+            if cuda and ev is not None:
+                st.wait_event(ev)
+
+        trace = self.trace = [] if (cuda and os.environ.get("CSPBO_CHOL_TRACE")) else None
+
+        def mark(st):
             if trace is None:
                 return None
             e = torch.cuda.Event(enable_timing=True)
-            e.record(self.s_panel)
+            e.record(st)
             return e
+
+        mine = [s for s in range(S) if self._owner(s) == me]
+        e_first, e_look, e_wtrmm = {}, {}, {}     # see the waits below for what each event certifies
+        bounds = lambda s: (s * nbw, min((s + 1) * nbw, N), min((s + 2) * nbw, N), min((s + 3) * nbw, N))
 
         for s in range(S):
             o = self._owner(s)
-            r0 = s * nbw
-            h = min(nbw, N - r0)
-            with on_panel():
-                t0 = mark()
-                if me == o:
-                    l0 = (s // W) * nbw
-                    if self.cuda and s >= 2:
-                        self.s_panel.wait_event(e_bulk[s - 2])   # panels <= s-2 applied in bulk; s-1 by the look-ahead
-                    t0 = mark()
-                    ops.panel_factor_to(loc[l0:l0 + h], r0, h, N, U[r0:r0 + h], self.info[s:s + 1], sp)
-                t1 = mark()
-                if W > 1:
-                    torch.distributed.broadcast(U[r0:r0 + h], src=self._src[o], group=self.group)
-                t2 = mark()
-                if self.cuda:
-                    e_bcast = torch.cuda.Event()
-                    e_bcast.record(self.s_panel)
-                # look-ahead: the next panel gets panel s first, on the panel stream
-                ahead = s + 1 < S and self._owner(s + 1) == me
-                if ahead:
-                    if self.cuda and s >= 1:
-                        self.s_panel.wait_event(e_bulk[s - 1])
-                    t = s + 1
-                    l0, c0 = (t // W) * nbw, t * nbw
-                    ht = min(nbw, N - c0)
-                    t3 = mark()
-                    ops.panel_update(U[r0:r0 + h], h, loc[l0:l0 + ht], c0, ht, N, sp)
-                    if trace is not None:
-                        trace.append(("lookahead", s, t3, mark()))
+            own = me == o
+            r0, r1, r2, r3 = bounds(s)
+            h, wn = r1 - r0, r3 - r1                   # panel height, width of the narrow piece (next two blocks)
+            l0 = (s // W) * nbw                        # first local row of panel s on its owner
+            slot = s % R
+            msg = self.stage[slot][: h * (h + wn)].view(h, h + wn)     # [diag block | narrow piece], contiguous
+            inv = self.inv[slot][: h * h].view(h, h)
+            nxt = s + 1 < S and self._owner(s + 1) == me
+            lt = ((s + 1) // W) * nbw
+            # ------------------------------------------------------------------ diagonal chain
+            with on(SD):
+                t0 = mark(SD)
+                if own:
+                    wait(SD, e_first.get(s - 2))      # bulk updates of panels <= s-2 have reached rows s
+                    wait(SD, e_wtrmm.get(s - R))      # the wide trmm that used this inverse slot is done
+                    # (panel s-1 reached [diag | next block] through the narrow update below, in stream order)
+                    t0 = mark(SD)
+                    ops.diag(loc[l0:l0 + h, r0:r1], inv, self.info[s:s + 1], sd)
+                    msg[:, :h].copy_(loc[l0:l0 + h, r0:r1], non_blocking=True)
+                    if wn:
+                        wait(SD, e_look.get(s - 1))   # panel s-1 has reached the second block through the look-ahead
+                        ops.apply_inv(inv, loc[l0:l0 + h, r1:r3], msg[:, h:], sd)
+                    U[r0:r1, r0:r3].copy_(msg, non_blocking=True)
+                t1 = mark(SD)
+                if W > 1 and wn:
+                    dist.broadcast(msg, src=self._src[o], group=self.g_narrow)
+                t2 = mark(SD)
+                e_diag = record(SD) if own else None
+                if nxt:
+                    # rows s+1: [diag block | next block] -= P_s[:, cols(s+1)]^T P_s[:, cols(s+1) u cols(s+2)]
+                    wait(SD, e_first.get(s - 1))      # bulk updates of panels <= s-1 have reached rows s+1
+                    ops.update(loc[lt:lt + (r2 - r1), r1:r3], msg[:, h:h + (r2 - r1)], msg[:, h:], sd)
                 if trace is not None:
-                    if me == o:
-                        trace.append(("factor", s, t0, t1))
-                    trace.append(("bcast_owner" if me == o else "bcast_wait", s, t1, t2))
-            with on_update():
-                if self.cuda:
-                    self.s_update.wait_event(e_bcast)
-                todo = [t for t in mine if t > s and not (ahead and t == s + 1)]
-                i = 0
+                    if own:
+                        trace.append(("diag+narrow", t0, t1))
+                    trace.append(("narrow_bcast" if own else "narrow_wait", t1, t2))
+            # ------------------------------------------------------------------ wide panel
+            with on(SP):
+                if own:
+                    wait(SP, e_diag)
+                    wait(SP, e_first.get(s - 2))
+                    t3 = mark(SP)
+                    if r3 < N:
+                        ops.apply_inv(inv, loc[l0:l0 + h, r3:N], U[r0:r1, r3:N], sp)
+                    e_wtrmm[s] = record(SP)
+                    if trace is not None:
+                        trace.append(("wide_trmm", t3, mark(SP)))
+                t4 = mark(SP)
+                if W > 1:
+                    dist.broadcast(U[r0:r1], src=self._src[o], group=self.group)
+                e_wide = record(SP)
+                if trace is not None:
+                    trace.append(("wide_bcast" if own else "wide_wait", t4, mark(SP)))
+                if nxt:
+                    wait(SP, e_first.get(s - 1))
+                    if r3 < N:
+                        t5 = mark(SP)
+                        ops.update(loc[lt:lt + (r2 - r1), r3:N], U[r0:r1, r1:r2], U[r0:r1, r3:N], sp)
+                        if trace is not None:
+                            trace.append(("lookahead", t5, mark(SP)))
+                    e_look[s] = record(SP)
+            # ------------------------------------------------------------------ bulk updates of this rank's rows
+            with on(SU):
+                wait(SU, e_wide)
+                todo = [t for t in mine if t >= s + 2]
+                i, first = 0, True
                 while i < len(todo):
-                    # superblocks that are neighbours in the matrix AND in this rank's buffer (world 1) share one
-                    # dgemm: the few extra nbw x nbw blocks left of their diagonals are never read again
+                    # superblocks that are neighbours in the matrix AND in this rank's buffer (world 1, zigzag turns)
+                    # share one dgemm: the few extra nbw x nbw blocks left of their diagonals are never read again
                     j = i + 1
                     while j < len(todo) and j - i < self.max_chunk and todo[j] == todo[j - 1] + 1 and \
                             todo[j] // W == todo[j - 1] // W + 1:
                         j += 1
                     t = todo[i]
-                    l0, c0 = (t // W) * nbw, t * nbw
+                    lr, c0 = (t // W) * nbw, t * nbw
                     ht = min((todo[j - 1] + 1) * nbw, N) - c0
-                    ops.panel_update(U[r0:r0 + h], h, loc[l0:l0 + ht], c0, ht, N, su)
+                    ops.update(loc[lr:lr + ht, c0:N], U[r0:r1, c0:c0 + ht], U[r0:r1, c0:N], su)
+                    if first:
+                        e_first[s] = record(SU)      # rows s+2 (if they are mine) now carry panel s
+                        first = False
                     i = j
-                if self.cuda:
-                    e_bulk[s] = torch.cuda.Event()
-                    e_bulk[s].record(self.s_update)
-                    e_bulk.pop(s - 3, None)
-        if self.cuda:
+                if first:
+                    e_first[s] = record(SU)
+                for d in (e_first, e_look, e_wtrmm):
+                    d.pop(s - R - 2, None)
+        if cuda:
             cur = torch.cuda.current_stream()
-            cur.wait_stream(self.s_panel)
-            cur.wait_stream(self.s_update)
+            for st in (self.s_diag, self.s_panel, self.s_update):
+                cur.wait_stream(st)
         return self
 
     def trace_summary(self):
-        """Per-phase device time on the panel stream (CSPBO_CHOL_TRACE=1), ms summed over panels."""
+        """Per-phase device time (CSPBO_CHOL_TRACE=1), ms summed over panels."""
         out = {}
-        for name, s, a, b in (self.trace or []):
+        for name, a, b in (self.trace or []):
             out[name] = out.get(name, 0.0) + a.elapsed_time(b)
         return out
 

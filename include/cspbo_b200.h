@@ -254,26 +254,20 @@ int cspbo_gp_cholesky_solve(double *K, int N, double *y_inout, int nrhs, double 
 int cspbo_gp_cho_solve(const double *L, int N, double *B, int nrhs);
 /* Kinv = (L L^T)^-1 (cuSOLVER potri), full symmetric matrix.  gaussianprocess.py:497 */
 int cspbo_gp_cholesky_inverse(const double *L, int N, double *Kinv);
-/* Panel operations of the sharded Cholesky K = U^T U (row-major; rows of U live where the rows of K live;
- * csp_bo_b200/distributed.py).  Both are asynchronous on `stream` (a cudaStream_t).
- * panel_factor: `rows` = the first of h consecutive matrix rows (leading dimension ld) whose diagonal block
- *   sits at columns [col0, col0+h): factorise it in place (cuSOLVER potrf; *info_dev > 0 <=> not positive
- *   definite, device memory, never read by the call) and solve the rest of the panel, columns [col0+h, ncols).
- * panel_update: rows[0:nb, col0:ncols] -= panel[0:h, col0:col0+nb]^T . panel[0:h, col0:ncols]  (cuBLAS dgemm),
- *   the trailing update of the nb matrix rows whose diagonal block starts at column col0.
- * Distributed restatement of the single scipy `cholesky` of gaussianprocess.py:116. */
-int cspbo_gp_panel_factor(double *rows, long long ld, long long col0, int h, long long ncols, int *info_dev,
-                          void *stream);
-int cspbo_gp_panel_update(const double *panel, long long ldp, int h, double *rows, long long ld, long long col0,
-                          int nb, long long ncols, void *stream);
-/* panel_factor_to: like panel_factor, but the finished panel rows are written to `out` (leading dimension ldo, same
- * column positions) -- the replicated factor the owner broadcasts from -- and the rest of the panel is obtained through
- * the explicit inverse of the h x h diagonal factor (small trsm against the identity + one wide trmm) instead of a
- * wide, latency-bound trsm.  Only the diagonal block of `rows` is modified. */
-int cspbo_gp_panel_factor_to(double *rows, long long ld, long long col0, int h, long long ncols, double *out,
-                             long long ldo, int *info_dev, void *stream);
-/* limit the cuBLAS kernels issued on `stream` by the panel operations to sm_count SMs (0 = all): keeps a few SMs
- * free for the latency-critical panel stream while the bulk updates run (cublasSetSmCountTarget). */
+/* Building blocks of the sharded Cholesky K = U^T U (row-major; rows of U live where the rows of K live;
+ * csp_bo_b200/distributed.py: ShardedCholesky).  All asynchronous on `stream` (a cudaStream_t); matrices are row-major
+ * views given by pointer + leading dimension.  Distributed restatement of the single scipy `cholesky` of
+ * gaussianprocess.py:116.
+ *   chol_diag      D[h,h] (symmetric diagonal block) -> its upper factor in place (cuSOLVER potrf; *info_dev > 0 <=> not
+ *                  positive definite: device memory, never read by the call) and inv[h*h] = the factor's inverse
+ *   chol_apply_inv dst[h,w] = U_ss^-T src[h,w]: the panel rows right of the diagonal block (cuBLAS trmm with the inverse)
+ *   chol_update    C[nb,w] -= A[h,nb]^T B[h,w]: trailing update of nb matrix rows by an h-row panel (cuBLAS dgemm) */
+int cspbo_gp_chol_diag(double *D, long long ld, int h, double *inv, int *info_dev, void *stream);
+int cspbo_gp_chol_apply_inv(const double *inv, int h, const double *src, long long ldb, long long w, double *dst,
+                            long long ldc, void *stream);
+int cspbo_gp_chol_update(double *C, long long ldc, int nb, long long w, const double *A, long long lda, const double *B,
+                         long long ldb, int h, void *stream);
+/* limit the cuBLAS kernels issued on `stream` by these operations to sm_count SMs (0 = all; cublasSetSmCountTarget) */
 int cspbo_gp_stream_sm_target(void *stream, int sm_count);
 /* pred[n] = Kstar[n, N] . alpha[N]    gaussianprocess.py:140,359 */
 int cspbo_gp_predict(const double *Kstar, int n, int N, const double *alpha, double *pred);

@@ -62,24 +62,20 @@ def test_gloo_world2_gather_and_unpermute(m, golden):
 # sharded Cholesky: the rank choreography (ownership, look-ahead, broadcasts, triangular updates) with a
 # torch-CPU twin of the device panel operations, world 1 in-process and world 2 over gloo
 class TorchOps:
-    """CPU twin of distributed._DeviceOps (csrc/gp.cu panel_factor / panel_update), test-only."""
+    """CPU twin of distributed._DeviceOps (csrc/gp.cu chol_diag / chol_apply_inv / chol_update), test-only."""
     cuda = False
 
-    def panel_factor(self, rows, col0, h, ncols, info, stream):
-        D = rows[:h, col0:col0 + h]
+    def diag(self, D, inv, info, stream):
         Uss, inf = torch.linalg.cholesky_ex(D, upper=True)
         info.copy_(inf.to(info.dtype).reshape(1))
         D.copy_(torch.triu(Uss) + torch.tril(D, -1))
-        if col0 + h < ncols:
-            R = rows[:h, col0 + h:ncols]
-            R.copy_(torch.linalg.solve_triangular(Uss.T, R, upper=False))
+        inv.copy_(torch.linalg.solve_triangular(torch.triu(Uss), torch.eye(D.shape[0], dtype=D.dtype), upper=True))
 
-    def panel_factor_to(self, rows, col0, h, ncols, out, info, stream):
-        self.panel_factor(rows, col0, h, ncols, info, stream)
-        out.copy_(rows)
+    def apply_inv(self, inv, src, dst, stream):
+        dst.copy_(inv.T @ src)
 
-    def panel_update(self, panel, h, rows, col0, nb, ncols, stream):
-        rows[:nb, col0:ncols] -= panel[:h, col0:col0 + nb].T @ panel[:h, col0:ncols]
+    def update(self, C, A, B, stream):
+        C -= A.T @ B
 
     def solve(self, U, B):
         Ut = torch.triu(U)
@@ -102,7 +98,8 @@ def _rows_of(K, N, nbw, rank, world, zigzag):
     return local
 
 
-@pytest.mark.parametrize("N,nbw,zigzag", [(24, 24, False), (100, 24, True), (193, 48, True), (96, 48, False)])
+@pytest.mark.parametrize("N,nbw,zigzag", [(24, 24, False), (30, 24, False), (49, 24, True), (73, 24, True), (100, 24, True),
+                                          (193, 48, True), (96, 48, False), (240, 24, False)])
 def test_sharded_cholesky_world1(N, nbw, zigzag):
     K = _spd(N, N)
     ch = D.ShardedCholesky(_rows_of(K, N, nbw, 0, 1, zigzag), N, nbw, 0, 1, zigzag, ops=TorchOps())
@@ -140,10 +137,9 @@ def _chol_worker(rank, world, port, K, N, nbw, zigzag, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("N,nbw,zigzag", [(100, 24, True), (170, 24, False)])
-def test_sharded_cholesky_gloo_world2(N, nbw, zigzag):
+@pytest.mark.parametrize("N,nbw,zigzag,world", [(100, 24, True, 2), (170, 24, False, 2), (130, 24, True, 3)])
+def test_sharded_cholesky_gloo(N, nbw, zigzag, world):
     K = _spd(N, 11)
-    world = 2
     with mp.Manager() as mgr:
         out = mgr.dict()
         port = 31500 + (os.getpid() % 2000) + N
