@@ -3,6 +3,7 @@
 //   noise add + K*.alpha GEMV : hand-written HBM-bound kernels
 //   Cholesky factorisation / solve : cuSOLVER potrf / potrs (as BASELINE.json's north_star asks)
 #include <cublas_v2.h>
+#include <cuda.h>
 #include <cusolverDn.h>
 
 #include <cstdlib>
@@ -381,5 +382,92 @@ extern "C" int cspbo_gp_stream_sm_target(void *stream, int sm_count)
     int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
     if (rc) return rc;
     if (cublasSetSmCountTarget(sh->blas, sm_count) != CUBLAS_STATUS_SUCCESS) { set_error("cublasSetSmCountTarget(%d) failed", sm_count); return CSPBO_E_SOLVER; }
+    return CSPBO_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// SM partition for the sharded Cholesky.  Measured on B200 (tools/chol_probe.py, CSPBO_CHOL_TRACE=1): the
+// potrf + inverse of a 384 x 384 diagonal block takes 0.37 ms alone but 1.1-1.4 ms while the trailing dgemm updates
+// run -- stream priorities only order CTA dispatch, the latency-bound potrf kernels still share SMs (and their FP64
+// pipes) with DMMA-saturating dgemm CTAs.  CUDA green contexts give the diagonal chain a small set of SMs of its
+// own: one green context with `diag_sms` SMs (diagonal stream) and one with the remaining SMs (panel and update
+// streams).  Driver entry points are resolved at run time (no link-time dependency on libcuda).
+// ------------------------------------------------------------------------------------------
+namespace cspbo {
+struct GreenStreams {
+    bool tried = false, ok = false;
+    cudaStream_t diag = nullptr, panel = nullptr, update = nullptr;
+    int diag_sms = 0, rest_sms = 0;
+};
+static GreenStreams g_green[64];
+
+template <typename F>
+static bool drv(const char *name, F *fn)
+{
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+        cudaGetLastError();
+        return false;
+    }
+    *fn = reinterpret_cast<F>(p);
+    return true;
+}
+}  // namespace cspbo
+
+extern "C" int cspbo_gp_chol_streams(int diag_sms, void **diag, void **panel, void **update, int *diag_sms_got, int *rest_sms_got)
+{
+    if (!diag || !panel || !update) { set_error("gp_chol_streams: null argument"); return CSPBO_E_ARG; }
+    int dev = 0;
+    CSPBO_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return CSPBO_E_ARG; }
+    std::lock_guard<std::mutex> lk(g_solver_mu);
+    GreenStreams &g = g_green[dev];
+    if (!g.tried) {
+        g.tried = true;
+        CSPBO_CUDA(cudaFree(0));   // primary context
+        CUresult (*pDeviceGet)(CUdevice *, int) = nullptr;
+        CUresult (*pGetDevResource)(CUdevice, CUdevResource *, CUdevResourceType) = nullptr;
+        CUresult (*pSplit)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int) = nullptr;
+        CUresult (*pGenDesc)(CUdevResourceDesc *, CUdevResource *, unsigned int) = nullptr;
+        CUresult (*pGreenCreate)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+        CUresult (*pStreamCreate)(CUstream *, CUgreenCtx, unsigned int, int) = nullptr;
+        if (!drv("cuDeviceGet", &pDeviceGet) || !drv("cuDeviceGetDevResource", &pGetDevResource) ||
+            !drv("cuDevSmResourceSplitByCount", &pSplit) || !drv("cuDevResourceGenerateDesc", &pGenDesc) ||
+            !drv("cuGreenCtxCreate", &pGreenCreate) || !drv("cuGreenCtxStreamCreate", &pStreamCreate)) {
+            set_error("gp_chol_streams: the driver has no green-context entry points");
+            return CSPBO_E_CUDA;
+        }
+        CUdevice cudev;
+        CUdevResource all, grp[1], rest;
+        unsigned int nb = 1;
+        CUdevResourceDesc d1, d2;
+        CUgreenCtx c1, c2;
+        CUstream s1, s2, s3;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CUresult r;
+#define GREEN_TRY(call) if ((r = (call)) != CUDA_SUCCESS) { set_error("gp_chol_streams: %s failed (%d)", #call, (int)r); return CSPBO_E_CUDA; }
+        GREEN_TRY(pDeviceGet(&cudev, dev));
+        GREEN_TRY(pGetDevResource(cudev, &all, CU_DEV_RESOURCE_TYPE_SM));
+        GREEN_TRY(pSplit(grp, &nb, &all, &rest, 0, (unsigned)std::max(diag_sms, 8)));
+        if (nb < 1 || rest.sm.smCount < 8) { set_error("gp_chol_streams: SM split gave %u groups, %u SMs left", nb, rest.sm.smCount); return CSPBO_E_CUDA; }
+        GREEN_TRY(pGenDesc(&d1, &grp[0], 1));
+        GREEN_TRY(pGenDesc(&d2, &rest, 1));
+        GREEN_TRY(pGreenCreate(&c1, d1, cudev, CU_GREEN_CTX_DEFAULT_STREAM));
+        GREEN_TRY(pGreenCreate(&c2, d2, cudev, CU_GREEN_CTX_DEFAULT_STREAM));
+        GREEN_TRY(pStreamCreate(&s1, c1, CU_STREAM_NON_BLOCKING, hi));
+        GREEN_TRY(pStreamCreate(&s2, c2, CU_STREAM_NON_BLOCKING, hi));
+        GREEN_TRY(pStreamCreate(&s3, c2, CU_STREAM_NON_BLOCKING, lo));
+#undef GREEN_TRY
+        g.diag = s1; g.panel = s2; g.update = s3;
+        g.diag_sms = (int)grp[0].sm.smCount; g.rest_sms = (int)rest.sm.smCount;
+        g.ok = true;
+    }
+    if (!g.ok) { set_error("gp_chol_streams: green contexts unavailable on this device"); return CSPBO_E_CUDA; }
+    *diag = g.diag; *panel = g.panel; *update = g.update;
+    if (diag_sms_got) *diag_sms_got = g.diag_sms;
+    if (rest_sms_got) *rest_sms_got = g.rest_sms;
     return CSPBO_OK;
 }

@@ -264,12 +264,25 @@ _NARROW_GROUPS = {}
 
 
 def _chol_streams():
-    """(diagonal, panel, update) CUDA streams of the current device, shared by every ShardedCholesky of the process."""
+    """(diagonal, panel, update) CUDA streams of the current device, shared by every ShardedCholesky of the process.
+    Preferred: green-context streams from the library (the diagonal chain gets CSPBO_CHOL_DIAG_SMS SMs of its own,
+    default 16); fallback: plain priority streams."""
     import torch
     dev = torch.cuda.current_device()
     if dev not in _STREAMS:
-        lo, hi = torch.cuda.Stream.priority_range()
-        _STREAMS[dev] = (torch.cuda.Stream(priority=hi), torch.cuda.Stream(priority=min(hi + 1, lo)), torch.cuda.Stream(priority=lo))
+        made = None
+        want = int(os.environ.get("CSPBO_CHOL_DIAG_SMS", "16"))
+        if want > 0:
+            lib = _lib.load()
+            a, b, c = c_vp(), c_vp(), c_vp()
+            n1, n2 = ctypes.c_int(0), ctypes.c_int(0)
+            rc = lib.cspbo_gp_chol_streams(want, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(n1), ctypes.byref(n2))
+            if rc == 0:
+                made = tuple(torch.cuda.ExternalStream(p.value, device=dev) for p in (a, b, c)) + ((n1.value, n2.value),)
+        if made is None:
+            lo, hi = torch.cuda.Stream.priority_range()
+            made = (torch.cuda.Stream(priority=hi), torch.cuda.Stream(priority=min(hi + 1, lo)), torch.cuda.Stream(priority=lo), None)
+        _STREAMS[dev] = made
     return _STREAMS[dev]
 
 
@@ -323,7 +336,7 @@ class ShardedCholesky:
         self.inv = torch.zeros((self.RING, self.nbw * self.nbw), dtype=torch.float64, device=dev)
         self.stage = torch.zeros((self.RING, self.nbw * 3 * self.nbw), dtype=torch.float64, device=dev)
         if self.cuda:
-            self.s_diag, self.s_panel, self.s_update = _chol_streams()
+            self.s_diag, self.s_panel, self.s_update, self.sm_split = _chol_streams()
         self._src = [torch.distributed.get_global_rank(group, r) if (group is not None and world > 1) else r
                      for r in range(world)]
         self.g_narrow = _narrow_group(group, world) if world > 1 else None
@@ -381,6 +394,9 @@ class ShardedCholesky:
                 st.wait_event(ev)
 
         trace = self.trace = [] if (cuda and os.environ.get("CSPBO_CHOL_TRACE")) else None
+        if trace is not None:
+            self.t_start = torch.cuda.Event(enable_timing=True)
+            self.t_start.record(torch.cuda.current_stream())
 
         def mark(st):
             if trace is None:
@@ -414,10 +430,16 @@ class ShardedCholesky:
                     t0 = mark(SD)
                     ops.diag(loc[l0:l0 + h, r0:r1], inv, self.info[s:s + 1], sd)
                     msg[:, :h].copy_(loc[l0:l0 + h, r0:r1], non_blocking=True)
+                    ta = mark(SD)
                     if wn:
                         wait(SD, e_look.get(s - 1))   # panel s-1 has reached the second block through the look-ahead
+                        tb = mark(SD)
                         ops.apply_inv(inv, loc[l0:l0 + h, r1:r3], msg[:, h:], sd)
+                        if trace is not None:
+                            trace.append(("wait_look", s, ta, tb))
                     U[r0:r1, r0:r3].copy_(msg, non_blocking=True)
+                    if trace is not None:
+                        trace.append(("potrf+inv", s, t0, ta))
                 t1 = mark(SD)
                 if W > 1 and wn:
                     dist.broadcast(msg, src=self._src[o], group=self.g_narrow)
@@ -429,8 +451,8 @@ class ShardedCholesky:
                     ops.update(loc[lt:lt + (r2 - r1), r1:r3], msg[:, h:h + (r2 - r1)], msg[:, h:], sd)
                 if trace is not None:
                     if own:
-                        trace.append(("diag+narrow", t0, t1))
-                    trace.append(("narrow_bcast" if own else "narrow_wait", t1, t2))
+                        trace.append(("diag+narrow", s, t0, t1))
+                    trace.append(("narrow_bcast" if own else "narrow_wait", s, t1, t2))
             # ------------------------------------------------------------------ wide panel
             with on(SP):
                 if own:
@@ -441,20 +463,20 @@ class ShardedCholesky:
                         ops.apply_inv(inv, loc[l0:l0 + h, r3:N], U[r0:r1, r3:N], sp)
                     e_wtrmm[s] = record(SP)
                     if trace is not None:
-                        trace.append(("wide_trmm", t3, mark(SP)))
+                        trace.append(("wide_trmm", s, t3, mark(SP)))
                 t4 = mark(SP)
                 if W > 1:
                     dist.broadcast(U[r0:r1], src=self._src[o], group=self.group)
                 e_wide = record(SP)
                 if trace is not None:
-                    trace.append(("wide_bcast" if own else "wide_wait", t4, mark(SP)))
+                    trace.append(("wide_bcast" if own else "wide_wait", s, t4, mark(SP)))
                 if nxt:
                     wait(SP, e_first.get(s - 1))
                     if r3 < N:
                         t5 = mark(SP)
                         ops.update(loc[lt:lt + (r2 - r1), r3:N], U[r0:r1, r1:r2], U[r0:r1, r3:N], sp)
                         if trace is not None:
-                            trace.append(("lookahead", t5, mark(SP)))
+                            trace.append(("lookahead", s, t5, mark(SP)))
                     e_look[s] = record(SP)
             # ------------------------------------------------------------------ bulk updates of this rank's rows
             with on(SU):
@@ -489,9 +511,14 @@ class ShardedCholesky:
     def trace_summary(self):
         """Per-phase device time (CSPBO_CHOL_TRACE=1), ms summed over panels."""
         out = {}
-        for name, a, b in (self.trace or []):
+        for name, s, a, b in (self.trace or []):
             out[name] = out.get(name, 0.0) + a.elapsed_time(b)
         return out
+
+    def trace_timeline(self, panels):
+        """[(panel, phase, begin_ms, end_ms)] relative to the start of factor() for the given panels."""
+        return [(s, name, round(self.t_start.elapsed_time(a), 3), round(self.t_start.elapsed_time(b), 3))
+                for name, s, a, b in (self.trace or []) if s in panels]
 
     def check(self):
         """Raise CspboError(CSPBO_E_NOTPD) if a diagonal block was not positive definite (one host sync)."""

@@ -63,6 +63,9 @@ for G in sbs:
         sync(); t4 = time.perf_counter()
         if os.environ.get("CSPBO_CHOL_TRACE") and it == 2:
             print(json.dumps(dict(rank=rank, G=G, trace={k: round(v, 2) for k, v in chol.trace_summary().items()})), flush=True)
+            if rank <= 1:
+                for row in chol.trace_timeline(range(8, 14)):
+                    print("TL rank%d %s" % (rank, json.dumps(row)), flush=True)
         rec.append(dict(build=(t1 - t0) * 1e3, alloc_noise=(t2 - t1) * 1e3, factor=(t3 - t2) * 1e3, solve=(t4 - t3) * 1e3, total=(t4 - t0) * 1e3))
         del chol
     err = float(((Ktest @ ref) - (Ktest @ alpha.reshape(-1))).abs().max() / (Ktest @ ref).abs().max()) if ref is not None else None
