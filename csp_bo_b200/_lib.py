@@ -91,8 +91,8 @@ SIGNATURES = {
     "cspbo_gp_chol_apply_inv": [c_vp, c_int, c_vp, c_ll, c_ll, c_vp, c_ll, c_vp],
     "cspbo_gp_chol_update": [c_vp, c_ll, c_int, c_ll, c_vp, c_ll, c_vp, c_ll, c_int, c_vp],
     "cspbo_gp_stream_sm_target": [c_vp, c_int],
-    "cspbo_gp_chol_streams": [c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_int),
-                              ctypes.POINTER(c_int)],
+    "cspbo_gp_chol_streams": [c_int, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp),
+                              ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
 }
 _RESTYPE = {"cspbo_last_error": ctypes.c_char_p, "cspbo_launch_count": c_ll, "cspbo_pack_bytes": c_ll,
             "cspbo_pack_pair_count": c_ll, "cspbo_sharded_rows": c_ll, "cspbo_sharded_rows_ex": c_ll}

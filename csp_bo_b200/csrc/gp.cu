@@ -391,13 +391,13 @@ extern "C" int cspbo_gp_stream_sm_target(void *stream, int sm_count)
 // potrf + inverse of a 384 x 384 diagonal block takes 0.37 ms alone but 1.1-1.4 ms while the trailing dgemm updates
 // run -- stream priorities only order CTA dispatch, the latency-bound potrf kernels still share SMs (and their FP64
 // pipes) with DMMA-saturating dgemm CTAs.  CUDA green contexts give the diagonal chain a small set of SMs of its
-// own: one green context with `diag_sms` SMs (diagonal stream) and one with the remaining SMs (panel and update
-// streams).  Driver entry points are resolved at run time (no link-time dependency on libcuda).
+// own: one green context with `diag_sms` SMs (diagonal stream) and one with the remaining SMs (panel, look-ahead and
+// update streams).  Driver entry points are resolved at run time (no link-time dependency on libcuda).
 // ------------------------------------------------------------------------------------------
 namespace cspbo {
 struct GreenStreams {
     bool tried = false, ok = false;
-    cudaStream_t diag = nullptr, panel = nullptr, update = nullptr;
+    cudaStream_t diag = nullptr, panel = nullptr, look = nullptr, update = nullptr;
     int diag_sms = 0, rest_sms = 0;
 };
 static GreenStreams g_green[64];
@@ -416,9 +416,10 @@ static bool drv(const char *name, F *fn)
 }
 }  // namespace cspbo
 
-extern "C" int cspbo_gp_chol_streams(int diag_sms, void **diag, void **panel, void **update, int *diag_sms_got, int *rest_sms_got)
+extern "C" int cspbo_gp_chol_streams(int diag_sms, void **diag, void **panel, void **look, void **update, int *diag_sms_got,
+                                     int *rest_sms_got)
 {
-    if (!diag || !panel || !update) { set_error("gp_chol_streams: null argument"); return CSPBO_E_ARG; }
+    if (!diag || !panel || !look || !update) { set_error("gp_chol_streams: null argument"); return CSPBO_E_ARG; }
     int dev = 0;
     CSPBO_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) { set_error("device ordinal %d out of range", dev); return CSPBO_E_ARG; }
@@ -444,7 +445,7 @@ extern "C" int cspbo_gp_chol_streams(int diag_sms, void **diag, void **panel, vo
         unsigned int nb = 1;
         CUdevResourceDesc d1, d2;
         CUgreenCtx c1, c2;
-        CUstream s1, s2, s3;
+        CUstream s1, s2, s3, s4;
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         CUresult r;
@@ -459,14 +460,15 @@ extern "C" int cspbo_gp_chol_streams(int diag_sms, void **diag, void **panel, vo
         GREEN_TRY(pGreenCreate(&c2, d2, cudev, CU_GREEN_CTX_DEFAULT_STREAM));
         GREEN_TRY(pStreamCreate(&s1, c1, CU_STREAM_NON_BLOCKING, hi));
         GREEN_TRY(pStreamCreate(&s2, c2, CU_STREAM_NON_BLOCKING, hi));
-        GREEN_TRY(pStreamCreate(&s3, c2, CU_STREAM_NON_BLOCKING, lo));
+        GREEN_TRY(pStreamCreate(&s3, c2, CU_STREAM_NON_BLOCKING, std::min(hi + 1, lo)));
+        GREEN_TRY(pStreamCreate(&s4, c2, CU_STREAM_NON_BLOCKING, lo));
 #undef GREEN_TRY
-        g.diag = s1; g.panel = s2; g.update = s3;
+        g.diag = s1; g.panel = s2; g.look = s3; g.update = s4;
         g.diag_sms = (int)grp[0].sm.smCount; g.rest_sms = (int)rest.sm.smCount;
         g.ok = true;
     }
     if (!g.ok) { set_error("gp_chol_streams: green contexts unavailable on this device"); return CSPBO_E_CUDA; }
-    *diag = g.diag; *panel = g.panel; *update = g.update;
+    *diag = g.diag; *panel = g.panel; *look = g.look; *update = g.update;
     if (diag_sms_got) *diag_sms_got = g.diag_sms;
     if (rest_sms_got) *rest_sms_got = g.rest_sms;
     return CSPBO_OK;

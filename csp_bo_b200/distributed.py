@@ -264,7 +264,7 @@ _NARROW_GROUPS = {}
 
 
 def _chol_streams():
-    """(diagonal, panel, update) CUDA streams of the current device, shared by every ShardedCholesky of the process.
+    """(diagonal, panel, look-ahead, update) CUDA streams of the current device, shared by every ShardedCholesky of the process.
     Preferred: green-context streams from the library (the diagonal chain gets CSPBO_CHOL_DIAG_SMS SMs of its own,
     default 16); fallback: plain priority streams."""
     import torch
@@ -274,14 +274,16 @@ def _chol_streams():
         want = int(os.environ.get("CSPBO_CHOL_DIAG_SMS", "16"))
         if want > 0:
             lib = _lib.load()
-            a, b, c = c_vp(), c_vp(), c_vp()
+            a, b, c, d = c_vp(), c_vp(), c_vp(), c_vp()
             n1, n2 = ctypes.c_int(0), ctypes.c_int(0)
-            rc = lib.cspbo_gp_chol_streams(want, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(n1), ctypes.byref(n2))
+            rc = lib.cspbo_gp_chol_streams(want, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d), ctypes.byref(n1),
+                                           ctypes.byref(n2))
             if rc == 0:
-                made = tuple(torch.cuda.ExternalStream(p.value, device=dev) for p in (a, b, c)) + ((n1.value, n2.value),)
+                made = tuple(torch.cuda.ExternalStream(p.value, device=dev) for p in (a, b, c, d)) + ((n1.value, n2.value),)
         if made is None:
             lo, hi = torch.cuda.Stream.priority_range()
-            made = (torch.cuda.Stream(priority=hi), torch.cuda.Stream(priority=min(hi + 1, lo)), torch.cuda.Stream(priority=lo), None)
+            made = (torch.cuda.Stream(priority=hi), torch.cuda.Stream(priority=hi), torch.cuda.Stream(priority=min(hi + 1, lo)),
+                    torch.cuda.Stream(priority=lo), None)
         _STREAMS[dev] = made
     return _STREAMS[dev]
 
@@ -329,6 +331,7 @@ class ShardedCholesky:
         self.S = (self.N + self.nbw - 1) // self.nbw
         self.max_chunk = 4      # neighbouring superblocks updated by one dgemm (world 1 only)
         self.bulk_sms = int(os.environ.get("CSPBO_BULK_SMS", "0"))
+        self.depth = max(1, int(os.environ.get("CSPBO_CHOL_DEPTH", "3")))    # panels of look-ahead
         self.cuda = bool(getattr(self.ops, "cuda", False))
         dev = local2d.device
         self.U = torch.empty((self.N, self.N), dtype=torch.float64, device=dev)
@@ -336,7 +339,7 @@ class ShardedCholesky:
         self.inv = torch.zeros((self.RING, self.nbw * self.nbw), dtype=torch.float64, device=dev)
         self.stage = torch.zeros((self.RING, self.nbw * 3 * self.nbw), dtype=torch.float64, device=dev)
         if self.cuda:
-            self.s_diag, self.s_panel, self.s_update, self.sm_split = _chol_streams()
+            self.s_diag, self.s_panel, self.s_look, self.s_update, self.sm_split = _chol_streams()
         self._src = [torch.distributed.get_global_rank(group, r) if (group is not None and world > 1) else r
                      for r in range(world)]
         self.g_narrow = _narrow_group(group, world) if world > 1 else None
@@ -366,12 +369,14 @@ class ShardedCholesky:
         torch, ops, dist = self.torch, self.ops, self.torch.distributed
         N, nbw, S, W, me, R = self.N, self.nbw, self.S, self.world, self.rank, self.RING
         U, loc, cuda = self.U, self.local, self.cuda
+        D = self.depth
         sd = self.s_diag.cuda_stream if cuda else None
         sp = self.s_panel.cuda_stream if cuda else None
+        sl = self.s_look.cuda_stream if cuda else None
         su = self.s_update.cuda_stream if cuda else None
         if cuda:
             cur = torch.cuda.current_stream()
-            for st in (self.s_diag, self.s_panel, self.s_update):
+            for st in (self.s_diag, self.s_panel, self.s_look, self.s_update):
                 st.wait_stream(cur)
             if self.bulk_sms:
                 ops.sm_target(su, self.bulk_sms)
@@ -380,7 +385,7 @@ class ShardedCholesky:
             def __enter__(self): return self
             def __exit__(self, *a): return False
         on = (lambda st: torch.cuda.stream(st)) if cuda else (lambda st: _Null())
-        SD, SP, SU = (self.s_diag, self.s_panel, self.s_update) if cuda else (None, None, None)
+        SD, SP, SL, SU = (self.s_diag, self.s_panel, self.s_look, self.s_update) if cuda else (None, None, None, None)
 
         def record(st):
             if not cuda:
@@ -406,7 +411,10 @@ class ShardedCholesky:
             return e
 
         mine = [s for s in range(S) if self._owner(s) == me]
-        e_first, e_look, e_wtrmm = {}, {}, {}     # see the waits below for what each event certifies
+        # e_first[k]: the first bulk dgemm of panel k is done (rows k+D+1 carry panel k); e_sl[t]: the latest look-ahead
+        # update of rows t is done; e_look[k]: rows k+1 carry panel k in the columns right of the narrow piece;
+        # e_wtrmm[k]: the wide trmm of panel k has consumed its inverse slot
+        e_first, e_look, e_wtrmm, e_sl = {}, {}, {}, {}
         bounds = lambda s: (s * nbw, min((s + 1) * nbw, N), min((s + 2) * nbw, N), min((s + 3) * nbw, N))
 
         for s in range(S):
@@ -424,9 +432,9 @@ class ShardedCholesky:
             with on(SD):
                 t0 = mark(SD)
                 if own:
-                    wait(SD, e_first.get(s - 2))      # bulk updates of panels <= s-2 have reached rows s
                     wait(SD, e_wtrmm.get(s - R))      # the wide trmm that used this inverse slot is done
-                    # (panel s-1 reached [diag | next block] through the narrow update below, in stream order)
+                    # (every earlier panel has reached [diag | next block]: the narrow update below, in stream order,
+                    # waited for the bulk and look-ahead updates of these rows)
                     t0 = mark(SD)
                     ops.diag(loc[l0:l0 + h, r0:r1], inv, self.info[s:s + 1], sd)
                     msg[:, :h].copy_(loc[l0:l0 + h, r0:r1], non_blocking=True)
@@ -447,7 +455,8 @@ class ShardedCholesky:
                 e_diag = record(SD) if own else None
                 if nxt:
                     # rows s+1: [diag block | next block] -= P_s[:, cols(s+1)]^T P_s[:, cols(s+1) u cols(s+2)]
-                    wait(SD, e_first.get(s - 1))      # bulk updates of panels <= s-1 have reached rows s+1
+                    wait(SD, e_first.get(s - D))      # bulk updates (panels <= s-D) and look-ahead updates (panels
+                    wait(SD, e_sl.get(s + 1))         # s-D+1 .. s-1) have reached rows s+1
                     ops.update(loc[lt:lt + (r2 - r1), r1:r3], msg[:, h:h + (r2 - r1)], msg[:, h:], sd)
                 if trace is not None:
                     if own:
@@ -457,7 +466,6 @@ class ShardedCholesky:
             with on(SP):
                 if own:
                     wait(SP, e_diag)
-                    wait(SP, e_first.get(s - 2))
                     t3 = mark(SP)
                     if r3 < N:
                         ops.apply_inv(inv, loc[l0:l0 + h, r3:N], U[r0:r1, r3:N], sp)
@@ -471,17 +479,30 @@ class ShardedCholesky:
                 if trace is not None:
                     trace.append(("wide_bcast" if own else "wide_wait", s, t4, mark(SP)))
                 if nxt:
-                    wait(SP, e_first.get(s - 1))
+                    wait(SP, e_first.get(s - D))
+                    wait(SP, e_sl.get(s + 1))
                     if r3 < N:
                         t5 = mark(SP)
                         ops.update(loc[lt:lt + (r2 - r1), r3:N], U[r0:r1, r1:r2], U[r0:r1, r3:N], sp)
                         if trace is not None:
                             trace.append(("lookahead", s, t5, mark(SP)))
                     e_look[s] = record(SP)
+            # ------------------------------------------------------------------ deeper look-ahead: rows s+2 .. s+D
+            with on(SL):
+                for d in range(2, D + 1):
+                    t = s + d
+                    if t >= S or self._owner(t) != me:
+                        continue
+                    wait(SL, e_wide)
+                    wait(SL, e_first.get(t - D - 1))  # the bulk updates of rows t are over
+                    lr, c0 = (t // W) * nbw, t * nbw
+                    ht = min(c0 + nbw, N) - c0
+                    ops.update(loc[lr:lr + ht, c0:N], U[r0:r1, c0:c0 + ht], U[r0:r1, c0:N], sl)
+                    e_sl[t] = record(SL)
             # ------------------------------------------------------------------ bulk updates of this rank's rows
             with on(SU):
                 wait(SU, e_wide)
-                todo = [t for t in mine if t >= s + 2]
+                todo = [t for t in mine if t >= s + D + 1]
                 i, first = 0, True
                 while i < len(todo):
                     # superblocks that are neighbours in the matrix AND in this rank's buffer (world 1, zigzag turns)
@@ -495,16 +516,16 @@ class ShardedCholesky:
                     ht = min((todo[j - 1] + 1) * nbw, N) - c0
                     ops.update(loc[lr:lr + ht, c0:N], U[r0:r1, c0:c0 + ht], U[r0:r1, c0:N], su)
                     if first:
-                        e_first[s] = record(SU)      # rows s+2 (if they are mine) now carry panel s
+                        e_first[s] = record(SU)      # rows s+D+1 (if they are mine) now carry panel s
                         first = False
                     i = j
                 if first:
                     e_first[s] = record(SU)
-                for d in (e_first, e_look, e_wtrmm):
-                    d.pop(s - R - 2, None)
+                for d in (e_first, e_look, e_wtrmm, e_sl):
+                    d.pop(s - R - D - 2, None)
         if cuda:
             cur = torch.cuda.current_stream()
-            for st in (self.s_diag, self.s_panel, self.s_update):
+            for st in (self.s_diag, self.s_panel, self.s_look, self.s_update):
                 cur.wait_stream(st)
         return self
 

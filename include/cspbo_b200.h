@@ -267,11 +267,12 @@ int cspbo_gp_chol_apply_inv(const double *inv, int h, const double *src, long lo
                             long long ldc, void *stream);
 int cspbo_gp_chol_update(double *C, long long ldc, int nb, long long w, const double *A, long long lda, const double *B,
                          long long ldb, int h, void *stream);
-/* Three streams for the factorisation with the SMs partitioned by CUDA green contexts: `diag` owns diag_sms SMs
- * (the latency-bound potrf chain no longer shares FP64 pipes with the trailing dgemms), `panel` (high priority) and
- * `update` (low priority) share the rest.  Created once per device; fails (callers fall back to plain priority
- * streams) when the driver has no green contexts. */
-int cspbo_gp_chol_streams(int diag_sms, void **diag, void **panel, void **update, int *diag_sms_got, int *rest_sms_got);
+/* Four streams for the factorisation with the SMs partitioned by CUDA green contexts: `diag` owns diag_sms SMs
+ * (the latency-bound potrf chain no longer shares FP64 pipes with the trailing dgemms), `panel` (high priority),
+ * `look` (look-ahead updates, medium) and `update` (bulk updates, low priority) share the rest.  Created once per
+ * device; fails (callers fall back to plain priority streams) when the driver has no green contexts. */
+int cspbo_gp_chol_streams(int diag_sms, void **diag, void **panel, void **look, void **update, int *diag_sms_got,
+                          int *rest_sms_got);
 /* limit the cuBLAS kernels issued on `stream` by these operations to sm_count SMs (0 = all; cublasSetSmCountTarget) */
 int cspbo_gp_stream_sm_target(void *stream, int sm_count);
 /* pred[n] = Kstar[n, N] . alpha[N]    gaussianprocess.py:140,359 */
