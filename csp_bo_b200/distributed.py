@@ -410,6 +410,8 @@ class ShardedCholesky:
             e.record(st)
             return e
 
+        import time as _time
+        host_t0 = _time.perf_counter()
         mine = [s for s in range(S) if self._owner(s) == me]
         # e_first[k]: the first bulk dgemm of panel k is done (rows k+D+1 carry panel k); e_sl[t]: the latest look-ahead
         # update of rows t is done; e_look[k]: rows k+1 carry panel k in the columns right of the narrow piece;
@@ -523,6 +525,7 @@ class ShardedCholesky:
                     e_first[s] = record(SU)
                 for d in (e_first, e_look, e_wtrmm, e_sl):
                     d.pop(s - R - D - 2, None)
+        self.host_ms = (_time.perf_counter() - host_t0) * 1e3     # host time spent issuing the whole factorisation
         if cuda:
             cur = torch.cuda.current_stream()
             for st in (self.s_diag, self.s_panel, self.s_look, self.s_update):

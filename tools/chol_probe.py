@@ -66,7 +66,7 @@ for G in sbs:
             if rank <= 1:
                 for row in chol.trace_timeline(range(8, 14)):
                     print("TL rank%d %s" % (rank, json.dumps(row)), flush=True)
-        rec.append(dict(build=(t1 - t0) * 1e3, alloc_noise=(t2 - t1) * 1e3, factor=(t3 - t2) * 1e3, solve=(t4 - t3) * 1e3, total=(t4 - t0) * 1e3))
+        rec.append(dict(host_issue=chol.host_ms, build=(t1 - t0) * 1e3, alloc_noise=(t2 - t1) * 1e3, factor=(t3 - t2) * 1e3, solve=(t4 - t3) * 1e3, total=(t4 - t0) * 1e3))
         del chol
     err = float(((Ktest @ ref) - (Ktest @ alpha.reshape(-1))).abs().max() / (Ktest @ ref).abs().max()) if ref is not None else None
     if rank == 0:
