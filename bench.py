@@ -249,12 +249,19 @@ def run_ours(args):
         outh = torch.empty(sh.local.shape, dtype=torch.float64).pin_memory()
         d2h = int(outh.numel() * 8) * world
 
+        e2e_parts = []
+
         def e2e_step():
+            t0 = time.perf_counter()
             pk = packing.Pack(Xh[0], Xh[1], Xh[2], Xh[3])             # H2D of the replicated descriptors + pack
+            torch.cuda.synchronize(); t1 = time.perf_counter()
             sh.pack = pk
             sh.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
+            t2 = time.perf_counter()
             outh.copy_(sh.local, non_blocking=False)                  # this rank's complete rows -> host
+            t3 = time.perf_counter()
             sh.pack = full
+            e2e_parts.append([round((b - a) * 1e3, 2) for a, b in ((t0, t1), (t1, t2), (t2, t3))])
             return float(outh.view(-1)[0])
     e2e_ms, chk = [], 0.0
     for i in range(1 + n_e2e):
@@ -269,6 +276,7 @@ def run_ours(args):
     e2e = {"value": entries / (float(te.item()) * 1e-3), "unit": "entries/s", "ms_per_step": float(te.item()),
            "h2d_bytes_per_step": int(X[0].nbytes + X[1].nbytes + 2 * 4 * len(X[0])) * world,
            "d2h_bytes_per_step": d2h, "check": chk, "ms_all": [round(v, 2) for v in e2e_ms],
+           "rank0_h2d_pack__build__d2h_ms": (e2e_parts[-1] if world > 1 else None),
            "api": "kernels.dot_kernel.kff_C(host tuple, host tuple, out=pinned)" if world == 1 else
                   "packing.Pack(host) + distributed.ShardedSymmetricBlock.build + row-block copy to pinned host"}
     del outh
@@ -304,8 +312,9 @@ def run_ours(args):
                 barrier(); t2 = time.perf_counter()
                 fit_ms.append(((t2 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3))
             shf.close()
-            how = ("K_FF sharded by %d-row panels (packed order, zigzag owners) -> sharded Cholesky (owner potrf/trsm, "
-                   "NCCL panel broadcast, per-rank dgemm updates, look-ahead 1) -> potrs on the replicated factor" % (24 * FIT_SB_BLOCKS))
+            how = ("K_FF sharded by %d-row panels (packed order, zigzag owners) -> sharded Cholesky (diagonal chain: potrf + "
+                   "inverse + narrow piece on its own SMs and communicator; wide trmm, NCCL panel broadcast, look-ahead and "
+                   "per-rank dgemm updates behind it) -> potrs on the replicated factor" % (24 * FIT_SB_BLOCKS))
         best = min(fit_ms[1:], key=lambda v: v[0])
         tl = torch.tensor(list(best), dtype=torch.float64, device="cuda")
         if world > 1:
