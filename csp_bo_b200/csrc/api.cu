@@ -24,7 +24,8 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
                        int accumulate, cudaStream_t st, int rank = 0, int nranks = 1, double *const *outs = nullptr,
                        int a_begin = 0, int a_end = -1, int diag = 0, int sb_blocks = 1, int zigzag = 0,
-                       int packed_cols = 0);
+                       int packed_cols = 0, const struct PanelArgs *panel = nullptr);
+struct PanelArgs { long long ld; int nbw; long long row0_a, row0_b; };
 int sharded_superblocks(int n_blocks, int rank, int nranks, int sb_blocks, int zigzag);
 
 struct DevBuf {
@@ -455,6 +456,36 @@ extern "C" int cspbo_block_build_sharded_ex(const cspbo_block_desc *desc, const 
     }
     return build_block_device(d, a, a, 0, 0, outs[rank], nullptr, si, sk, sj, sl, 0, 0, rank, nranks, outs, 0, -1, 0,
                               sb_blocks, zigzag, packed_cols);
+}
+
+extern "C" int cspbo_block_build_panel(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b, int rank, int nranks,
+                                       double *const *outs, long long ld, int nbw, long long row0_a, long long row0_b)
+{
+    if (!desc || !a || !b || !outs) { set_error("block_build_panel: null argument"); return CSPBO_E_ARG; }
+    if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) { set_error("block_build_panel: bad rank %d/%d", rank, nranks); return CSPBO_E_ARG; }
+    for (int r = 0; r < nranks; r++)
+        if (!outs[r]) { set_error("block_build_panel: outs[%d] is null", r); return CSPBO_E_ARG; }
+    cspbo_block_desc d = *desc;
+    if (d.stress || d.with_grad) { set_error("block_build_panel: no stress / grad variants"); return CSPBO_E_ARG; }
+    if (d.family == CSPBO_RBF && !(d.l > 0.0)) { set_error("block_build_panel: RBF needs l > 0"); return CSPBO_E_ARG; }
+    if (nbw <= 0 || nbw % 24 != 0) { set_error("block_build_panel: nbw must be a positive multiple of 24"); return CSPBO_E_ARG; }
+    if (row0_a < 0 || row0_b < 0 || row0_a % nbw || row0_b % nbw) { set_error("block_build_panel: packs must start at panel boundaries"); return CSPBO_E_ARG; }
+    if (a->row_classes != 1 || b->row_classes != 1) { set_error("block_build_panel: packs with row_classes = 1 only"); return CSPBO_E_ARG; }
+    long long rows_a, rows_b;
+    if (d.block == CSPBO_KEE) {
+        if (a != b || a->nc != 0) { set_error("block_build_panel: K_EE needs one energy pack on both sides"); return CSPBO_E_ARG; }
+        rows_a = rows_b = a->m; d.symmetric = 1;
+    } else if (d.block == CSPBO_KFF) {
+        if (a != b || a->nc < 3) { set_error("block_build_panel: K_FF needs one force pack on both sides"); return CSPBO_E_ARG; }
+        rows_a = rows_b = 3LL * a->m; d.symmetric = 1;
+    } else if (d.block == CSPBO_KEF) {
+        if (a->nc != 0 || b->nc < 3) { set_error("block_build_panel: K_EF needs (energy, force) packs"); return CSPBO_E_ARG; }
+        rows_a = a->m; rows_b = 3LL * b->m; d.symmetric = 0;
+    } else { set_error("block_build_panel: bad block"); return CSPBO_E_ARG; }
+    if (row0_a + rows_a > ld || row0_b + rows_b > ld) { set_error("block_build_panel: block does not fit (ld %lld)", ld); return CSPBO_E_ARG; }
+    if (row0_a == row0_b && a != b) { set_error("block_build_panel: two packs at the same rows"); return CSPBO_E_ARG; }
+    PanelArgs pa = {ld, nbw, row0_a, row0_b};
+    return build_block_device(d, a, b, 0, 0, outs[rank], nullptr, 0, 0, 0, 0, 0, 0, rank, nranks, outs, 0, -1, 0, 1, 1, 1, &pa);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -51,6 +51,8 @@ struct SideDev {
     int ns;            // species buckets per block
 };
 
+struct PanelSide { int g, sb0; long long col0; };
+
 struct TileParams {
     SideDev A, B;
     int a_nblk, b_nblk;
@@ -80,6 +82,13 @@ struct TileParams {
     int sharded, nranks, rank;
     int sb_blocks, zigzag, packed_cols, a_slots;   // a_slots: blocks (incl. a ragged tail) this rank enumerates
     double *outs[kMaxRanks];
+    // sharded == 2, "panel layout": the blocks of SEVERAL packs (energies, forces) live in one distributed matrix of
+    // leading dimension ldo whose rows are dealt to the ranks by superblocks of nbw ROWS (zigzag); a pack starts at a
+    // superblock boundary (global superblock sb0, global row = column col0) and g of its 8-group blocks make a superblock.
+    // Side A = rows of the tile, side B = columns; the mirrored tile goes to the owner of the B rows.
+    int nbw, cyc0, pair;      // pair: A and B are different packs (K_EF): every tile is mirrored
+    long long ldo;
+    PanelSide pa, pb;
 };
 
 __device__ __host__ __forceinline__ int sb_owner(int sb, int nranks, int zigzag)
@@ -242,7 +251,13 @@ block_tile_kernel(const TileParams p)
     const int pg = strip * p.strip + (rem - q * strip_w);
     const int a_idx = pg * a_units + (p.split ? 0 : warp);
     int a_blk = p.a_begin + a_idx;
-    if (p.sharded) {   // a_idx-th block of this rank's buffer -> global block id
+    if (p.sharded == 2) {   // panel layout: a_idx-th block slot of this rank within pack A's superblock range
+        const int c = a_idx / p.pa.g, within = a_idx - c * p.pa.g;
+        const int cyc = p.cyc0 + c;
+        const int pos = (cyc & 1) ? p.nranks - 1 - p.rank : p.rank;
+        const int sl = cyc * p.nranks + pos - p.pa.sb0;       // superblock index inside pack A (may fall outside)
+        a_blk = sl < 0 ? p.a_nblk : sl * p.pa.g + within;
+    } else if (p.sharded) {   // a_idx-th block of this rank's buffer -> global block id
         const int cyc = a_idx / p.sb_blocks, within = a_idx - cyc * p.sb_blocks;
         const int pos = (p.zigzag && (cyc & 1)) ? p.nranks - 1 - p.rank : p.rank;
         a_blk = (cyc * p.nranks + pos) * p.sb_blocks + within;
@@ -441,6 +456,32 @@ block_tile_kernel(const TileParams p)
             }
         return;
     }
+    if (p.sharded == 2) {
+        // panel layout: own tile -> local rows, mirrored tile -> the rows of the B groups on their owner (NVLink peer store)
+        double *mine = p.outs[p.rank];
+        const int sA = p.pa.sb0 + a_blk / p.pa.g;
+        const long long row_i = (long long)(sA / p.nranks) * p.nbw + ((a_blk % p.pa.g) * 8 + ar) * NC1;
+        const long long col_i = p.pa.col0 + ((long long)a_blk * 8 + ar) * NC1;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int gj = p.B.slot_group[b_blk * 8 + bq + e];
+            if (gj < 0) continue;
+            const int sB = p.pb.sb0 + b_blk / p.pb.g;
+            double *peer = p.outs[sb_owner(sB, p.nranks, 1)];
+            const long long row_j = (long long)(sB / p.nranks) * p.nbw + ((b_blk % p.pb.g) * 8 + bq + e) * NC2;
+            const long long col_j = p.pb.col0 + ((long long)b_blk * 8 + bq + e) * NC2;
+            const bool mirror = p.pair || b_blk != a_blk;
+#pragma unroll
+            for (int k = 0; k < NC1; k++)
+#pragma unroll
+                for (int l = 0; l < NC2; l++) {
+                    const double v = p.scale * acc[e][k][l];
+                    mine[(row_i + k) * p.ldo + col_j + l] = v;
+                    if (mirror) peer[(row_j + l) * p.ldo + col_i + k] = v;
+                }
+        }
+        return;
+    }
     if (p.sharded) {
         // sharded symmetric build: rows are block-cyclic over ranks in packed order, columns keep the
         // caller's group ids.  Own tile -> local HBM, mirrored tile -> peer HBM of the owner of b.
@@ -553,6 +594,9 @@ static int launch_ks(int mode, int fam, bool z2, const TileParams &p, int nwarps
     }
 }
 
+// Panel-layout arguments of build_block_device (cspbo_block_build_panel).
+struct PanelArgs { long long ld; int nbw; long long row0_a, row0_b; };
+
 // Number of superblocks (a ragged last one included) owned by `rank`.
 int sharded_superblocks(int n_blocks, int rank, int nranks, int sb_blocks, int zigzag)
 {
@@ -566,7 +610,7 @@ int sharded_superblocks(int n_blocks, int rank, int nranks, int sb_blocks, int z
 int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
                        int accumulate, cudaStream_t st, int rank, int nranks, double *const *outs, int a_begin, int a_end,
-                       int diag, int sb_blocks, int zigzag, int packed_cols)
+                       int diag, int sb_blocks, int zigzag, int packed_cols, const PanelArgs *panel)
 {
     if (a->ks != b->ks || a->d != b->d) {
         set_error("block_build: packs have different descriptor lengths (%d vs %d)", a->d, b->d);
@@ -604,6 +648,21 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.a_begin = p.sharded ? 0 : std::max(a_begin, 0);
     p.a_nblk = (a_end < 0 || p.sharded) ? (int)a->n_blocks : std::min(a_end, (int)a->n_blocks);
     p.a_slots = p.sharded ? sharded_superblocks((int)a->n_blocks, p.rank, p.nranks, p.sb_blocks, p.zigzag) * p.sb_blocks : 0;
+    p.nbw = 0; p.cyc0 = 0; p.pair = 0; p.ldo = 0;
+    p.pa = {1, 0, 0}; p.pb = {1, 0, 0};
+    if (panel && p.sharded) {
+        const int nca = (mode == MODE_KFF) ? 3 : 1, ncb = (mode == MODE_KEE) ? 1 : 3;
+        p.sharded = 2;
+        p.zigzag = 1;
+        p.nbw = panel->nbw; p.ldo = panel->ld;
+        p.pa = {panel->nbw / (8 * nca), (int)(panel->row0_a / panel->nbw), panel->row0_a};
+        p.pb = {panel->nbw / (8 * ncb), (int)(panel->row0_b / panel->nbw), panel->row0_b};
+        p.pair = (a != b) ? 1 : 0;
+        const int nsbA = ((int)a->n_blocks + p.pa.g - 1) / p.pa.g;
+        p.cyc0 = p.pa.sb0 / p.nranks;
+        const int cyc1 = (p.pa.sb0 + std::max(nsbA, 1) - 1) / p.nranks;
+        p.a_slots = (cyc1 - p.cyc0 + 1) * p.pa.g;
+    }
     p.b_nblk = diag ? 1 : (int)b->n_blocks;
     if (p.a_nblk <= p.a_begin || b->n_blocks == 0) return CSPBO_OK;
 

@@ -585,3 +585,184 @@ def fit_alpha_sharded(sh, y, noise2, ops=None, return_solver=False):
     alpha[order] = ap.reshape(sh.m, sh.ncomp)
     alpha = alpha.reshape(-1)
     return (alpha, chol) if return_solver else alpha
+
+
+# ----------------------------------------------------------------------------- whole covariance, sharded
+class ShardedCovariance:
+    """[[K_EE, K_EF], [K_FE, K_FF]] (reference base.py:13-14, Dot_mb.py:87-119) of a training set as ONE matrix
+    distributed over the ranks in the panel layout of cspbo_block_build_panel, ready for ShardedCholesky:
+
+        global rows = columns:  [ energies in packed order | identity padding up to a panel boundary | forces in
+                                  packed order, 3 rows per atom ]
+        superblock s = rows [s*nbw, (s+1)*nbw), owner zigzag(s), stored at local rows [(s // world)*nbw, +nbw).
+
+    Every rank packs the same (replicated) descriptors; K_EE and K_FF are built as symmetric sharded blocks, K_EF by
+    the owners of the energy rows, each tile also stored transposed (K_FE) into the force rows of its owner over
+    NVLink peer memory.  The reference's post-scalings (/N_i N_j, /N_i; dot_kernel.py:45,129-130) are applied to
+    the local rows afterwards.
+    """
+
+    def __init__(self, kernel, data, group=None, nbw=384):
+        import torch
+        import torch.distributed as dist
+        from .kernels import device as kdev
+        self.torch, self.lib, self.group, self.nbw = torch, _lib.load(), group, int(nbw)
+        if nbw % 24:
+            raise ValueError("nbw must be a multiple of 24")
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.h = kdev._hyper(kernel, quirk=True)
+        self.pe, self.pf = kdev._tuples(data)
+        self.mE = self.pe.m if self.pe else 0
+        self.mF = self.pf.m if self.pf else 0
+        self.NE_pad = ((self.mE + nbw - 1) // nbw) * nbw
+        self.N = self.NE_pad + 3 * self.mF
+        self.S = (self.N + nbw - 1) // nbw
+        self.mine = [s for s in range(self.S) if superblock_owner(s, self.world, True) == self.rank]
+        self.rows = len(self.mine) * nbw
+        self.order_e = self._order(self.pe) if self.pe else np.zeros(0, dtype=np.int64)
+        self.order_f = self._order(self.pf) if self.pf else np.zeros(0, dtype=np.int64)
+        nbytes = 8 * max(self.rows, 1) * self.N
+        ptr = c_vp()
+        _lib.check(self.lib.cspbo_dev_alloc(nbytes, ctypes.byref(ptr)))
+        self._own, self._peers = ptr, [None] * self.world
+        self._ptrs = (c_vp * self.world)()
+        self._ptrs[self.rank] = ptr
+        if self.world > 1:
+            handle = (ctypes.c_ubyte * 64)()
+            _lib.check(self.lib.cspbo_ipc_export(ptr, ctypes.cast(handle, c_vp)))
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
+            allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(self.world)]
+            dist.all_gather(allh, mine, group=group)
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                hb = (ctypes.c_ubyte * 64)(*allh[r].cpu().tolist())
+                pp = c_vp()
+                _lib.check(self.lib.cspbo_ipc_open(ctypes.cast(hb, c_vp), ctypes.byref(pp)))
+                self._peers[r] = pp
+                self._ptrs[r] = pp
+        self.local = torch.as_tensor(_RawCuda(ptr.value, (max(self.rows, 1), self.N)), device="cuda")[: self.rows]
+
+    def _order(self, pack):
+        nb = (pack.m + 7) // 8
+        order = np.empty(nb * 8, dtype=np.int32)
+        _lib.check(self.lib.cspbo_pack_order(pack.handle, c_vp(order.ctypes.data), len(order)))
+        return order[: pack.m].astype(np.int64)
+
+    def _barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.torch.distributed.barrier(group=self.group)
+
+    def _panel(self, block, zeta, scale, a, b, row0_a, row0_b, tol=0.0, use_tol=False):
+        h = self.h
+        desc = BlockDesc(h["family"], block, float(zeta), float(h["sigma2"]), float(h["sigma02"]), float(h["l"]), float(tol),
+                         int(bool(use_tol)), 0, 0, float(scale), 1.0, 0)
+        _lib.check(self.lib.cspbo_block_build_panel(ctypes.byref(desc), a.handle, b.handle, self.rank, self.world, self._ptrs,
+                                                    self.N, self.nbw, int(row0_a), int(row0_b)))
+
+    def _local_rows(self, g0, g1):
+        """(local row indices, global row indices) of this rank's rows inside the global range [g0, g1)."""
+        loc, glob = [], []
+        for i, s in enumerate(self.mine):
+            a, b = max(s * self.nbw, g0), min((s + 1) * self.nbw, g1)
+            if b > a:
+                glob.append(np.arange(a, b))
+                loc.append(np.arange(a, b) - s * self.nbw + i * self.nbw)
+        if not loc:
+            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+        return np.concatenate(loc), np.concatenate(glob)
+
+    def build(self, noise_e, f_coef, tol=1e-10):
+        """Build K + noise into the distributed rows (gaussianprocess.py:105-113)."""
+        torch, h, nbw = self.torch, self.h, self.nbw
+        self.local.zero_()
+        self._barrier()                    # every buffer is zeroed before peers store mirrored tiles into it
+        if self.pe:
+            self._panel(_lib.KEE, h["zee"], h["see"], self.pe, self.pe, 0, 0)
+        if self.pe and self.pf:
+            self._panel(_lib.KEF, h["zef"], h["sef"], self.pe, self.pf, 0, self.NE_pad)
+        if self.pf:
+            self._panel(_lib.KFF, h["zff"], h["sff"], self.pf, self.pf, self.NE_pad, self.NE_pad, tol=tol,
+                        use_tol=(h["family"] == _lib.RBF))
+        self._barrier()                    # peer stores have landed
+        dev = self.local.device
+        if self.pe:
+            ce = torch.as_tensor(self.pe.counts[self.order_e], dtype=torch.float64, device=dev)      # packed order
+            le, ge = self._local_rows(0, self.mE)
+            if len(le):
+                lt = torch.as_tensor(le, device=dev)
+                rows = self.local[lt]
+                rows[:, : self.mE] /= ce[None, :]
+                rows /= ce[torch.as_tensor(ge, device=dev)][:, None]
+                self.local[lt] = rows
+            lf, _ = self._local_rows(self.NE_pad, self.N)
+            if len(lf):
+                lt = torch.as_tensor(lf, device=dev)
+                self.local[lt, : self.mE] = self.local[lt, : self.mE] / ce[None, :]
+        # noise on the diagonal, identity on the padding rows
+        for rng, val in (((0, self.mE), float(noise_e) ** 2), ((self.mE, self.NE_pad), 1.0),
+                         ((self.NE_pad, self.N), (float(f_coef) * float(noise_e)) ** 2)):
+            lr, gr = self._local_rows(*rng)
+            if len(lr):
+                self.local[torch.as_tensor(lr, device=dev), torch.as_tensor(gr, device=dev)] += val
+        return self.local
+
+    def to_packed(self, y):
+        """caller's [E; F] vector (energies, then forces atom-major) -> the matrix's row order (zeros on the padding)."""
+        torch = self.torch
+        yt = torch.as_tensor(np.asarray(y, dtype=np.float64).reshape(-1) if not isinstance(y, torch.Tensor) else y.reshape(-1),
+                             dtype=torch.float64, device=self.local.device)
+        out = torch.zeros(self.N, dtype=torch.float64, device=self.local.device)
+        if self.mE:
+            out[: self.mE] = yt[: self.mE][torch.as_tensor(self.order_e, device=out.device)]
+        if self.mF:
+            of = torch.as_tensor(self.order_f, device=out.device)
+            out[self.NE_pad:] = yt[self.mE:].reshape(self.mF, 3)[of].reshape(-1)
+        return out
+
+    def from_packed(self, v):
+        torch = self.torch
+        out = torch.empty(self.mE + 3 * self.mF, dtype=torch.float64, device=v.device)
+        if self.mE:
+            out[: self.mE][torch.as_tensor(self.order_e, device=v.device)] = v[: self.mE]
+        if self.mF:
+            of = torch.as_tensor(self.order_f, device=v.device)
+            tmp = torch.empty((self.mF, 3), dtype=torch.float64, device=v.device)
+            tmp[of] = v[self.NE_pad:].reshape(self.mF, 3)
+            out[self.mE:] = tmp.reshape(-1)
+        return out
+
+    def close(self):
+        self._barrier()
+        self.local = None
+        for r, pp in enumerate(self._peers):
+            if pp is not None:
+                self.lib.cspbo_ipc_close(pp)
+                self._peers[r] = None
+        if self._own is not None:
+            self.lib.cspbo_dev_free(self._own)
+            self._own = None
+
+    def __del__(self):
+        try:
+            if self._own is not None:
+                self.close()
+        except Exception:
+            pass
+
+
+def fit_sharded(kernel, data, y, noise_e, f_coef, group=None, nbw=384, tol=1e-10, return_solver=False):
+    """The fit of gaussianprocess.py:105-127 (opt=False) on all ranks at once: K + noise built in the panel layout,
+    factorised in place by the sharded Cholesky, alpha = K^-1 y returned in the caller's [E; F] order on every rank."""
+    cov = ShardedCovariance(kernel, data, group=group, nbw=nbw)
+    cov.build(noise_e, f_coef, tol=tol)
+    chol = ShardedCholesky(cov.local, cov.N, nbw, cov.rank, cov.world, True, group)
+    chol.factor()
+    chol.check()
+    alpha = cov.from_packed(chol.solve(cov.to_packed(y)))
+    if return_solver:
+        return alpha, chol, cov
+    cov.close()
+    return alpha

@@ -240,6 +240,16 @@ long long cspbo_sharded_rows_ex(const cspbo_pack *a, int rank, int nranks, int s
 int cspbo_block_build_sharded_ex(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
                                  double *const *outs, int sb_blocks, int zigzag, int packed_cols);
 
+/* Panel layout: the whole covariance [[K_EE, K_EF], [K_FE, K_FF]] (base.py:13-14) as ONE distributed matrix, the input
+ * of the sharded Cholesky.  Global rows = columns: each pack in packed order (cspbo_pack_order), starting at a multiple
+ * of nbw (row0_a / row0_b; callers pad the energy part with identity rows); rows are dealt to the ranks by superblocks
+ * of nbw rows in zigzag order, superblock s being rows [(s / nranks) * nbw, +nbw) of its owner's buffer outs[r], a
+ * row-major matrix of leading dimension ld.  block = K_EE / K_FF: a == b, the upper block triangle is computed and
+ * mirrored; K_EF: a = energy pack (rows), b = force pack (columns), every tile is also stored transposed (K_FE) on the
+ * owner of the force rows.  Mirrored tiles travel as NVLink peer stores; barrier across ranks before and after. */
+int cspbo_block_build_panel(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b, int rank, int nranks,
+                            double *const *outs, long long ld, int nbw, long long row0_a, long long row0_b);
+
 /* ------------------------------------------------------------------------------------------
  * (3) GP algebra on the device (all pointers are DEVICE pointers, column count = N)
  * ------------------------------------------------------------------------------------------ */

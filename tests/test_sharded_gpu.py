@@ -139,3 +139,71 @@ def test_sharded_cholesky_two_gpus():
         out = mgr.dict()
         mp.spawn(_chol_rank_main, args=(2, 29631, out), nprocs=2, join=True)
         assert len(out) == 2 and all(v < 1e-8 for v in out.values()), dict(out)
+
+
+def _mixed_problem(n_struct, n_atoms, single=False, rows=64):
+    from csp_bo_b200 import synthetic
+    E = synthetic.energy_set(n_struct, seed=21, single_element=single, rows_per_structure=rows)
+    F = synthetic.force_set(n_atoms, seed=22, single_element=single)
+    y = np.random.default_rng(5).standard_normal(n_struct + 3 * n_atoms)
+    return {"energy": E, "force": F}, y
+
+
+@pytest.mark.parametrize("fam", ["dot", "rbf"])
+@pytest.mark.parametrize("n_struct,n_atoms,nbw", [(5, 40, 24), (30, 100, 48), (50, 0, 24), (0, 70, 48)])
+def test_sharded_covariance_world1(fam, n_struct, n_atoms, nbw):
+    """whole [[EE, EF], [FE, FF]] in the panel layout + sharded Cholesky against the dense single-GPU fit."""
+    import torch
+    from csp_bo_b200.distributed import fit_sharded
+    from csp_bo_b200.kernels import Dot_mb, RBF_mb
+    kernel = Dot_mb(para=[18.555440586011372, 0.01], zeta=2) if fam == "dot" else RBF_mb(para=[6.244955524643115, 0.5611029935713949], zeta=2)
+    data, y = _mixed_problem(max(n_struct, 1), max(n_atoms, 1))
+    if n_struct == 0:
+        data.pop("energy"); y = y[1:]
+    if n_atoms == 0:
+        data.pop("force"); y = y[:n_struct]
+    from csp_bo_b200 import gp
+    from csp_bo_b200.kernels import device as kdev
+    K = kdev.k_total_device(kernel, data)
+    Kc = K.clone()
+    ne = len(data["energy"][2]) if "energy" in data else 0
+    ref = gp.fit_alpha(K, torch.from_numpy(y).cuda(), n_energy=ne, noise_e=0.01, f_coef=20.0, overwrite=True)
+    alpha = fit_sharded(kernel, data, y, 0.01, 20.0, nbw=nbw)
+    pr, pa = Kc @ ref, Kc @ alpha
+    assert float((pr - pa).abs().max() / pr.abs().max()) < 1e-8
+    assert float((ref - alpha).abs().max() / ref.abs().max()) < 1e-6
+
+
+def _cov_rank_main(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    from csp_bo_b200 import _lib, gp
+    from csp_bo_b200.distributed import fit_sharded
+    from csp_bo_b200.kernels import RBF_mb
+    from csp_bo_b200.kernels import device as kdev
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    _lib.check(_lib.load().cspbo_set_device(rank))
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        kernel = RBF_mb(para=[6.244955524643115, 0.5611029935713949], zeta=2)
+        data, y = _mixed_problem(130, 300)
+        K = kdev.k_total_device(kernel, data)
+        Kc = K.clone()
+        ref = gp.fit_alpha(K, torch.from_numpy(y).cuda(), n_energy=130, noise_e=0.01, f_coef=20.0, overwrite=True)
+        alpha = fit_sharded(kernel, data, y, 0.01, 20.0, nbw=96)
+        pr, pa = Kc @ ref, Kc @ alpha
+        out[rank] = float((pr - pa).abs().max() / pr.abs().max())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_covariance_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_cov_rank_main, args=(2, 29651, out), nprocs=2, join=True)
+        assert len(out) == 2 and all(v < 1e-8 for v in out.values()), dict(out)
