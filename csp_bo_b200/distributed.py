@@ -709,30 +709,14 @@ class ShardedCovariance:
                 self.local[torch.as_tensor(lr, device=dev), torch.as_tensor(gr, device=dev)] += val
         return self.local
 
-    def to_packed(self, y):
-        """caller's [E; F] vector (energies, then forces atom-major) -> the matrix's row order (zeros on the padding)."""
-        torch = self.torch
-        yt = torch.as_tensor(np.asarray(y, dtype=np.float64).reshape(-1) if not isinstance(y, torch.Tensor) else y.reshape(-1),
-                             dtype=torch.float64, device=self.local.device)
-        out = torch.zeros(self.N, dtype=torch.float64, device=self.local.device)
-        if self.mE:
-            out[: self.mE] = yt[: self.mE][torch.as_tensor(self.order_e, device=out.device)]
-        if self.mF:
-            of = torch.as_tensor(self.order_f, device=out.device)
-            out[self.NE_pad:] = yt[self.mE:].reshape(self.mF, 3)[of].reshape(-1)
-        return out
-
-    def from_packed(self, v):
-        torch = self.torch
-        out = torch.empty(self.mE + 3 * self.mF, dtype=torch.float64, device=v.device)
-        if self.mE:
-            out[: self.mE][torch.as_tensor(self.order_e, device=v.device)] = v[: self.mE]
-        if self.mF:
-            of = torch.as_tensor(self.order_f, device=v.device)
-            tmp = torch.empty((self.mF, 3), dtype=torch.float64, device=v.device)
-            tmp[of] = v[self.NE_pad:].reshape(self.mF, 3)
-            out[self.mE:] = tmp.reshape(-1)
-        return out
+    def permutation(self):
+        """perm[i] = row of the distributed matrix that holds row i of the caller's [E; F] ordering."""
+        inv_e = np.empty(self.mE, dtype=np.int64)
+        inv_e[self.order_e] = np.arange(self.mE)
+        inv_f = np.empty(self.mF, dtype=np.int64)
+        inv_f[self.order_f] = np.arange(self.mF)
+        pf = (self.NE_pad + inv_f[:, None] * 3 + np.arange(3)[None, :]).reshape(-1)
+        return np.concatenate((inv_e, pf))
 
     def close(self):
         self._barrier()
@@ -753,16 +737,39 @@ class ShardedCovariance:
             pass
 
 
+class ShardedSolver:
+    """K^-1 applied through the replicated factor of a ShardedCholesky, in the caller's [E; F] row order."""
+
+    def __init__(self, chol, perm):
+        self.chol = chol
+        self.perm = chol.torch.as_tensor(perm, device=chol.U.device)
+
+    def solve(self, B):
+        """B: [N] or [N, nrhs] CUDA tensor in the caller's order -> K^-1 B, same shape."""
+        torch = self.chol.torch
+        B2 = B.reshape(B.shape[0], -1)
+        P = torch.zeros((self.chol.N, B2.shape[1]), dtype=torch.float64, device=B.device)
+        P[self.perm] = B2
+        return self.chol.solve(P)[self.perm].reshape(B.shape)
+
+    def logdet(self):
+        return self.chol.logdet()        # the identity padding rows contribute log 1 = 0
+
+
 def fit_sharded(kernel, data, y, noise_e, f_coef, group=None, nbw=384, tol=1e-10, return_solver=False):
     """The fit of gaussianprocess.py:105-127 (opt=False) on all ranks at once: K + noise built in the panel layout,
-    factorised in place by the sharded Cholesky, alpha = K^-1 y returned in the caller's [E; F] order on every rank."""
+    factorised in place by the sharded Cholesky, alpha = K^-1 y returned in the caller's [E; F] order on every rank
+    (with return_solver=True also a ShardedSolver for the predictive variance and the LML)."""
+    import torch
     cov = ShardedCovariance(kernel, data, group=group, nbw=nbw)
     cov.build(noise_e, f_coef, tol=tol)
     chol = ShardedCholesky(cov.local, cov.N, nbw, cov.rank, cov.world, True, group)
     chol.factor()
     chol.check()
-    alpha = cov.from_packed(chol.solve(cov.to_packed(y)))
-    if return_solver:
-        return alpha, chol, cov
-    cov.close()
-    return alpha
+    solver = ShardedSolver(chol, cov.permutation())
+    yt = torch.as_tensor(np.asarray(y, dtype=np.float64).reshape(-1) if not isinstance(y, torch.Tensor) else y.reshape(-1),
+                         dtype=torch.float64, device=chol.U.device)
+    alpha = solver.solve(yt)
+    chol.local = None
+    cov.close()                          # the distributed rows are no longer needed: U is replicated
+    return (alpha, solver) if return_solver else alpha

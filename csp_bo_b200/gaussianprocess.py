@@ -1,8 +1,12 @@
 """GPU-resident Gaussian-process regressor: the fit / prediction / log-marginal-likelihood slice of the
 reference's `cspbo.gaussianprocess.GaussianProcess` (gaussianprocess.py:71-184, 325-390, 453-509) on top of
 the CUDA covariance kernels, plus remove_train_pts / sparsify / CUR (:230-270, :754-790).  Same method
-names, arguments and return values; what is NOT carried over is everything that needs ase / pyxtal /
-the ASE database (save/load/export_ase_db, add_structure): those stay in the reference.
+names, arguments and return values (load / load_from_dict / extract_db read the reference's json + ASE-sqlite
+files through csp_bo_b200.asedb); what is NOT carried over is what writes ASE databases or needs pyxtal
+(save, export_ase_db, add_structure): those stay in the reference.
+
+Under torch.distributed (one process per GPU, torchrun) fit(opt=False) builds K across the ranks and factorises it
+with the sharded Cholesky (csp_bo_b200/distributed.py: fit_sharded); every rank keeps alpha and the factor.
 
 Device residency: K is assembled block by block straight into one CUDA matrix
 (kernels/device.py), the noise is added and K is factorised in place by cuSOLVER
@@ -25,6 +29,13 @@ _SYMBOLS = ("X H He Li Be B C N O F Ne Na Mg Al Si P S Cl Ar K Ca Sc Ti V Cr Mn 
             "Rb Sr Y Zr Nb Mo Tc Ru Rh Pd Ag Cd In Sn Sb Te I Xe Cs Ba La Ce Pr Nd Pm Sm Eu Gd Tb Dy Ho Er Tm Yb Lu "
             "Hf Ta W Re Os Ir Pt Au Hg Tl Pb Bi Po At Rn").split()
 _Z = {s: i for i, s in enumerate(_SYMBOLS)}
+
+
+def _world_size():
+    import torch
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_world_size()
+    return 1
 
 
 class GaussianProcess():
@@ -204,10 +215,19 @@ class GaussianProcess():
             self.noise_e = params[-1]
             self.noise_f = self.f_coef * params[-1]
 
-        K = kdev.k_total_device(self.kernel, self._train_dict())          # CUDA [N,N]
         try:
-            alpha, logdet = gp.fit_alpha(K, self.y_train[:, 0], n_energy=self._n_energy(), noise_e=self.noise_e,
-                                         f_coef=self.f_coef, return_logdet=True, overwrite=True)
+            if _world_size() > 1:
+                # one process per GPU (torchrun): K is built in the panel layout across the ranks and factorised by the
+                # sharded Cholesky; every rank ends up with alpha and the replicated factor (csp_bo_b200/distributed.py)
+                from .distributed import fit_sharded
+                alpha, self._solver = fit_sharded(self.kernel, self._train_dict(), self.y_train[:, 0], self.noise_e,
+                                                  self.f_coef, return_solver=True)
+                K, logdet = None, self._solver.logdet()
+            else:
+                self._solver = None
+                K = kdev.k_total_device(self.kernel, self._train_dict())          # CUDA [N,N]
+                alpha, logdet = gp.fit_alpha(K, self.y_train[:, 0], n_energy=self._n_energy(), noise_e=self.noise_e,
+                                             f_coef=self.f_coef, return_logdet=True, overwrite=True)
         except _lib.CspboError as exc:
             if exc.code == 5:    # CSPBO_E_NOTPD, the LinAlgError of gaussianprocess.py:118-125
                 raise np.linalg.LinAlgError("The kernel, %s, is not returning a positive definite matrix. Try gradually "
@@ -348,7 +368,7 @@ class GaussianProcess():
         y_mean *= factors
 
         if return_cov:
-            v = gp.cho_solve(self.L_, K_trans.T.contiguous())
+            v = self._kinv(K_trans.T.contiguous())
             y_cov = kdev.k_total_device(self.kernel, X) - K_trans @ v
             return y_mean, y_cov.cpu().numpy()
         if return_std:
@@ -361,9 +381,15 @@ class GaussianProcess():
             return y_mean, gp.predict_mean(K_trans1, self._alpha_dev).cpu().numpy()
         return y_mean
 
+    def _kinv(self, B):
+        """K^-1 B through the resident factor (cuSOLVER potrs; the sharded solver after a multi-GPU fit)."""
+        if getattr(self, "_solver", None) is not None:
+            return self._solver.solve(B)
+        return gp.cho_solve(self.L_, B)
+
     def _variance(self, data, K_trans):
         """diag(k(X,X)) - diag(K* K^-1 K*^T)  (gaussianprocess.py:167-175,377-383) without forming K^-1."""
-        v = gp.cho_solve(self.L_, K_trans.T.contiguous())                  # [N, n*]
+        v = self._kinv(K_trans.T.contiguous())                             # [N, n*]
         y_var = self.kernel.diag(data)
         y_var = y_var - (K_trans * v.T).sum(dim=1).cpu().numpy()
         return y_var
