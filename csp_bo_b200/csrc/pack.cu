@@ -20,55 +20,66 @@
 
 namespace cspbo {
 
+// Four stacked rows per warp, eight lanes per row (lane l8 owns the features l8, l8+8, ...): the eight lanes of a row
+// store 64 contiguous bytes of a tile per (vector, feature octet) -- the fragment order of common.h keeps a slot's
+// features f..f+7 of one vector together -- the derivative columns are read three at a time as contiguous 24-byte
+// triplets, and a warp has four rows' worth of loads in flight.
+constexpr int kPackRowsPerWarp = 4;
+
 __global__ void pack_rows_kernel(int n, int d, int nc, int ks, int nv,
                                  const double *__restrict__ x, const double *__restrict__ dxdr,
                                  const long long *__restrict__ dest, double *__restrict__ tiles,
                                  unsigned *__restrict__ tile_valid, long long tile_doubles, double norm_shift)
 {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n) return;
-    const long long dst = dest[row];
-    if (dst < 0) return;
-    const long long tile = dst >> 3;
-    const int slot = (int)(dst & 7);
-    const double *xr = x + row * d;
+    const int lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
+    const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPackRowsPerWarp + sub;
+    const long long dst = row < n ? dest[row] : -1;
+    const bool live = dst >= 0;                      // the same for the eight lanes of a row
+    const double *xr = x + (live ? row : 0) * d;
 
     double ss = 0.0;
-    for (int f = lane; f < d; f += 32) {
-        double v = xr[f];
-        ss += v * v;
-    }
+    if (live)
+        for (int f = l8; f < d; f += 8) {
+            const double v = xr[f];
+            ss += v * v;
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    for (int o = 4; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     // norm_shift = 0: the C++ path (rows with |x| <= 1e-8 are skipped, dot_kernel.cpp:25);
     // norm_shift = eps: the NumPy single-pair functions used by diag(), which add eps to every norm and
     // skip nothing (Dot_mb.py:188-191,206,212)
     const double nrm = sqrt(ss) + norm_shift;
-    if (norm_shift == 0.0 && !(nrm > 1e-8)) return;
-    const double inv = 1.0 / nrm;
-
-    double *t = tiles + tile * tile_doubles;
+    const bool ok = live && (norm_shift != 0.0 || nrm > 1e-8);
+    const double inv = ok ? 1.0 / nrm : 0.0;
+    double *t = tiles + (ok ? (dst >> 3) : 0) * tile_doubles;
+    const int slot = (int)(dst & 7);
     const int half = ks >> 1;
-    for (int f = lane; f < d; f += 32) {
-        const long long idx = (((long long)(0 * half + (f >> 3)) * 32) + slot * 4 + (f & 3)) * 2 + ((f >> 2) & 1);
-        t[idx] = xr[f] * inv;
-    }
+    auto at = [&](int v, int f) { return (((long long)(v * half + (f >> 3)) * 32) + slot * 4 + (f & 3)) * 2 + ((f >> 2) & 1); };
+    if (ok)
+        for (int f = l8; f < d; f += 8) t[at(0, f)] = xr[f] * inv;
     if (nc > 0) {
-        const double *dr = dxdr + row * (long long)d * nc;
-        for (int k = 0; k < nc; k++) {
-            double al = 0.0;  // alpha_k = dxdr[:,k] . u
-            for (int f = lane; f < d; f += 32) al += dr[(long long)f * nc + k] * (xr[f] * inv);
+        const double *dr = dxdr + (live ? row : 0) * (long long)d * nc;
+        for (int k0 = 0; k0 < nc; k0 += 3) {
+            double al[3] = {0.0, 0.0, 0.0};  // alpha_k = dxdr[:,k] . u
+            if (ok)
+                for (int f = l8; f < d; f += 8) {
+                    const double u = xr[f] * inv;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) al += __shfl_xor_sync(0xffffffffu, al, o);
-            const int v = 1 + k;
-            for (int f = lane; f < d; f += 32) {
-                const long long idx = (((long long)(v * half + (f >> 3)) * 32) + slot * 4 + (f & 3)) * 2 + ((f >> 2) & 1);
-                t[idx] = (dr[(long long)f * nc + k] - al * (xr[f] * inv)) * inv;
-            }
+                    for (int c = 0; c < 3; c++) al[c] += dr[(long long)f * nc + k0 + c] * u;
+                }
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) al[c] += __shfl_xor_sync(0xffffffffu, al[c], o);
+            if (ok)
+                for (int f = l8; f < d; f += 8) {
+                    const double u = xr[f] * inv;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) t[at(1 + k0 + c, f)] = (dr[(long long)f * nc + k0 + c] - al[c] * u) * inv;
+                }
         }
     }
-    if (lane == 0) atomicOr(tile_valid + tile, 1u << slot);
+    if (ok && l8 == 0) atomicOr(tile_valid + (dst >> 3), 1u << slot);
 }
 
 }  // namespace cspbo
@@ -253,8 +264,8 @@ extern "C" int cspbo_pack_create_ex(int n, int d, int nc, int m, int row_start, 
                 dxs = d_dx;
             }
         }
-        const int wpb = 8;
-        pack_rows_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32>>>(n, d, nc, ks, p->nv, xs, dxs, d_dest,
+        const int rpb = 8 * kPackRowsPerWarp;   // 8 warps x 4 rows per CTA
+        pack_rows_kernel<<<(unsigned)((n + rpb - 1) / rpb), 256>>>(n, d, nc, ks, p->nv, xs, dxs, d_dest,
                                                                         p->d_tiles, p->d_tile_valid, p->tile_doubles, norm_shift);
         g_launches++;
         PACK_CUDA(cudaGetLastError());
