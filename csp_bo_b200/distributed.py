@@ -587,6 +587,67 @@ def fit_alpha_sharded(sh, y, noise2, ops=None, return_solver=False):
     return (alpha, chol) if return_solver else alpha
 
 
+# ----------------------------------------------------------------------------- peer-mapped buffers
+_IPC_POOL = {}
+
+
+def _shared_buffer(nbytes, group, world, rank):
+    """A device buffer of >= nbytes on every rank, each mapped into every other rank's address space (CUDA IPC):
+    (own pointer, ctypes array of the world pointers valid in THIS process).  Grow-only and cached per process group,
+    because cudaIpcOpenMemHandle costs milliseconds per peer (80 ms of set-up per fit at 8 GPUs when done every time).
+    `nbytes` must be the same on all ranks."""
+    import torch
+    import torch.distributed as dist
+    lib = _lib.load()
+    key = (id(group), world)
+    ent = _IPC_POOL.get(key)
+    if ent is not None and ent["bytes"] >= nbytes:
+        return ent["own"], ent["ptrs"]
+    if ent is not None:
+        _release_shared(ent, group, world)
+    want = int(nbytes) + int(nbytes) // 8
+    own = c_vp()
+    _lib.check(lib.cspbo_dev_alloc(want, ctypes.byref(own)))
+    ptrs = (c_vp * world)()
+    ptrs[rank] = own
+    peers = [None] * world
+    if world > 1:
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(lib.cspbo_ipc_export(own, ctypes.cast(handle, c_vp)))
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
+        allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        for r in range(world):
+            if r == rank:
+                continue
+            hb = (ctypes.c_ubyte * 64)(*allh[r].cpu().tolist())
+            pp = c_vp()
+            _lib.check(lib.cspbo_ipc_open(ctypes.cast(hb, c_vp), ctypes.byref(pp)))
+            peers[r] = pp
+            ptrs[r] = pp
+    _IPC_POOL[key] = dict(bytes=want, own=own, ptrs=ptrs, peers=peers)
+    return own, ptrs
+
+
+def _release_shared(ent, group, world):
+    import torch
+    lib = _lib.load()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier(group=group)
+    for pp in ent["peers"]:
+        if pp is not None:
+            lib.cspbo_ipc_close(pp)
+    lib.cspbo_dev_free(ent["own"])
+
+
+def release_shared_buffers():
+    """Free the cached peer-mapped buffers (collective: call on every rank)."""
+    for (gid, world), ent in list(_IPC_POOL.items()):
+        _release_shared(ent, None, world)
+    _IPC_POOL.clear()
+
+
 # ----------------------------------------------------------------------------- whole covariance, sharded
 class ShardedCovariance:
     """[[K_EE, K_EF], [K_FE, K_FF]] (reference base.py:13-14, Dot_mb.py:87-119) of a training set as ONE matrix
@@ -622,26 +683,9 @@ class ShardedCovariance:
         self.rows = len(self.mine) * nbw
         self.order_e = self._order(self.pe) if self.pe else np.zeros(0, dtype=np.int64)
         self.order_f = self._order(self.pf) if self.pf else np.zeros(0, dtype=np.int64)
-        nbytes = 8 * max(self.rows, 1) * self.N
-        ptr = c_vp()
-        _lib.check(self.lib.cspbo_dev_alloc(nbytes, ctypes.byref(ptr)))
-        self._own, self._peers = ptr, [None] * self.world
-        self._ptrs = (c_vp * self.world)()
-        self._ptrs[self.rank] = ptr
-        if self.world > 1:
-            handle = (ctypes.c_ubyte * 64)()
-            _lib.check(self.lib.cspbo_ipc_export(ptr, ctypes.cast(handle, c_vp)))
-            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
-            allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(self.world)]
-            dist.all_gather(allh, mine, group=group)
-            for r in range(self.world):
-                if r == self.rank:
-                    continue
-                hb = (ctypes.c_ubyte * 64)(*allh[r].cpu().tolist())
-                pp = c_vp()
-                _lib.check(self.lib.cspbo_ipc_open(ctypes.cast(hb, c_vp), ctypes.byref(pp)))
-                self._peers[r] = pp
-                self._ptrs[r] = pp
+        max_rows = ((self.S + self.world - 1) // self.world) * nbw          # the same on every rank
+        ptr, self._ptrs = _shared_buffer(8 * max(max_rows, 1) * self.N, group, self.world, self.rank)
+        self._own = ptr
         self.local = torch.as_tensor(_RawCuda(ptr.value, (max(self.rows, 1), self.N)), device="cuda")[: self.rows]
 
     def _order(self, pack):
@@ -719,22 +763,11 @@ class ShardedCovariance:
         return np.concatenate((inv_e, pf))
 
     def close(self):
-        self._barrier()
-        self.local = None
-        for r, pp in enumerate(self._peers):
-            if pp is not None:
-                self.lib.cspbo_ipc_close(pp)
-                self._peers[r] = None
+        """The buffer itself is pooled (_shared_buffer); only drop the view, after every rank is done with it."""
         if self._own is not None:
-            self.lib.cspbo_dev_free(self._own)
-            self._own = None
-
-    def __del__(self):
-        try:
-            if self._own is not None:
-                self.close()
-        except Exception:
-            pass
+            self._barrier()
+        self.local = None
+        self._own = None
 
 
 class ShardedSolver:
