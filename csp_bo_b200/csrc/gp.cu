@@ -280,11 +280,35 @@ struct StreamHandles {
     int lwork;
 };
 
-__global__ void set_identity_kernel(double *A, int h)
+// inv = L^-1 for the h x h Cholesky factor that potrf left in D (row-major upper U == column-major lower L,
+// L(i,k) = D[k*ld + i]); inv is column-major lower with leading dimension h, the operand of the wide trmm.
+// One warp per column j: forward substitution of L x = e_j in shared memory, the column of L needed at step k is
+// row k of D (contiguous, coalesced).  The diagonal chain of the sharded Cholesky is latency bound, and cuBLAS'
+// trsm against the identity took 0.2 ms for h = 384; this kernel's longest column is ~h dependent steps of one
+// shared-memory round trip each.
+__global__ void __launch_bounds__(256) tri_inverse_kernel(const double *__restrict__ D, long long ld, int h, double *__restrict__ inv)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < h * h) A[i] = (i / h == i % h) ? 1.0 : 0.0;
+    extern __shared__ double tsm[];          // [h] reciprocal diagonal, then [warps][h] right-hand sides
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double *rdiag = tsm;
+    double *b = tsm + h + (size_t)w * h;
+    for (int i = threadIdx.x; i < h; i += blockDim.x) rdiag[i] = 1.0 / D[(long long)i * ld + i];
+    __syncthreads();
+    const int j = blockIdx.x * nw + w;
+    if (j >= h) return;                      // whole warps leave; no block-wide barrier below
+    for (int i = lane; i < h; i += 32) b[i] = (i == j) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int k = j; k < h; k++) {
+        const double xk = b[k] * rdiag[k];
+        const double *col = D + (long long)k * ld;       // L(i,k) = col[i]
+        for (int i = k + 1 + lane; i < h; i += 32) b[i] = fma(-col[i], xk, b[i]);
+        __syncwarp();
+        if (lane == 0) b[k] = xk;
+    }
+    __syncwarp();
+    for (int i = lane; i < h; i += 32) inv[(long long)j * h + i] = (i >= j) ? b[i] : 0.0;
 }
+
 static StreamHandles g_sh[16];
 static int g_nsh = 0;
 
@@ -333,11 +357,16 @@ extern "C" int cspbo_gp_chol_diag(double *D, long long ld, int h, double *inv, i
     }
     s = cusolverDnDpotrf(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, sh->work, sh->lwork, info_dev);
     if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf failed (status %d)", (int)s); return CSPBO_E_SOLVER; }
-    const double one = 1.0;
-    set_identity_kernel<<<(h * h + 255) / 256, 256, 0, sh->stream>>>(inv, h);
-    cublasStatus_t b = cublasDtrsm(sh->blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, h, h, &one,
-                                   D, (int)ld, inv, h);
-    if (b != CUBLAS_STATUS_SUCCESS) { set_error("trsm(identity) failed (status %d)", (int)b); return CSPBO_E_SOLVER; }
+    const int warps = 8;
+    const size_t smem = (size_t)(1 + warps) * h * sizeof(double);
+    if (smem > 200 * 1024) { set_error("gp_chol_diag: diagonal block of %d rows is too large", h); return CSPBO_E_ARG; }
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        CSPBO_CUDA(cudaFuncSetAttribute(tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    tri_inverse_kernel<<<(h + warps - 1) / warps, warps * 32, smem, sh->stream>>>(D, ld, h, inv);
+    CSPBO_CUDA(cudaGetLastError());
     g_launches += 2;
     return CSPBO_OK;
 }
