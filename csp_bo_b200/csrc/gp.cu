@@ -282,31 +282,64 @@ struct StreamHandles {
 
 // inv = L^-1 for the h x h Cholesky factor that potrf left in D (row-major upper U == column-major lower L,
 // L(i,k) = D[k*ld + i]); inv is column-major lower with leading dimension h, the operand of the wide trmm.
-// One warp per column j: forward substitution of L x = e_j in shared memory, the column of L needed at step k is
-// row k of D (contiguous, coalesced).  The diagonal chain of the sharded Cholesky is latency bound, and cuBLAS'
-// trsm against the identity took 0.2 ms for h = 384; this kernel's longest column is ~h dependent steps of one
-// shared-memory round trip each.
-__global__ void __launch_bounds__(256) tri_inverse_kernel(const double *__restrict__ D, long long ld, int h, double *__restrict__ inv)
+// One CTA = 8 warps = 8 consecutive columns j of L^-1, one warp per column: forward substitution of L x = e_j with
+// the right-hand side in shared memory.  Step k needs column k of L = row k of D: the CTA stages kInvChunk rows at
+// a time in shared memory (coalesced loads, issued one chunk ahead into registers so that their L2 latency hides
+// behind the substitution steps of the current chunk); a step then costs one shared-memory round trip per warp.
+// The diagonal chain of the sharded Cholesky is latency bound: cuBLAS' trsm against the identity took 0.2 ms (h = 384).
+constexpr int kInvWarps = 8;
+constexpr int kInvChunk = kInvWarps;      // one staged row per warp
+
+__global__ void __launch_bounds__(kInvWarps * 32, 3) tri_inverse_kernel(const double *__restrict__ D, long long ld, int h, double *__restrict__ inv)
 {
-    extern __shared__ double tsm[];          // [h] reciprocal diagonal, then [warps][h] right-hand sides
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    extern __shared__ double tsm[];          // [h] reciprocal diagonal | [warps][h] right-hand sides | [chunk][h] rows of D
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     double *rdiag = tsm;
     double *b = tsm + h + (size_t)w * h;
-    for (int i = threadIdx.x; i < h; i += blockDim.x) rdiag[i] = 1.0 / D[(long long)i * ld + i];
-    __syncthreads();
-    const int j = blockIdx.x * nw + w;
-    if (j >= h) return;                      // whole warps leave; no block-wide barrier below
+    double *rows = tsm + (size_t)(1 + kInvWarps) * h;
+    const int j0 = blockIdx.x * kInvWarps, j = j0 + w;
+    for (int i = tid; i < h; i += blockDim.x) rdiag[i] = 1.0 / D[(long long)i * ld + i];
     for (int i = lane; i < h; i += 32) b[i] = (i == j) ? 1.0 : 0.0;
-    __syncwarp();
-    for (int k = j; k < h; k++) {
-        const double xk = b[k] * rdiag[k];
-        const double *col = D + (long long)k * ld;       // L(i,k) = col[i]
-        for (int i = k + 1 + lane; i < h; i += 32) b[i] = fma(-col[i], xk, b[i]);
-        __syncwarp();
-        if (lane == 0) b[k] = xk;
+
+    constexpr int kPer = 16;                 // columns per lane: h <= 512
+    double stage[kPer];
+    auto fetch = [&](int kc) {               // warp w brings row kc + w of D (columns right of the diagonal) into registers
+        const int k = kc + w;
+        const double *src = D + (long long)k * ld;
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const int i = lane + 32 * u;
+            stage[u] = (k < h && i < h && i > k) ? src[i] : 0.0;
+        }
+    };
+    auto commit = [&]() {
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const int i = lane + 32 * u;
+            if (i < h) rows[(size_t)w * h + i] = stage[u];
+        }
+    };
+    fetch(j0);
+    for (int kc = j0; kc < h; kc += kInvChunk) {
+        __syncthreads();                     // the previous chunk has been consumed (and rdiag / b are set up)
+        commit();
+        __syncthreads();
+        if (kc + kInvChunk < h) fetch(kc + kInvChunk);
+        if (j < h) {
+            for (int r = 0; r < kInvChunk; r++) {
+                const int k = kc + r;
+                if (k < j || k >= h) continue;           // uniform per warp
+                const double xk = b[k] * rdiag[k];
+                const double *col = rows + (size_t)r * h;   // L(i,k) = col[i]
+                for (int i = k + 1 + lane; i < h; i += 32) b[i] = fma(-col[i], xk, b[i]);
+                __syncwarp();
+                if (lane == 0) b[k] = xk;
+            }
+        }
     }
     __syncwarp();
-    for (int i = lane; i < h; i += 32) inv[(long long)j * h + i] = (i >= j) ? b[i] : 0.0;
+    if (j < h)
+        for (int i = lane; i < h; i += 32) inv[(long long)j * h + i] = (i >= j) ? b[i] : 0.0;
 }
 
 static StreamHandles g_sh[16];
@@ -357,9 +390,9 @@ extern "C" int cspbo_gp_chol_diag(double *D, long long ld, int h, double *inv, i
     }
     s = cusolverDnDpotrf(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, sh->work, sh->lwork, info_dev);
     if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf failed (status %d)", (int)s); return CSPBO_E_SOLVER; }
-    const int warps = 8;
-    const size_t smem = (size_t)(1 + warps) * h * sizeof(double);
-    if (smem > 200 * 1024) { set_error("gp_chol_diag: diagonal block of %d rows is too large", h); return CSPBO_E_ARG; }
+    const int warps = kInvWarps;
+    const size_t smem = (size_t)(1 + warps + kInvChunk) * h * sizeof(double);
+    if (h > 512) { set_error("gp_chol_diag: diagonal block of %d rows is too large (max 512)", h); return CSPBO_E_ARG; }
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         CSPBO_CUDA(cudaFuncSetAttribute(tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
