@@ -282,64 +282,75 @@ struct StreamHandles {
 
 // inv = L^-1 for the h x h Cholesky factor that potrf left in D (row-major upper U == column-major lower L,
 // L(i,k) = D[k*ld + i]); inv is column-major lower with leading dimension h, the operand of the wide trmm.
-// One CTA = 8 warps = 8 consecutive columns j of L^-1, one warp per column: forward substitution of L x = e_j with
-// the right-hand side in shared memory.  Step k needs column k of L = row k of D: the CTA stages kInvChunk rows at
-// a time in shared memory (coalesced loads, issued one chunk ahead into registers so that their L2 latency hides
-// behind the substitution steps of the current chunk); a step then costs one shared-memory round trip per warp.
-// The diagonal chain of the sharded Cholesky is latency bound: cuBLAS' trsm against the identity took 0.2 ms (h = 384).
+// One CTA = 8 warps = 8 consecutive columns j of L^-1, one warp per column: forward substitution of L x = e_j with the
+// right-hand side in REGISTERS (lane owns the rows i = lane + 32u), x_k broadcast by one shuffle per step.  Step k needs
+// column k of L = row k of D: the CTA stages 8 rows at a time in shared memory (one row per warp, coalesced, fetched
+// one chunk ahead into registers so that the L2 latency hides behind the current chunk's steps).  A step's critical
+// path is shuffle + multiply + one FMA.  The diagonal chain of the sharded Cholesky is latency bound: cuBLAS' trsm
+// against the identity took 0.2 ms for h = 384, a first version with the right-hand side in shared memory 0.14 ms.
 constexpr int kInvWarps = 8;
-constexpr int kInvChunk = kInvWarps;      // one staged row per warp
 
-__global__ void __launch_bounds__(kInvWarps * 32, 3) tri_inverse_kernel(const double *__restrict__ D, long long ld, int h, double *__restrict__ inv)
+template <int KPER>      // rows per lane: h <= 32 * KPER
+__global__ void __launch_bounds__(kInvWarps * 32, 2) tri_inverse_kernel(const double *__restrict__ D, long long ld, int h, double *__restrict__ inv)
 {
-    extern __shared__ double tsm[];          // [h] reciprocal diagonal | [warps][h] right-hand sides | [chunk][h] rows of D
+    extern __shared__ double tsm[];          // [h] reciprocal diagonal | [8][h] staged rows of D
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     double *rdiag = tsm;
-    double *b = tsm + h + (size_t)w * h;
-    double *rows = tsm + (size_t)(1 + kInvWarps) * h;
+    double *rows = tsm + h;
     const int j0 = blockIdx.x * kInvWarps, j = j0 + w;
     for (int i = tid; i < h; i += blockDim.x) rdiag[i] = 1.0 / D[(long long)i * ld + i];
-    for (int i = lane; i < h; i += 32) b[i] = (i == j) ? 1.0 : 0.0;
 
-    constexpr int kPer = 16;                 // columns per lane: h <= 512
-    double stage[kPer];
+    double bv[KPER], stage[KPER];
+#pragma unroll
+    for (int u = 0; u < KPER; u++) bv[u] = (lane + 32 * u == j) ? 1.0 : 0.0;
     auto fetch = [&](int kc) {               // warp w brings row kc + w of D (columns right of the diagonal) into registers
         const int k = kc + w;
         const double *src = D + (long long)k * ld;
 #pragma unroll
-        for (int u = 0; u < kPer; u++) {
+        for (int u = 0; u < KPER; u++) {
             const int i = lane + 32 * u;
             stage[u] = (k < h && i < h && i > k) ? src[i] : 0.0;
         }
     };
     auto commit = [&]() {
 #pragma unroll
-        for (int u = 0; u < kPer; u++) {
+        for (int u = 0; u < KPER; u++) {
             const int i = lane + 32 * u;
             if (i < h) rows[(size_t)w * h + i] = stage[u];
         }
     };
     fetch(j0);
-    for (int kc = j0; kc < h; kc += kInvChunk) {
-        __syncthreads();                     // the previous chunk has been consumed (and rdiag / b are set up)
-        commit();
-        __syncthreads();
-        if (kc + kInvChunk < h) fetch(kc + kInvChunk);
-        if (j < h) {
-            for (int r = 0; r < kInvChunk; r++) {
-                const int k = kc + r;
-                if (k < j || k >= h) continue;           // uniform per warp
-                const double xk = b[k] * rdiag[k];
-                const double *col = rows + (size_t)r * h;   // L(i,k) = col[i]
-                for (int i = k + 1 + lane; i < h; i += 32) b[i] = fma(-col[i], xk, b[i]);
-                __syncwarp();
-                if (lane == 0) b[k] = xk;
+#pragma unroll
+    for (int s = 0; s < KPER; s++) {
+        if (32 * s >= h || 32 * (s + 1) <= j0) continue;          // uniform over the CTA
+        for (int kk = 0; kk < 32; kk++) {
+            const int k = 32 * s + kk;
+            if (k < j0 || k >= h) continue;                        // uniform over the CTA (j0 is a multiple of 8)
+            if ((k & 7) == 0) {
+                __syncthreads();             // the previous chunk has been consumed (first time: rdiag is set up)
+                commit();
+                __syncthreads();
+                if (k + kInvWarps < h) fetch(k + kInvWarps);
+            }
+            const double xk = __shfl_sync(0xffffffffu, bv[s], kk) * rdiag[k];
+            if (k >= j && j < h) {                                 // uniform over the warp
+                const double *col = rows + (size_t)(k & 7) * h;    // L(i,k) = col[i]
+#pragma unroll
+                for (int u = s; u < KPER; u++) {
+                    const int i = lane + 32 * u;
+                    if (i > k && i < h) bv[u] = fma(-col[i], xk, bv[u]);
+                }
+                if (lane == kk) bv[s] = xk;
             }
         }
     }
-    __syncwarp();
-    if (j < h)
-        for (int i = lane; i < h; i += 32) inv[(long long)j * h + i] = (i >= j) ? b[i] : 0.0;
+    if (j < h) {
+#pragma unroll
+        for (int u = 0; u < KPER; u++) {
+            const int i = lane + 32 * u;
+            if (i < h) inv[(long long)j * h + i] = (i >= j) ? bv[u] : 0.0;
+        }
+    }
 }
 
 static StreamHandles g_sh[16];
@@ -390,15 +401,12 @@ extern "C" int cspbo_gp_chol_diag(double *D, long long ld, int h, double *inv, i
     }
     s = cusolverDnDpotrf(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, sh->work, sh->lwork, info_dev);
     if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf failed (status %d)", (int)s); return CSPBO_E_SOLVER; }
-    const int warps = kInvWarps;
-    const size_t smem = (size_t)(1 + warps + kInvChunk) * h * sizeof(double);
     if (h > 512) { set_error("gp_chol_diag: diagonal block of %d rows is too large (max 512)", h); return CSPBO_E_ARG; }
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        CSPBO_CUDA(cudaFuncSetAttribute(tri_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    tri_inverse_kernel<<<(h + warps - 1) / warps, warps * 32, smem, sh->stream>>>(D, ld, h, inv);
+    const size_t smem = (size_t)(1 + kInvWarps) * h * sizeof(double);     // <= 36 KB
+    const unsigned grid = (unsigned)((h + kInvWarps - 1) / kInvWarps);
+    if (h <= 192) tri_inverse_kernel<6><<<grid, kInvWarps * 32, smem, sh->stream>>>(D, ld, h, inv);
+    else if (h <= 384) tri_inverse_kernel<12><<<grid, kInvWarps * 32, smem, sh->stream>>>(D, ld, h, inv);
+    else tri_inverse_kernel<16><<<grid, kInvWarps * 32, smem, sh->stream>>>(D, ld, h, inv);
     CSPBO_CUDA(cudaGetLastError());
     g_launches += 2;
     return CSPBO_OK;
