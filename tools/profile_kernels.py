@@ -3,7 +3,7 @@
 
 Order of the launches (each twice: warm-up + the one to read):
   pack_rows (force 6667 atoms, energy 833 structures), K_EF Dot, K_EE Dot (sym), K_EF RBF, K_EE RBF (sym),
-  K_FF RBF (sym), K_FF Dot (sym), predict_gemv [20001 x 20001], SO3 of a 192-atom structure.
+  K_FF RBF (sym), K_FF Dot (sym), predict_gemv [20001 x 20001], SO3 of a 192-atom structure, tri_inverse (h = 384).
 """
 import os
 import sys
@@ -66,5 +66,15 @@ st = Struct(g * 2.6 + rng.normal(0, 0.25, g.shape), rng.choice([1, 8, 78], size=
 desc = SO3(nmax=3, lmax=3, rcut=3.5, alpha=2.0, derivative=True, stress=True)
 for _ in range(reps):
     desc.calculate(st)
+torch.cuda.synchronize()
+# the hand-written triangular inverse of the sharded Cholesky's diagonal chain (h = 384)
+from csp_bo_b200.distributed import _DeviceOps
+A = torch.randn(384, 384, dtype=torch.float64, device="cuda")
+D0 = A @ A.T / 384 + torch.eye(384, dtype=torch.float64, device="cuda")
+inv = torch.zeros(384, 384, dtype=torch.float64, device="cuda")
+info = torch.zeros(1, dtype=torch.int32, device="cuda")
+for _ in range(reps):
+    Dw = D0.clone()
+    _DeviceOps().diag(Dw, inv, info, torch.cuda.current_stream().cuda_stream)
 torch.cuda.synchronize()
 print("ok", float(p[0]))
