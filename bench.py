@@ -292,7 +292,7 @@ def run_ours(args):
         fit_ms = []
         nf2 = (30.0 * 0.005) ** 2
         if world == 1:
-            for i in range(2):
+            for i in range(4):
                 barrier(); t0 = time.perf_counter()
                 step(); Kfull = out.view(3 * m, 3 * m)
                 torch.cuda.synchronize(); t1 = time.perf_counter()
