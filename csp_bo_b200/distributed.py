@@ -806,3 +806,78 @@ def fit_sharded(kernel, data, y, noise_e, f_coef, group=None, nbw=384, tol=1e-10
     chol.local = None
     cov.close()                          # the distributed rows are no longer needed: U is replicated
     return (alpha, solver) if return_solver else alpha
+
+
+# ----------------------------------------------------------------------------- sharded prediction
+def group_slice(n, rank, world):
+    """[lo, hi) of the n groups (structures / force atoms) handled by `rank`: contiguous, sizes differ by at most 1."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def slice_groups(data, lo, hi, mode='force'):
+    """Groups [lo, hi) of a stacked tuple or of a list, in the same format (cspbo/utilities.py:350-416)."""
+    if isinstance(data, list):
+        return data[lo:hi]
+    counts = np.asarray(data[-1], dtype=np.int64)
+    off = np.concatenate(([0], np.cumsum(counts)))
+    r0, r1 = int(off[lo]), int(off[hi])
+    if mode == 'force':
+        X, dXdR, ELE, indices = data
+        return (X[r0:r1], dXdR[r0:r1], ELE[r0:r1], list(indices[lo:hi]))
+    X, ELE, indices = data
+    return (X[r0:r1], ELE[r0:r1], list(indices[lo:hi]))
+
+
+def _n_groups(d):
+    return len(d) if isinstance(d, list) else len(d[-1])
+
+
+def predict_sharded(model, X, group=None, return_std=False, total_E=False, gather=None):
+    """K* . alpha (gaussianprocess.py:133-184) with the TEST groups sharded over the ranks: every rank builds the K*
+    rows of its slice of the energy structures and force atoms against the (replicated) training set and the
+    predictions are all-gathered -- K* blocks are independent, no other exchange.  Returns what
+    model.predict(X, ...) returns, on every rank.  `gather`: test hook replacing the all_gather of a list of arrays."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    nE = _n_groups(X["energy"]) if "energy" in X and len(X["energy"]) > 0 else 0
+    nF = _n_groups(X["force"]) if "force" in X and len(X["force"]) > 0 else 0
+    e0, e1 = group_slice(nE, rank, world)
+    f0, f1 = group_slice(nF, rank, world)
+    mine = {}
+    if e1 > e0:
+        mine["energy"] = slice_groups(X["energy"], e0, e1, mode='energy')
+    if f1 > f0:
+        mine["force"] = slice_groups(X["force"], f0, f1, mode='force')
+    if mine:
+        res = model.predict(mine, total_E=total_E, return_std=return_std)
+        mean, std = (res if return_std else (res, None))
+    else:
+        mean, std = np.zeros(0), (np.zeros(0) if return_std else None)
+
+    def all_gather(vec):
+        """variable-length float64 vectors -> list of per-rank numpy arrays"""
+        if gather is not None:
+            return gather(vec)
+        if world == 1:
+            return [np.asarray(vec)]
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        n = torch.tensor([len(vec)], dtype=torch.int64, device=dev)
+        ns = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(ns, n, group=group)
+        mx = max(int(v.item()) for v in ns)
+        buf = torch.zeros(max(mx, 1), dtype=torch.float64, device=dev)
+        buf[: len(vec)] = torch.as_tensor(np.asarray(vec, dtype=np.float64), device=dev)
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf, group=group)
+        return [p[: int(k.item())].cpu().numpy() for p, k in zip(parts, ns)]
+
+    def assemble(vec):
+        ne = e1 - e0
+        E = np.concatenate(all_gather(vec[:ne]))
+        F = np.concatenate(all_gather(vec[ne:]))
+        return np.concatenate((E, F))
+
+    out = assemble(mean)
+    return (out, assemble(std)) if return_std else out

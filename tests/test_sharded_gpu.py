@@ -212,7 +212,11 @@ def _cov_rank_main(rank, world, port, out):
         var_ref = kernel.diag(test) - (Ks * gp.cho_solve(K, Ks.T.contiguous()).T).sum(dim=1).cpu().numpy()
         err2 = float(np.abs(mean - mean_ref).max() / np.abs(mean_ref).max())
         err3 = float(np.abs(std - np.sqrt(np.maximum(var_ref, 0))).max() / np.sqrt(np.maximum(var_ref, 0)).max())
-        out[rank] = max(err, err2, err3 * 1e-2)
+        # test groups sharded over the ranks, predictions all-gathered: identical to the replicated prediction
+        from csp_bo_b200.distributed import predict_sharded
+        m2, s2 = predict_sharded(model, test, return_std=True)
+        err4 = float(max(np.abs(m2 - mean).max() / np.abs(mean).max(), np.abs(s2 - std).max() / np.abs(std).max()))
+        out[rank] = max(err, err2, err3 * 1e-2, err4 * 1e2)
     finally:
         dist.destroy_process_group()
 
