@@ -274,7 +274,10 @@ block_tile_kernel(const TileParams p)
         mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
+    // CTAs none of whose warps has work (the lower block triangle of a symmetric build, ragged tails of a sharded one)
+    // leave before streaming any B tile: for K_EE, where a tile pair is only KS DMMAs, an idle CTA that still walked
+    // the TMA pipeline cost almost as much as a busy one
+    if (!__syncthreads_or((int)active)) return;
 
     double acc[2][NC1][NC2];
     double accg[2][GRAD ? NC1 : 1][GRAD ? NC2 : 1];
@@ -693,12 +696,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     const size_t tile_bytes = (size_t)b->tile_doubles * sizeof(double);
     // K_FF: 36 KB stages (a whole (block, species) run of 6 KB tiles).  The narrower K_EE / K_EF tiles need less, and
     // smaller stages raise the resident CTAs per SM (measured: K_EE RBF 18.4 -> 16.8 ms at 18 KB, K_EF RBF 75.7 -> 73.7 at 24 KB)
-    size_t stage_bytes = mode == MODE_KEE ? (size_t)18 * 1024 : (mode == MODE_KEF ? (size_t)24 * 1024 : kSmemChunk);
-    {
-        static const char *kb_ee = getenv("CSPBO_STAGE_KB_EE"), *kb_ef = getenv("CSPBO_STAGE_KB_EF");
-        if (mode == MODE_KEE && kb_ee) stage_bytes = (size_t)atoi(kb_ee) * 1024;
-        if (mode == MODE_KEF && kb_ef) stage_bytes = (size_t)atoi(kb_ef) * 1024;
-    }
+    const size_t stage_bytes = mode == MODE_KEE ? (size_t)18 * 1024 : (mode == MODE_KEF ? (size_t)24 * 1024 : kSmemChunk);
     const int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, stage_bytes / tile_bytes));
     p.tbc = tbc;
     // the stage buffers double as the scratch of the split-mode reduction (NACC accumulators per thread of 3 warps)
