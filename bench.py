@@ -446,7 +446,7 @@ def real_data_leg():
     from csp_bo_b200.SO3 import SO3
     from csp_bo_b200.gaussianprocess import GaussianProcess
     from csp_bo_b200.kernels import Dot_mb
-    from csp_bo_b200.utilities import convert_train_data, mae, r2
+    from csp_bo_b200.utilities import mae, r2
     G = os.path.join(ROOT, "tests", "golden")
     d = dict(np.load(os.path.join(G, "datasets.npz")))
     out = {}

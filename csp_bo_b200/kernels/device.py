@@ -5,8 +5,6 @@ built straight into one CUDA matrix (`cspbo_block_build_into`) so that the GP fi
 """
 import ctypes
 
-import numpy as np
-
 from .. import _lib
 from .._lib import BlockDesc, c_vp
 from ..packing import build_block, pack_energy, pack_force

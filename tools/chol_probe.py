@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import torch.distributed as dist
 from csp_bo_b200 import _lib, gp, synthetic
-from csp_bo_b200.distributed import ShardedSymmetricBlock, ShardedCholesky, fit_alpha_sharded
+from csp_bo_b200.distributed import ShardedSymmetricBlock, ShardedCholesky
 from csp_bo_b200.packing import Pack, build_block
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -1,8 +1,7 @@
 """Isolated timings of the sharded-Cholesky building blocks (C ABI, csrc/gp.cu) on one GPU."""
-import ctypes, json, os, sys
+import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from csp_bo_b200 import _lib
 from csp_bo_b200.distributed import _DeviceOps
 ops = _DeviceOps()
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 20001
