@@ -327,10 +327,12 @@ def run_ours(args):
     # ---- one MD / validation step (config 1 of BASELINE.json): SO3 descriptor of a 192-atom Pt/H/O structure
     # + K* against a 16-energy + 409-force model + K*.alpha, through GaussianProcess.predict_structure.
     # The reference's README quotes 35.767 s for 10 such structures (README.md:28).
+    import contextlib
     md = None
     if world == 1:
         try:
-            md = md_step_leg()
+            with contextlib.redirect_stdout(sys.stderr):     # stdout carries the one JSON line only
+                md = md_step_leg()
         except Exception as exc:
             md = {"error": str(exc)[:200]}
 
@@ -339,7 +341,8 @@ def run_ours(args):
     real = None
     if world == 1:
         try:
-            real = real_data_leg()
+            with contextlib.redirect_stdout(sys.stderr):
+                real = real_data_leg()
         except Exception as exc:
             real = {"error": str(exc)[:200]}
 
