@@ -39,6 +39,28 @@ FIT_SB_BLOCKS = 16                # panel width of the sharded Cholesky fit leg:
 FP64_PEAK_FALLBACK = 37.03        # TFLOP/s, DMMA.8x8x4 issue-bound peak measured on this pool (profiles/fp64_peak_r01.json)
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Everything except the one JSON line goes to stderr: NCCL / library banners and the reference-style prints of
+    the regressor would otherwise share stdout with it."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def fp64_peak():
     """MEASURED_PEAKS.json carries no FP64 entry; the denominator is the DMMA peak measured on this
     pool's B200 with tools/fp64_peak.cu and committed under profiles/."""
@@ -146,7 +168,7 @@ def run_reference(args):
             "config": config_dict(X, pairs), "gpu_launches": 0,
             "cpu_baseline": {"value": value, "unit": "entries/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_dict(X, pairs):
@@ -392,7 +414,7 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(X, pairs), "clocks": clocks, "gpu_launches": int(launches),
             "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "fit": fit, "md_step": md, "real_data": real}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -502,6 +524,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
