@@ -201,3 +201,48 @@ def test_pipelined_host_copyback_equals_device_build():
         host, _ = build_block(_lib.RBF, _lib.KFF, a, b, 2.0, sigma2=39.0, l=0.56, tol=1e-10, use_tol=True, **kw)
         assert host.nbytes >= 64 << 20
         assert np.array_equal(host, dev.cpu().numpy()), kw
+
+
+def test_panel_and_cholesky_entry_points_reject_bad_arguments():
+    """The multi-GPU layer of the ABI (cspbo_block_build_panel, cspbo_gp_chol_*) returns CSPBO_E_ARG with a message
+    instead of touching memory when the layout contract is violated."""
+    import torch
+    from csp_bo_b200 import _lib, synthetic
+    from csp_bo_b200._lib import BlockDesc
+    from csp_bo_b200.packing import Pack
+    lib = _lib.load()
+    F = synthetic.force_set(20, seed=1)
+    E = synthetic.energy_set(3, seed=2, rows_per_structure=16)
+    pf, pe = Pack(F[0], F[1], F[2], F[3]), Pack(E[0], None, E[1], E[2])
+    buf = torch.zeros((96, 96 + 60), dtype=torch.float64, device="cuda")
+    outs = (c_vp * 1)(c_vp(buf.data_ptr()))
+    desc = BlockDesc(_lib.DOT, _lib.KFF, 2.0, 1.0, 0.0, 1.0, 0.0, 0, 0, 0, 1.0, 1.0, 0)
+
+    def call(block, a, b, ld, nbw, r0a, r0b, rank=0, nranks=1):
+        desc.block = block
+        return lib.cspbo_block_build_panel(ctypes.byref(desc), a.handle, b.handle, rank, nranks, outs, ld, nbw, r0a, r0b)
+
+    assert call(_lib.KFF, pf, pf, 156, 50, 96, 96) == 2 and b"multiple of 24" in lib.cspbo_last_error()
+    assert call(_lib.KFF, pf, pf, 156, 48, 90, 90) == 2 and b"panel boundaries" in lib.cspbo_last_error()
+    assert call(_lib.KFF, pf, pf, 100, 48, 96, 96) == 2 and b"does not fit" in lib.cspbo_last_error()
+    assert call(_lib.KEF, pf, pe, 156, 48, 0, 96) == 2                      # K_EF needs (energy, force)
+    assert call(_lib.KEE, pe, pf, 156, 48, 0, 96) == 2                      # K_EE needs the same energy pack twice
+    assert call(_lib.KFF, pf, pf, 156, 48, 96, 96, rank=1, nranks=1) == 2
+    # the valid call fills the force block and leaves the rest alone
+    assert call(_lib.KFF, pf, pf, 156, 48, 96, 96) == 0
+    torch.cuda.synchronize()
+    assert float(buf[:, :96].abs().max()) == 0.0 and float(buf[:60, 96:].abs().max()) > 0.0
+    # Cholesky building blocks
+    D = torch.eye(8, dtype=torch.float64, device="cuda")
+    inv = torch.zeros(64, dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = c_vp(torch.cuda.current_stream().cuda_stream)
+    assert lib.cspbo_gp_chol_diag(c_vp(D.data_ptr()), 4, 8, c_vp(inv.data_ptr()), c_vp(info.data_ptr()), st) == 2   # ld < h
+    assert lib.cspbo_gp_chol_diag(None, 8, 8, c_vp(inv.data_ptr()), c_vp(info.data_ptr()), st) == 2
+    assert lib.cspbo_gp_chol_apply_inv(c_vp(inv.data_ptr()), 8, c_vp(D.data_ptr()), 4, 8, c_vp(D.data_ptr()), 8, st) == 2   # ldb < w
+    assert lib.cspbo_gp_chol_update(c_vp(D.data_ptr()), 8, 8, 8, c_vp(D.data_ptr()), 4, c_vp(D.data_ptr()), 8, 8, st) == 2   # lda < nb
+    # not positive definite: reported through the device-side info word, no exception, no host sync
+    Dn = -torch.eye(8, dtype=torch.float64, device="cuda")
+    assert lib.cspbo_gp_chol_diag(c_vp(Dn.data_ptr()), 8, 8, c_vp(inv.data_ptr()), c_vp(info.data_ptr()), st) == 0
+    torch.cuda.synchronize()
+    assert int(info.item()) > 0
