@@ -214,7 +214,7 @@ def test_panel_and_cholesky_entry_points_reject_bad_arguments():
     F = synthetic.force_set(20, seed=1)
     E = synthetic.energy_set(3, seed=2, rows_per_structure=16)
     pf, pe = Pack(F[0], F[1], F[2], F[3]), Pack(E[0], None, E[1], E[2])
-    buf = torch.zeros((96, 96 + 60), dtype=torch.float64, device="cuda")
+    buf = torch.zeros((192, 96 + 60), dtype=torch.float64, device="cuda")     # 4 panels of 48 rows, ld = N = 156
     outs = (c_vp * 1)(c_vp(buf.data_ptr()))
     desc = BlockDesc(_lib.DOT, _lib.KFF, 2.0, 1.0, 0.0, 1.0, 0.0, 0, 0, 0, 1.0, 1.0, 0)
 
@@ -231,7 +231,9 @@ def test_panel_and_cholesky_entry_points_reject_bad_arguments():
     # the valid call fills the force block and leaves the rest alone
     assert call(_lib.KFF, pf, pf, 156, 48, 96, 96) == 0
     torch.cuda.synchronize()
-    assert float(buf[:, :96].abs().max()) == 0.0 and float(buf[:60, 96:].abs().max()) > 0.0
+    assert float(buf[:, :96].abs().max()) == 0.0 and float(buf[:96].abs().max()) == 0.0
+    blk = buf[96:156, 96:156]
+    assert float(blk.abs().max()) > 0.0 and float((blk - blk.T).abs().max()) <= 1e-12 * float(blk.abs().max())
     # Cholesky building blocks
     D = torch.eye(8, dtype=torch.float64, device="cuda")
     inv = torch.zeros(64, dtype=torch.float64, device="cuda")
