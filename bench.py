@@ -11,7 +11,7 @@ stacked descriptor rows, d = 24, Pt/H/O species mix, Dot kernel sigma=18.555 zet
 second with the packed descriptors already resident in HBM; `e2e` = the same through the public
 kff_C() call with pinned HOST buffers in and the K_FF matrix back in pinned HOST memory.
 
-N > 1 (torchrun): the symmetric build is sharded over ranks by interleaved 8-atom row blocks
+N > 1 (torchrun): the symmetric build is sharded over ranks by 8-atom row blocks dealt in zigzag order
 (strong scaling, fixed total work, no data-path collective; the max over ranks of the
 device-timed region is reported).
 
@@ -212,7 +212,7 @@ def run_ours(args):
         # strong scaling: the symmetric build is sharded by block-cyclic row blocks; mirrored tiles go
         # to the owner's HBM over NVLink peer memory inside the tile kernel (csp_bo_b200/distributed.py)
         from csp_bo_b200.distributed import ShardedSymmetricBlock
-        sh = ShardedSymmetricBlock(full, _lib.KFF)
+        sh = ShardedSymmetricBlock(full, _lib.KFF, zigzag=True)   # zigzag dealing: every rank gets the same triangular work
         algo_pairs = (pairs + len(X[0])) / 2 / world
 
         def step():
