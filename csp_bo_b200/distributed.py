@@ -649,6 +649,32 @@ def release_shared_buffers():
 
 
 # ----------------------------------------------------------------------------- whole covariance, sharded
+def panel_local_rows(mine, nbw, g0, g1):
+    """(local row indices, global row indices) of the rows a rank holds inside the global range [g0, g1), for a rank
+    that owns the superblocks `mine` (ascending; the i-th owned superblock is stored at local rows [i*nbw, +nbw))."""
+    loc, glob = [], []
+    for i, s in enumerate(mine):
+        a, b = max(s * nbw, g0), min((s + 1) * nbw, g1)
+        if b > a:
+            glob.append(np.arange(a, b))
+            loc.append(np.arange(a, b) - s * nbw + i * nbw)
+    if not loc:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    return np.concatenate(loc), np.concatenate(glob)
+
+
+def panel_permutation(order_e, order_f, NE_pad):
+    """perm[i] = row of the panel-layout matrix that holds row i of the caller's [E; F] ordering (energies, then forces
+    atom-major); order_x[p] = group id at packed position p (cspbo_pack_order)."""
+    order_e, order_f = np.asarray(order_e, dtype=np.int64), np.asarray(order_f, dtype=np.int64)
+    inv_e = np.empty(len(order_e), dtype=np.int64)
+    inv_e[order_e] = np.arange(len(order_e))
+    inv_f = np.empty(len(order_f), dtype=np.int64)
+    inv_f[order_f] = np.arange(len(order_f))
+    pf = (NE_pad + inv_f[:, None] * 3 + np.arange(3)[None, :]).reshape(-1)
+    return np.concatenate((inv_e, pf))
+
+
 class ShardedCovariance:
     """[[K_EE, K_EF], [K_FE, K_FF]] (reference base.py:13-14, Dot_mb.py:87-119) of a training set as ONE matrix
     distributed over the ranks in the panel layout of cspbo_block_build_panel, ready for ShardedCholesky:
@@ -707,16 +733,7 @@ class ShardedCovariance:
                                                     self.N, self.nbw, int(row0_a), int(row0_b)))
 
     def _local_rows(self, g0, g1):
-        """(local row indices, global row indices) of this rank's rows inside the global range [g0, g1)."""
-        loc, glob = [], []
-        for i, s in enumerate(self.mine):
-            a, b = max(s * self.nbw, g0), min((s + 1) * self.nbw, g1)
-            if b > a:
-                glob.append(np.arange(a, b))
-                loc.append(np.arange(a, b) - s * self.nbw + i * self.nbw)
-        if not loc:
-            return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
-        return np.concatenate(loc), np.concatenate(glob)
+        return panel_local_rows(self.mine, self.nbw, g0, g1)
 
     def build(self, noise_e, f_coef, tol=1e-10):
         """Build K + noise into the distributed rows (gaussianprocess.py:105-113)."""
@@ -754,13 +771,7 @@ class ShardedCovariance:
         return self.local
 
     def permutation(self):
-        """perm[i] = row of the distributed matrix that holds row i of the caller's [E; F] ordering."""
-        inv_e = np.empty(self.mE, dtype=np.int64)
-        inv_e[self.order_e] = np.arange(self.mE)
-        inv_f = np.empty(self.mF, dtype=np.int64)
-        inv_f[self.order_f] = np.arange(self.mF)
-        pf = (self.NE_pad + inv_f[:, None] * 3 + np.arange(3)[None, :]).reshape(-1)
-        return np.concatenate((inv_e, pf))
+        return panel_permutation(self.order_e, self.order_f, self.NE_pad)
 
     def close(self):
         """The buffer itself is pooled (_shared_buffer); only drop the view, after every rank is done with it."""

@@ -252,3 +252,38 @@ def test_predict_sharded_gloo_world2():
         out = mgr.dict()
         mp.spawn(_pred_worker, args=(2, 33500 + (os.getpid() % 2000), X, out), nprocs=2, join=True)
         assert len(out) == 2 and all(out.values()), dict(out)
+
+
+def test_panel_layout_host_logic():
+    """panel_local_rows / panel_permutation: the rows a rank holds cover every global row exactly once, local rows follow
+    the kernel's formula (s // world) * nbw + r % nbw, and the permutation sends the caller's [E; F] rows to
+    [energies packed | padding | forces packed x 3]."""
+    nbw = 24
+    for world in (1, 2, 3):
+        for N in (24, 50, 97, 240):
+            S = (N + nbw - 1) // nbw
+            seen = np.zeros(N, dtype=int)
+            for r in range(world):
+                mine = [s for s in range(S) if D.superblock_owner(s, world, True) == r]
+                loc, glob = D.panel_local_rows(mine, nbw, 0, N)
+                seen[glob] += 1
+                for l, g in zip(loc, glob):
+                    s = g // nbw
+                    assert l == (s // world) * nbw + g % nbw
+                # sub-ranges partition the rows of the rank
+                l1, g1 = D.panel_local_rows(mine, nbw, 0, N // 2)
+                l2, g2 = D.panel_local_rows(mine, nbw, N // 2, N)
+                assert sorted(np.concatenate((g1, g2)).tolist()) == sorted(glob.tolist())
+            assert np.all(seen == 1)
+    rng = np.random.default_rng(0)
+    mE, mF, NE_pad = 5, 7, 24
+    oe, of = rng.permutation(mE), rng.permutation(mF)
+    perm = D.panel_permutation(oe, of, NE_pad)
+    assert len(perm) == mE + 3 * mF and len(set(perm.tolist())) == len(perm)
+    y = np.arange(mE + 3 * mF, dtype=float)
+    packed = np.zeros(NE_pad + 3 * mF)
+    packed[perm] = y
+    assert np.array_equal(packed[:mE], y[:mE][oe])                                   # energies in packed order
+    assert np.all(packed[mE:NE_pad] == 0)                                            # identity padding rows
+    assert np.array_equal(packed[NE_pad:].reshape(mF, 3), y[mE:].reshape(mF, 3)[of])  # forces, 3 rows per atom
+    assert np.array_equal(packed[perm], y)
