@@ -126,6 +126,24 @@ extern "C" int cspbo_pack_create_ex(int n, int d, int nc, int m, int row_start, 
     double *d_x = nullptr, *d_dx = nullptr;
     std::vector<long long> dest((size_t)std::max(n, 1), -1);
 
+    // ---- host-resident inputs: start their upload first, the DMA runs while the host plans the layout ----
+    bool uploading = false;
+    if (mem == CSPBO_MEM_HOST && n > 0) {
+        if ((rc = scratch_get(SCRATCH_X, (size_t)n * d * sizeof(double), (void **)&d_x)) != CSPBO_OK) { delete p; return rc; }
+        if (nc > 0 && (rc = scratch_get(SCRATCH_DX, (size_t)n * d * nc * sizeof(double), (void **)&d_dx)) != CSPBO_OK) { delete p; return rc; }
+        cudaError_t e = cudaMemcpyAsync(d_x, x, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && nc > 0) e = cudaMemcpyAsync(d_dx, dxdr, (size_t)n * d * nc * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            set_error("pack_create: upload of the descriptors failed: %s", cudaGetErrorString(e));
+            cudaStreamSynchronize(0);
+            delete p;
+            return CSPBO_E_CUDA;
+        }
+        uploading = true;
+    }
+    // every early return below must wait for the upload: the caller may free x / dxdr as soon as we return
+    auto plan_fail = [&](int code) { if (uploading) cudaStreamSynchronize(0); delete p; return code; };
+
     // ---- host plan -------------------------------------------------------------------
     {
         // species, most populous first
@@ -133,7 +151,7 @@ extern "C" int cspbo_pack_create_ex(int n, int d, int nc, int m, int row_start, 
         for (int r = row_start; r < row_end; r++) {
             if (inds[r] < 0 || inds[r] >= m) {
                 set_error("pack_create: group id %d of row %d outside [0,%d)", inds[r], r, m);
-                delete p; return CSPBO_E_ARG;
+                return plan_fail(CSPBO_E_ARG);
             }
             sp.push_back(ele[r]);
         }
@@ -217,7 +235,7 @@ extern "C" int cspbo_pack_create_ex(int n, int d, int nc, int m, int row_start, 
             dest[r] = first_dest[k] + 8LL * (rank[k]++);
         }
         p->n_tiles = tiles;
-        if (tiles > 0x7fffffffLL / 8) { set_error("pack_create: too many tiles"); delete p; return CSPBO_E_ARG; }
+        if (tiles > 0x7fffffffLL / 8) { set_error("pack_create: too many tiles"); return plan_fail(CSPBO_E_ARG); }
     }
 
     // ---- device allocations ------------------------------------------------------------
@@ -253,17 +271,7 @@ extern "C" int cspbo_pack_create_ex(int n, int d, int nc, int m, int row_start, 
     if (n > 0 && p->n_tiles > 0) {
         if ((rc = scratch_get(SCRATCH_DEST, (size_t)n * sizeof(long long), (void **)&d_dest)) != CSPBO_OK) goto fail;
         PACK_CUDA(cudaMemcpyAsync(d_dest, dest.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
-        const double *xs = x, *dxs = dxdr;
-        if (mem == CSPBO_MEM_HOST) {
-            if ((rc = scratch_get(SCRATCH_X, (size_t)n * d * sizeof(double), (void **)&d_x)) != CSPBO_OK) goto fail;
-            PACK_CUDA(cudaMemcpyAsync(d_x, x, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice));
-            xs = d_x;
-            if (nc > 0) {
-                if ((rc = scratch_get(SCRATCH_DX, (size_t)n * d * nc * sizeof(double), (void **)&d_dx)) != CSPBO_OK) goto fail;
-                PACK_CUDA(cudaMemcpyAsync(d_dx, dxdr, (size_t)n * d * nc * sizeof(double), cudaMemcpyHostToDevice));
-                dxs = d_dx;
-            }
-        }
+        const double *xs = uploading ? d_x : x, *dxs = (uploading && nc > 0) ? d_dx : dxdr;   // uploaded above (stream order)
         const int rpb = 8 * kPackRowsPerWarp;   // 8 warps x 4 rows per CTA
         pack_rows_kernel<<<(unsigned)((n + rpb - 1) / rpb), 256>>>(n, d, nc, ks, p->nv, xs, dxs, d_dest,
                                                                         p->d_tiles, p->d_tile_valid, p->tile_doubles, norm_shift);
@@ -274,6 +282,7 @@ extern "C" int cspbo_pack_create_ex(int n, int d, int nc, int m, int row_start, 
     *out = p;
     return CSPBO_OK;
 fail:
+    if (uploading) cudaStreamSynchronize(0);
     cspbo_pack_destroy(p);
     return rc;
 #undef PACK_CUDA
