@@ -62,3 +62,24 @@ def test_gp_fit_oracle(oracle_built, golden):
     Kn = K.copy()
     Kn[np.diag_indices(len(K))] += np.r_[np.full(4, 0.005 ** 2), np.full(len(K) - 4, (30 * 0.005) ** 2)]
     assert np.allclose(Kn @ alpha[:, 0], y, atol=1e-8 * np.abs(y).max())
+
+
+def test_bench_reference_arm_prints_one_contract_line(oracle_built):
+    """`bench.py --impl reference` (the reference's own CPU code on a bounded slab) prints exactly one JSON line with the
+    keys the driver reads; runs without a GPU."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-500:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "K_FF entries/s (fp64)" and d["unit"] == "entries/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in d["config"]
