@@ -101,3 +101,37 @@ def test_kernel_object_api():
     r.update([4.0, 0.25])
     assert r.parameters() == [4.0, 0.25] and r.save_dict()["l"] == 0.25
     assert str(r) == "4.000**2 *RBF(length=0.250)"
+
+
+def test_gpr_calculator_glue():
+    """csp_bo_b200.calculator.GPR (cspbo/calculator.py:9-64) with a stand-in model: results keys, stress summation over
+    atoms, variances, getters, and the property getters of the ase-free base."""
+    from csp_bo_b200.calculator import GPR
+
+    class FF:
+        def __init__(self):
+            self.calls = []
+
+        def predict_structure(self, struc, stress, return_std, f_tol=1e-8):
+            self.calls.append((stress, return_std, f_tol))
+            n = len(struc)
+            E, F = -3.0 * n, np.arange(3 * n, dtype=float).reshape(n, 3)
+            S = np.ones((n, 6)) if stress else None
+            if return_std:
+                return E, F, S, 0.25, np.full((n, 3), 0.5)
+            return E, F, S
+
+    atoms = [0] * 4
+    ff = FF()
+    calc = GPR(ff=ff, stress=True, return_std=True, f_tol=1e-10)
+    calc.calculate(atoms)
+    assert ff.calls[-1] == (True, True, 1e-10)
+    r = calc.results
+    assert r['energy'] == r['free_energy'] == -12.0 and r['forces'].shape == (4, 3)
+    assert np.array_equal(r['stress'], np.full(6, 4.0))
+    assert calc.get_var_e() == 0.25 and calc.get_var_e(total=True) == 1.0 and calc.get_var_f().shape == (4, 3)
+    assert calc.get_e() == -3.0 and calc.get_e(peratom=False) == -12.0
+    calc2 = GPR(ff=ff)                               # defaults: no stress, no std, f_tol 1e-12 (calculator.py:22-35)
+    assert calc2.get_potential_energy(atoms) == -12.0 and ff.calls[-1] == (False, False, 1e-12)
+    assert calc2.results['stress'] is None and 'var_e' not in calc2.results
+    assert calc2.get_forces().shape == (4, 3)
