@@ -144,6 +144,18 @@ def cpu_reference_rate(X, n_x1_atoms, threads, backend="auto"):
     return C.size / dt, dt, ("reference" if be.kind == "ref" else "port"), C
 
 
+def native_cpu_rate(X, n_x1_atoms, threads):
+    """the CPU number again with -O3 -march=native (the C restatement, bit-identical to the reference on
+    the goldens, compiled on this host); None when the compiler is unavailable."""
+    try:
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port_native"], check=True, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL)
+        rate, dt, _, _ = cpu_reference_rate(X, n_x1_atoms, threads, backend="port_native")
+        return {"value": rate, "unit": "entries/s", "kind": "port", "flags": "-O3 -march=native", "seconds": dt}
+    except Exception:
+        return None
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path on the host cores, bounded slab per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -166,7 +178,8 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(X, pairs), "gpu_launches": 0,
-            "cpu_baseline": {"value": value, "unit": "entries/s", "cores": cores, "kind": kind, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "entries/s", "cores": cores, "kind": kind, "sample": sample,
+                             "flags": "-O2 (what the reference's setup.py builds)", "o3_native": native_cpu_rate(X, n_x1, cores)},
             "e2e": {"value": value, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -405,7 +418,8 @@ def run_ours(args):
             cpu = {"value": rate, "unit": "entries/s", "cores": cores, "kind": kind, "seconds": dt,
                    "sample": "K_FF slab: first %d of %d x1 atoms x all x2 atoms (%d entries), reference C++ "
                              "threaded over x2 like its MPI split" % (n_x1, m, C.size),
-                   "max_norm_err_vs_gpu": err}
+                   "max_norm_err_vs_gpu": err, "flags": "-O2 (what the reference's setup.py builds)",
+                   "o3_native": native_cpu_rate(X, max(2, n_x1 // 2), cores)}
         except Exception as exc:  # the baseline is reported, never required for the GPU number
             cpu = {"value": None, "unit": "entries/s", "cores": os.cpu_count(), "kind": "unavailable", "sample": str(exc)}
 

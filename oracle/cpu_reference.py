@@ -51,9 +51,11 @@ class Backend:
             self._dot = ctypes.CDLL(ref_dot)
             self._rbf = ctypes.CDLL(ref_rbf)
             self._prefix = {"dot": "", "rbf": ""}
-        elif kind == "port":
+        elif kind in ("port", "port_native"):
+            if kind == "port_native":       # -O3 -march=native build of the same restatement (make -C oracle port_native)
+                port = os.path.join(_HERE, "_build", "libcspbo_oracle_native.so")
             if not os.path.exists(port):
-                raise FileNotFoundError(port + " missing: run `make -C oracle port`")
+                raise FileNotFoundError(port + " missing: run `make -C oracle %s`" % kind)
             self._dot = self._rbf = ctypes.CDLL(port)
             self._prefix = {"dot": "oracle_dot_", "rbf": "oracle_rbf_"}
         else:
