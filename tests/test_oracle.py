@@ -83,3 +83,57 @@ def test_bench_reference_arm_prints_one_contract_line(oracle_built):
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def _random_sets(rng, d, mE=5, mF=9, species=(1, 8, 78)):
+    """ragged random energy / force sets with zero-norm rows and 1-row groups (positive descriptors: pow(c, zeta) real)"""
+    def rows(m, lo, hi):
+        counts = rng.integers(lo, hi, size=m)
+        counts[rng.integers(0, m)] = 1
+        n = int(counts.sum())
+        x = (np.abs(rng.standard_normal((n, d))) + 0.05) * rng.uniform(0.5, 50.0, size=(n, 1))
+        x[rng.integers(0, n, size=2)] = 0.0
+        return counts, x, rng.choice(species, size=n).astype(np.int64)
+    ce, xe, ee = rows(mE, 3, 12)
+    cf, xf, ef = rows(mF, 2, 8)
+    dxf = rng.standard_normal((len(xf), d, 9)) * 3.0
+    return (xe, ee, [int(c) for c in ce]), (xf, dxf, ef, [int(c) for c in cf])
+
+
+@pytest.mark.parametrize("d,zeta", [(24, 2.0), (10, 1.0), (50, 2.5), (24, 3.0)])
+def test_port_equals_compiled_reference_on_random_inputs(oracle_built, d, zeta):
+    """The C restatement against the compiled UNMODIFIED reference beyond the fixtures: all wrappers (plain, grad,
+    stress), ragged groups, zero-norm rows, d not a multiple of 4, non-integer zeta."""
+    from oracle import cpu_reference as cr
+    if not cr.have_ref():
+        pytest.skip("oracle/_ref not built (reference tree not mounted)")
+    rng = np.random.default_rng(int(d * 100 + zeta * 10))
+    E1, F1 = _random_sets(rng, d)
+    E2, F2 = _random_sets(rng, d, mE=4, mF=7)
+    F1_3 = (F1[0], F1[1][:, :, :3], F1[2], F1[3])
+    F2_3 = (F2[0], F2[1][:, :, :3], F2[2], F2[3])
+    s, s0, l = 7.3, 0.02, 0.61
+
+    def both(fn, *a, **k):
+        return fn(*a, backend="port", **k), fn(*a, backend="ref", **k)
+
+    cases = {
+        "dot_kee": both(cr.dot_kee_C, E1, E2, s, s0, zeta, grad=True),
+        "dot_kef": both(cr.dot_kef_C, E1, F2_3, s, s0, zeta),
+        "dot_kef_stress": both(cr.dot_kef_C, E1, F2, s, s0, zeta, stress=True),
+        "dot_kff": both(cr.dot_kff_C, F1_3, F2_3, s, s0, zeta),
+        "dot_kff_stress": both(cr.dot_kff_C, F1, F2_3, s, s0, zeta, stress=True),
+        "rbf_kee": both(cr.rbf_kee_C, E1, E2, s, l, zeta, grad=True),
+        "rbf_kef": both(cr.rbf_kef_C, E1, F2_3, s, l, zeta),
+        "rbf_kef_grad": both(cr.rbf_kef_C, E1, F2_3, s, l, zeta, grad=True),
+        "rbf_kef_stress": both(cr.rbf_kef_C, E1, F2, s, l, zeta, stress=True),
+        "rbf_kff": both(cr.rbf_kff_C, F1_3, F2_3, s, l, zeta, tol=1e-10),
+        "rbf_kff_grad": both(cr.rbf_kff_C, F1_3, F2_3, s, l, zeta, grad=True),
+        "rbf_kff_stress": both(cr.rbf_kff_C, F1, F2_3, s, l, zeta, stress=True, tol=1e-10),
+    }
+    for name, (p, r) in cases.items():
+        p, r = (p, r) if isinstance(p, tuple) else ((p,), (r,))
+        assert len(p) == len(r), name
+        for a, b in zip(p, r):
+            assert a.shape == b.shape, name
+            assert max_norm_err(a, b) <= 1e-13 or np.abs(b).max() == 0.0, (name, max_norm_err(a, b))
