@@ -277,7 +277,6 @@ def run_ours(args):
         d2h = int(outh.numel() * 8)
 
         def e2e_step():
-            packing.clear_cache()
             K = kff_C(Xh, Xh, SIGMA, SIGMA0, ZETA, out=outh.numpy())   # H2D + pack + build + D2H inside
             return float(K[0, 0])
     else:

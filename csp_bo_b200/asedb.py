@@ -46,25 +46,41 @@ class Structure:
         return len(self.positions)
 
 
+def _inline_arrays(obj):
+    """Older ASE files (db version < 9) keep `data` as text JSON with arrays inlined as
+    {'__ndarray__': [shape, dtype, flat_list]}: turn those into numpy arrays (complex data is out of scope)."""
+    if isinstance(obj, dict):
+        if '__ndarray__' in obj and len(obj) == 1:
+            shape, dtype, flat = obj['__ndarray__']
+            if isinstance(flat, (list, tuple)):
+                return np.array(flat, dtype=dtype).reshape(shape)
+            return obj
+        return {k: _inline_arrays(v) for k, v in obj.items()}
+    return obj
+
+
 def _decode_data(blob):
     if blob is None:
         return {}
     if isinstance(blob, str):
-        return json.loads(blob)
+        return _inline_arrays(json.loads(blob))
     b = bytes(blob)
     try:
         off = struct.unpack('<q', b[:8])[0]
         js = json.loads(b[off:].decode())
     except Exception:
-        return json.loads(b.decode())
+        return _inline_arrays(json.loads(b.decode()))
     out = {}
     for k, v in js.items():
         if isinstance(v, dict) and '__ndarray__' in v:
             shape, dtype, o = v['__ndarray__']
+            if isinstance(o, (list, tuple)):                 # inlined array inside a binary record
+                out[k] = np.array(o, dtype=dtype).reshape(shape)
+                continue
             n = int(np.prod(shape)) if len(shape) else 1
             out[k] = np.frombuffer(b, dtype=dtype, count=n, offset=o).reshape(shape).copy()
         else:
-            out[k] = v
+            out[k] = _inline_arrays(v)
     return out
 
 

@@ -24,8 +24,9 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
                        int accumulate, cudaStream_t st, int rank = 0, int nranks = 1, double *const *outs = nullptr,
                        int a_begin = 0, int a_end = -1, int diag = 0, int sb_blocks = 1, int zigzag = 0,
-                       int packed_cols = 0, const struct PanelArgs *panel = nullptr);
+                       int packed_cols = 0, const struct PanelArgs *panel = nullptr, const struct PassArgs *passes = nullptr);
 struct PanelArgs { long long ld; int nbw; long long row0_a, row0_b; };
+struct PassArgs { int npass, side; long long off; };
 int sharded_superblocks(int n_blocks, int rank, int nranks, int sb_blocks, int zigzag);
 
 struct DevBuf {
@@ -244,9 +245,12 @@ extern "C" int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack 
             const int b0 = classes ? a->h_class_blk0[(size_t)s] : (int)((long long)nb * s / nslab);
             const int b1 = classes ? a->h_class_blk0[(size_t)s + 1] : (int)((long long)nb * (s + 1) / nslab);
             if (b1 <= b0) continue;
-            for (int pa = 0; pa < passesA && rc == CSPBO_OK; pa++)
-                rc = build_block_device(d, a, b, pa * 3, 0, dout + (long long)pa * 3 * sk, dgrad, si, sk, sj, sl,
-                                        accumulate, 0, 0, 1, nullptr, b0, b1);
+            {
+                // stress: the three row triplets are the gridDim.y passes of ONE launch
+                const PassArgs ps = {passesA, 0, 3 * sk};
+                rc = build_block_device(d, a, b, 0, 0, dout, dgrad, si, sk, sj, sl, accumulate, 0, 0, 1, nullptr, b0, b1,
+                                        0, 1, 0, 0, nullptr, &ps);
+            }
             if (rc) break;
             cudaEventRecord(ev, 0);
             cudaStreamWaitEvent(cs, ev, 0);
@@ -294,13 +298,14 @@ extern "C" int cspbo_block_build(const cspbo_block_desc *desc, const cspbo_pack 
         return CSPBO_OK;
     }
 
-    for (int pa = 0; pa < passesA; pa++)
-        for (int pb = 0; pb < passesB; pb++) {
-            // stress: the 9 derivative columns are processed as three independent triplets
-            const long long off = (d.block == CSPBO_KFF) ? (long long)pa * 3 * sk : (long long)pb * 3 * sl;
-            int rc = build_block_device(d, a, b, pa * 3, pb * 3, dout + off, dgrad, si, sk, sj, sl, accumulate, 0);
-            if (rc) return rc;
-        }
+    {
+        // stress: the 9 derivative columns are three independent triplets, run as the gridDim.y passes of ONE launch
+        // (3x the CTAs of a plain build: the K* builds of an MD step are grid-bound, dot_kernel.cpp:336-506)
+        const PassArgs ps = (d.block == CSPBO_KFF) ? PassArgs{passesA, 0, 3 * sk} : PassArgs{passesB, 1, 3 * sl};
+        int rc = build_block_device(d, a, b, 0, 0, dout, dgrad, si, sk, sj, sl, accumulate, 0, 0, 1, nullptr, 0, -1, 0, 1, 0, 0,
+                                    nullptr, &ps);
+        if (rc) return rc;
+    }
 
     if (mem == CSPBO_MEM_HOST) {
         CSPBO_CUDA(cudaMemcpyAsync(out, dout, (size_t)n_out * sizeof(double), cudaMemcpyDeviceToHost));

@@ -48,12 +48,16 @@ int scratch_get(int slot, size_t bytes, void **ptr);
 int dev_alloc_cached(size_t bytes, void **ptr);
 void dev_free_cached(void *ptr);
 
+// k-steps (of 4 features) per vector of a tile: 6 for d <= 24 and 14 for d <= 56 (A fragments live in registers),
+// a multiple of 6 beyond that (chunked kernels, tiles.cu) -- any descriptor length is accepted, like the reference's
+// `for i < d` loops (dot_kernel.cpp:257-289).
 inline int ksteps_for(int d)
 {
     if (d <= 0) return -1;
     if (d <= 24) return 6;
     if (d <= 56) return 14;
-    return -1;
+    if (d > (1 << 20)) return -1;
+    return 6 * ((d + 23) / 24);
 }
 
 }  // namespace cspbo

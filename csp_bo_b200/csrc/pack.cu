@@ -113,7 +113,7 @@ extern "C" int cspbo_pack_create_ex(int n, int d, int nc, int m, int row_start, 
     if (dxdr == nullptr) nc = 0;
     if (!(nc == 0 || nc == 3 || nc == 9)) { set_error("pack_create: nc must be 3 or 9 (got %d)", nc); return CSPBO_E_ARG; }
     const int ks = ksteps_for(d);
-    if (ks < 0) { set_error("pack_create: descriptor length d=%d unsupported (max %d)", d, 56); return CSPBO_E_ARG; }
+    if (ks < 0) { set_error("pack_create: descriptor length d=%d out of range", d); return CSPBO_E_ARG; }
     row_start = std::max(row_start, 0);
     row_end = std::min(row_end, n);
 

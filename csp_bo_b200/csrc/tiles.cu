@@ -24,7 +24,7 @@
 
 namespace cspbo {
 
-constexpr int kMaxSpecies = 16;
+constexpr int kMaxSpecies = 32;   // species buckets mapped through kernel parameters; larger sets go through a device array
 constexpr int kMaxRanks = 8;
 // 3 CTAs x 4 warps per SM = 3 warps per scheduler: while one warp runs its chain-rule epilogue the
 // other two keep the FP64 tensor pipe fed (<= 170 registers/thread, <= 75 KB shared memory per CTA)
@@ -58,6 +58,11 @@ struct TileParams {
     int a_nblk, b_nblk;
     int a_begin;  // first A block of this launch (row-slab pipelining of host-bound builds); a_nblk is the end
     int emap[kMaxSpecies];  // species bucket of A -> bucket of B holding the same species id, or -1
+    const int *emap_dev;    // the same map in device memory when A has more than kMaxSpecies buckets (else null)
+    int nch, staged;        // chunked kernels (d > 56): k-chunks of 6 steps per tile; staged = B tiles go through shared memory
+    int npass;              // stress variants: gridDim.y passes, pass q uses derivative vectors 1+3q .. 3+3q of the side
+    int pass_side;          //   pass_side (0 = A: K_FF stress rows, 1 = B: K_EF stress columns) and stores at out + q*pass_off
+    long long pass_off;
     int tbc;  // B tiles per shared-memory chunk
     int strip;  // A-block groups per rasterisation strip
     int symmetric;
@@ -149,7 +154,7 @@ struct ChunkIter {
     __device__ __forceinline__ void next_species(const TileParams &p, int b_blk)
     {
         for (++eA; eA < p.A.ns; ++eA) {
-            const int eB = p.emap[eA];
+            const int eB = p.emap_dev ? p.emap_dev[eA] : p.emap[eA];
             if (eB < 0) continue;
             b_t0 = p.B.tile_start[b_blk * p.B.ns + eB];
             Tb = p.B.tile_start[b_blk * p.B.ns + eB + 1] - b_t0;
@@ -223,8 +228,12 @@ __device__ __forceinline__ Weights pair_weights(double c, bool valid, const Tile
     return w;
 }
 
-template <int MODE, int FAM, int KS, bool Z2>
-__global__ void __launch_bounds__(kMaxWarps * 32, (KS <= 6 && FAM != FAM_RBF_GRAD) ? kMinCtas : (kMinCtas > 1 ? 2 : 1))
+// CHUNKED (descriptor lengths above 56): a tile holds p.nch chunks of KS k-steps per vector; the dot products of a
+// tile pair accumulate over the chunks with the A fragments re-read from global memory (L1) per chunk instead of living
+// in registers for the whole sweep, so any d runs at the register budget of the d <= 24 kernel (dot_kernel.cpp:257-289
+// loops `i < d` for any d; SO3.py:205 gives d = 90 at nmax = lmax = 5).
+template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED>
+__global__ void __launch_bounds__(kMaxWarps * 32, (KS <= 6 && FAM != FAM_RBF_GRAD && !CHUNKED) ? kMinCtas : (kMinCtas > 1 ? 2 : 1))
 block_tile_kernel(const TileParams p)
 {
     constexpr int NV1 = (MODE == MODE_KFF) ? 4 : 1;
@@ -233,6 +242,14 @@ block_tile_kernel(const TileParams p)
     constexpr int NC2 = (MODE == MODE_KEE) ? 1 : 3;
     constexpr bool GRAD = (FAM == FAM_RBF_GRAD);
     constexpr int HALF = KS / 2;
+    const int nch = CHUNKED ? p.nch : 1;
+    const int halft = HALF * nch;                        // 128-bit fragment rows per vector of a tile
+    const bool staged = CHUNKED ? (p.staged != 0) : true;
+    // stress variants: pass q (blockIdx.y) works on derivative vectors 1+3q .. 3+3q of one side
+    const int pass = blockIdx.y;
+    const int voffA = p.A.voff + ((p.npass > 1 && p.pass_side == 0) ? 3 * pass : 0);
+    const int voffB = p.B.voff + ((p.npass > 1 && p.pass_side == 1) ? 3 * pass : 0);
+    double *const out = p.out + pass * p.pass_off;
 
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
@@ -267,9 +284,9 @@ block_tile_kernel(const TileParams p)
     const bool active = a_blk < p.a_nblk && !(p.symmetric && b_blk < a_blk);
 
     // two stage buffers of p.tbc tiles, filled by 1-D bulk TMA copies that complete on an mbarrier
-    const int stage_doubles = p.tbc * p.B.tile_doubles;
+    const int stage_doubles = staged ? p.tbc * p.B.tile_doubles : 0;
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem + 2 * (size_t)stage_doubles);
-    if (threadIdx.x == 0) {
+    if (staged && threadIdx.x == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -302,35 +319,39 @@ block_tile_kernel(const TileParams p)
         mbar_expect_tx(&full[st], bytes);
         tma_bulk_g2s(smem + (size_t)st * stage_doubles, p.B.tiles + (size_t)(c.b_t0 + c.c0) * p.B.tile_doubles, bytes, &full[st]);
     };
-    if (!cur.done(p) && threadIdx.x == 0) issue(cur, 0);
+    if (staged && !cur.done(p) && threadIdx.x == 0) issue(cur, 0);
     for (int it = 0; !cur.done(p); it++) {
         ChunkIter nxt = cur;
         nxt.next(p, b_blk);
         const int st = it & 1;
         // prefetch the next run into the other stage (its last readers passed the barrier below)
-        if (!nxt.done(p) && threadIdx.x == 0) issue(nxt, st ^ 1);
+        if (staged && !nxt.done(p) && threadIdx.x == 0) issue(nxt, st ^ 1);
         const int eA = cur.eA;
         const int nt = cur.nt(p);
         const int b_tile0 = cur.b_t0 + cur.c0;
         const int a_t0 = active ? p.A.tile_start[a_blk * p.A.ns + eA] : 0;
         const int Ta = active ? p.A.tile_start[a_blk * p.A.ns + eA + 1] - a_t0 : 0;
-        const double *sB = smem + (size_t)st * stage_doubles;
-        mbar_wait(&full[st], (unsigned)(it >> 1) & 1u);
+        // unstaged (tiles too long for a shared-memory stage): B fragments are read straight from global memory
+        const double *sB = staged ? smem + (size_t)st * stage_doubles : p.B.tiles + (size_t)b_tile0 * p.B.tile_doubles;
+        if (staged) mbar_wait(&full[st], (unsigned)(it >> 1) & 1u);
 
         for (int ta = p.split ? warp : 0; ta < Ta; ta += p.split ? nwarps : 1) {
             // A fragments of this slab: registers for the whole sweep over the chunk
             double a[NV1][KS];
             const double2 *at = reinterpret_cast<const double2 *>(p.A.tiles + (size_t)(a_t0 + ta) * p.A.tile_doubles);
+            auto load_a = [&](int ch) {
 #pragma unroll
-            for (int v = 0; v < NV1; v++) {
-                const int tv = (v == 0) ? 0 : (p.A.voff + v);
+                for (int v = 0; v < NV1; v++) {
+                    const int tv = (v == 0) ? 0 : (voffA + v);
 #pragma unroll
-                for (int h = 0; h < HALF; h++) {
-                    const double2 t = __ldg(at + (tv * HALF + h) * 32 + lane);
-                    a[v][2 * h] = t.x;
-                    a[v][2 * h + 1] = t.y;
+                    for (int h = 0; h < HALF; h++) {
+                        const double2 t = __ldg(at + (tv * halft + ch * HALF + h) * 32 + lane);
+                        a[v][2 * h] = t.x;
+                        a[v][2 * h + 1] = t.y;
+                    }
                 }
-            }
+            };
+            if (!CHUNKED) load_a(0);
             const unsigned va = p.A.tile_valid[a_t0 + ta];
             const bool a_ok = (va >> ar) & 1u;
 
@@ -342,24 +363,27 @@ block_tile_kernel(const TileParams p)
                     for (int v2 = 0; v2 < NV2; v2++) H[v1][v2][0] = H[v1][v2][1] = 0.0;
 
                 const double2 *bt = reinterpret_cast<const double2 *>(sB + (size_t)tb * p.B.tile_doubles);
+                for (int ch = 0; ch < nch; ch++) {
+                    if (CHUNKED) load_a(ch);
 #pragma unroll
-                for (int h = 0; h < HALF; h++) {
-                    // one 128-bit LDS per B vector = operands of k-steps 2h and 2h+1; the 16 accumulators
-                    // of a k-step are independent, so consecutive DMMAs never wait on each other
-                    double2 b[NV2];
+                    for (int h = 0; h < HALF; h++) {
+                        // one 128-bit LDS per B vector = operands of k-steps 2h and 2h+1; the 16 accumulators
+                        // of a k-step are independent, so consecutive DMMAs never wait on each other
+                        double2 b[NV2];
 #pragma unroll
-                    for (int v2 = 0; v2 < NV2; v2++) {
-                        const int tv = (v2 == 0) ? 0 : (p.B.voff + v2);
-                        b[v2] = bt[(tv * HALF + h) * 32 + lane];
+                        for (int v2 = 0; v2 < NV2; v2++) {
+                            const int tv = (v2 == 0) ? 0 : (voffB + v2);
+                            b[v2] = bt[(tv * halft + ch * HALF + h) * 32 + lane];
+                        }
+#pragma unroll
+                        for (int v2 = 0; v2 < NV2; v2++)
+#pragma unroll
+                            for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h], b[v2].x);
+#pragma unroll
+                        for (int v2 = 0; v2 < NV2; v2++)
+#pragma unroll
+                            for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h + 1], b[v2].y);
                     }
-#pragma unroll
-                    for (int v2 = 0; v2 < NV2; v2++)
-#pragma unroll
-                        for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h], b[v2].x);
-#pragma unroll
-                    for (int v2 = 0; v2 < NV2; v2++)
-#pragma unroll
-                        for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h + 1], b[v2].y);
                 }
 
                 const unsigned vb = __ldg(p.B.tile_valid + b_tile0 + tb);
@@ -520,8 +544,8 @@ block_tile_kernel(const TileParams p)
             for (int l = 0; l < NC2; l++) {
                 const long long o = gi * p.si + k * p.sk + gj * p.sj + l * p.sl;
                 double v = p.scale * acc[e][k][l];
-                if (p.accumulate) v += p.out[o];
-                if (p.stream_out) __stcs(p.out + o, v); else p.out[o] = v;
+                if (p.accumulate) v += out[o];
+                if (p.stream_out) __stcs(out + o, v); else out[o] = v;
                 if (GRAD) {
                     double g = p.scale_grad * accg[e][k][l];
                     if (p.accumulate) g += p.out_grad[o];
@@ -536,8 +560,8 @@ block_tile_kernel(const TileParams p)
                 for (int l = 0; l < NC2; l++) {
                     const long long o = gj * p.si + l * p.sk + gi * p.sj + k * p.sl;
                     double v = p.scale * acc[e][k][l];
-                    if (p.accumulate) v += p.out[o];
-                    if (p.stream_out) __stcs(p.out + o, v); else p.out[o] = v;
+                    if (p.accumulate) v += out[o];
+                    if (p.stream_out) __stcs(out + o, v); else out[o] = v;
                     if (GRAD) {
                         double g = p.scale_grad * accg[e][k][l];
                         if (p.accumulate) g += p.out_grad[o];
@@ -549,56 +573,63 @@ block_tile_kernel(const TileParams p)
 }
 
 // ------------------------------------------------------------------------------------------
-template <int MODE, int FAM, int KS, bool Z2>
+template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED>
 static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t st)
 {
-    auto kern = block_tile_kernel<MODE, FAM, KS, Z2>;
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    auto kern = block_tile_kernel<MODE, FAM, KS, Z2, CHUNKED>;
+    // the opt-in is a per-device attribute of the function: remember it per device ordinal (a thread may switch
+    // devices through cspbo_set_device); races between threads only repeat a cheap idempotent call
+    static size_t configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t &conf = configured[(dev >= 0 && dev < 64) ? dev : 0];
+    if (smem > 48 * 1024 && (smem > conf || dev < 0 || dev >= 64)) {
         CSPBO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        conf = smem;
     }
     const int a_mine = p.sharded ? p.a_slots : (p.a_nblk - p.a_begin);
     const int npg = p.split ? a_mine : (a_mine + nwarps - 1) / nwarps;
     const long long grid = (long long)npg * p.b_nblk;
     if (grid <= 0) return CSPBO_OK;
     if (grid > 0x7fffffffLL) { set_error("block_build: grid too large"); return CSPBO_E_ARG; }
-    kern<<<(unsigned)grid, nwarps * 32, smem, st>>>(p);
+    kern<<<dim3((unsigned)grid, (unsigned)std::max(p.npass, 1)), nwarps * 32, smem, st>>>(p);
     g_launches++;
     {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {
-            set_error("tile kernel launch failed: %s (grid %lld, block %d, smem %zu, tbc %d)", cudaGetErrorString(e), grid,
-                      nwarps * 32, smem, p.tbc);
+            set_error("tile kernel launch failed: %s (grid %lld x %d, block %d, smem %zu, tbc %d)", cudaGetErrorString(e), grid,
+                      p.npass, nwarps * 32, smem, p.tbc);
             return CSPBO_E_CUDA;
         }
     }
     return CSPBO_OK;
 }
 
-template <int MODE, int KS>
+template <int MODE, int KS, bool CHUNKED>
 static int launch_mode(int fam, bool z2, const TileParams &p, int nwarps, size_t smem, cudaStream_t st)
 {
-    if (fam == FAM_DOT) return z2 ? launch_one<MODE, FAM_DOT, KS, true>(p, nwarps, smem, st)
-                                  : launch_one<MODE, FAM_DOT, KS, false>(p, nwarps, smem, st);
-    if (fam == FAM_RBF) return z2 ? launch_one<MODE, FAM_RBF, KS, true>(p, nwarps, smem, st)
-                                  : launch_one<MODE, FAM_RBF, KS, false>(p, nwarps, smem, st);
-    return z2 ? launch_one<MODE, FAM_RBF_GRAD, KS, true>(p, nwarps, smem, st)
-              : launch_one<MODE, FAM_RBF_GRAD, KS, false>(p, nwarps, smem, st);
+    if (fam == FAM_DOT) return z2 ? launch_one<MODE, FAM_DOT, KS, true, CHUNKED>(p, nwarps, smem, st)
+                                  : launch_one<MODE, FAM_DOT, KS, false, CHUNKED>(p, nwarps, smem, st);
+    if (fam == FAM_RBF) return z2 ? launch_one<MODE, FAM_RBF, KS, true, CHUNKED>(p, nwarps, smem, st)
+                                  : launch_one<MODE, FAM_RBF, KS, false, CHUNKED>(p, nwarps, smem, st);
+    return z2 ? launch_one<MODE, FAM_RBF_GRAD, KS, true, CHUNKED>(p, nwarps, smem, st)
+              : launch_one<MODE, FAM_RBF_GRAD, KS, false, CHUNKED>(p, nwarps, smem, st);
 }
 
-template <int KS>
+template <int KS, bool CHUNKED>
 static int launch_ks(int mode, int fam, bool z2, const TileParams &p, int nwarps, size_t smem, cudaStream_t st)
 {
     switch (mode) {
-        case MODE_KEE: return launch_mode<MODE_KEE, KS>(fam, z2, p, nwarps, smem, st);
-        case MODE_KEF: return launch_mode<MODE_KEF, KS>(fam, z2, p, nwarps, smem, st);
-        default: return launch_mode<MODE_KFF, KS>(fam, z2, p, nwarps, smem, st);
+        case MODE_KEE: return launch_mode<MODE_KEE, KS, CHUNKED>(fam, z2, p, nwarps, smem, st);
+        case MODE_KEF: return launch_mode<MODE_KEF, KS, CHUNKED>(fam, z2, p, nwarps, smem, st);
+        default: return launch_mode<MODE_KFF, KS, CHUNKED>(fam, z2, p, nwarps, smem, st);
     }
 }
 
 // Panel-layout arguments of build_block_device (cspbo_block_build_panel).
 struct PanelArgs { long long ld; int nbw; long long row0_a, row0_b; };
+// Stress passes of one launch: npass column triplets of side `side` (0 = A, 1 = B), pass q stored at out + q*off.
+struct PassArgs { int npass, side; long long off; };
 
 // Number of superblocks (a ragged last one included) owned by `rank`.
 int sharded_superblocks(int n_blocks, int rank, int nranks, int sb_blocks, int zigzag)
@@ -613,7 +644,7 @@ int sharded_superblocks(int n_blocks, int rank, int nranks, int sb_blocks, int z
 int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
                        int accumulate, cudaStream_t st, int rank, int nranks, double *const *outs, int a_begin, int a_end,
-                       int diag, int sb_blocks, int zigzag, int packed_cols, const PanelArgs *panel)
+                       int diag, int sb_blocks, int zigzag, int packed_cols, const PanelArgs *panel, const PassArgs *passes)
 {
     if (a->ks != b->ks || a->d != b->d) {
         set_error("block_build: packs have different descriptor lengths (%d vs %d)", a->d, b->d);
@@ -625,10 +656,9 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     TileParams p;
     p.A = {a->d_tiles, a->d_tile_start, a->d_slot_group, a->d_tile_valid, (int)a->tile_doubles, voffA, (int)a->species.size()};
     p.B = {b->d_tiles, b->d_tile_start, b->d_slot_group, b->d_tile_valid, (int)b->tile_doubles, voffB, (int)b->species.size()};
-    if (a->species.size() > (size_t)kMaxSpecies || b->species.size() > (size_t)kMaxSpecies) {
-        set_error("block_build: more than %d species in one pack", kMaxSpecies);
-        return CSPBO_E_ARG;
-    }
+    p.npass = passes ? std::max(passes->npass, 1) : 1;
+    p.pass_side = passes ? passes->side : 0;
+    p.pass_off = passes ? passes->off : 0;
     p.zeta = d.zeta; p.sigma2 = d.sigma2; p.sigma02 = d.sigma02;
     p.inv2l2 = d.family == CSPBO_RBF ? 1.0 / (2.0 * d.l * d.l) : 0.0;
     p.inv_l = d.family == CSPBO_RBF ? 1.0 / d.l : 0.0;
@@ -670,15 +700,29 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     if (p.a_nblk <= p.a_begin || b->n_blocks == 0) return CSPBO_OK;
 
     int maxTb = 1;
-    for (int e = 0; e < kMaxSpecies; e++) p.emap[e] = -1;
-    const int nsB = (int)b->species.size();
-    for (size_t ea = 0; ea < a->species.size(); ea++)
-        for (size_t eb = 0; eb < b->species.size(); eb++)
-            if (b->species[eb] == a->species[ea]) {
-                p.emap[ea] = (int)eb;
+    const int nsA = (int)a->species.size(), nsB = (int)b->species.size();
+    std::vector<int> emap((size_t)std::max(nsA, kMaxSpecies), -1);
+    for (int ea = 0; ea < nsA; ea++)
+        for (int eb = 0; eb < nsB; eb++)
+            if (b->species[(size_t)eb] == a->species[(size_t)ea]) {
+                emap[(size_t)ea] = eb;
                 for (int q = 0; q < (int)b->n_blocks; q++)
                     maxTb = std::max(maxTb, b->h_tile_start[(size_t)q * nsB + eb + 1] - b->h_tile_start[(size_t)q * nsB + eb]);
             }
+    for (int e = 0; e < kMaxSpecies; e++) p.emap[e] = emap[(size_t)e];
+    p.emap_dev = nullptr;
+    int *emap_dev = nullptr;
+    if (nsA > kMaxSpecies) {
+        // more species buckets than the kernel parameters carry (labels beyond the usual handful of elements): the map
+        // goes through device memory.  Rare, so a blocking copy and a stream sync after the launch are acceptable.
+        void *q = nullptr;
+        const int rca = dev_alloc_cached((size_t)nsA * sizeof(int), &q);
+        if (rca) return rca;
+        emap_dev = static_cast<int *>(q);
+        cudaError_t e = cudaMemcpy(emap_dev, emap.data(), (size_t)nsA * sizeof(int), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { dev_free_cached(emap_dev); set_error("block_build: species map upload failed: %s", cudaGetErrorString(e)); return CSPBO_E_CUDA; }
+        p.emap_dev = emap_dev;
+    }
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -691,17 +735,27 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     // (decided on the whole A side, not on the row slab of a pipelined host-bound build, so that every
     // way of building the same block sums in the same order and gives bit-identical results)
     const long long a_all = ((long long)a->n_blocks + p.nranks - 1) / p.nranks;
-    p.split = (diag || a_all * p.b_nblk < 32LL * sms) ? 1 : 0;
+    p.split = (diag || a_all * p.b_nblk * p.npass < 32LL * sms) ? 1 : 0;
     // B tiles per stage: a whole (block, species) run if it fits in 36 KB
     const size_t tile_bytes = (size_t)b->tile_doubles * sizeof(double);
     // K_FF: 36 KB stages (a whole (block, species) run of 6 KB tiles).  The narrower K_EE / K_EF tiles need less, and
     // smaller stages raise the resident CTAs per SM (measured: K_EE RBF 18.4 -> 16.8 ms at 18 KB, K_EF RBF 75.7 -> 73.7 at 24 KB)
-    const size_t stage_bytes = mode == MODE_KEE ? (size_t)18 * 1024 : (mode == MODE_KEF ? (size_t)24 * 1024 : kSmemChunk);
-    const int tbc = (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, stage_bytes / tile_bytes));
+    size_t stage_bytes = mode == MODE_KEE ? (size_t)18 * 1024 : (mode == MODE_KEF ? (size_t)24 * 1024 : kSmemChunk);
+    // chunked kernels (d > 56): tiles are nch x longer; a stage must hold at least one whole B tile.  Up to 96 KB per
+    // stage they are staged like the short ones, beyond that (d > ~400, or d > ~160 with 9 derivative columns on the B
+    // side) the B fragments are read straight from global memory
+    const bool chunked = a->ks != 6 && a->ks != 14;
+    p.nch = chunked ? a->ks / 6 : 1;
+    p.staged = 1;
+    if (chunked && tile_bytes > stage_bytes) {
+        if (tile_bytes <= (size_t)96 * 1024) stage_bytes = tile_bytes;
+        else p.staged = 0;
+    }
+    const int tbc = p.staged ? (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, stage_bytes / tile_bytes)) : maxTb;
     p.tbc = tbc;
     // the stage buffers double as the scratch of the split-mode reduction (NACC accumulators per thread of 3 warps)
     const int nacc = 2 * (mode == MODE_KFF ? 9 : (mode == MODE_KEF ? 3 : 1)) * (fam == FAM_RBF_GRAD ? 2 : 1);
-    const size_t smem = std::max<size_t>(2 * (size_t)tbc * tile_bytes, (size_t)(kMaxWarps - 1) * 32 * nacc * sizeof(double)) +
+    const size_t smem = std::max<size_t>(p.staged ? 2 * (size_t)tbc * tile_bytes : 0, (size_t)(kMaxWarps - 1) * 32 * nacc * sizeof(double)) +
                         2 * sizeof(unsigned long long);
     p.strip = std::max(1, std::min(kStrip, p.split ? a_mine : (a_mine + nwarps - 1) / nwarps));
     // Keep the packed tiles L2-resident while the write-once output streams through: an access-policy
@@ -733,8 +787,13 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
             cudaGetLastError();
         }
     }
-    const int rc_launch = (a->ks == 6) ? launch_ks<6>(mode, fam, z2, p, nwarps, smem, st)
-                                       : launch_ks<14>(mode, fam, z2, p, nwarps, smem, st);
+    const int rc_launch = (a->ks == 6) ? launch_ks<6, false>(mode, fam, z2, p, nwarps, smem, st)
+                          : (a->ks == 14) ? launch_ks<14, false>(mode, fam, z2, p, nwarps, smem, st)
+                                          : launch_ks<6, true>(mode, fam, z2, p, nwarps, smem, st);
+    if (emap_dev) {
+        cudaStreamSynchronize(st);
+        dev_free_cached(emap_dev);
+    }
     if (window) {   // the window is captured at launch; do not leak it onto later work of this stream
         cudaStreamAttrValue av;
         memset(&av, 0, sizeof(av));

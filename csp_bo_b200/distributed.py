@@ -97,16 +97,51 @@ def assemble_full(parts, order, m, ncomp=3, sb_blocks=1, zigzag=False, packed_co
     return full.reshape(m * ncomp, m * ncomp)
 
 
+def _exchange_bytes(blob, group, world):
+    """Every rank's `blob` (bytes) on every rank.  Control-plane only (IPC handles); works on any backend, so the
+    peer-memory paths also run with two processes on ONE GPU over gloo (the single-GPU test mode of
+    tests/test_sharded_gpu.py -- NCCL refuses two ranks on one device)."""
+    import torch.distributed as dist
+    out = [None] * world
+    dist.all_gather_object(out, bytes(blob), group=group)
+    return out
+
+
+def _open_peers(lib, own, group, world, rank):
+    """Export `own` (a cudaMalloc'd pointer), open every peer's buffer through CUDA IPC.
+    Returns (ctypes array of the world pointers valid in this process, list of opened peer pointers)."""
+    ptrs = (c_vp * world)()
+    ptrs[rank] = own
+    peers = [None] * world
+    if world > 1:
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(lib.cspbo_ipc_export(own, ctypes.cast(handle, c_vp)))
+        for r, blob in enumerate(_exchange_bytes(bytes(handle), group, world)):
+            if r == rank:
+                continue
+            hb = (ctypes.c_ubyte * 64)(*blob)
+            pp = c_vp()
+            _lib.check(lib.cspbo_ipc_open(ctypes.cast(hb, c_vp), ctypes.byref(pp)))
+            peers[r] = pp
+            ptrs[r] = pp
+    return ptrs, peers
+
+
 def gather_row_blocks(local, n_blocks, rank, world, group=None, sb_blocks=1, zigzag=False):
     """all_gather of the (unequal) per-rank row blocks; device-agnostic (NCCL on CUDA tensors, gloo on
-    CPU tensors).  Returns the list of per-rank arrays, trimmed to their true row counts."""
+    CPU tensors; CUDA tensors under gloo are staged through the host).  Returns the list of per-rank arrays,
+    trimmed to their true row counts."""
     import torch
     import torch.distributed as dist
     max_rows = max(sharded_rows(n_blocks, r, world, sb_blocks, zigzag) for r in range(world))
-    pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    via_host = local.is_cuda and dist.get_backend(group) != "nccl"
+    dev = "cpu" if via_host else local.device
+    pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
     pad[: local.shape[0]] = local
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad, group=group)
+    if via_host:
+        parts = [p.to(local.device) for p in parts]
     return [p[: sharded_rows(n_blocks, r, world, sb_blocks, zigzag)] for r, p in enumerate(parts)]
 
 
@@ -146,23 +181,7 @@ class ShardedSymmetricBlock:
         ptr = c_vp()
         _lib.check(self.lib.cspbo_dev_alloc(nbytes, ctypes.byref(ptr)))
         self._own = ptr
-        self._peers = [None] * self.world
-        self._ptrs = (c_vp * self.world)()
-        self._ptrs[self.rank] = ptr
-        if self.world > 1:
-            handle = (ctypes.c_ubyte * 64)()
-            _lib.check(self.lib.cspbo_ipc_export(ptr, ctypes.cast(handle, c_vp)))
-            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
-            allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(self.world)]
-            dist.all_gather(allh, mine, group=group)
-            for r in range(self.world):
-                if r == self.rank:
-                    continue
-                hb = (ctypes.c_ubyte * 64)(*allh[r].cpu().tolist())
-                pp = c_vp()
-                _lib.check(self.lib.cspbo_ipc_open(ctypes.cast(hb, c_vp), ctypes.byref(pp)))
-                self._peers[r] = pp
-                self._ptrs[r] = pp
+        self._ptrs, self._peers = _open_peers(self.lib, ptr, group, self.world, self.rank)
         self.local = torch.as_tensor(_RawCuda(ptr.value, (max(self.rows, 1),) + self.row_shape), device="cuda")[: self.rows]
 
     def _barrier(self):
@@ -608,23 +627,7 @@ def _shared_buffer(nbytes, group, world, rank):
     want = int(nbytes) + int(nbytes) // 8
     own = c_vp()
     _lib.check(lib.cspbo_dev_alloc(want, ctypes.byref(own)))
-    ptrs = (c_vp * world)()
-    ptrs[rank] = own
-    peers = [None] * world
-    if world > 1:
-        handle = (ctypes.c_ubyte * 64)()
-        _lib.check(lib.cspbo_ipc_export(own, ctypes.cast(handle, c_vp)))
-        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device="cuda")
-        allh = [torch.empty(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
-        dist.all_gather(allh, mine, group=group)
-        for r in range(world):
-            if r == rank:
-                continue
-            hb = (ctypes.c_ubyte * 64)(*allh[r].cpu().tolist())
-            pp = c_vp()
-            _lib.check(lib.cspbo_ipc_open(ctypes.cast(hb, c_vp), ctypes.byref(pp)))
-            peers[r] = pp
-            ptrs[r] = pp
+    ptrs, peers = _open_peers(lib, own, group, world, rank)
     _IPC_POOL[key] = dict(bytes=want, own=own, ptrs=ptrs, peers=peers)
     return own, ptrs
 

@@ -50,7 +50,9 @@ class GaussianProcess():
         noise_e: [value, lower bound, upper bound]
     """
 
-    def __init__(self, kernel, descriptor=None, base_potential=None, f_coef=5, noise_e=[5e-3, 2e-3, 1e-1]):
+    def __init__(self, kernel=None, descriptor=None, base_potential=None, f_coef=5, noise_e=[5e-3, 2e-3, 1e-1]):
+        # kernel / descriptor default to None so that `gpr()` followed by load() works like the constructor the
+        # reference's example scripts rely on (gaussianprocess_kang.py:28, examples/example_validate.py:20)
         self.noise_e = noise_e[0]
         self.f_coef = f_coef
         self.noise_f = self.f_coef * self.noise_e
@@ -65,6 +67,7 @@ class GaussianProcess():
         self.alpha_ = None
         self.L_ = None            # CUDA tensor: cuSOLVER factor of K + noise (its lower triangle, column-major)
         self._alpha_dev = None
+        self._packs = None        # the training set as resident packs, snapshot taken by fit()
         self.N_energy = 0
         self.N_forces = 0
         self.N_energy_queue = 0
@@ -149,6 +152,14 @@ class GaussianProcess():
     def _train_dict(self):
         return {k: v for k, v in self.train_x.items() if len(v) > 0}
 
+    def _fitted(self):
+        """The training set alpha_ belongs to: the packs fit() built (HBM-resident, one upload per fit).  Points
+        queued by set_train_pts(mode='a+') after the last fit are not in it -- the reference's get_train_x()
+        (gaussianprocess.py:392-405) drops them the same way -- so K* always has as many columns as alpha_ has rows."""
+        if self._packs is None:
+            raise RuntimeError("GaussianProcess: fit() has not been called")
+        return self._packs
+
     def remove_train_pts(self, e_ids, f_ids):
         """Drop the energy points `e_ids` and force points `f_ids` and refit (gaussianprocess.py:230-270;
         the ASE-database bookkeeping of the reference is kept only as far as train_db entries exist)."""
@@ -207,6 +218,8 @@ class GaussianProcess():
                 return (-lml, -grad)
             return -self.log_marginal_likelihood(params, clone_kernel=False)
 
+        from .packing import resident
+        self._packs = resident(self._train_dict())     # the one upload of the training descriptors of this fit
         hyper_params = self.kernel.parameters() + [self.noise_e]
         hyper_bounds = self.kernel.bounds + [self.noise_bounds]
         if opt:
@@ -220,12 +233,12 @@ class GaussianProcess():
                 # one process per GPU (torchrun): K is built in the panel layout across the ranks and factorised by the
                 # sharded Cholesky; every rank ends up with alpha and the replicated factor (csp_bo_b200/distributed.py)
                 from .distributed import fit_sharded
-                alpha, self._solver = fit_sharded(self.kernel, self._train_dict(), self.y_train[:, 0], self.noise_e,
+                alpha, self._solver = fit_sharded(self.kernel, self._packs, self.y_train[:, 0], self.noise_e,
                                                   self.f_coef, return_solver=True)
                 K, logdet = None, self._solver.logdet()
             else:
                 self._solver = None
-                K = kdev.k_total_device(self.kernel, self._train_dict())          # CUDA [N,N]
+                K = kdev.k_total_device(self.kernel, self._packs)                 # CUDA [N,N]
                 alpha, logdet = gp.fit_alpha(K, self.y_train[:, 0], n_energy=self._n_energy(), noise_e=self.noise_e,
                                              f_coef=self.f_coef, return_logdet=True, overwrite=True)
         except _lib.CspboError as exc:
@@ -251,7 +264,10 @@ class GaussianProcess():
         import torch
         kernel = self.kernel
         kernel.update(params[:-1])
-        data = self._train_dict()
+        if self._packs is None:
+            from .packing import resident
+            self._packs = resident(self._train_dict())
+        data = self._packs
         if eval_gradient:
             K, dKs = kdev.k_total_with_grad_device(kernel, data)
         else:
@@ -346,7 +362,7 @@ class GaussianProcess():
     def predict(self, X, stress=False, total_E=False, return_std=False, return_cov=False):
         """gaussianprocess.py:133-184."""
         import torch
-        train = self._train_dict()
+        train = self._fitted()
         if stress:
             K_trans, K_trans1 = kdev.k_total_with_stress_device(self.kernel, X, train)
         else:
@@ -444,7 +460,7 @@ class GaussianProcess():
             dX = np.concatenate((dX, rd), axis=2)
         data = {"energy": (np.ascontiguousarray(d['x']), ele, [len(ele)]),
                 "force": (np.ascontiguousarray(d['x'][centres]), np.ascontiguousarray(dX), ele[centres], [int(c) for c in counts])}
-        train = self._train_dict()
+        train = self._fitted()
         if stress:
             K_trans, K_trans1 = kdev.k_total_with_stress_device(self.kernel, data, train, f_tol)
         else:

@@ -12,7 +12,9 @@ from ..utilities import list_to_tuple
 
 
 def _tuples(data, stress=False):
-    """{'energy': tuple|list, 'force': tuple|list} -> packs (None when absent/empty)."""
+    """{'energy': tuple|list|Pack, 'force': tuple|list|Pack} -> packs (None when absent/empty).  Tuples and lists are
+    packed afresh on every call (stateless, like the reference wrappers); caller-held Packs (packing.resident) pass
+    through."""
     pe = pf = None
     E = data.get("energy")
     if E is not None and len(E) > 0:

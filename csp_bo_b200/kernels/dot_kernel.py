@@ -8,11 +8,12 @@ row split + Allreduce (dot_kernel.py:188-247) is replaced by the GPU grid.
 import numpy as np
 
 from .. import _lib
-from ..packing import HOST_ROW_CLASSES, build_block, pack_energy, pack_force
+from ..packing import HOST_ROW_CLASSES, Pack, build_block, pack_energy, pack_force
 from ..utilities import list_to_tuple
 
 
 def _energy(X):
+    """list | stacked tuple | caller-held Pack (packing.resident) -> tuple | Pack"""
     if isinstance(X, list):
         X = list_to_tuple(X, mode='energy')
     return X
@@ -22,6 +23,27 @@ def _force(X, stress=False):
     if isinstance(X, list):
         X = list_to_tuple(X, stress=stress)
     return X
+
+
+def _same(X1, X2):
+    """Both sides are the same stacked set (K(X, X): one pack, symmetric build)."""
+    if X1 is X2:
+        return True
+    if isinstance(X1, Pack) or isinstance(X2, Pack):
+        return False
+    return X1[0] is X2[0] and X1[1] is X2[1]
+
+
+def _force_packs(X1, X2, stress, on_dev):
+    """Packs of the two force sets of a K_FF build.  A host-bound result above 64 MB packs side 1 in row classes so
+    that finished classes stream back while the next one is computed (cspbo_block_build, pipelined path)."""
+    m1 = len(X1) if isinstance(X1, Pack) else len(X1[3])
+    m2 = len(X2) if isinstance(X2, Pack) else len(X2[3])
+    big = (not on_dev) and 72.0 * m1 * m2 * (3 if stress else 1) >= (64 << 20) and m1 >= 512
+    a = pack_force(X1, row_classes=HOST_ROW_CLASSES if big else 1)
+    same = _same(X1, X2)
+    b = a if same else pack_force(X2)
+    return a, b, same
 
 
 def kee_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False):
@@ -62,13 +84,8 @@ def kff_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False, stress=False, out
 
     `out` (extension): optional preallocated (pinned) float64 buffer of m1*nc1*m2*3 elements."""
     X1, X2 = _force(X1, stress), _force(X2)
-    # host-bound result above 64 MB: pack side 1 in row classes so finished classes stream back while
-    # the next one is computed (cspbo_block_build, pipelined path)
     on_dev = out is not None and type(out).__module__.startswith('torch') and out.is_cuda
-    big = (not on_dev) and 72.0 * len(X1[3]) * len(X2[3]) * (3 if stress else 1) >= (64 << 20) and len(X1[3]) >= 512
-    a = pack_force(X1, row_classes=HOST_ROW_CLASSES if big else 1)
-    same = (X1 is X2) or (X1[0] is X2[0] and X1[1] is X2[1])
-    b = a if same else pack_force(X2)
+    a, b, same = _force_packs(X1, X2, stress, on_dev)
     m1, m2 = a.m, b.m
     res, _ = build_block(_lib.DOT, _lib.KFF, a, b, zeta, stress=stress, scale=sigma * sigma * zeta,
                          symmetric=(same and not stress), out=out)

@@ -7,8 +7,8 @@ kernels of libcspbo_b200.so (csrc/tiles.cu) instead of rbf_kernel.cpp.
 import numpy as np
 
 from .. import _lib
-from ..packing import HOST_ROW_CLASSES, build_block, pack_energy, pack_force
-from .dot_kernel import _energy, _force
+from ..packing import build_block, pack_energy, pack_force
+from .dot_kernel import _energy, _force, _force_packs
 
 
 def kee_C(X1, X2, sigma=1.0, l=1.0, zeta=2.0, grad=False):
@@ -55,13 +55,8 @@ def kef_C(X1, X2, sigma=1.0, l=1.0, zeta=2.0, grad=False, stress=False, transpos
 def kff_C(X1, X2, sigma=1.0, l=1.0, zeta=2.0, grad=False, stress=False, tol=1e-12, out=None):
     """Force-force block; pairs with dK/dD <= tol are skipped unless grad=True (rbf_kernel.cpp:394)."""
     X1, X2 = _force(X1, stress), _force(X2)
-    # host-bound result above 64 MB: pack side 1 in row classes so finished classes stream back while
-    # the next one is computed (cspbo_block_build, pipelined path)
     on_dev = out is not None and type(out).__module__.startswith('torch') and out.is_cuda
-    big = (not on_dev) and 72.0 * len(X1[3]) * len(X2[3]) * (3 if stress else 1) >= (64 << 20) and len(X1[3]) >= 512
-    a = pack_force(X1, row_classes=HOST_ROW_CLASSES if big else 1)
-    same = (X1 is X2) or (X1[0] is X2[0] and X1[1] is X2[1])
-    b = a if same else pack_force(X2)
+    a, b, same = _force_packs(X1, X2, stress, on_dev)
     m1, m2 = a.m, b.m
     with_grad = grad and not stress
     res, res_l = build_block(_lib.RBF, _lib.KFF, a, b, zeta, sigma2=sigma * sigma, l=l, tol=tol,

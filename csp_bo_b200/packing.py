@@ -7,7 +7,6 @@ the reference wrappers (cspbo/kernels/dot_kernel.py:207-216).
 """
 import ctypes
 import os
-from collections import OrderedDict
 
 import numpy as np
 
@@ -68,6 +67,10 @@ class Pack:
         self.row_classes = int(row_classes)
         self._h = h
 
+    def __len__(self):
+        """Number of groups, so that the `len(d) > 0` tests of k_total treat a Pack like a stacked tuple."""
+        return self.m
+
     @property
     def handle(self):
         return self._h
@@ -92,60 +95,43 @@ class Pack:
 
 
 # ---------------------------------------------------------------------------------------------
-# A tiny identity-keyed cache: the GP calls k_total(test, train) at every prediction with the same
-# training tuple; packing it once keeps the training descriptors resident in HBM.
-_CACHE = OrderedDict()
-_CACHE_MAX = 8
-
-
-def _fingerprint(arrs, extra):
-    key = [extra]
-    for a in arrs:
-        if a is None:
-            key.append(None)
-        elif _is_torch(a):
-            key.append(("t", a.data_ptr(), tuple(a.shape)))
-        else:
-            a = np.asarray(a)
-            flat = a.reshape(-1)
-            probe = tuple(flat[:: max(1, flat.size // 7)][:8].tolist()) if flat.size else ()
-            key.append(("n", a.__array_interface__["data"][0], a.shape, probe))
-    return tuple(key)
-
-
-def pack_energy(X, cache=True):
+# Packing is STATELESS, like the reference wrappers (cspbo/kernels/dot_kernel.py:207-258 copy their inputs on every
+# call): a stacked tuple handed to kee_C / kef_C / kff_C / k_total is uploaded and tiled again each time, so an array
+# that was updated in place (MD loops, finite differences, NEB images reusing buffers) can never be served from a
+# stale copy.  Residency is explicit: build the packs once with `resident()` (or `Pack(...)`) and pass THEM wherever a
+# stacked tuple is accepted -- that is what GaussianProcess does with its training set.
+def pack_energy(X):
+    """Stacked energy tuple (X, ELE, indices) -> Pack; a Pack passes through."""
+    if isinstance(X, Pack):
+        return X
     x, ele, indices = X
-    key = _fingerprint((x, ele), ("E", tuple(np.asarray(indices).tolist()[:4]), len(indices)))
-    if cache and key in _CACHE:
-        _CACHE.move_to_end(key)
-        return _CACHE[key]
-    p = Pack(x, None, ele, indices)
-    if cache:
-        _CACHE[key] = p
-        while len(_CACHE) > _CACHE_MAX:
-            _CACHE.popitem(last=False)
-    return p
+    return Pack(x, None, ele, indices)
 
 
 HOST_ROW_CLASSES = int(os.environ.get("CSPBO_HOST_ROW_CLASSES", "6"))     # row classes of packs that feed large host-bound K_FF builds (see cspbo_pack_create_ex)
 
 
-def pack_force(X, cache=True, row_range=None, row_classes=1):
+def pack_force(X, row_range=None, row_classes=1):
+    """Stacked force tuple (X, dXdR, ELE, indices) -> Pack; a Pack passes through."""
+    if isinstance(X, Pack):
+        return X
     x, dxdr, ele, indices = X
-    key = _fingerprint((x, dxdr, ele), ("F", tuple(np.asarray(indices).tolist()[:4]), len(indices), row_range, row_classes))
-    if cache and key in _CACHE:
-        _CACHE.move_to_end(key)
-        return _CACHE[key]
-    p = Pack(x, dxdr, ele, indices, row_range=row_range, row_classes=row_classes)
-    if cache:
-        _CACHE[key] = p
-        while len(_CACHE) > _CACHE_MAX:
-            _CACHE.popitem(last=False)
-    return p
+    return Pack(x, dxdr, ele, indices, row_range=row_range, row_classes=row_classes)
 
 
-def clear_cache():
-    _CACHE.clear()
+def resident(data, stress=False):
+    """{'energy': tuple|list, 'force': tuple|list} -> {'energy': Pack, 'force': Pack}: the caller-held handles that
+    keep a descriptor set in HBM across calls.  The packs are snapshots: later changes of the source arrays do not
+    reach them (build new ones)."""
+    from .utilities import list_to_tuple
+    out = {}
+    E = data.get("energy")
+    if E is not None and len(E) > 0:
+        out["energy"] = pack_energy(list_to_tuple(E, mode='energy') if isinstance(E, list) else E)
+    F = data.get("force")
+    if F is not None and len(F) > 0:
+        out["force"] = pack_force(list_to_tuple(F, stress=stress) if isinstance(F, list) else F)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

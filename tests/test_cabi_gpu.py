@@ -56,7 +56,10 @@ def both(libs, family, name, args, out_shapes, init=0.0):
     return outs_g, outs_o
 
 
-@pytest.mark.parametrize("d,zeta,seed", [(24, 2.0, 0), (24, 3.0, 1), (10, 2.5, 2), (50, 2.0, 3), (24, 1.0, 4)])
+# d = 90 (nmax = lmax = 5, SO3.py:205) and 140 run the chunked kernels (k-chunks of 24 features, tiles.cu), d = 450 the
+# unstaged ones (tiles longer than a shared-memory stage): the reference loops `i < d` for any d (dot_kernel.cpp:257-289)
+@pytest.mark.parametrize("d,zeta,seed", [(24, 2.0, 0), (24, 3.0, 1), (10, 2.5, 2), (50, 2.0, 3), (24, 1.0, 4),
+                                         (90, 2.0, 5), (140, 3.0, 6), (57, 2.5, 7), (450, 2.0, 8)])
 def test_dot_entry_points(libs, d, zeta, seed):
     rng = np.random.default_rng(seed)
     x1, _, e1, g1, m1 = make_side(rng, 11, d, 0)
@@ -84,7 +87,8 @@ def test_dot_entry_points(libs, d, zeta, seed):
     assert max_norm_err(g[0], o[0]) < 1e-12
 
 
-@pytest.mark.parametrize("d,zeta,l,seed", [(24, 2.0, 0.56, 10), (24, 3.0, 0.9, 11), (50, 2.0, 0.5, 12), (7, 2.5, 1.3, 13)])
+@pytest.mark.parametrize("d,zeta,l,seed", [(24, 2.0, 0.56, 10), (24, 3.0, 0.9, 11), (50, 2.0, 0.5, 12), (7, 2.5, 1.3, 13),
+                                           (90, 2.0, 0.7, 14), (140, 2.5, 0.9, 15), (450, 2.0, 0.6, 16)])
 def test_rbf_entry_points(libs, d, zeta, l, seed):
     rng = np.random.default_rng(seed)
     x1, _, e1, g1, m1 = make_side(rng, 10, d, 0)
@@ -122,6 +126,56 @@ def test_rbf_entry_points(libs, d, zeta, l, seed):
     assert max_norm_err(g[0], o[0]) < 1e-12
 
 
+@pytest.mark.parametrize("nspecies,d", [(20, 24), (20, 90), (40, 24)])
+def test_many_species(libs, nspecies, d):
+    """More species than any shipped model has: 20 go through the kernel-parameter species map, 40 through the
+    device-memory one (the reference compares `ele1[a] == ele2[b]` for any labels, dot_kernel.cpp:255)."""
+    rng = np.random.default_rng(100 + nspecies + d)
+    species = tuple(int(v) for v in rng.choice(np.arange(1, 119), size=nspecies, replace=False))
+    x1, _, e1, g1, m1 = make_side(rng, 14, d, 0, species=species, max_rows=14)
+    x2, dx2, e2, g2, m2 = make_side(rng, 17, d, 3, species=species[: nspecies - 3] + (200, 201, 202), max_rows=14)
+    n1, n2 = len(x1), len(x2)
+    assert len(np.unique(e1)) > 16 and len(np.unique(e2)) > 16
+    I = c_int
+    g, o = both(libs, "dot", "kee_many", [I(n1), I(n1), I(d), I(m1), c_dbl(2.0), c_dbl(7.3), c_dbl(0.04),
+                                          P(x1), P(e1), P(g1), P(x1), P(e1), P(g1)], [(m1, m1)])
+    assert max_norm_err(g[0], o[0]) < 1e-12
+    g, o = both(libs, "dot", "kef_many", [I(n1), I(n2), I(d), I(m2), c_dbl(2.0), P(x1), P(e1), P(g1),
+                                          P(x2), P(dx2), P(e2), P(g2)], [(m1, m2, 3)])
+    assert max_norm_err(g[0], o[0]) < 1e-12
+    g, o = both(libs, "dot", "kff_many", [I(n2), I(n2), I(0), I(n2), I(d), I(m2), c_dbl(2.0),
+                                          P(x2), P(dx2), P(e2), P(g2), P(x2), P(dx2), P(e2), P(g2)], [(m2, 3, m2 * 3)])
+    assert max_norm_err(g[0], o[0]) < 1e-12
+    g, o = both(libs, "rbf", "kff_many_with_grad", [I(n2), I(n2), I(0), I(n2), I(d), I(m2), c_dbl(2.0), c_dbl(39.0),
+                                                    c_dbl(0.7), P(x2), P(dx2), P(e2), P(g2),
+                                                    P(x2), P(dx2), P(e2), P(g2)], [(m2, 3, m2 * 3), (m2, 3, m2 * 3)])
+    assert max_norm_err(g[0], o[0]) < 1e-12 and max_norm_err(g[1], o[1]) < 1e-12
+
+
+def test_in_place_update_of_the_inputs_is_seen(oracle_built):
+    """Packing is stateless like the reference wrappers (dot_kernel.py:207-258 copy their inputs on every call): an
+    array updated in place between two calls -- MD loops and finite differences reuse buffers -- must give the new
+    K.  (Round 1 cached packs on (address, shape, 8 probed values) and returned the stale matrix here.)"""
+    from csp_bo_b200 import synthetic
+    from csp_bo_b200.kernels.dot_kernel import kee_C, kff_C
+    from oracle import cpu_reference as cr
+    X = synthetic.force_set(40, seed=3)
+    E = synthetic.energy_set(5, seed=4, rows_per_structure=16)
+    K0 = kff_C(X, X, 18.5, 0.01, 2.0).copy()
+    E0 = kee_C(E, E, 18.5, 0.01, 2.0).copy()
+    X[0][5] *= 1.5            # one row that no sparse probe would have looked at, same buffers
+    X[1][5] *= -0.5
+    E[0][3] = E[0][3][::-1].copy()      # (a rescaled row would leave the normalised kernel unchanged)
+    K1, E1 = kff_C(X, X, 18.5, 0.01, 2.0), kee_C(E, E, 18.5, 0.01, 2.0)
+    assert np.abs(K1 - K0).max() > 1e-6 * np.abs(K0).max() and np.abs(E1 - E0).max() > 1e-9 * np.abs(E0).max()
+    assert max_norm_err(K1, cr.dot_kff_C(X, X, 18.5, 0.01, 2.0, backend="port")) < 1e-12
+    assert max_norm_err(E1, cr.dot_kee_C(E, E, 18.5, 0.01, 2.0, backend="port")) < 1e-12
+    # explicit residency: a caller-held pack is a snapshot and is accepted wherever a stacked tuple is
+    from csp_bo_b200.packing import resident
+    held = resident({"force": X})
+    assert np.array_equal(kff_C(held["force"], held["force"], 18.5, 0.01, 2.0), K1)
+
+
 def test_reference_named_shims(libs, fixtures):
     """libdot_kernel_b200.so / librbf_kernel_b200.so: the exact names the reference's cffi binds."""
     lib, port, _lib = libs
@@ -148,11 +202,9 @@ def test_empty_and_bad_arguments(libs):
     assert lib.cspbo_dot_kee_many(I(0), I(4), I(24), I(1), c_dbl(2.0), c_dbl(1.0), c_dbl(0.0),
                                   P(x), P(e), P(g), P(x), P(e), P(g), P(out)) == 0
     assert np.all(out == 0)
-    # unsupported descriptor length
-    xb = np.ones((4, 100))
-    assert lib.cspbo_dot_kee_many(I(4), I(4), I(100), I(1), c_dbl(2.0), c_dbl(1.0), c_dbl(0.0),
-                                  P(xb), P(e), P(g), P(xb), P(e), P(g), P(out)) == 2
-    assert b"unsupported" in lib.cspbo_last_error()
+    # descriptor length out of range
+    assert lib.cspbo_dot_kee_many(I(4), I(4), I(0), I(1), c_dbl(2.0), c_dbl(1.0), c_dbl(0.0),
+                                  P(x), P(e), P(g), P(x), P(e), P(g), P(out)) == 2
     # group id outside [0, x2i)
     gbad = np.array([0, 0, 0, 7], dtype=np.int32)
     assert lib.cspbo_dot_kee_many(I(4), I(4), I(24), I(1), c_dbl(2.0), c_dbl(1.0), c_dbl(0.0),

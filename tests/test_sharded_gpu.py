@@ -1,6 +1,8 @@
 """CUDA side of the sharded symmetric build.  Single process: exercises the packed-order row layout
-and the write path of the sharded kernel with world = 1.  With >= 2 GPUs it also spawns two NCCL
-ranks that store mirrored tiles into each other's HBM over NVLink peer memory."""
+and the write path of the sharded kernel with world = 1.  The world-2 tests spawn two ranks: on a box with >= 2 GPUs
+they are NCCL ranks on two devices that store mirrored tiles into each other's HBM over NVLink peer memory; on a
+ONE-GPU box both ranks sit on cuda:0 (gloo for the control plane and the panel broadcasts, CUDA IPC for the peer
+buffers), so the `sharded` store paths of the tile kernel and the CUDA ShardedCholesky choreography still execute."""
 import os
 
 import numpy as np
@@ -25,39 +27,57 @@ def test_sharded_world1_matches_golden(fixtures, golden):
     sh.close()
 
 
+def _init_rank(rank, world, port):
+    """NCCL on `world` devices when the box has them, otherwise every rank on cuda:0 over gloo."""
+    import torch
+    import torch.distributed as dist
+    from csp_bo_b200 import _lib
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    multi = torch.cuda.device_count() >= world
+    dev = rank if multi else 0
+    torch.cuda.set_device(dev)
+    _lib.check(_lib.load().cspbo_set_device(dev))
+    if multi:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+
+
+def _spawn2(fn, port, tol):
+    import torch.multiprocessing as mp
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(fn, args=(2, port, out), nprocs=2, join=True)
+        assert len(out) == 2 and all(v < tol for v in out.values()), dict(out)
+
+
 def _rank_main(rank, world, port, out):
     import torch
     import torch.distributed as dist
     from csp_bo_b200 import _lib, synthetic
     from csp_bo_b200.distributed import ShardedSymmetricBlock
     from csp_bo_b200.packing import Pack, build_block
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    _lib.check(_lib.load().cspbo_set_device(rank))
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    _init_rank(rank, world, port)
     try:
         X = synthetic.force_set(300, seed=11)
         p = Pack(X[0], X[1], X[2], X[3])
         ref, _ = build_block(_lib.RBF, _lib.KFF, p, p, 2.0, sigma2=39.0, l=0.56, tol=1e-10, use_tol=True, device=True)
-        sh = ShardedSymmetricBlock(p, _lib.KFF)
-        for _ in range(2):
-            sh.build(_lib.RBF, 2.0, sigma2=39.0, l=0.56, tol=1e-10, use_tol=True)
-        K = sh.gather_full()
-        out[rank] = float((K - ref.reshape(900, 900)).abs().max() / ref.abs().max())
-        sh.close()
+        err = 0.0
+        # plain block-cyclic rows / caller-order columns, and the superblock + zigzag + packed-column layout of the fit
+        for kw in (dict(), dict(sb_blocks=4, zigzag=True, packed_cols=True)):
+            sh = ShardedSymmetricBlock(p, _lib.KFF, **kw)
+            for _ in range(2):
+                sh.build(_lib.RBF, 2.0, sigma2=39.0, l=0.56, tol=1e-10, use_tol=True)
+            K = sh.gather_full()
+            err = max(err, float((K - ref.reshape(900, 900)).abs().max() / ref.abs().max()))
+            sh.close()
+        out[rank] = err
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_two_gpus_peer_stores():
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import torch.multiprocessing as mp
-    with mp.Manager() as mgr:
-        out = mgr.dict()
-        mp.spawn(_rank_main, args=(2, 29611, out), nprocs=2, join=True)
-        assert len(out) == 2 and all(v < 1e-12 for v in out.values()), dict(out)
+def test_sharded_two_ranks_peer_stores():
+    _spawn2(_rank_main, 29611, 1e-12)
 
 
 @pytest.mark.parametrize("sb_blocks,zigzag", [(1, False), (2, True), (4, True)])
@@ -109,10 +129,7 @@ def _chol_rank_main(rank, world, port, out):
     from csp_bo_b200 import _lib, gp, synthetic
     from csp_bo_b200.distributed import ShardedSymmetricBlock, fit_alpha_sharded
     from csp_bo_b200.packing import Pack, build_block
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    _lib.check(_lib.load().cspbo_set_device(rank))
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    _init_rank(rank, world, port)
     try:
         X = synthetic.force_set(500, seed=12)
         p = Pack(X[0], X[1], X[2], X[3])
@@ -130,15 +147,8 @@ def _chol_rank_main(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_sharded_cholesky_two_gpus():
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import torch.multiprocessing as mp
-    with mp.Manager() as mgr:
-        out = mgr.dict()
-        mp.spawn(_chol_rank_main, args=(2, 29631, out), nprocs=2, join=True)
-        assert len(out) == 2 and all(v < 1e-8 for v in out.values()), dict(out)
+def test_sharded_cholesky_two_ranks():
+    _spawn2(_chol_rank_main, 29631, 1e-8)
 
 
 def _mixed_problem(n_struct, n_atoms, single=False, rows=64):
@@ -181,10 +191,7 @@ def _cov_rank_main(rank, world, port, out):
     from csp_bo_b200.distributed import fit_sharded
     from csp_bo_b200.kernels import RBF_mb
     from csp_bo_b200.kernels import device as kdev
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    torch.cuda.set_device(rank)
-    _lib.check(_lib.load().cspbo_set_device(rank))
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    _init_rank(rank, world, port)
     try:
         kernel = RBF_mb(para=[6.244955524643115, 0.5611029935713949], zeta=2)
         data, y = _mixed_problem(130, 300)
@@ -221,12 +228,5 @@ def _cov_rank_main(rank, world, port, out):
         dist.destroy_process_group()
 
 
-def test_sharded_covariance_two_gpus():
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    import torch.multiprocessing as mp
-    with mp.Manager() as mgr:
-        out = mgr.dict()
-        mp.spawn(_cov_rank_main, args=(2, 29651, out), nprocs=2, join=True)
-        assert len(out) == 2 and all(v < 1e-8 for v in out.values()), dict(out)
+def test_sharded_covariance_two_ranks():
+    _spawn2(_cov_rank_main, 29651, 1e-8)

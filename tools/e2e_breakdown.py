@@ -26,7 +26,6 @@ print("build -> pinned host     %.1f ms" % T(lambda: build_block(_lib.DOT, _lib.
 outp = np.empty(m * 3 * m * 3)
 print("build -> pageable host   %.1f ms" % T(lambda: build_block(_lib.DOT, _lib.KFF, p, p, 2.0, scale=3.0, symmetric=True, out=outp), 2)[0])
 def full():
-    packing.clear_cache()
     return kff_C(Xh, Xh, 18.55, 0.01, 2.0, out=outh.numpy())
 print("kff_C(host,host,out=pin) %.1f ms" % T(full)[0])
 def alloc():

@@ -15,7 +15,7 @@ def t(f):
     torch.cuda.synchronize(); t0 = time.perf_counter(); f(); torch.cuda.synchronize(); return round((time.perf_counter() - t0) * 1e3, 1)
 print("build->pinned", [t(lambda: build_block(_lib.DOT, _lib.KFF, p, p, 2.0, scale=3.0, symmetric=True, out=o)) for _ in range(6)])
 def full():
-    packing.clear_cache(); kff_C(Xh, Xh, 18.55, 0.01, 2.0, out=o)
+    kff_C(Xh, Xh, 18.55, 0.01, 2.0, out=o)
 print("kff_C e2e    ", [t(full) for _ in range(6)])
 print("build->pinned", [t(lambda: build_block(_lib.DOT, _lib.KFF, p, p, 2.0, scale=3.0, symmetric=True, out=o)) for _ in range(4)])
 pc = Pack(Xh[0], Xh[1], Xh[2], Xh[3], row_classes=6)
