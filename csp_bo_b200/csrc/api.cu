@@ -439,6 +439,12 @@ extern "C" int cspbo_block_build_sharded(const cspbo_block_desc *desc, const csp
 extern "C" int cspbo_block_build_sharded_ex(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
                                             double *const *outs, int sb_blocks, int zigzag, int packed_cols)
 {
+    return cspbo_block_build_sharded_ld(desc, a, rank, nranks, outs, sb_blocks, zigzag, packed_cols, 0);
+}
+
+extern "C" int cspbo_block_build_sharded_ld(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
+                                            double *const *outs, int sb_blocks, int zigzag, int packed_cols, long long ld)
+{
     if (!desc || !a || !outs) { set_error("block_build_sharded: null argument"); return CSPBO_E_ARG; }
     if (sb_blocks < 1) { set_error("block_build_sharded: sb_blocks must be >= 1"); return CSPBO_E_ARG; }
     if (packed_cols && a->row_classes != 1) { set_error("block_build_sharded: packed_cols needs a pack with row_classes = 1"); return CSPBO_E_ARG; }
@@ -451,13 +457,16 @@ extern "C" int cspbo_block_build_sharded_ex(const cspbo_block_desc *desc, const 
     if (d.family == CSPBO_RBF && !(d.l > 0.0)) { set_error("block_build_sharded: RBF needs l > 0"); return CSPBO_E_ARG; }
     d.symmetric = 1;
     const long long m = a->m;
+    const long long cols = (d.block == CSPBO_KEE) ? m : 3 * m;
+    if (ld == 0) ld = cols;
+    if (ld < cols) { set_error("block_build_sharded: row pitch %lld is below the %lld columns of the block", ld, cols); return CSPBO_E_ARG; }
     long long si, sk, sj, sl;
     if (d.block == CSPBO_KEE) {
         if (a->nc != 0) { set_error("block_build_sharded: K_EE needs an energy pack"); return CSPBO_E_ARG; }
-        si = m; sk = 0; sj = 1; sl = 0;
+        si = ld; sk = 0; sj = 1; sl = 0;
     } else {
         if (a->nc < 3) { set_error("block_build_sharded: K_FF needs a force pack"); return CSPBO_E_ARG; }
-        si = 3 * m * 3; sk = m * 3; sj = 3; sl = 1;
+        si = 3 * ld; sk = ld; sj = 3; sl = 1;
     }
     return build_block_device(d, a, a, 0, 0, outs[rank], nullptr, si, sk, sj, sl, 0, 0, rank, nranks, outs, 0, -1, 0,
                               sb_blocks, zigzag, packed_cols);

@@ -49,6 +49,7 @@ struct SideDev {
     int tile_doubles;  // NV*KS*32
     int voff;          // first derivative vector used is 1+voff
     int ns;            // species buckets per block
+    int m;             // groups of the pack (packed positions >= m are padding slots)
 };
 
 struct PanelSide { int g, sb0; long long col0; };
@@ -470,6 +471,55 @@ block_tile_kernel(const TileParams p)
         }
     }
     if (!active) return;
+    if (p.sharded == 2 || (p.sharded == 1 && p.packed_cols)) {
+        // Packed column order (the layouts the sharded Cholesky factorises): the warp's (8 NC1) x (8 NC2) output tile is
+        // contiguous in both directions, so it goes through shared memory and leaves as full rows -- 192-byte runs for
+        // K_FF, whole 32-byte sectors when the row pitch is a multiple of 4 doubles -- to the local rows and, transposed,
+        // to the rows of the B groups on their owner (NVLink peer stores of 192-byte runs instead of 24-byte pieces).
+        constexpr int R = 8 * NC1, C = 8 * NC2, TS = R * (C + 1);
+        constexpr int NACC = 2 * NC1 * NC2 * (GRAD ? 2 : 1);
+        // behind the scratch of the split-mode reduction; the stage buffers are free (every warp passed the last
+        // __syncthreads of the run loop and no bulk copy is outstanding)
+        double *T = smem + (size_t)(kMaxWarps - 1) * 32 * NACC + (size_t)warp * TS;
+#pragma unroll
+        for (int e = 0; e < 2; e++)
+#pragma unroll
+            for (int k = 0; k < NC1; k++)
+#pragma unroll
+                for (int l = 0; l < NC2; l++) T[(ar * NC1 + k) * (C + 1) + (bq + e) * NC2 + l] = p.scale * acc[e][k][l];
+        __syncwarp();
+        const int rv = min(8, p.A.m - a_blk * 8) * NC1, cv = min(8, p.B.m - b_blk * 8) * NC2;   // padding slots trail
+        double *mine = p.outs[p.rank], *peer;
+        long long row_i0, row_j0, col_i0, col_j0;
+        bool mirror;
+        if (p.sharded == 2) {
+            const int sA = p.pa.sb0 + a_blk / p.pa.g, sB = p.pb.sb0 + b_blk / p.pb.g;
+            row_i0 = (long long)(sA / p.nranks) * p.nbw + (a_blk % p.pa.g) * R;
+            col_i0 = p.pa.col0 + (long long)a_blk * R;
+            peer = p.outs[sb_owner(sB, p.nranks, 1)];
+            row_j0 = (long long)(sB / p.nranks) * p.nbw + (b_blk % p.pb.g) * C;
+            col_j0 = p.pb.col0 + (long long)b_blk * C;
+            mirror = p.pair || b_blk != a_blk;
+        } else {
+            const int sa = a_blk / p.sb_blocks, sb = b_blk / p.sb_blocks;
+            row_i0 = ((long long)(sa / p.nranks) * p.sb_blocks + (a_blk - sa * p.sb_blocks)) * R;
+            col_i0 = (long long)a_blk * R;
+            peer = p.outs[sb_owner(sb, p.nranks, p.zigzag)];
+            row_j0 = ((long long)(sb / p.nranks) * p.sb_blocks + (b_blk - sb * p.sb_blocks)) * C;
+            col_j0 = (long long)b_blk * C;
+            mirror = b_blk != a_blk;
+        }
+        for (int idx = lane; idx < R * C; idx += 32) {
+            const int r = idx / C, c = idx - r * C;
+            if (r < rv && c < cv) mine[(row_i0 + r) * p.ldo + col_j0 + c] = T[r * (C + 1) + c];
+        }
+        if (mirror)
+            for (int idx = lane; idx < R * C; idx += 32) {
+                const int c = idx / R, r = idx - c * R;
+                if (r < rv && c < cv) peer[(row_j0 + c) * p.ldo + col_i0 + r] = T[r * (C + 1) + c];
+            }
+        return;
+    }
     const int gi = p.A.slot_group[a_blk * 8 + ar];
     if (gi < 0) return;
     if (p.diag) {
@@ -483,46 +533,20 @@ block_tile_kernel(const TileParams p)
             }
         return;
     }
-    if (p.sharded == 2) {
-        // panel layout: own tile -> local rows, mirrored tile -> the rows of the B groups on their owner (NVLink peer store)
-        double *mine = p.outs[p.rank];
-        const int sA = p.pa.sb0 + a_blk / p.pa.g;
-        const long long row_i = (long long)(sA / p.nranks) * p.nbw + ((a_blk % p.pa.g) * 8 + ar) * NC1;
-        const long long col_i = p.pa.col0 + ((long long)a_blk * 8 + ar) * NC1;
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int gj = p.B.slot_group[b_blk * 8 + bq + e];
-            if (gj < 0) continue;
-            const int sB = p.pb.sb0 + b_blk / p.pb.g;
-            double *peer = p.outs[sb_owner(sB, p.nranks, 1)];
-            const long long row_j = (long long)(sB / p.nranks) * p.nbw + ((b_blk % p.pb.g) * 8 + bq + e) * NC2;
-            const long long col_j = p.pb.col0 + ((long long)b_blk * 8 + bq + e) * NC2;
-            const bool mirror = p.pair || b_blk != a_blk;
-#pragma unroll
-            for (int k = 0; k < NC1; k++)
-#pragma unroll
-                for (int l = 0; l < NC2; l++) {
-                    const double v = p.scale * acc[e][k][l];
-                    mine[(row_i + k) * p.ldo + col_j + l] = v;
-                    if (mirror) peer[(row_j + l) * p.ldo + col_i + k] = v;
-                }
-        }
-        return;
-    }
     if (p.sharded) {
         // sharded symmetric build: rows are block-cyclic over ranks in packed order, columns keep the
         // caller's group ids.  Own tile -> local HBM, mirrored tile -> peer HBM of the owner of b.
         double *mine = p.outs[p.rank];
         const int sa = a_blk / p.sb_blocks, sb = b_blk / p.sb_blocks;
         const long long lrow_i = ((long long)(sa / p.nranks) * p.sb_blocks + (a_blk - sa * p.sb_blocks)) * 8 + ar;
-        const long long ci = p.packed_cols ? (long long)a_blk * 8 + ar : gi;
+        const long long ci = gi;
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const int gj = p.B.slot_group[b_blk * 8 + bq + e];
             if (gj < 0) continue;
             double *peer = p.outs[sb_owner(sb, p.nranks, p.zigzag)];
             const long long lrow_j = ((long long)(sb / p.nranks) * p.sb_blocks + (b_blk - sb * p.sb_blocks)) * 8 + bq + e;
-            const long long cj = p.packed_cols ? (long long)b_blk * 8 + bq + e : gj;
+            const long long cj = gj;
 #pragma unroll
             for (int k = 0; k < NC1; k++)
 #pragma unroll
@@ -654,8 +678,8 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     int fam = d.family == CSPBO_DOT ? FAM_DOT : (d.with_grad ? FAM_RBF_GRAD : FAM_RBF);
     const bool z2 = (d.zeta == 2.0);
     TileParams p;
-    p.A = {a->d_tiles, a->d_tile_start, a->d_slot_group, a->d_tile_valid, (int)a->tile_doubles, voffA, (int)a->species.size()};
-    p.B = {b->d_tiles, b->d_tile_start, b->d_slot_group, b->d_tile_valid, (int)b->tile_doubles, voffB, (int)b->species.size()};
+    p.A = {a->d_tiles, a->d_tile_start, a->d_slot_group, a->d_tile_valid, (int)a->tile_doubles, voffA, (int)a->species.size(), a->m};
+    p.B = {b->d_tiles, b->d_tile_start, b->d_slot_group, b->d_tile_valid, (int)b->tile_doubles, voffB, (int)b->species.size(), b->m};
     p.npass = passes ? std::max(passes->npass, 1) : 1;
     p.pass_side = passes ? passes->side : 0;
     p.pass_off = passes ? passes->off : 0;
@@ -681,7 +705,9 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.a_begin = p.sharded ? 0 : std::max(a_begin, 0);
     p.a_nblk = (a_end < 0 || p.sharded) ? (int)a->n_blocks : std::min(a_end, (int)a->n_blocks);
     p.a_slots = p.sharded ? sharded_superblocks((int)a->n_blocks, p.rank, p.nranks, p.sb_blocks, p.zigzag) * p.sb_blocks : 0;
-    p.nbw = 0; p.cyc0 = 0; p.pair = 0; p.ldo = 0;
+    p.nbw = 0; p.cyc0 = 0; p.pair = 0;
+    // packed-column sharded layout: the distributed matrix is [rows * NC1, ldo] (K_FF: sk = row pitch, K_EE: si)
+    p.ldo = (mode == MODE_KFF) ? sk : si;
     p.pa = {1, 0, 0}; p.pb = {1, 0, 0};
     if (panel && p.sharded) {
         const int nca = (mode == MODE_KFF) ? 3 : 1, ncb = (mode == MODE_KEE) ? 1 : 3;
@@ -755,9 +781,19 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.tbc = tbc;
     // the stage buffers double as the scratch of the split-mode reduction (NACC accumulators per thread of 3 warps)
     const int nacc = 2 * (mode == MODE_KFF ? 9 : (mode == MODE_KEF ? 3 : 1)) * (fam == FAM_RBF_GRAD ? 2 : 1);
-    const size_t smem = std::max<size_t>(p.staged ? 2 * (size_t)tbc * tile_bytes : 0, (size_t)(kMaxWarps - 1) * 32 * nacc * sizeof(double)) +
+    // ... and, for the packed-column layouts, as the staging area of the full-row output stores (behind that scratch)
+    const int oR = 8 * (mode == MODE_KFF ? 3 : 1), oC = 8 * (mode == MODE_KEE ? 1 : 3);
+    const size_t out_stage = (p.sharded == 2 || (p.sharded == 1 && p.packed_cols)) ? (size_t)kMaxWarps * oR * (oC + 1) * sizeof(double) : 0;
+    const size_t smem = std::max<size_t>(p.staged ? 2 * (size_t)tbc * tile_bytes : 0,
+                                         (size_t)(kMaxWarps - 1) * 32 * nacc * sizeof(double) + out_stage) +
                         2 * sizeof(unsigned long long);
-    p.strip = std::max(1, std::min(kStrip, p.split ? a_mine : (a_mine + nwarps - 1) / nwarps));
+    // Rasterisation.  Caller-order outputs: one strip (kStrip).  Packed-column layouts: strips of 48 A-block groups
+    // (192 row blocks): the strip's A tiles stay L2-hot while the B blocks stream, and -- now that the output leaves as
+    // whole sectors -- DRAM reads drop from 3.8 GB to 0.30 GB per 20 001-row build at unchanged run time (measured,
+    // profiles/kff_traffic_r02.md); with 24-byte output pieces the same strips cost 1.5 % (round 1's finding).
+    static const int strip_env = getenv("CSPBO_STRIP") ? atoi(getenv("CSPBO_STRIP")) : 0;    // experiments only
+    const int strip_def = (p.sharded == 2 || (p.sharded == 1 && p.packed_cols)) ? 48 : kStrip;
+    p.strip = std::max(1, std::min(strip_env > 0 ? strip_env : strip_def, p.split ? a_mine : (a_mine + nwarps - 1) / nwarps));
     // Keep the packed tiles L2-resident while the write-once output streams through: an access-policy
     // window (persisting on hit, streaming on miss) over the B tiles.  Measured at 20 001 force rows:
     // DRAM reads 20.5 -> 9.5 GB per build at unchanged run time (profiles/).

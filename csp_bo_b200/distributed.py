@@ -171,7 +171,11 @@ class ShardedSymmetricBlock:
         self.m = pack.m
         self.n_blocks = (self.m + 7) // 8
         self.ncomp = 3 if block == _lib.KFF else 1
-        self.row_shape = (3, self.m * 3) if block == _lib.KFF else (self.m,)
+        self.ncols = self.m * self.ncomp
+        # packed columns: pad the row pitch to 16 doubles so that the kernel's staged full-row stores (local and NVLink
+        # peer) are whole 32-byte sectors / 128-byte lines; caller-order columns keep the dense pitch
+        self.ld = ((self.ncols + 15) // 16) * 16 if self.packed_cols else self.ncols
+        self.row_shape = (3, self.ld) if block == _lib.KFF else (self.ld,)
         self.rows = int(self.lib.cspbo_sharded_rows_ex(pack.handle, self.rank, self.world, self.sb_blocks, int(self.zigzag)))
         assert self.rows == sharded_rows(self.n_blocks, self.rank, self.world, self.sb_blocks, self.zigzag)
         order = np.empty(self.n_blocks * 8, dtype=np.int32)
@@ -182,7 +186,12 @@ class ShardedSymmetricBlock:
         _lib.check(self.lib.cspbo_dev_alloc(nbytes, ctypes.byref(ptr)))
         self._own = ptr
         self._ptrs, self._peers = _open_peers(self.lib, ptr, group, self.world, self.rank)
-        self.local = torch.as_tensor(_RawCuda(ptr.value, (max(self.rows, 1),) + self.row_shape), device="cuda")[: self.rows]
+        self._full = torch.as_tensor(_RawCuda(ptr.value, (max(self.rows, 1),) + self.row_shape), device="cuda")[: self.rows]
+        self.local = self._full[..., : self.ncols]        # [rows, 3, 3m] / [rows, m] view of the pitched buffer
+
+    def local2d(self):
+        """The local rows as a [rows * ncomp, N] matrix view (row pitch self.ld)."""
+        return self._full.reshape(self.rows * self.ncomp, self.ld)[:, : self.ncols]
 
     def _barrier(self):
         import torch
@@ -198,8 +207,9 @@ class ShardedSymmetricBlock:
             self._barrier()
         desc = BlockDesc(family, self.block, float(zeta), float(sigma2), float(sigma02), float(l), float(tol),
                          int(bool(use_tol)), 0, 0, float(scale), 1.0, 1)
-        _lib.check(self.lib.cspbo_block_build_sharded_ex(ctypes.byref(desc), self.pack.handle, self.rank, self.world,
-                                                         self._ptrs, self.sb_blocks, int(self.zigzag), int(self.packed_cols)))
+        _lib.check(self.lib.cspbo_block_build_sharded_ld(ctypes.byref(desc), self.pack.handle, self.rank, self.world,
+                                                         self._ptrs, self.sb_blocks, int(self.zigzag), int(self.packed_cols),
+                                                         self.ld))
         if sync:
             self._barrier()
         return self.local
@@ -221,7 +231,7 @@ class ShardedSymmetricBlock:
         if self.world > 1:
             import torch.distributed as dist
             dist.barrier(group=self.group)
-        self.local = None
+        self.local = self._full = None
         for r, pp in enumerate(self._peers):
             if pp is not None:
                 self.lib.cspbo_ipc_close(pp)
@@ -370,7 +380,7 @@ class ShardedCholesky:
         if not sh.packed_cols:
             raise ValueError("ShardedCholesky needs a block built with packed_cols=True")
         N = sh.m * sh.ncomp
-        return cls(sh.local.reshape(-1, N), N, 8 * sh.sb_blocks * sh.ncomp, sh.rank, sh.world, sh.zigzag, sh.group, ops)
+        return cls(sh.local2d(), N, 8 * sh.sb_blocks * sh.ncomp, sh.rank, sh.world, sh.zigzag, sh.group, ops)
 
     def _owner(self, s):
         return superblock_owner(s, self.world, self.zigzag)
@@ -713,9 +723,10 @@ class ShardedCovariance:
         self.order_e = self._order(self.pe) if self.pe else np.zeros(0, dtype=np.int64)
         self.order_f = self._order(self.pf) if self.pf else np.zeros(0, dtype=np.int64)
         max_rows = ((self.S + self.world - 1) // self.world) * nbw          # the same on every rank
-        ptr, self._ptrs = _shared_buffer(8 * max(max_rows, 1) * self.N, group, self.world, self.rank)
+        self.ld = ((self.N + 15) // 16) * 16       # row pitch: the kernel's full-row stores are whole sectors / lines
+        ptr, self._ptrs = _shared_buffer(8 * max(max_rows, 1) * self.ld, group, self.world, self.rank)
         self._own = ptr
-        self.local = torch.as_tensor(_RawCuda(ptr.value, (max(self.rows, 1), self.N)), device="cuda")[: self.rows]
+        self.local = torch.as_tensor(_RawCuda(ptr.value, (max(self.rows, 1), self.ld)), device="cuda")[: self.rows, : self.N]
 
     def _order(self, pack):
         nb = (pack.m + 7) // 8
@@ -733,7 +744,7 @@ class ShardedCovariance:
         desc = BlockDesc(h["family"], block, float(zeta), float(h["sigma2"]), float(h["sigma02"]), float(h["l"]), float(tol),
                          int(bool(use_tol)), 0, 0, float(scale), 1.0, 0)
         _lib.check(self.lib.cspbo_block_build_panel(ctypes.byref(desc), a.handle, b.handle, self.rank, self.world, self._ptrs,
-                                                    self.N, self.nbw, int(row0_a), int(row0_b)))
+                                                    self.ld, self.nbw, int(row0_a), int(row0_b)))
 
     def _local_rows(self, g0, g1):
         return panel_local_rows(self.mine, self.nbw, g0, g1)

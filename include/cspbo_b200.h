@@ -239,6 +239,12 @@ int cspbo_block_build_sharded(const cspbo_block_desc *desc, const cspbo_pack *a,
 long long cspbo_sharded_rows_ex(const cspbo_pack *a, int rank, int nranks, int sb_blocks, int zigzag);
 int cspbo_block_build_sharded_ex(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
                                  double *const *outs, int sb_blocks, int zigzag, int packed_cols);
+/* The same with an explicit row pitch: the buffers are [rows * nc, ld] matrices with ld >= 3m (K_FF) or m (K_EE)
+ * doubles (ld = 0: dense).  With packed_cols every warp stores its 24 x 24 (8 x 8) output tile as full rows staged
+ * through shared memory; a pitch that is a multiple of 4 doubles makes those rows whole 32-byte sectors, for the
+ * local stores and for the mirrored tiles that cross NVLink as peer stores. */
+int cspbo_block_build_sharded_ld(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
+                                 double *const *outs, int sb_blocks, int zigzag, int packed_cols, long long ld);
 
 /* Panel layout: the whole covariance [[K_EE, K_EF], [K_FE, K_FF]] (base.py:13-14) as ONE distributed matrix, the input
  * of the sharded Cholesky.  Global rows = columns: each pack in packed order (cspbo_pack_order), starting at a multiple
