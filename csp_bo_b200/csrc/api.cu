@@ -24,9 +24,29 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
                        int accumulate, cudaStream_t st, int rank = 0, int nranks = 1, double *const *outs = nullptr,
                        int a_begin = 0, int a_end = -1, int diag = 0, int sb_blocks = 1, int zigzag = 0,
-                       int packed_cols = 0, const struct PanelArgs *panel = nullptr, const struct PassArgs *passes = nullptr);
+                       int packed_cols = 0, const struct PanelArgs *panel = nullptr, const struct PassArgs *passes = nullptr,
+                       const struct TraceArgs *trace = nullptr);
 struct PanelArgs { long long ld; int nbw; long long row0_a, row0_b; };
 struct PassArgs { int npass, side; long long off; };
+struct TraceArgs { const double *alpha, *w; double *partial; long long ld, row0, col0; };
+
+// deterministic sum of the per-warp partial traces (fixed tree, one CTA)
+__global__ void trace_sum_kernel(const double *__restrict__ part, long long n, double *__restrict__ out, int accumulate)
+{
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (threadIdx.x == 0) *out = accumulate ? *out + acc : acc;
+    }
+}
 int sharded_superblocks(int n_blocks, int rank, int nranks, int sb_blocks, int zigzag);
 
 struct DevBuf {
@@ -340,6 +360,39 @@ extern "C" int cspbo_block_build_into(const cspbo_block_desc *desc, const cspbo_
         return CSPBO_E_ARG;
     }
     return build_block_device(d, a, b, 0, 0, K + row0 * ldk + col0, nullptr, si, sk, sj, sl, 0, 0);
+}
+
+// sum over the block of dK/dl[r,c] * (alpha[r] alpha[c] - W[min(r,c), max(r,c)])  ->  *result (device double)
+extern "C" int cspbo_block_trace(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b, const double *alpha,
+                                 const double *W, long long ldw, long long row0, long long col0, double *result, int accumulate)
+{
+    if (!desc || !a || !b || !alpha || !W || !result) { set_error("block_trace: null argument"); return CSPBO_E_ARG; }
+    cspbo_block_desc d = *desc;
+    if (d.family != CSPBO_RBF || !(d.l > 0.0)) { set_error("block_trace: RBF blocks only (Dot gradients are closed-form traces)"); return CSPBO_E_ARG; }
+    if (d.block < CSPBO_KEE || d.block > CSPBO_KFF || d.stress) { set_error("block_trace: bad block"); return CSPBO_E_ARG; }
+    if (d.symmetric && (a != b || d.block == CSPBO_KEF || row0 != col0)) { set_error("block_trace: symmetric needs a == b on the diagonal"); return CSPBO_E_ARG; }
+    const int nc1 = d.block == CSPBO_KFF ? 3 : 0, nc2 = d.block == CSPBO_KEE ? 0 : 3;
+    if ((nc1 ? a->nc < 3 : a->nc != 0) || (nc2 ? b->nc < 3 : b->nc != 0)) { set_error("block_trace: pack kinds do not match the block"); return CSPBO_E_ARG; }
+    const long long rows = (long long)a->m * std::max(nc1, 1), cols = (long long)b->m * std::max(nc2, 1);
+    if (row0 < 0 || col0 < 0 || col0 + cols > ldw || row0 + rows > ldw) { set_error("block_trace: block does not fit (ld %lld)", ldw); return CSPBO_E_ARG; }
+    if (a->m == 0 || b->m == 0) {
+        if (!accumulate) CSPBO_CUDA(cudaMemsetAsync(result, 0, sizeof(double)));
+        return CSPBO_OK;
+    }
+    d.with_grad = 1; d.use_tol = 0;
+    // one partial per warp of the largest possible grid (split mapping: one A block per CTA)
+    const long long nparts = (long long)a->n_blocks * b->n_blocks * 4;
+    void *sp = nullptr;
+    int rc = scratch_get(SCRATCH_GRAD, (size_t)nparts * sizeof(double), &sp);
+    if (rc) return rc;
+    CSPBO_CUDA(cudaMemsetAsync(sp, 0, (size_t)nparts * sizeof(double)));
+    const TraceArgs tr = {alpha, W, static_cast<double *>(sp), ldw, row0, col0};
+    rc = build_block_device(d, a, b, 0, 0, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 1, nullptr, 0, -1, 0, 1, 0, 0, nullptr, nullptr, &tr);
+    if (rc) return rc;
+    trace_sum_kernel<<<1, 1024>>>(static_cast<const double *>(sp), nparts, result, accumulate);
+    g_launches++;
+    CSPBO_CUDA(cudaGetLastError());
+    return CSPBO_OK;
 }
 
 extern "C" int cspbo_block_diag(const cspbo_block_desc *desc, const cspbo_pack *a, double *out, int mem)

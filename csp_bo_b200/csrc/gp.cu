@@ -8,6 +8,7 @@
 
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "common.h"
 
@@ -141,6 +142,29 @@ extern "C" int cspbo_gp_add_noise(double *K, int N, int n_energy, double noise_e
     return CSPBO_OK;
 }
 
+namespace cspbo {
+// Workspace of the single-GPU factorisation: cached blocks (dev_alloc_cached: no cudaMalloc / cudaFree per call once
+// warm) and ONE readback of the two info words + log-determinant at the end instead of a blocking copy per step.
+struct CholScratch {
+    double *work = nullptr;
+    double *small = nullptr;     // [0] logdet, then 2 ints: potrf info, potrs info
+    ~CholScratch() { dev_free_cached(work); dev_free_cached(small); }
+};
+
+// diag_out[i] = sum_{j >= i} A[i*N + j]^2: with A = L^-1 (column-major lower == row-major upper) this is (K^-1)_ii
+__global__ void row_sumsq_upper_kernel(const double *__restrict__ A, int N, double *__restrict__ out)
+{
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= N) return;
+    const double *r = A + (size_t)row * N;
+    double acc = 0.0;
+    for (int j = row + lane; j < N; j += 32) acc = fma(r[j], r[j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[row] = acc;
+}
+}  // namespace cspbo
+
 extern "C" int cspbo_gp_cholesky_solve(double *K, int N, double *y, int nrhs, double *logdet)
 {
     if (!K || N <= 0 || (nrhs > 0 && !y)) { set_error("gp_cholesky_solve: bad argument"); return CSPBO_E_ARG; }
@@ -152,40 +176,29 @@ extern "C" int cspbo_gp_cholesky_solve(double *K, int N, double *y, int nrhs, do
     const cublasFillMode_t uplo = CUBLAS_FILL_MODE_LOWER;
     cusolverStatus_t s = cusolverDnDpotrf_bufferSize(h, uplo, N, K, N, &lwork);
     if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
-    double *work = nullptr;
-    int *info = nullptr;
-    CSPBO_CUDA(cudaMalloc(&work, (size_t)std::max(lwork, 1) * sizeof(double)));
-    cudaError_t e = cudaMalloc(&info, sizeof(int));
-    if (e != cudaSuccess) { cudaFree(work); set_error("cudaMalloc(info) failed"); return CSPBO_E_NOMEM; }
-    int hinfo = 0;
-    s = cusolverDnDpotrf(h, uplo, N, K, N, work, lwork, info);
-    cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
-    if (s != CUSOLVER_STATUS_SUCCESS || hinfo != 0) {
-        cudaFree(work); cudaFree(info);
-        if (hinfo > 0) { set_error("K is not positive definite (leading minor %d)", hinfo); return CSPBO_E_NOTPD; }
-        set_error("potrf failed (status %d, info %d)", (int)s, hinfo);
-        return CSPBO_E_SOLVER;
-    }
+    CholScratch sc;
+    if ((rc = dev_alloc_cached((size_t)std::max(lwork, 1) * sizeof(double), (void **)&sc.work)) != CSPBO_OK) return rc;
+    if ((rc = dev_alloc_cached(32, (void **)&sc.small)) != CSPBO_OK) return rc;
+    int *info = reinterpret_cast<int *>(sc.small + 1);
+    CSPBO_CUDA(cudaMemsetAsync(sc.small, 0, 32));
+    s = cusolverDnDpotrf(h, uplo, N, K, N, sc.work, lwork, info);
+    if (s != CUSOLVER_STATUS_SUCCESS) { cudaDeviceSynchronize(); set_error("potrf failed (status %d)", (int)s); return CSPBO_E_SOLVER; }
+    // a failed factorisation leaves garbage behind its leading minor; the solve below is then meaningless but harmless,
+    // and the info word read back once at the end decides
     if (nrhs > 0) {
-        s = cusolverDnDpotrs(h, uplo, N, nrhs, K, N, y, N, info);
-        cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
-        if (s != CUSOLVER_STATUS_SUCCESS || hinfo != 0) {
-            cudaFree(work); cudaFree(info);
-            set_error("potrs failed (status %d, info %d)", (int)s, hinfo);
-            return CSPBO_E_SOLVER;
-        }
+        s = cusolverDnDpotrs(h, uplo, N, nrhs, K, N, y, N, info + 1);
+        if (s != CUSOLVER_STATUS_SUCCESS) { cudaDeviceSynchronize(); set_error("potrs failed (status %d)", (int)s); return CSPBO_E_SOLVER; }
     }
     if (logdet) {
-        double *dl = nullptr;
-        if (cudaMalloc(&dl, sizeof(double)) == cudaSuccess) {
-            logdet_kernel<<<1, 1024>>>(K, N, dl);
-            g_launches++;
-            cudaMemcpy(logdet, dl, sizeof(double), cudaMemcpyDeviceToHost);
-            cudaFree(dl);
-        }
+        logdet_kernel<<<1, 1024>>>(K, N, sc.small);
+        g_launches++;
     }
-    cudaFree(work);
-    cudaFree(info);
+    struct { double logdet; int info[2]; int pad[4]; } host;
+    static_assert(sizeof(host) == 32, "readback layout");
+    CSPBO_CUDA(cudaMemcpy(&host, sc.small, 32, cudaMemcpyDeviceToHost));     // the one synchronisation of the call
+    if (host.info[0] > 0) { set_error("K is not positive definite (leading minor %d)", host.info[0]); return CSPBO_E_NOTPD; }
+    if (host.info[0] != 0 || host.info[1] != 0) { set_error("potrf / potrs failed (info %d, %d)", host.info[0], host.info[1]); return CSPBO_E_SOLVER; }
+    if (logdet) *logdet = host.logdet;
     CSPBO_CUDA(cudaGetLastError());
     return CSPBO_OK;
 }
@@ -226,38 +239,73 @@ extern "C" int cspbo_gp_cho_solve(const double *L, int N, double *B, int nrhs)
     cusolverDnHandle_t h;
     int rc = solver_handle(&h);
     if (rc) return rc;
-    int *info = nullptr, hinfo = 0;
-    CSPBO_CUDA(cudaMalloc(&info, sizeof(int)));
+    CholScratch sc;
+    if ((rc = dev_alloc_cached(32, (void **)&sc.small)) != CSPBO_OK) return rc;
+    int *info = reinterpret_cast<int *>(sc.small), hinfo = 0;
     cusolverStatus_t s = cusolverDnDpotrs(h, CUBLAS_FILL_MODE_LOWER, N, nrhs, L, N, B, N, info);
     cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
-    cudaFree(info);
     if (s != CUSOLVER_STATUS_SUCCESS || hinfo != 0) { set_error("potrs failed (status %d, info %d)", (int)s, hinfo); return CSPBO_E_SOLVER; }
+    return CSPBO_OK;
+}
+
+// In place: the factor L (column-major lower == row-major upper triangle of the buffer) -> K^-1, same triangle
+// (cuSOLVER potri).  With mirror != 0 the other triangle is filled too.
+extern "C" int cspbo_gp_cholesky_inverse_inplace(double *L, int N, int mirror)
+{
+    if (!L || N <= 0) { set_error("gp_cholesky_inverse_inplace: bad argument"); return CSPBO_E_ARG; }
+    cusolverDnHandle_t h;
+    int rc = solver_handle(&h);
+    if (rc) return rc;
+    int lwork = 0;
+    cusolverStatus_t s = cusolverDnDpotri_bufferSize(h, CUBLAS_FILL_MODE_LOWER, N, L, N, &lwork);
+    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potri_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
+    CholScratch sc;
+    if ((rc = dev_alloc_cached((size_t)std::max(lwork, 1) * sizeof(double), (void **)&sc.work)) != CSPBO_OK) return rc;
+    if ((rc = dev_alloc_cached(32, (void **)&sc.small)) != CSPBO_OK) return rc;
+    int *info = reinterpret_cast<int *>(sc.small), hinfo = 0;
+    s = cusolverDnDpotri(h, CUBLAS_FILL_MODE_LOWER, N, L, N, sc.work, lwork, info);
+    if (mirror) {
+        const long long total = (long long)N * N;
+        symmetrize_kernel<<<(unsigned)((total + 255) / 256), 256>>>(L, N);
+        g_launches++;
+    }
+    cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
+    if (s != CUSOLVER_STATUS_SUCCESS || hinfo != 0) { set_error("potri failed (status %d, info %d)", (int)s, hinfo); return CSPBO_E_SOLVER; }
+    CSPBO_CUDA(cudaGetLastError());
     return CSPBO_OK;
 }
 
 extern "C" int cspbo_gp_cholesky_inverse(const double *L, int N, double *Kinv)
 {
     if (!L || !Kinv || N <= 0) { set_error("gp_cholesky_inverse: bad argument"); return CSPBO_E_ARG; }
+    CSPBO_CUDA(cudaMemcpyAsync(Kinv, L, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToDevice));
+    return cspbo_gp_cholesky_inverse_inplace(Kinv, N, 1);
+}
+
+// diag_out[N] = diag((L L^T)^-1), destroying L: the factor is inverted in place (cuSOLVER trtri, N^3/3 flop, no second
+// N x N array) and (K^-1)_ii = sum_j (L^-1)_ji^2 is a row-wise sum of squares of what is left.  This is all the Dot
+// kernel's hyper-gradient needs of K^-1 (dK/dsigma = 2K/sigma, dK/dnoise diagonal; gaussianprocess.py:490-499).
+extern "C" int cspbo_gp_inverse_diag(double *L, int N, double *diag_out)
+{
+    if (!L || !diag_out || N <= 0) { set_error("gp_inverse_diag: bad argument"); return CSPBO_E_ARG; }
     cusolverDnHandle_t h;
     int rc = solver_handle(&h);
     if (rc) return rc;
-    CSPBO_CUDA(cudaMemcpyAsync(Kinv, L, (size_t)N * N * sizeof(double), cudaMemcpyDeviceToDevice));
-    int lwork = 0;
-    cusolverStatus_t s = cusolverDnDpotri_bufferSize(h, CUBLAS_FILL_MODE_LOWER, N, Kinv, N, &lwork);
-    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potri_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
-    double *work = nullptr;
-    int *info = nullptr, hinfo = 0;
-    CSPBO_CUDA(cudaMalloc(&work, (size_t)std::max(lwork, 1) * sizeof(double)));
-    if (cudaMalloc(&info, sizeof(int)) != cudaSuccess) { cudaFree(work); set_error("cudaMalloc(info) failed"); return CSPBO_E_NOMEM; }
-    s = cusolverDnDpotri(h, CUBLAS_FILL_MODE_LOWER, N, Kinv, N, work, lwork, info);
-    cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
-    cudaFree(work);
-    cudaFree(info);
-    if (s != CUSOLVER_STATUS_SUCCESS || hinfo != 0) { set_error("potri failed (status %d, info %d)", (int)s, hinfo); return CSPBO_E_SOLVER; }
-    const long long total = (long long)N * N;
-    // potri filled the column-major lower triangle, i.e. the row-major UPPER one: mirror it
-    symmetrize_kernel<<<(unsigned)((total + 255) / 256), 256>>>(Kinv, N);
+    size_t wdev = 0, whost = 0;
+    cusolverStatus_t s = cusolverDnXtrtri_bufferSize(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, (int64_t)N, CUDA_R_64F, L, (int64_t)N,
+                                                     &wdev, &whost);
+    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("trtri_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
+    CholScratch sc;
+    if ((rc = dev_alloc_cached(std::max<size_t>(wdev, 8), (void **)&sc.work)) != CSPBO_OK) return rc;
+    if ((rc = dev_alloc_cached(32, (void **)&sc.small)) != CSPBO_OK) return rc;
+    std::vector<char> hbuf(std::max<size_t>(whost, 1));
+    int *info = reinterpret_cast<int *>(sc.small), hinfo = 0;
+    s = cusolverDnXtrtri(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, (int64_t)N, CUDA_R_64F, L, (int64_t)N, sc.work, wdev, hbuf.data(),
+                         whost, info);
+    row_sumsq_upper_kernel<<<(unsigned)((N + 7) / 8), 256>>>(L, N, diag_out);
     g_launches++;
+    cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
+    if (s != CUSOLVER_STATUS_SUCCESS || hinfo != 0) { set_error("trtri failed (status %d, info %d)", (int)s, hinfo); return CSPBO_E_SOLVER; }
     CSPBO_CUDA(cudaGetLastError());
     return CSPBO_OK;
 }

@@ -76,6 +76,15 @@ struct TileParams {
     int use_tol;
     double scale, scale_grad;
     double *out, *out_grad;
+    // trace mode (FAM_RBF_GRAD only): nothing is stored; every warp reduces sum over its output elements of
+    //   scale_grad * dK/dl[r, c] * (tr_alpha[r] tr_alpha[c] - tr_w[min(r,c) * tr_ld + max(r,c)])
+    // (r = tr_row0 + group_i * NC1 + k, c = tr_col0 + group_j * NC2 + l, caller order; off-diagonal tiles of a symmetric
+    // build count twice) into tr_partial[cta * kMaxWarps + warp]: the hyper-gradient trace tr((aa^T - K^-1) dK/dl) of
+    // gaussianprocess.py:496-499 without dK/dl ever existing in memory
+    int trace;
+    const double *tr_alpha, *tr_w;
+    double *tr_partial;
+    long long tr_ld, tr_row0, tr_col0;
     long long si, sk, sj, sl;  // out index = i*si + k*sk + j*sj + l*sl
     // sharded symmetric build (one process per GPU): rank r owns the A blocks a with a % nranks == r
     // and stores row block a at local block a / nranks of outs[r]; mirrored tiles are stored
@@ -471,6 +480,35 @@ block_tile_kernel(const TileParams p)
         }
     }
     if (!active) return;
+    if (GRAD && p.trace) {
+        const int gi = p.A.slot_group[a_blk * 8 + ar];
+        double sum = 0.0;
+        if (gi >= 0) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int gj = p.B.slot_group[b_blk * 8 + bq + e];
+                if (gj < 0) continue;
+#pragma unroll
+                for (int k = 0; k < NC1; k++) {
+                    const long long r = p.tr_row0 + (long long)gi * NC1 + k;
+                    const double ar_ = p.tr_alpha[r];
+#pragma unroll
+                    for (int l = 0; l < NC2; l++) {
+                        const long long c = p.tr_col0 + (long long)gj * NC2 + l;
+                        const long long lo = r < c ? r : c, hi = r < c ? c : r;
+                        const double w = ar_ * p.tr_alpha[c] - p.tr_w[lo * p.tr_ld + hi];
+                        sum = fma(accg[e][k][l], w, sum);
+                    }
+                }
+            }
+        }
+        if (p.symmetric && b_blk != a_blk) sum *= 2.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0)
+            p.tr_partial[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * kMaxWarps + warp] = p.scale_grad * sum;
+        return;
+    }
     if (p.sharded == 2 || (p.sharded == 1 && p.packed_cols)) {
         // Packed column order (the layouts the sharded Cholesky factorises): the warp's (8 NC1) x (8 NC2) output tile is
         // contiguous in both directions, so it goes through shared memory and leaves as full rows -- 192-byte runs for
@@ -652,6 +690,8 @@ static int launch_ks(int mode, int fam, bool z2, const TileParams &p, int nwarps
 
 // Panel-layout arguments of build_block_device (cspbo_block_build_panel).
 struct PanelArgs { long long ld; int nbw; long long row0_a, row0_b; };
+// Trace mode of the RBF dK/dl kernels (cspbo_block_trace).
+struct TraceArgs { const double *alpha, *w; double *partial; long long ld, row0, col0; };
 // Stress passes of one launch: npass column triplets of side `side` (0 = A, 1 = B), pass q stored at out + q*off.
 struct PassArgs { int npass, side; long long off; };
 
@@ -668,7 +708,8 @@ int sharded_superblocks(int n_blocks, int rank, int nranks, int sb_blocks, int z
 int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const cspbo_pack *b, int voffA, int voffB,
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
                        int accumulate, cudaStream_t st, int rank, int nranks, double *const *outs, int a_begin, int a_end,
-                       int diag, int sb_blocks, int zigzag, int packed_cols, const PanelArgs *panel, const PassArgs *passes)
+                       int diag, int sb_blocks, int zigzag, int packed_cols, const PanelArgs *panel, const PassArgs *passes,
+                       const TraceArgs *trace)
 {
     if (a->ks != b->ks || a->d != b->d) {
         set_error("block_build: packs have different descriptor lengths (%d vs %d)", a->d, b->d);
@@ -680,6 +721,9 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     TileParams p;
     p.A = {a->d_tiles, a->d_tile_start, a->d_slot_group, a->d_tile_valid, (int)a->tile_doubles, voffA, (int)a->species.size(), a->m};
     p.B = {b->d_tiles, b->d_tile_start, b->d_slot_group, b->d_tile_valid, (int)b->tile_doubles, voffB, (int)b->species.size(), b->m};
+    p.trace = trace ? 1 : 0;
+    p.tr_alpha = trace ? trace->alpha : nullptr; p.tr_w = trace ? trace->w : nullptr; p.tr_partial = trace ? trace->partial : nullptr;
+    p.tr_ld = trace ? trace->ld : 0; p.tr_row0 = trace ? trace->row0 : 0; p.tr_col0 = trace ? trace->col0 : 0;
     p.npass = passes ? std::max(passes->npass, 1) : 1;
     p.pass_side = passes ? passes->side : 0;
     p.pass_off = passes ? passes->off : 0;

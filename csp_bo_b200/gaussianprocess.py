@@ -268,10 +268,7 @@ class GaussianProcess():
             from .packing import resident
             self._packs = resident(self._train_dict())
         data = self._packs
-        if eval_gradient:
-            K, dKs = kdev.k_total_with_grad_device(kernel, data)
-        else:
-            K = kdev.k_total_device(kernel, data)
+        K = kdev.k_total_device(kernel, data, grad_semantics=eval_gradient)       # the ONE N x N array of the evaluation
         N, NE = K.shape[0], self._n_energy()
         y = torch.from_numpy(np.ascontiguousarray(self.y_train[:, 0])).cuda()
         try:
@@ -284,13 +281,36 @@ class GaussianProcess():
         MLL = float(-0.5 * torch.dot(y, alpha) - 0.5 * logdet - N / 2 * np.log(2 * np.pi))
         if not eval_gradient:
             return MLL
-        # 0.5 * tr((alpha alpha^T - K^-1) dK/dtheta), eq. 5.9 of GPML
-        Kinv = gp.cholesky_inverse(K)
-        W = torch.outer(alpha, alpha) - Kinv
-        llg = [0.5 * float((W * dK).sum()) for dK in dKs]
-        noise_diag = torch.full((N,), 2 * self.f_coef ** 2 * params[-1], dtype=torch.float64, device="cuda")
-        noise_diag[:NE] = 2 * params[-1]
-        llg.append(0.5 * float((torch.diagonal(W) * noise_diag).sum()))
+        # 0.5 tr((alpha alpha^T - Ky^-1) dKy/dtheta)  (GPML eq. 5.9, gaussianprocess.py:490-499) as FUSED TRACES: neither the
+        # [N,N,3] K_gradient nor alpha alpha^T is formed and K^-1 only where a kernel really needs it; K's buffer (now the
+        # factor) is the only N x N array of the whole evaluation.
+        ne, nf = float(params[-1]), float(self.f_coef * params[-1])
+        d = torch.full((N,), nf * nf, dtype=torch.float64, device="cuda")            # noise on the diagonal of Ky
+        d[:NE] = ne * ne
+        b = torch.full((N,), 2 * self.f_coef ** 2 * ne, dtype=torch.float64, device="cuda")   # dKy/dnoise (diagonal)
+        b[:NE] = 2 * ne
+        a2 = alpha * alpha
+        if kernel.name == 'Dot_mb':
+            # dK/dsigma = 2 K/sigma with K = Ky - D  =>  tr = (2/sigma) [alpha.(y - D alpha) - (N - sum_i d_i (Ky^-1)_ii)]
+            # dK/dsigma0 = c0 1_E 1_E^T (dot_kernel.py:57, constant as is)  =>  tr = c0 [(sum_E alpha)^2 - 1_E^T Ky^-1 1_E]
+            g_s0 = 0.0
+            if NE > 0:
+                ones = torch.zeros((N, 1), dtype=torch.float64, device="cuda")
+                ones[:NE] = 1.0
+                u = gp.cho_solve(K, ones)[:, 0]                  # before the factor is destroyed below
+                c0 = 0.8 * 2 * kernel.sigma ** 2 * kernel.sigma0
+                g_s0 = 0.5 * c0 * float(alpha[:NE].sum() ** 2 - u[:NE].sum())
+            dinv = gp.inverse_diag(K)                            # diag(Ky^-1); K now holds L^-1
+            g_s = (1.0 / kernel.sigma) * float(torch.dot(alpha, y) - torch.dot(d, a2) - N + torch.dot(d, dinv))
+            llg = [g_s, g_s0]
+        else:
+            gp.cholesky_inverse_inplace(K)                       # K now holds Ky^-1 (upper triangle), in place
+            dinv = torch.diagonal(K).clone()
+            g_s = (1.0 / kernel.sigma) * float(torch.dot(alpha, y) - torch.dot(d, a2) - N + torch.dot(d, dinv))
+            g_noise_now = 0.5 * float(torch.dot(b, a2 - dinv))   # before rbf_dl_trace rescales alpha / K^-1
+            g_l = 0.5 * float(kdev.rbf_dl_trace(kernel, data, alpha.clone(), K))
+            return MLL, np.array([g_s, g_l, g_noise_now])
+        llg.append(0.5 * float(torch.dot(b, a2 - dinv)))
         return MLL, np.array(llg)
 
     # ------------------------------------------------------------------ model files

@@ -69,3 +69,17 @@ def cholesky_inverse(L):
     out = torch.empty_like(L)
     _lib.check(lib.cspbo_gp_cholesky_inverse(c_vp(L.data_ptr()), N, c_vp(out.data_ptr())))
     return out
+
+
+def cholesky_inverse_inplace(L, mirror=False):
+    """The factor in L becomes K^-1 in place (row-major upper triangle; both with mirror=True)."""
+    _lib.check(_lib.load().cspbo_gp_cholesky_inverse_inplace(c_vp(L.data_ptr()), int(L.shape[0]), int(bool(mirror))))
+    return L
+
+
+def inverse_diag(L):
+    """diag(K^-1) from the in-place factor, which is destroyed (trtri in place + row sums of squares): no second N x N array."""
+    import torch
+    out = torch.empty(L.shape[0], dtype=torch.float64, device=L.device)
+    _lib.check(_lib.load().cspbo_gp_inverse_diag(c_vp(L.data_ptr()), int(L.shape[0]), c_vp(out.data_ptr())))
+    return out

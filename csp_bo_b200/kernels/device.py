@@ -50,10 +50,14 @@ def _into(h, block, zeta, scale, a, b, K, row0, col0, tol=0.0, use_tol=False, sy
                                                   K.shape[1], int(row0), int(col0)))
 
 
-def k_total_device(kernel, data1, data2=None, tol=1e-10):
-    """[[K_EE, K_EF], [K_FE, K_FF]] between data1 (rows) and data2 (columns) as a CUDA tensor."""
+def k_total_device(kernel, data1, data2=None, tol=1e-10, grad_semantics=False):
+    """[[K_EE, K_EF], [K_FE, K_FF]] between data1 (rows) and data2 (columns) as a CUDA tensor.
+
+    grad_semantics=True gives the K that `k_total_with_grad` returns instead of `k_total`'s: the Dot K_EF / K_FF blocks
+    use the kernel's own zeta (Dot_mb.py:138-143 vs the zeta-in-sigma0-slot calls of :108-117) and the RBF K_FF has no
+    `tol` test (rbf_kernel.cpp `kff_many_with_grad` vs :394)."""
     import torch
-    h = _hyper(kernel, quirk=True)
+    h = _hyper(kernel, quirk=not grad_semantics)
     same = data2 is None
     e1, f1 = _tuples(data1)
     e2, f2 = (e1, f1) if same else _tuples(data2)
@@ -77,8 +81,8 @@ def k_total_device(kernel, data1, data2=None, tol=1e-10):
             tmp /= torch.as_tensor(e2.counts, dtype=torch.float64, device="cuda")[:, None]
             K[ne1:, :ne2] = tmp.T
     if f1 and f2:
-        _into(h, _lib.KFF, h["zff"], h["sff"], f1, f2, K, ne1, ne2, tol=tol, use_tol=(h["family"] == _lib.RBF),
-              symmetric=same)
+        _into(h, _lib.KFF, h["zff"], h["sff"], f1, f2, K, ne1, ne2, tol=tol,
+              use_tol=(h["family"] == _lib.RBF and not grad_semantics), symmetric=same)
     return K
 
 
@@ -157,3 +161,38 @@ def k_total_with_stress_device(kernel, data1, data2, tol=1e-10):
         K[ne1:, ne2:] = out[:, :3, :].reshape(3 * m1, nf2)
         Ks[:, ne2:] = out[:, 3:, :].reshape(6 * m1, nf2)
     return K, Ks
+
+
+def rbf_dl_trace(kernel, data1, alpha, W):
+    """sum_ij (alpha alpha^T - W)_ij (dK/dl)_ij over the whole training covariance of an RBF_mb kernel, with dK/dl
+    evaluated tile by tile inside the kernel epilogue and never stored (cspbo_block_trace; the reference materialises
+    it as one plane of the [N,N,3] K_gradient, gaussianprocess.py:462,492-499).  alpha: [N] CUDA tensor; W: [N,N] CUDA
+    tensor whose row-major UPPER triangle holds K^-1.  Both are modified: the 1/N_i normalisations of the energy rows
+    (rbf_kernel.py:55-60,157) are folded into them.  Returns a 0-dim CUDA tensor."""
+    import torch
+    h = _hyper(kernel, quirk=False)
+    assert h["family"] == _lib.RBF
+    e1, f1 = _tuples(data1)
+    ne = e1.m if e1 else 0
+    l = kernel.l
+    if e1:
+        f = 1.0 / torch.as_tensor(e1.counts, dtype=torch.float64, device="cuda")
+        alpha[:ne] *= f
+        W[:ne, :] *= f[:, None]           # rows of the energy part (upper triangle: E-E and E-F blocks)
+        W[:ne, :ne] *= f[None, :]
+    res = torch.zeros(1, dtype=torch.float64, device="cuda")
+    lib = _lib.load()
+
+    def trace(block, a, b, row0, col0, scale_grad, symmetric):
+        desc = BlockDesc(_lib.RBF, block, float(h["zee"]), float(h["sigma2"]), 0.0, float(l), 0.0, 0, 1, 0, 1.0, float(scale_grad),
+                         int(bool(symmetric)))
+        _lib.check(lib.cspbo_block_trace(ctypes.byref(desc), a.handle, b.handle, c_vp(alpha.data_ptr()), c_vp(W.data_ptr()),
+                                         W.shape[1], int(row0), int(col0), c_vp(res.data_ptr()), 1))
+    if e1:
+        trace(_lib.KEE, e1, e1, 0, 0, 1.0 / (l * l * l), True)
+    if e1 and f1:
+        # the E-F block appears twice in the symmetric matrix (K_EF and K_FE = K_EF^T)
+        trace(_lib.KEF, e1, f1, 0, ne, 2.0, False)
+    if f1:
+        trace(_lib.KFF, f1, f1, ne, ne, 1.0, True)
+    return res[0]

@@ -270,6 +270,20 @@ int cspbo_gp_cholesky_solve(double *K, int N, double *y_inout, int nrhs, double 
 int cspbo_gp_cho_solve(const double *L, int N, double *B, int nrhs);
 /* Kinv = (L L^T)^-1 (cuSOLVER potri), full symmetric matrix.  gaussianprocess.py:497 */
 int cspbo_gp_cholesky_inverse(const double *L, int N, double *Kinv);
+/* The same in place: the factor in the buffer becomes K^-1 (row-major upper triangle; mirror != 0 fills both). */
+int cspbo_gp_cholesky_inverse_inplace(double *L, int N, int mirror);
+/* diag_out[N] = diag((L L^T)^-1), destroying the factor (cuSOLVER trtri in place + a row-wise sum of squares): all the
+ * Dot kernel's hyper-gradient needs of K^-1, with no second N x N array.  gaussianprocess.py:490-499 */
+int cspbo_gp_inverse_diag(double *L, int N, double *diag_out);
+/* Hyper-gradient trace of an RBF block without materialising dK/dl (gaussianprocess.py:496-499, rbf_kernel.cpp:87-92,
+ * 239-246, 621-629): *result (device double) = [accumulate ? *result : 0] +
+ *     sum over the block's entries (r, c) of  desc->scale_grad * dK/dl[r, c] * (alpha[r] alpha[c] - W[min(r,c)*ldw + max(r,c)])
+ * with r = row0 + i*nc1 + k, c = col0 + j*nc2 + l in the caller's group order (the layout cspbo_block_build_into writes);
+ * W is read in its row-major upper triangle (what cspbo_gp_cholesky_inverse_inplace leaves).  desc->symmetric (a == b,
+ * row0 == col0) evaluates the upper block triangle and counts the off-diagonal tiles twice.  Per-warp partial sums are
+ * added in a fixed order: the result is deterministic. */
+int cspbo_block_trace(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b, const double *alpha,
+                      const double *W, long long ldw, long long row0, long long col0, double *result, int accumulate);
 /* Building blocks of the sharded Cholesky K = U^T U (row-major; rows of U live where the rows of K live;
  * csp_bo_b200/distributed.py: ShardedCholesky).  All asynchronous on `stream` (a cudaStream_t); matrices are row-major
  * views given by pointer + leading dimension.  Distributed restatement of the single scipy `cholesky` of

@@ -87,6 +87,68 @@ def test_log_marginal_likelihood_and_gradient(problem, fam, para, bounds):
         assert abs(model.log_marginal_likelihood(np.array(params)) - lml_r) <= 1e-8 * abs(lml_r)
 
 
+@pytest.mark.parametrize("fam,para,bounds,zeta,subset", [("dot", [18.5, 0.05], KERNELS[0][2], 3.0, "both"), ("dot", [18.5, 0.05], KERNELS[0][2], 2.0, "force"),
+                                                         ("rbf", [6.2, 0.56], KERNELS[1][2], 3.0, "both"), ("rbf", [6.2, 0.56], KERNELS[1][2], 2.0, "energy"),
+                                                         ("rbf", [6.2, 0.9], KERNELS[1][2], 2.0, "force")])
+def test_lml_gradient_fused_traces(problem, fam, para, bounds, zeta, subset):
+    """The fused-trace gradient (no dK, no alpha alpha^T; K^-1 only for RBF, in place) against the reference's einsum
+    over the materialised [N,N,3] K_gradient (gaussianprocess.py:490-499, restated in oracle/gp_reference.py), including
+    zeta = 3 -- where k_total_with_grad and k_total differ for Dot (Dot_mb.py:108-117 vs :138-143) -- and training sets
+    with only energies or only forces."""
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from csp_bo_b200.kernels import Dot_mb, RBF_mb
+    from oracle.gp_reference import RefGaussianProcess
+    train_x, y, _ = problem
+    if subset == "force":
+        train_x, y = {"energy": [], "force": train_x["force"]}, y[4:]
+    elif subset == "energy":
+        train_x, y = {"energy": train_x["energy"], "force": []}, y[:4]
+    ref = RefGaussianProcess(fam, para, zeta, bounds, f_coef=30, noise_e=(0.005, 0.002, 0.1))
+    ref.set_train({k: v for k, v in train_x.items() if len(v)}, y)
+    kern = (Dot_mb if fam == "dot" else RBF_mb)(para=list(para), bounds=bounds, zeta=zeta)
+    model = GaussianProcess(kern, f_coef=30, noise_e=[0.005, 0.002, 0.1])
+    lists = {}
+    ne = len(train_x["energy"][-1]) if len(train_x["energy"]) else 0
+    if ne:
+        lists["energy"] = [(x, float(y[i]), ele) for i, (x, ele) in enumerate(energy_list(train_x["energy"]))]
+    if len(train_x["force"]):
+        lists["force"] = [(x, dx, y[ne + 3 * i: ne + 3 * i + 3], ele) for i, (x, dx, ele) in enumerate(force_list(train_x["force"]))]
+    model.set_train_pts(lists)
+    params = np.array(list(para) + [0.01])
+    lml, grad = model.log_marginal_likelihood(params, eval_gradient=True)
+    lml_r, grad_r = ref.log_marginal_likelihood(params, eval_gradient=True)
+    assert abs(lml - lml_r) <= 1e-8 * abs(lml_r)
+    assert max_norm_err(grad, grad_r) < 1e-7, (grad, grad_r)
+
+
+def test_lml_gradient_memory_is_one_matrix():
+    """f-1: an LML + gradient evaluation holds ONE N x N array (K -> factor -> inverse, in place), not the reference's
+    K + [N,N,3] K_gradient + alpha alpha^T - K^-1 (gaussianprocess.py:462-499): peak <= 1.2 N^2 doubles."""
+    import torch
+    from csp_bo_b200 import synthetic
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from csp_bo_b200.kernels import Dot_mb, RBF_mb
+    from csp_bo_b200.utilities import tuple_to_list
+    F, E = synthetic.force_set(1100, seed=3), synthetic.energy_set(60, seed=4, rows_per_structure=32)
+    rng = np.random.default_rng(1)
+    data = {"energy": [(x, float(rng.normal()), ele) for x, ele in tuple_to_list(E, mode='energy')],
+            "force": [(x, dx, rng.normal(size=3), ele) for x, dx, ele in tuple_to_list(F)]}
+    N = 60 + 3300
+    for kern in (Dot_mb(para=[18.5, 0.01], zeta=2), RBF_mb(para=[6.2, 0.56], zeta=2)):
+        model = GaussianProcess(kern, f_coef=30, noise_e=[0.005, 0.002, 0.1])
+        model.set_train_pts(data)
+        params = np.array(kern.parameters() + [0.005])
+        model.log_marginal_likelihood(params, eval_gradient=True)        # warm: packs, cuSOLVER workspaces
+        torch.cuda.synchronize()
+        base = torch.cuda.memory_allocated()
+        torch.cuda.reset_peak_memory_stats()
+        lml, grad = model.log_marginal_likelihood(params, eval_gradient=True)
+        torch.cuda.synchronize()
+        peak = torch.cuda.max_memory_allocated() - base
+        assert np.isfinite(lml) and np.all(np.isfinite(grad))
+        assert peak <= 1.2 * N * N * 8, (kern.name, peak / (N * N * 8.0))
+
+
 def test_fit_with_hyperparameter_optimisation(problem):
     from csp_bo_b200.gaussianprocess import GaussianProcess
     from oracle.gp_reference import RefGaussianProcess
