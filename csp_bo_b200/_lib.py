@@ -73,12 +73,15 @@ SIGNATURES = {
     "cspbo_ipc_export": [c_vp, c_vp],
     "cspbo_ipc_open": [c_vp, ctypes.POINTER(c_vp)],
     "cspbo_ipc_close": [c_vp],
+    "cspbo_copy_rows_to_host": [c_vp, c_ll, c_vp, c_ll, c_ll, c_ll, c_vp],
     "cspbo_sharded_rows": [c_vp, c_int, c_int],
     "cspbo_pack_order": [c_vp, c_vp, c_ll],
     "cspbo_block_build_sharded": [ctypes.POINTER(BlockDesc), c_vp, c_int, c_int, ctypes.POINTER(c_vp)],
     "cspbo_sharded_rows_ex": [c_vp, c_int, c_int, c_int, c_int],
     "cspbo_block_build_sharded_ex": [ctypes.POINTER(BlockDesc), c_vp, c_int, c_int, ctypes.POINTER(c_vp), c_int, c_int, c_int],
     "cspbo_block_build_sharded_ld": [ctypes.POINTER(BlockDesc), c_vp, c_int, c_int, ctypes.POINTER(c_vp), c_int, c_int, c_int, c_ll],
+    "cspbo_block_build_sharded_slab": [ctypes.POINTER(BlockDesc), c_vp, c_int, c_int, ctypes.POINTER(c_vp), c_int, c_int, c_int, c_ll,
+                                       c_int, c_int, c_vp],
     "cspbo_block_build_panel": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_int, c_int, ctypes.POINTER(c_vp), c_ll, c_int, c_ll, c_ll],
     "cspbo_so3_create": [c_int, c_int, c_dbl, c_dbl, c_int, c_int, ctypes.POINTER(c_vp)],
     "cspbo_so3_destroy": [c_vp],

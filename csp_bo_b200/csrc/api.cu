@@ -464,6 +464,17 @@ extern "C" int cspbo_ipc_close(void *ptr)
     return CSPBO_OK;
 }
 
+// dst[height rows of width bytes, pitch dpitch] (pinned host) <- src (device, pitch spitch), asynchronous on `stream`
+extern "C" int cspbo_copy_rows_to_host(void *dst, long long dpitch, const void *src, long long spitch, long long width, long long height,
+                                       void *stream)
+{
+    if (!dst || !src || width < 0 || height < 0 || dpitch < width || spitch < width) { set_error("copy_rows_to_host: bad argument"); return CSPBO_E_ARG; }
+    if (width == 0 || height == 0) return CSPBO_OK;
+    CSPBO_CUDA(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height, cudaMemcpyDeviceToHost,
+                                 static_cast<cudaStream_t>(stream)));
+    return CSPBO_OK;
+}
+
 extern "C" long long cspbo_sharded_rows(const cspbo_pack *a, int rank, int nranks)
 {
     return cspbo_sharded_rows_ex(a, rank, nranks, 1, 0);
@@ -498,6 +509,13 @@ extern "C" int cspbo_block_build_sharded_ex(const cspbo_block_desc *desc, const 
 extern "C" int cspbo_block_build_sharded_ld(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
                                             double *const *outs, int sb_blocks, int zigzag, int packed_cols, long long ld)
 {
+    return cspbo_block_build_sharded_slab(desc, a, rank, nranks, outs, sb_blocks, zigzag, packed_cols, ld, 0, -1, nullptr);
+}
+
+extern "C" int cspbo_block_build_sharded_slab(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
+                                              double *const *outs, int sb_blocks, int zigzag, int packed_cols, long long ld,
+                                              int slot0, int slot1, void *stream)
+{
     if (!desc || !a || !outs) { set_error("block_build_sharded: null argument"); return CSPBO_E_ARG; }
     if (sb_blocks < 1) { set_error("block_build_sharded: sb_blocks must be >= 1"); return CSPBO_E_ARG; }
     if (packed_cols && a->row_classes != 1) { set_error("block_build_sharded: packed_cols needs a pack with row_classes = 1"); return CSPBO_E_ARG; }
@@ -521,8 +539,8 @@ extern "C" int cspbo_block_build_sharded_ld(const cspbo_block_desc *desc, const 
         if (a->nc < 3) { set_error("block_build_sharded: K_FF needs a force pack"); return CSPBO_E_ARG; }
         si = 3 * ld; sk = ld; sj = 3; sl = 1;
     }
-    return build_block_device(d, a, a, 0, 0, outs[rank], nullptr, si, sk, sj, sl, 0, 0, rank, nranks, outs, 0, -1, 0,
-                              sb_blocks, zigzag, packed_cols);
+    return build_block_device(d, a, a, 0, 0, outs[rank], nullptr, si, sk, sj, sl, 0, static_cast<cudaStream_t>(stream), rank, nranks, outs,
+                              slot0, slot1, 0, sb_blocks, zigzag, packed_cols);
 }
 
 extern "C" int cspbo_block_build_panel(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b, int rank, int nranks,

@@ -96,6 +96,7 @@ struct TileParams {
     // distributed matrix the symmetric permutation P K P^T that the sharded Cholesky factorises in place.
     int sharded, nranks, rank;
     int sb_blocks, zigzag, packed_cols, a_slots;   // a_slots: blocks (incl. a ragged tail) this rank enumerates
+    int a_slot0;   // sharded == 1: first block slot of this launch in the rank's buffer (row-slab pipelining)
     double *outs[kMaxRanks];
     // sharded == 2, "panel layout": the blocks of SEVERAL packs (energies, forces) live in one distributed matrix of
     // leading dimension ldo whose rows are dealt to the ranks by superblocks of nbw ROWS (zigzag); a pack starts at a
@@ -276,7 +277,8 @@ block_tile_kernel(const TileParams p)
     const int strip_w = min(p.strip, npg - strip * p.strip);
     const int q = rem / strip_w;
     const int pg = strip * p.strip + (rem - q * strip_w);
-    const int a_idx = pg * a_units + (p.split ? 0 : warp);
+    const int a_rel = pg * a_units + (p.split ? 0 : warp);
+    const int a_idx = a_rel + (p.sharded == 1 ? p.a_slot0 : 0);
     int a_blk = p.a_begin + a_idx;
     if (p.sharded == 2) {   // panel layout: a_idx-th block slot of this rank within pack A's superblock range
         const int c = a_idx / p.pa.g, within = a_idx - c * p.pa.g;
@@ -291,7 +293,7 @@ block_tile_kernel(const TileParams p)
     }
     const int b_blk = p.diag ? a_blk : q;
     // symmetric build: only blocks with b >= a are computed (mirrored at write time)
-    const bool active = a_blk < p.a_nblk && !(p.symmetric && b_blk < a_blk);
+    const bool active = a_rel < a_mine && a_blk < p.a_nblk && !(p.symmetric && b_blk < a_blk);
 
     // two stage buffers of p.tbc tiles, filled by 1-D bulk TMA copies that complete on an mbarrier
     const int stage_doubles = staged ? p.tbc * p.B.tile_doubles : 0;
@@ -749,6 +751,12 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.a_begin = p.sharded ? 0 : std::max(a_begin, 0);
     p.a_nblk = (a_end < 0 || p.sharded) ? (int)a->n_blocks : std::min(a_end, (int)a->n_blocks);
     p.a_slots = p.sharded ? sharded_superblocks((int)a->n_blocks, p.rank, p.nranks, p.sb_blocks, p.zigzag) * p.sb_blocks : 0;
+    p.a_slot0 = 0;
+    if (p.sharded && !panel && a_end >= 0) {      // a slab [a_begin, a_end) of this rank's block slots
+        p.a_slot0 = std::min(std::max(a_begin, 0), p.a_slots);
+        p.a_slots = std::max(std::min(a_end, p.a_slots) - p.a_slot0, 0);
+        if (p.a_slots == 0) return CSPBO_OK;
+    }
     p.nbw = 0; p.cyc0 = 0; p.pair = 0;
     // packed-column sharded layout: the distributed matrix is [rows * NC1, ldo] (K_FF: sk = row pitch, K_EE: si)
     p.ldo = (mode == MODE_KFF) ? sk : si;

@@ -214,6 +214,59 @@ class ShardedSymmetricBlock:
             self._barrier()
         return self.local
 
+    SLAB_FRACTIONS = (0.0, 0.03, 0.1, 0.2, 0.35, 0.5, 0.65, 0.8, 1.0)
+
+    def slab_slots(self, fractions=None):
+        """Block-slot boundaries of the row slabs of build_to_host: the same on every rank and aligned to superblock
+        cycles, so that slab k of all ranks together covers a contiguous range of packed row blocks."""
+        fractions = self.SLAB_FRACTIONS if fractions is None else fractions
+        cycles = (self.n_blocks + self.sb_blocks * self.world - 1) // (self.sb_blocks * self.world)
+        cuts = sorted(set(int(round(f * cycles)) for f in fractions) | {0, cycles})
+        return [c * self.sb_blocks for c in cuts]
+
+    def build_to_host(self, family, zeta, out_host, sigma2=1.0, sigma02=0.0, l=1.0, tol=0.0, use_tol=False, scale=1.0,
+                      fractions=None):
+        """Host-bound sharded build: this rank's rows [rows, ncomp, ncols] (packed row order) land in the PINNED CPU
+        tensor `out_host` (dense).  The local block slots are cut into slabs that every rank builds in ascending order
+        on a compute stream; once all ranks have finished slab k (a 1-element all-reduce on a side stream -- mirrored
+        tiles come from peers) its rows are final and their copy-back overlaps the slabs still being computed.  The
+        reference instead Allreduces the whole matrix to every rank's host memory (dot_kernel.py:242-247)."""
+        import torch
+        import torch.distributed as dist
+        assert out_host.is_pinned() and out_host.dtype == torch.float64 and out_host.numel() == self.rows * self.ncomp * self.ncols
+        desc = BlockDesc(family, self.block, float(zeta), float(sigma2), float(sigma02), float(l), float(tol),
+                         int(bool(use_tol)), 0, 0, float(scale), 1.0, 1)
+        if not hasattr(self, "_s_build"):
+            self._s_build, self._s_copy = torch.cuda.Stream(), torch.cuda.Stream()
+            self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
+        sb, sc = self._s_build, self._s_copy
+        cur = torch.cuda.current_stream()
+        sb.wait_stream(cur)
+        sc.wait_stream(cur)
+        cuts = self.slab_slots(fractions)
+        my_slots = self.rows // 8
+        rowb = self.ncomp * self.ld * 8                     # bytes per group row of the pitched device buffer
+        width = self.ncols * 8
+        for s0, s1 in zip(cuts[:-1], cuts[1:]):
+            _lib.check(self.lib.cspbo_block_build_sharded_slab(ctypes.byref(desc), self.pack.handle, self.rank, self.world,
+                                                               self._ptrs, self.sb_blocks, int(self.zigzag), int(self.packed_cols),
+                                                               self.ld, int(s0), int(s1), c_vp(sb.cuda_stream)))
+            ev = torch.cuda.Event()
+            ev.record(sb)
+            with torch.cuda.stream(sc):
+                sc.wait_event(ev)
+                if self.world > 1:
+                    w = dist.all_reduce(self._flag, group=self.group, async_op=True)   # every rank has finished slab k
+                    w.wait()
+                r0, r1 = min(s0, my_slots) * 8, min(s1, my_slots) * 8              # group rows of this slab held here
+                if r1 > r0:
+                    _lib.check(self.lib.cspbo_copy_rows_to_host(
+                        c_vp(out_host.data_ptr() + r0 * self.ncomp * width), width,
+                        c_vp(self._own.value + r0 * rowb), self.ld * 8, width, (r1 - r0) * self.ncomp, c_vp(sc.cuda_stream)))
+        cur.wait_stream(sb)
+        cur.wait_stream(sc)
+        return out_host
+
     def gather_full(self):
         """All-gather the row blocks (NCCL) and undo the packed order: the dense [3m,3m] (or [m,m])
         matrix in the caller's group order on every rank, e.g. for a replicated Cholesky."""

@@ -226,6 +226,10 @@ int cspbo_dev_free(void *ptr);
 int cspbo_ipc_export(void *ptr, unsigned char *handle64);    /* cudaIpcGetMemHandle (64 bytes) */
 int cspbo_ipc_open(const unsigned char *handle64, void **ptr);
 int cspbo_ipc_close(void *ptr);
+/* Pitched device -> pinned-host copy of `height` rows of `width` BYTES, asynchronous on `stream` (the copy-back of a
+ * finished row slab of a host-bound build). */
+int cspbo_copy_rows_to_host(void *dst, long long dpitch, const void *src, long long spitch, long long width, long long height,
+                            void *stream);
 long long cspbo_sharded_rows(const cspbo_pack *a, int rank, int nranks);
 int cspbo_pack_order(const cspbo_pack *a, int *order, long long n);   /* n >= 8*ceil(m/8) */
 int cspbo_block_build_sharded(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
@@ -245,6 +249,14 @@ int cspbo_block_build_sharded_ex(const cspbo_block_desc *desc, const cspbo_pack 
  * local stores and for the mirrored tiles that cross NVLink as peer stores. */
 int cspbo_block_build_sharded_ld(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
                                  double *const *outs, int sb_blocks, int zigzag, int packed_cols, long long ld);
+/* One row slab of the same build, asynchronous on `stream` (a cudaStream_t, NULL = default): only the 8-group block
+ * slots [slot0, slot1) of this rank's buffer are computed (slot1 < 0: all).  Slabs taken in ascending order by every
+ * rank have this property: once ALL ranks have finished their slab k, the rows of slab k are final on every rank
+ * (mirrored tiles only ever come from row blocks that are not later in packed order), so a host-bound build can copy
+ * slab k out while slab k+1 is computed (csp_bo_b200/distributed.py: ShardedSymmetricBlock.build_to_host). */
+int cspbo_block_build_sharded_slab(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
+                                   double *const *outs, int sb_blocks, int zigzag, int packed_cols, long long ld,
+                                   int slot0, int slot1, void *stream);
 
 /* Panel layout: the whole covariance [[K_EE, K_EF], [K_FE, K_FF]] (base.py:13-14) as ONE distributed matrix, the input
  * of the sharded Cholesky.  Global rows = columns: each pack in packed order (cspbo_pack_order), starting at a multiple

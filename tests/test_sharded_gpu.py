@@ -66,10 +66,23 @@ def _rank_main(rank, world, port, out):
         # plain block-cyclic rows / caller-order columns, and the superblock + zigzag + packed-column layout of the fit
         for kw in (dict(), dict(sb_blocks=4, zigzag=True, packed_cols=True)):
             sh = ShardedSymmetricBlock(p, _lib.KFF, **kw)
+            sh._full.zero_()             # rows of padding slots are never written: give them a defined value
+            torch.cuda.synchronize()
+            dist.barrier()
             for _ in range(2):
                 sh.build(_lib.RBF, 2.0, sigma2=39.0, l=0.56, tol=1e-10, use_tol=True)
             K = sh.gather_full()
             err = max(err, float((K - ref.reshape(900, 900)).abs().max() / ref.abs().max()))
+            # host-bound build in row slabs (copy-back of slab k overlaps slab k+1; slabs are final once every rank
+            # has finished them): bit-identical to the one-shot build
+            want = sh.local.cpu()
+            sh.local.zero_()
+            dist.barrier()
+            host = torch.empty(tuple(sh.local.shape), dtype=torch.float64).pin_memory()
+            sh.build_to_host(_lib.RBF, 2.0, host, sigma2=39.0, l=0.56, tol=1e-10, use_tol=True, fractions=(0.0, 0.1, 0.4, 1.0))
+            torch.cuda.synchronize()
+            dist.barrier()
+            err = max(err, float((host - want).abs().max()))
             sh.close()
         out[rank] = err
     finally:
@@ -78,6 +91,26 @@ def _rank_main(rank, world, port, out):
 
 def test_sharded_two_ranks_peer_stores():
     _spawn2(_rank_main, 29611, 1e-12)
+
+
+def test_build_to_host_world1():
+    import torch
+    from csp_bo_b200 import _lib, synthetic
+    from csp_bo_b200.distributed import ShardedSymmetricBlock
+    from csp_bo_b200.packing import Pack
+    X = synthetic.force_set(333, seed=2)
+    p = Pack(X[0], X[1], X[2], X[3])
+    for kw in (dict(), dict(zigzag=True, packed_cols=True), dict(sb_blocks=4, zigzag=True, packed_cols=True)):
+        sh = ShardedSymmetricBlock(p, _lib.KFF, **kw)
+        sh._full.zero_()                 # rows of padding slots are never written: give them a defined value
+        sh.build(_lib.DOT, 2.0, scale=700.0)
+        want = sh.local.cpu()
+        sh.local.zero_()
+        host = torch.empty(tuple(sh.local.shape), dtype=torch.float64).pin_memory()
+        sh.build_to_host(_lib.DOT, 2.0, host, scale=700.0)
+        torch.cuda.synchronize()
+        assert torch.equal(host, want), kw
+        sh.close()
 
 
 @pytest.mark.parametrize("sb_blocks,zigzag", [(1, False), (2, True), (4, True)])
