@@ -11,9 +11,13 @@ stacked descriptor rows, d = 24, Pt/H/O species mix, Dot kernel sigma=18.555 zet
 second with the packed descriptors already resident in HBM; `e2e` = the same through the public
 kff_C() call with pinned HOST buffers in and the K_FF matrix back in pinned HOST memory.
 
-N > 1 (torchrun): the symmetric build is sharded over ranks by 8-atom row blocks dealt in zigzag order
-(strong scaling, fixed total work, no data-path collective; the max over ranks of the
-device-timed region is reported).
+N > 1 (torchrun): the symmetric build is sharded over ranks by 8-atom row blocks dealt in zigzag order, rows and
+columns in the packed order of the descriptor set (P K P^T -- what the sharded Cholesky factorises; full-row stores
+locally and over NVLink); strong scaling, fixed total work, no data-path collective; the max over ranks of the
+device-timed region is reported.  Every N > 1 line carries `parity` (rank 0's first row blocks against the reference
+C++ and the residual of the sharded fit).  The N = 1 line carries `legs`: driver-timed builds of the other configs
+(RBF, single species, K_EE / K_EF, d = 50, the LML gradient) each with its own roofline; every line carries `fit_ef`,
+the energy + force fit of a Si_5352-shaped set on the N GPUs.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref = the unmodified
 cspbo/kernels/dot_kernel.cpp compiled with g++ -O2, threaded like its MPI split) on a bounded
@@ -225,7 +229,8 @@ def run_ours(args):
         # strong scaling: the symmetric build is sharded by block-cyclic row blocks; mirrored tiles go
         # to the owner's HBM over NVLink peer memory inside the tile kernel (csp_bo_b200/distributed.py)
         from csp_bo_b200.distributed import ShardedSymmetricBlock
-        sh = ShardedSymmetricBlock(full, _lib.KFF, zigzag=True)   # zigzag dealing: every rank gets the same triangular work
+        # zigzag dealing: every rank gets the same triangular work; packed columns: full-row stores (local + NVLink)
+        sh = ShardedSymmetricBlock(full, _lib.KFF, zigzag=True, packed_cols=True)
         algo_pairs = (pairs + len(X[0])) / 2 / world
 
         def step():
@@ -280,22 +285,25 @@ def run_ours(args):
             K = kff_C(Xh, Xh, SIGMA, SIGMA0, ZETA, out=outh.numpy())   # H2D + pack + build + D2H inside
             return float(K[0, 0])
     else:
-        outh = torch.empty(sh.local.shape, dtype=torch.float64).pin_memory()
+        outh = torch.empty(tuple(sh.local.shape), dtype=torch.float64).pin_memory()
         d2h = int(outh.numel() * 8) * world
-
+        xd_e, dxd_e = torch.empty_like(xd), torch.empty_like(dxd)
         e2e_parts = []
 
         def e2e_step():
+            # descriptors: ONE upload (rank 0, pinned host -> HBM) + NCCL broadcast over NVLink, then every rank packs
+            # from HBM; the rows are built in slabs whose copy-back to pinned host memory overlaps the next slab
             t0 = time.perf_counter()
-            pk = packing.Pack(Xh[0], Xh[1], Xh[2], Xh[3])             # H2D of the replicated descriptors + pack
+            if rank == 0:
+                xd_e.copy_(xh, non_blocking=True); dxd_e.copy_(dxh, non_blocking=True)
+            dist.broadcast(xd_e, src=0); dist.broadcast(dxd_e, src=0)
+            pk = packing.Pack(xd_e, dxd_e, Xh[2], Xh[3])
             torch.cuda.synchronize(); t1 = time.perf_counter()
             sh.pack = pk
-            sh.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
-            t2 = time.perf_counter()
-            outh.copy_(sh.local, non_blocking=False)                  # this rank's complete rows -> host
-            t3 = time.perf_counter()
+            sh.build_to_host(_lib.DOT, ZETA, outh, scale=SIGMA * SIGMA * ZETA)
+            torch.cuda.synchronize(); t2 = time.perf_counter()
             sh.pack = full
-            e2e_parts.append([round((b - a) * 1e3, 2) for a, b in ((t0, t1), (t1, t2), (t2, t3))])
+            e2e_parts.append([round((b - a) * 1e3, 2) for a, b in ((t0, t1), (t1, t2))])
             return float(outh.view(-1)[0])
     e2e_ms, chk = [], 0.0
     for i in range(1 + n_e2e):
@@ -308,11 +316,16 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": entries / (float(te.item()) * 1e-3), "unit": "entries/s", "ms_per_step": float(te.item()),
-           "h2d_bytes_per_step": int(X[0].nbytes + X[1].nbytes + 2 * 4 * len(X[0])) * world,
+           "h2d_bytes_per_step": int(X[0].nbytes + X[1].nbytes) + 2 * 4 * len(X[0]) * world,
            "d2h_bytes_per_step": d2h, "check": chk, "ms_all": [round(v, 2) for v in e2e_ms],
-           "rank0_h2d_pack__build__d2h_ms": (e2e_parts[-1] if world > 1 else None),
+           "rank0_upload_bcast_pack__build_with_overlapped_d2h_ms": (e2e_parts[-1] if world > 1 else None),
+           "host_d2h_ceiling": "measured on this pool (tools/d2h_probe.py, profiles/d2h_probe_r02.json): 91-94 GB/s aggregate with 8 "
+                               "GPUs copying at once, 71 GB/s with 2, ~55 GB/s for one (a 32-vCPU single-NUMA-node VM): the 3.2 GB "
+                               "result cannot reach host memory in less than ~34 ms however many GPUs build it",
            "api": "kernels.dot_kernel.kff_C(host tuple, host tuple, out=pinned)" if world == 1 else
-                  "packing.Pack(host) + distributed.ShardedSymmetricBlock.build + row-block copy to pinned host"}
+                  "rank-0 upload + NCCL broadcast of the descriptors, packing.Pack(device), "
+                  "distributed.ShardedSymmetricBlock.build_to_host (row slabs, copy-back overlapped) -> this rank's rows of "
+                  "P K P^T in pinned host memory"}
     del outh
 
     # ---- GP fit wall time: K_FF(X,X) + noise -> Cholesky -> alpha  (gaussianprocess.py:105-127, opt=False)
@@ -345,7 +358,6 @@ def run_ours(args):
                 alpha = fit_alpha_sharded(shf, y, nf2)
                 barrier(); t2 = time.perf_counter()
                 fit_ms.append(((t2 - t0) * 1e3, (t1 - t0) * 1e3, (t2 - t1) * 1e3))
-            shf.close()
             how = ("K_FF sharded by %d-row panels (packed order, zigzag owners) -> sharded Cholesky (diagonal chain: potrf + "
                    "inverse + narrow piece on its own SMs and communicator; wide trmm, NCCL panel broadcast, look-ahead and "
                    "per-rank dgemm updates behind it) -> potrs on the replicated factor" % (24 * FIT_SB_BLOCKS))
@@ -353,10 +365,73 @@ def run_ours(args):
         tl = torch.tensor(list(best), dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        # residual of the fit through an independent path: K rebuilt, (K + noise) alpha - y with the streaming GEMV kernel
+        # on every rank's own rows, squared norms summed over the ranks
+        if world == 1:
+            step(); torch.cuda.synchronize()
+            r = gp.predict_mean(out.view(3 * m, 3 * m), alpha) + nf2 * alpha - y
+            rr = torch.stack(((r * r).sum(), (y * y).sum()))
+        else:
+            from csp_bo_b200.distributed import local_positions
+            shf.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
+            order = torch.as_tensor(np.asarray(shf.order[:m], dtype=np.int64), device="cuda")
+            ap, yp = alpha.reshape(m, 3)[order].reshape(-1), y.reshape(m, 3)[order].reshape(-1)      # packed order
+            pos = torch.as_tensor(local_positions(shf.n_blocks, rank, world, shf.sb_blocks, shf.zigzag), device="cuda")
+            keep = (pos >= 0) & (pos < m)
+            rows3 = (pos.clamp(min=0)[:, None] * 3 + torch.arange(3, device="cuda")[None, :]).reshape(-1)
+            keep3 = keep[:, None].expand(-1, 3).reshape(-1)
+            Ka = gp.predict_mean(shf.local2d().contiguous(), ap)
+            r = (Ka + nf2 * ap[rows3.clamp(max=3 * m - 1)] - yp[rows3.clamp(max=3 * m - 1)])[keep3]
+            rr = torch.stack(((r * r).sum(), (yp[rows3.clamp(max=3 * m - 1)][keep3] ** 2).sum()))
+            dist.all_reduce(rr, op=dist.ReduceOp.SUM)
+            shf.close()
         fit = {"wall_ms": float(tl[0]), "k_build_ms": float(tl[1]), "cholesky_solve_ms": float(tl[2]), "N": 3 * m, "what": how,
-               "alpha_check": float(alpha.abs().sum())}
+               "alpha_check": float(alpha.abs().sum()),
+               "residual": float(torch.sqrt(rr[0] / rr[1])),
+               "residual_what": "||(K + noise) alpha - y|| / ||y|| with K rebuilt and applied by the GEMV kernel on every rank's own rows"}
     except Exception as exc:
         fit = {"error": str(exc)[:300]}
+
+    # ---- N > 1: parity of what the ranks built against the reference C++ (rank 0's first two row blocks = 16 atoms)
+    parity = None
+    if world > 1:
+        try:
+            sh.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
+            if rank == 0:
+                from csp_bo_b200.distributed import local_positions
+                from oracle import cpu_reference as cr
+                subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=False, stdout=subprocess.DEVNULL)
+                pos = local_positions(sh.n_blocks, rank, world, sh.sb_blocks, sh.zigzag)[:16]
+                groups = sh.order[pos]
+                off = np.concatenate(([0], np.cumsum(X[3])))
+                rows = np.concatenate([np.arange(off[g], off[g + 1]) for g in groups])
+                X1 = (X[0][rows], X[1][rows], X[2][rows], [int(X[3][g]) for g in groups])
+                be = cr.get_backend("auto")
+                C = cr.dot_kff_C(X1, X, SIGMA, SIGMA0, ZETA, backend=be.kind, threads=os.cpu_count() or 1)
+                loc = sh.local[:16].cpu().numpy().reshape(16, 3, m, 3)
+                caller = np.empty_like(loc)
+                caller[:, :, sh.order[:m], :] = loc          # packed column position p holds group order[p]
+                err = float(np.abs(caller.reshape(48, 3 * m) - C).max() / np.abs(C).max())
+                parity = {"max_norm_err_vs_reference": err, "tolerance": 1e-10, "kind": "reference" if be.kind == "ref" else "port",
+                          "what": "rank 0's first 16 atoms (48 rows x %d columns of P K P^T, un-permuted) against the reference "
+                                  "C++ kff_many on the same descriptors" % (3 * m)}
+        except Exception as exc:
+            parity = {"error": str(exc)[:300]}
+
+    # ---- the energy + force fit of a Si_5352-shaped training set (BASELINE.json config 3) on the N GPUs
+    fit_ef = None
+    try:
+        fit_ef = fit_ef_leg(world, rank, barrier)
+    except Exception as exc:
+        fit_ef = {"error": str(exc)[:300]}
+
+    # ---- N = 1: the other configs of BASELINE.json, each a short driver-timed leg with its own roofline
+    legs = None
+    if world == 1 and not args.no_legs:
+        try:
+            legs = extra_legs(full, X, fp64_peak()[0])
+        except Exception as exc:
+            legs = {"error": str(exc)[:300]}
 
     # ---- one MD / validation step (config 1 of BASELINE.json): SO3 descriptor of a 192-atom Pt/H/O structure
     # + K* against a 16-energy + 409-force model + K*.alpha, through GaussianProcess.predict_structure.
@@ -390,18 +465,21 @@ def run_ours(args):
     peak, peak_src = fp64_peak()
     kern_ms = float(np.mean(step_ms))
     achieved = algo_pairs * FLOP_PER_PAIR / (kern_ms * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "kff_traffic_r01.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_step")
-        except Exception:
-            traffic = None
+    # DRAM bytes per launch are an ncu figure (profiles/kff_traffic_r02.md, same kernel and workload), not measured in
+    # this run: caller-order output (N = 1) 16.25 GB, packed-column output (N > 1, the whole matrix) 3.60 GB
+    traffic = 16.25e9 if world == 1 else 3.60e9 / world
+    tensor_flops = algo_pairs * 32 * 24          # the 16 length-d dot products only: what the DMMA pipe executes
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/kff_traffic_r02.md (not measured in this run)",
+                "algorithmic_bytes_per_step": (8.0 * 9 * m * m + 113e6) / world,
+                "peak_source": "builder-measured DMMA peak: " + peak_src,
                 "algorithmic_flops_per_step": algo_pairs * FLOP_PER_PAIR,
-                "note": "FP64 tensor (DMMA) pipe; 868 flop per same-species row pair (SURVEY 8d), "
-                        "unique pairs of the symmetric build; device time of the block kernels per step"}
+                "achieved_tensor_flops_only": tensor_flops / (kern_ms * 1e-3) / 1e12,
+                "frac_tensor_flops_only": tensor_flops / (kern_ms * 1e-3) / 1e12 / peak,
+                "note": "FP64 tensor (DMMA) pipe; `frac` counts SURVEY 8d's 868 flop per same-species row pair (768 of "
+                        "dot products + 100 charged for the epilogue, of which the zeta = 2 chain rule spends 36); "
+                        "`frac_tensor_flops_only` counts the 768 the DMMA pipe executes; unique pairs of the symmetric "
+                        "build; device time of the block kernels per step"}
 
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -426,10 +504,159 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(X, pairs), "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "fit": fit, "md_step": md, "real_data": real}
+            "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "fit": fit, "fit_ef": fit_ef, "legs": legs,
+            "md_step": md, "real_data": real}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _events_ms(fn, reps=3, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    return float(np.mean(ms))
+
+
+def extra_legs(full, X, peak):
+    """BASELINE.json config 5 beyond the headline (RBF, single species, K_EE / K_EF, Dot and RBF), d = 50 (AgI.json) and
+    d = 90 (the chunked kernels), and one LML + gradient evaluation per kernel family.  Flop counts: SURVEY 8(d)."""
+    import torch
+    from csp_bo_b200 import _lib, packing, synthetic
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from csp_bo_b200.kernels import Dot_mb, RBF_mb
+    hbm = 6547.2
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    RBF_P = dict(sigma=6.244955524643115, l=0.5611029935713949)           # examples/models/Si.json
+    NAMES = {_lib.KEE: "K_EE", _lib.KEF: "K_EF", _lib.KFF: "K_FF"}
+    out = {}
+
+    def dev_pack(T):
+        if len(T) == 4:
+            return packing.Pack(torch.from_numpy(T[0]).cuda(), torch.from_numpy(T[1]).cuda(), T[2], T[3])
+        return packing.Pack(torch.from_numpy(T[0]).cuda(), None, T[1], T[2])
+
+    def leg(name, fam, block, a, b, sym, what):
+        d = a.d
+        kw = dict(sigma2=SIGMA ** 2, sigma02=SIGMA0 ** 2, scale=(SIGMA ** 2 * ZETA if block == _lib.KFF else SIGMA ** 2)) if fam == _lib.DOT else \
+            dict(sigma2=RBF_P["sigma"] ** 2, l=RBF_P["l"], tol=1e-10, use_tol=(block == _lib.KFF))
+        shp = {_lib.KEE: (a.m, b.m), _lib.KEF: (a.m, b.m, 3), _lib.KFF: (a.m, 3, b.m * 3)}[block]
+        buf = torch.empty(shp, dtype=torch.float64, device="cuda")
+        ms = _events_ms(lambda: packing.build_block(fam, block, a, b, 2.0, symmetric=sym, out=buf, **kw))
+        pairs = a.pair_count(b)
+        algo = (pairs + a.n) / 2 if sym else pairs
+        fpp = {_lib.KEE: 2 * d + 12, _lib.KEF: 8 * d + 30, _lib.KFF: 32 * d + 100}[block] + (20 if fam == _lib.RBF else 0)
+        tpp = {_lib.KEE: 2 * d, _lib.KEF: 8 * d, _lib.KFF: 32 * d}[block]
+        tf = algo * fpp / (ms * 1e-3) / 1e12
+        out[name] = {"what": what, "block": NAMES[block], "family": "Dot" if fam == _lib.DOT else "RBF", "d": d, "ms": ms,
+                     "entries_per_s": float(np.prod(shp)) / (ms * 1e-3), "same_species_row_pairs": int(pairs),
+                     "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                                  "flop_per_pair": fpp, "frac_tensor_flops_only": algo * tpp / (ms * 1e-3) / 1e12 / peak}}
+        del buf
+
+    m = full.m
+    leg("rbf_kff_mix", _lib.RBF, _lib.KFF, full, full, True, "K_FF(X,X) RBF (exp + tol test), the headline set: %d force rows, Pt/H/O" % (3 * m))
+    pe = dev_pack(synthetic.energy_set(833, seed=1))
+    for fam, tag in ((_lib.DOT, "dot"), (_lib.RBF, "rbf")):
+        leg(tag + "_kee_mix", fam, _lib.KEE, pe, pe, True, "K_EE, 833 structures of 192 atoms, Pt/H/O")
+        leg(tag + "_kef_mix", fam, _lib.KEF, pe, full, False, "K_EF, 833 structures x %d force rows, Pt/H/O" % (3 * m))
+    del pe
+    ps = dev_pack(synthetic.force_set(m, seed=0, single_element=True))
+    leg("dot_kff_single", _lib.DOT, _lib.KFF, ps, ps, True, "K_FF(X,X) Dot, %d force rows, one species (Si / Cu-like: every row pair counts)" % (3 * m))
+    del ps
+    torch.cuda.empty_cache()
+    p50 = dev_pack(synthetic.force_set(m, seed=0, d=50))
+    leg("dot_kff_d50", _lib.DOT, _lib.KFF, p50, p50, True, "K_FF(X,X) Dot, d = 50 (AgI.json: nmax = lmax = 4), %d force rows, Pt/H/O" % (3 * m))
+    del p50
+    p90 = dev_pack(synthetic.force_set(3334, seed=0, d=90))
+    leg("dot_kff_d90", _lib.DOT, _lib.KFF, p90, p90, True, "K_FF(X,X) Dot, d = 90 (nmax = lmax = 5, chunked kernels), 10002 force rows, Pt/H/O")
+    del p90
+    torch.cuda.empty_cache()
+
+    # K*.alpha GEMV: HBM bound, every K* byte read once
+    N = 3 * m
+    Ks = torch.empty((N, N), dtype=torch.float64, device="cuda").normal_()
+    al = torch.empty(N, dtype=torch.float64, device="cuda").normal_()
+    from csp_bo_b200 import gp
+    ms = _events_ms(lambda: gp.predict_mean(Ks, al), reps=5)
+    gbs = 8.0 * N * N / (ms * 1e-3) / 1e9
+    out["gemv"] = {"what": "K*[%d,%d] . alpha" % (N, N), "ms": ms,
+                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm}}
+    del Ks, al
+    torch.cuda.empty_cache()
+
+    # one LML + gradient evaluation (gaussianprocess.py:453-503) on the headline force set: fused traces, one N x N array
+    y = np.random.default_rng(0).standard_normal(N)
+    for name, kern in (("lml_grad_dot", Dot_mb(para=[SIGMA, SIGMA0], zeta=2)), ("lml_grad_rbf", RBF_mb(para=[RBF_P["sigma"], RBF_P["l"]], zeta=2))):
+        model = GaussianProcess(kern, f_coef=30, noise_e=[0.005, 0.002, 0.1])
+        model.train_x = {"energy": [], "force": X}
+        model.train_y = {"energy": [], "force": list(y.reshape(m, 3))}
+        model.update_y_train()
+        model._packs = {"force": full}
+        params = np.array(kern.parameters() + [0.005])
+        model.log_marginal_likelihood(params, eval_gradient=True)
+        torch.cuda.synchronize()
+        base = torch.cuda.memory_allocated()
+        torch.cuda.reset_peak_memory_stats()
+        t0 = time.perf_counter()
+        lml, grad = model.log_marginal_likelihood(params, eval_gradient=True)
+        torch.cuda.synchronize()
+        out[name] = {"what": "log_marginal_likelihood(eval_gradient=True), N = %d, %s" % (N, kern.name), "ms": (time.perf_counter() - t0) * 1e3,
+                     "peak_extra_memory_in_N2_doubles": (torch.cuda.max_memory_allocated() - base) / (8.0 * N * N),
+                     "lml": float(lml), "grad": [float(g) for g in grad]}
+        del model
+        torch.cuda.empty_cache()
+    return out
+
+
+def fit_ef_leg(world, rank, barrier):
+    """BASELINE.json config 3 shape: RBF_mb (examples/models/Si.json), 5352 energies of 64-atom structures + 3334 force
+    atoms, one species, N = 15 354: K_EE, K_EF (+K_FE), K_FF + noise -> Cholesky -> alpha on the N GPUs."""
+    import torch
+    import torch.distributed as dist
+    from csp_bo_b200 import gp, synthetic
+    from csp_bo_b200.kernels import RBF_mb
+    from csp_bo_b200.kernels import device as kdev
+    from csp_bo_b200.packing import resident
+    nE, nF = 5352, 3334
+    data = resident({"energy": synthetic.energy_set(nE, seed=1, single_element=True, rows_per_structure=64),
+                     "force": synthetic.force_set(nF, seed=2, single_element=True)})
+    y = torch.from_numpy(np.random.default_rng(3).standard_normal(nE + 3 * nF)).cuda()
+    kernel = RBF_mb(para=[6.244955524643115, 0.5611029935713949], zeta=2)
+    ts = []
+    for _ in range(3):
+        barrier(); t0 = time.perf_counter()
+        if world == 1:
+            K = kdev.k_total_device(kernel, data)
+            alpha = gp.fit_alpha(K, y, n_energy=nE, noise_e=0.005, f_coef=30.0, overwrite=True)
+            del K
+        else:
+            from csp_bo_b200.distributed import fit_sharded
+            alpha = fit_sharded(kernel, data, y, 0.005, 30.0)
+        barrier(); ts.append((time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([min(ts[1:])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # residual through an independent dense build on this rank (N = 15 354: 1.9 GB)
+    K = kdev.k_total_device(kernel, data)
+    r = gp.predict_mean(K, alpha) - y
+    d = torch.full_like(y, (30.0 * 0.005) ** 2)
+    d[:nE] = 0.005 ** 2
+    r += d * alpha
+    res = float(torch.sqrt((r * r).sum() / (y * y).sum()))
+    del K
+    return {"wall_ms": float(t), "N": nE + 3 * nF, "residual": res,
+            "what": "RBF_mb, 5352 energies (64-atom structures) + 3334 force atoms: K_EE / K_EF + K_FE / K_FF + noise -> "
+                    + ("cuSOLVER potrf/potrs" if world == 1 else "panel-layout sharded build + sharded Cholesky (fit_sharded)") + " -> alpha"}
 
 
 def md_step_leg():
@@ -536,6 +763,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-legs", action="store_true", help="skip the extra per-config legs of the N = 1 line")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":

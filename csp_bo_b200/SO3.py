@@ -70,9 +70,8 @@ class SO3:
             self._h = (h, key)
         return self._h[0]
 
-    def calculate(self, atoms, atom_ids=None):
-        if atom_ids is not None:
-            raise NotImplementedError("atom_ids subsets are not supported by the GPU descriptor")
+    def _compute(self, atoms, want_stress):
+        """Runs the descriptor kernels; returns (handle, n_atoms, n_seq, n_coefs, elements)."""
         lib = _lib.load()
         pos = np.ascontiguousarray(atoms.positions, dtype=np.float64)
         numbers = getattr(atoms, "numbers", None)
@@ -83,12 +82,37 @@ class SO3:
         pbc = np.ascontiguousarray(np.broadcast_to(np.asarray(atoms.pbc), (3,)).astype(np.int32))
         symbols = getattr(atoms, "symbols", None)
         elements = list(symbols) if symbols is not None else list(atoms.get_chemical_symbols())
-        n = len(pos)
         h = self._handle()
         nseq, nc = ctypes.c_int(0), ctypes.c_int(0)
-        want_stress = bool(self.stress) and bool(self.derivative)
-        _lib.check(lib.cspbo_so3_compute(h, n, c_vp(pos.ctypes.data), c_vp(numbers.ctypes.data), c_vp(cell.ctypes.data),
+        _lib.check(lib.cspbo_so3_compute(h, len(pos), c_vp(pos.ctypes.data), c_vp(numbers.ctypes.data), c_vp(cell.ctypes.data),
                                          c_vp(pbc.ctypes.data), int(want_stress), ctypes.byref(nseq), ctypes.byref(nc)))
+        return h, len(pos), nseq.value, nc.value, elements
+
+    def calculate_device(self, atoms, stress=None):
+        """Like calculate(), but x / dxdr / rdxdr are CUDA tensors viewing the descriptor's own device buffers (valid
+        until the next calculate* call on this object) -- nothing but `seq` crosses PCIe.  What
+        GaussianProcess.predict_structure consumes on the MD path (gaussianprocess.py:335-351)."""
+        import torch
+        from .distributed import _RawCuda
+        lib = _lib.load()
+        want_stress = bool(self.stress if stress is None else stress) and bool(self.derivative)
+        h, n, nseq, nc, elements = self._compute(atoms, want_stress)
+        px, pd, pr = c_vp(), c_vp(), c_vp()
+        _lib.check(lib.cspbo_so3_device_ptrs(h, ctypes.byref(px), ctypes.byref(pd), ctypes.byref(pr)))
+        seq = np.empty((nseq, 2), dtype=np.int64)
+        _lib.check(lib.cspbo_so3_fetch(h, None, None, None, c_vp(seq.ctypes.data)))
+        x = torch.as_tensor(_RawCuda(px.value, (n, nc)), device="cuda")
+        dxdr = torch.as_tensor(_RawCuda(pd.value, (nseq, nc, 3)), device="cuda")
+        rdxdr = torch.as_tensor(_RawCuda(pr.value, (nseq, nc, 3, 3)), device="cuda") if want_stress else None
+        return {'x': x, 'dxdr': dxdr, 'rdxdr': rdxdr, 'elements': elements, 'seq': seq}
+
+    def calculate(self, atoms, atom_ids=None):
+        if atom_ids is not None:
+            raise NotImplementedError("atom_ids subsets are not supported by the GPU descriptor")
+        lib = _lib.load()
+        want_stress = bool(self.stress) and bool(self.derivative)
+        h, n, nseq_v, nc_v, elements = self._compute(atoms, want_stress)
+        nseq, nc = ctypes.c_int(nseq_v), ctypes.c_int(nc_v)
         x = np.empty((n, nc.value))
         if not self.derivative:
             _lib.check(lib.cspbo_so3_fetch(h, c_vp(x.ctypes.data), None, None, None))

@@ -607,6 +607,13 @@ extern "C" int cspbo_so3_compute(cspbo_so3 *h, int n_atoms, const double *pos, c
 #undef SO3_CUDA
 }
 
+extern "C" int cspbo_so3_device_ptrs(const cspbo_so3 *h, double **x, double **dxdr, double **rdxdr)
+{
+    if (!h || !x || !dxdr || !rdxdr) { set_error("so3_device_ptrs: null argument"); return CSPBO_E_ARG; }
+    *x = h->d_x; *dxdr = h->d_dxdr; *rdxdr = h->stress ? h->d_rdxdr : nullptr;
+    return CSPBO_OK;
+}
+
 extern "C" int cspbo_so3_fetch(const cspbo_so3 *h, double *x, double *dxdr, double *rdxdr, long long *seq)
 {
     if (!h) { set_error("so3_fetch: null handle"); return CSPBO_E_ARG; }

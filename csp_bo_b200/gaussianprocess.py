@@ -68,6 +68,7 @@ class GaussianProcess():
         self.L_ = None            # CUDA tensor: cuSOLVER factor of K + noise (its lower triangle, column-major)
         self._alpha_dev = None
         self._packs = None        # the training set as resident packs, snapshot taken by fit()
+        self._packs_pred = None   # the same for K* builds (small energy sets spread over the tile slots)
         self.N_energy = 0
         self.N_forces = 0
         self.N_energy_queue = 0
@@ -158,7 +159,7 @@ class GaussianProcess():
         (gaussianprocess.py:392-405) drops them the same way -- so K* always has as many columns as alpha_ has rows."""
         if self._packs is None:
             raise RuntimeError("GaussianProcess: fit() has not been called")
-        return self._packs
+        return self._packs_pred
 
     def remove_train_pts(self, e_ids, f_ids):
         """Drop the energy points `e_ids` and force points `f_ids` and refit (gaussianprocess.py:230-270;
@@ -218,8 +219,12 @@ class GaussianProcess():
                 return (-lml, -grad)
             return -self.log_marginal_likelihood(params, clone_kernel=False)
 
-        from .packing import resident
+        from .packing import SPREAD_MAX_GROUPS, resident, spread_energy
         self._packs = resident(self._train_dict())     # the one upload of the training descriptors of this fit
+        # prediction side: a training set with few energy structures is packed spread over the tile slots
+        self._packs_pred = dict(self._packs)
+        if "energy" in self._packs and self._packs["energy"].m <= SPREAD_MAX_GROUPS:
+            self._packs_pred["energy"] = spread_energy(self.train_x["energy"])
         hyper_params = self.kernel.parameters() + [self.noise_e]
         hyper_bounds = self.kernel.bounds + [self.noise_bounds]
         if opt:
@@ -464,22 +469,40 @@ class GaussianProcess():
     def predict_structure(self, struc, stress=True, return_std=False, f_tol=1e-8):
         """Energy, forces (and stress, std) of one structure from descriptor.calculate(struc)
         (gaussianprocess.py:325-390)."""
-        d = self.descriptor.calculate(struc)
-        ele = np.array([e if isinstance(e, (int, np.integer)) else _Z[e] for e in d['elements']])
-        _n, l = d['x'].shape
         n_atoms = len(struc)
-        # the reference gathers, per atom i, the seq rows with seq[:,1] == i in ascending order
-        # (gaussianprocess.py:341-351); a stable sort on that column gives the same stacked tuple at once
-        seq = np.asarray(d['seq'])
-        order = np.argsort(seq[:, 1], kind='stable')
-        centres = seq[order, 0]
-        counts = np.bincount(seq[:, 1], minlength=n_atoms)
-        dX = d['dxdr'][order]
-        if stress:
-            rd = d['rdxdr'][order].reshape([len(order), l, 9])[:, :, [0, 4, 8, 1, 2, 5]]
-            dX = np.concatenate((dX, rd), axis=2)
-        data = {"energy": (np.ascontiguousarray(d['x']), ele, [len(ele)]),
-                "force": (np.ascontiguousarray(d['x'][centres]), np.ascontiguousarray(dX), ele[centres], [int(c) for c in counts])}
+        if hasattr(self.descriptor, "calculate_device"):
+            # GPU descriptor: x / dxdr / rdxdr stay in HBM; only `seq` (which neighbour rows belong to which atom) comes
+            # to the host for the stacked-tuple bookkeeping, and the gather by atom runs on the device
+            import torch
+            d = self.descriptor.calculate_device(struc, stress=stress)
+            ele = np.array([e if isinstance(e, (int, np.integer)) else _Z[e] for e in d['elements']])
+            seq = d['seq']
+            order = np.argsort(seq[:, 1], kind='stable')
+            centres = seq[order, 0]
+            counts = np.bincount(seq[:, 1], minlength=n_atoms)
+            order_d = torch.as_tensor(order, device="cuda")
+            dX = d['dxdr'].index_select(0, order_d)
+            if stress:
+                rd = d['rdxdr'].index_select(0, order_d).reshape(len(order), dX.shape[1], 9)[:, :, [0, 4, 8, 1, 2, 5]]
+                dX = torch.cat((dX, rd), dim=2)
+            data = {"energy": (d['x'], ele, [len(ele)]),
+                    "force": (d['x'].index_select(0, torch.as_tensor(centres, device="cuda")), dX, ele[centres], [int(c) for c in counts])}
+        else:
+            d = self.descriptor.calculate(struc)
+            ele = np.array([e if isinstance(e, (int, np.integer)) else _Z[e] for e in d['elements']])
+            _n, l = d['x'].shape
+            # the reference gathers, per atom i, the seq rows with seq[:,1] == i in ascending order
+            # (gaussianprocess.py:341-351); a stable sort on that column gives the same stacked tuple at once
+            seq = np.asarray(d['seq'])
+            order = np.argsort(seq[:, 1], kind='stable')
+            centres = seq[order, 0]
+            counts = np.bincount(seq[:, 1], minlength=n_atoms)
+            dX = d['dxdr'][order]
+            if stress:
+                rd = d['rdxdr'][order].reshape([len(order), l, 9])[:, :, [0, 4, 8, 1, 2, 5]]
+                dX = np.concatenate((dX, rd), axis=2)
+            data = {"energy": (np.ascontiguousarray(d['x']), ele, [len(ele)]),
+                    "force": (np.ascontiguousarray(d['x'][centres]), np.ascontiguousarray(dX), ele[centres], [int(c) for c in counts])}
         train = self._fitted()
         if stress:
             K_trans, K_trans1 = kdev.k_total_with_stress_device(self.kernel, data, train, f_tol)

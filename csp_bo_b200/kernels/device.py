@@ -7,11 +7,11 @@ import ctypes
 
 from .. import _lib
 from .._lib import BlockDesc, c_vp
-from ..packing import build_block, pack_energy, pack_force
+from ..packing import SPREAD_MAX_GROUPS, Pack, build_block, pack_energy, pack_force, spread_energy
 from ..utilities import list_to_tuple
 
 
-def _tuples(data, stress=False):
+def _tuples(data, stress=False, spread_small=False):
     """{'energy': tuple|list|Pack, 'force': tuple|list|Pack} -> packs (None when absent/empty).  Tuples and lists are
     packed afresh on every call (stateless, like the reference wrappers); caller-held Packs (packing.resident) pass
     through."""
@@ -20,7 +20,10 @@ def _tuples(data, stress=False):
     if E is not None and len(E) > 0:
         if isinstance(E, list):
             E = list_to_tuple(E, mode='energy')
-        pe = pack_energy(E)
+        if spread_small and not isinstance(E, Pack) and len(E[2]) <= SPREAD_MAX_GROUPS:
+            pe = spread_energy(E)         # few structures (an MD step has one): fill all 8 slots of the tiles
+        else:
+            pe = pack_energy(E)
     F = data.get("force")
     if F is not None and len(F) > 0:
         if isinstance(F, list):
@@ -44,10 +47,31 @@ def _hyper(kernel, quirk):
 
 
 def _into(h, block, zeta, scale, a, b, K, row0, col0, tol=0.0, use_tol=False, symmetric=False):
+    if a.spread > 1 or b.spread > 1:
+        # spread energy packs (packing.spread_energy): build the block of the pseudo-structures, then add their rows /
+        # columns up into the real structures' entries
+        import torch
+        rows = a.m * (3 if block == _lib.KFF else 1)
+        cols = b.m * (1 if block == _lib.KEE else 3)
+        tmp = torch.empty((rows, cols), dtype=torch.float64, device="cuda")
+        _into_plain(h, block, zeta, scale, a, b, tmp, 0, 0, tol, use_tol, symmetric)
+        ra, cb = rows // a.spread, cols // b.spread
+        red = tmp.view(ra, a.spread, cb, b.spread).sum(dim=(1, 3))
+        K[row0:row0 + ra, col0:col0 + cb] = red
+        return
+    _into_plain(h, block, zeta, scale, a, b, K, row0, col0, tol, use_tol, symmetric)
+
+
+def _into_plain(h, block, zeta, scale, a, b, K, row0, col0, tol=0.0, use_tol=False, symmetric=False):
     desc = BlockDesc(h["family"], block, float(zeta), float(h["sigma2"]), float(h["sigma02"]), float(h["l"]),
                      float(tol), int(bool(use_tol)), 0, 0, float(scale), 1.0, int(bool(symmetric)))
     _lib.check(_lib.load().cspbo_block_build_into(ctypes.byref(desc), a.handle, b.handle, c_vp(K.data_ptr()),
                                                   K.shape[1], int(row0), int(col0)))
+
+
+def _counts(p):
+    import torch
+    return torch.as_tensor(p.real_counts, dtype=torch.float64, device="cuda")
 
 
 def k_total_device(kernel, data1, data2=None, tol=1e-10, grad_semantics=False):
@@ -59,26 +83,25 @@ def k_total_device(kernel, data1, data2=None, tol=1e-10, grad_semantics=False):
     import torch
     h = _hyper(kernel, quirk=not grad_semantics)
     same = data2 is None
-    e1, f1 = _tuples(data1)
-    e2, f2 = (e1, f1) if same else _tuples(data2)
-    ne1, nf1 = (e1.m if e1 else 0), (3 * f1.m if f1 else 0)
-    ne2, nf2 = (e2.m if e2 else 0), (3 * f2.m if f2 else 0)
+    # K* (data2 given): energy sets of a few structures are packed spread over the 8 tile slots (see _tuples)
+    e1, f1 = _tuples(data1, spread_small=not same)
+    e2, f2 = (e1, f1) if same else _tuples(data2, spread_small=True)
+    ne1, nf1 = (e1.m_real if e1 else 0), (3 * f1.m if f1 else 0)
+    ne2, nf2 = (e2.m_real if e2 else 0), (3 * f2.m if f2 else 0)
     K = torch.empty((ne1 + nf1, ne2 + nf2), dtype=torch.float64, device="cuda")
     if e1 and e2:
         _into(h, _lib.KEE, h["zee"], h["see"], e1, e2, K, 0, 0, symmetric=same)
-        c1 = torch.as_tensor(e1.counts, dtype=torch.float64, device="cuda")
-        c2 = torch.as_tensor(e2.counts, dtype=torch.float64, device="cuda")
-        K[:ne1, :ne2] /= (c1[:, None] * c2[None, :])
+        K[:ne1, :ne2] /= (_counts(e1)[:, None] * _counts(e2)[None, :])
     if e1 and f2:
         _into(h, _lib.KEF, h["zef"], h["sef"], e1, f2, K, 0, ne2)
-        K[:ne1, ne2:] /= torch.as_tensor(e1.counts, dtype=torch.float64, device="cuda")[:, None]
+        K[:ne1, ne2:] /= _counts(e1)[:, None]
     if f1 and e2:
         if same:
             K[ne1:, :ne2] = K[:ne1, ne2:].T
         else:
             tmp = torch.empty((ne2, nf1), dtype=torch.float64, device="cuda")
             _into(h, _lib.KEF, h["zef"], h["sef"], e2, f1, tmp, 0, 0)
-            tmp /= torch.as_tensor(e2.counts, dtype=torch.float64, device="cuda")[:, None]
+            tmp /= _counts(e2)[:, None]
             K[ne1:, :ne2] = tmp.T
     if f1 and f2:
         _into(h, _lib.KFF, h["zff"], h["sff"], f1, f2, K, ne1, ne2, tol=tol,
@@ -135,24 +158,25 @@ def k_total_with_stress_device(kernel, data1, data2, tol=1e-10):
     """(K*, K*_stress) as CUDA tensors (Dot_mb.py:150-173); data1 force entries carry 9 columns."""
     import torch
     h = _hyper(kernel, quirk=True)
-    e1, f1 = _tuples(data1, stress=True)
-    e2, f2 = _tuples(data2)
-    ne1, m1 = (e1.m if e1 else 0), (f1.m if f1 else 0)
-    ne2, nf2 = (e2.m if e2 else 0), (3 * f2.m if f2 else 0)
+    e1, f1 = _tuples(data1, stress=True, spread_small=True)
+    e2, f2 = _tuples(data2, spread_small=True)
+    ne1, m1 = (e1.m_real if e1 else 0), (f1.m if f1 else 0)
+    ne2, nf2 = (e2.m_real if e2 else 0), (3 * f2.m if f2 else 0)
     K = torch.empty((ne1 + 3 * m1, ne2 + nf2), dtype=torch.float64, device="cuda")
     Ks = torch.empty((6 * m1, ne2 + nf2), dtype=torch.float64, device="cuda")
     fam = h["family"]
     if e1 and e2:
         _into(h, _lib.KEE, h["zee"], h["see"], e1, e2, K, 0, 0)
-        K[:ne1, :ne2] /= (torch.as_tensor(e1.counts, dtype=torch.float64, device="cuda")[:, None] *
-                          torch.as_tensor(e2.counts, dtype=torch.float64, device="cuda")[None, :])
+        K[:ne1, :ne2] /= (_counts(e1)[:, None] * _counts(e2)[None, :])
     if e1 and f2:
         _into(h, _lib.KEF, h["zef"], h["sef"], e1, f2, K, 0, ne2)
-        K[:ne1, ne2:] /= torch.as_tensor(e1.counts, dtype=torch.float64, device="cuda")[:, None]
+        K[:ne1, ne2:] /= _counts(e1)[:, None]
     if f1 and e2:
         out, _ = build_block(fam, _lib.KEF, e2, f1, h["zef"], sigma2=h["sigma2"], l=h["l"], stress=True,
-                             scale=h["sef"], device=True)                    # [ne2, m1, 9]
-        out = out / torch.as_tensor(e2.counts, dtype=torch.float64, device="cuda")[:, None, None]
+                             scale=h["sef"], device=True)                    # [ne2 (x spread), m1, 9]
+        if e2.spread > 1:
+            out = out.view(ne2, e2.spread, m1, 9).sum(dim=1)
+        out = out / _counts(e2)[:, None, None]
         K[ne1:, :ne2] = out[:, :, :3].reshape(ne2, 3 * m1).T
         Ks[:, :ne2] = out[:, :, 3:].reshape(ne2, 6 * m1).T
     if f1 and f2:

@@ -40,7 +40,8 @@ def kernel_diag(kernel, data):
             F = [(f[0], np.asarray(f[1])[:, :, :3], f[2]) for f in F]
             F = list_to_tuple(F)
         x, dxdr, ele, indices = F
-        p = Pack(x, np.ascontiguousarray(np.asarray(dxdr)[:, :, :3]), ele, indices, norm_shift=_EPS)
+        d3 = dxdr[:, :, :3].contiguous() if type(dxdr).__module__.startswith("torch") else np.ascontiguousarray(np.asarray(dxdr)[:, :, :3])
+        p = Pack(x, d3, ele, indices, norm_shift=_EPS)
         scale = fa["sigma2"] * zeta if fa["family"] == _lib.DOT else 1.0
         blocks = block_diag(fa["family"], _lib.KFF, p, zeta, fa["sigma2"], fa["sigma02"], fa["l"], scale=scale)
         C_ff = np.ascontiguousarray(np.diagonal(blocks, axis1=1, axis2=2)).reshape(-1)

@@ -66,6 +66,8 @@ class Pack:
                                             int(row_classes), ctypes.byref(h)))
         self.row_classes = int(row_classes)
         self._h = h
+        # spread packs (spread_energy): `spread` consecutive pseudo-groups make one real group
+        self.spread, self.m_real, self.real_counts = 1, self.m, self.counts
 
     def __len__(self):
         """Number of groups, so that the `len(d) > 0` tests of k_total treat a Pack like a stacked tuple."""
@@ -119,15 +121,56 @@ def pack_force(X, row_range=None, row_classes=1):
     return Pack(x, dxdr, ele, indices, row_range=row_range, row_classes=row_classes)
 
 
-def resident(data, stress=False):
+SPREAD_WAYS = 8
+SPREAD_MAX_GROUPS = 64
+
+
+def spread_energy(X, ways=SPREAD_WAYS):
+    """Cut every structure of a stacked energy tuple into `ways` pseudo-structures with (nearly) equal per-species row
+    counts.  A covariance block is a plain sum over the rows of a group (dot_kernel.cpp:45-47), so the block of the real
+    structure is the sum of its pseudo-structures' rows / columns -- but a pack with ONE structure fills one slot of
+    every 8-slot tile (1/8 of the DMMA work useful, one CTA column), while its 8 pseudo-structures fill them all: the
+    K_EE / K_EF / K_FE builds of an MD step (one 192-atom structure against the training set) get 8x shorter.
+    Returns a Pack whose .spread / .m_real / .real_counts describe the real groups."""
+    x, ele, indices = X
+    counts = np.asarray(indices, dtype=np.int64)
+    ele_np = np.asarray(ele).ravel()
+    n = len(ele_np)
+    struct = np.repeat(np.arange(len(counts)), counts)
+    # rank of every row among the rows of its (structure, species), in row order
+    key = struct * (int(ele_np.max(initial=0)) - int(ele_np.min(initial=0)) + 1) + (ele_np - int(ele_np.min(initial=0)))
+    order = np.argsort(key, kind='stable')
+    sk = key[order]
+    first = np.concatenate(([0], np.nonzero(sk[1:] != sk[:-1])[0] + 1)) if n else np.zeros(0, dtype=np.int64)
+    rank = np.arange(n) - np.repeat(first, np.diff(np.concatenate((first, [n])))) if n else np.zeros(0, dtype=np.int64)
+    pseudo = np.empty(n, dtype=np.int64)
+    pseudo[order] = struct[order] * ways + rank % ways
+    perm = np.argsort(pseudo, kind='stable')
+    new_counts = np.bincount(pseudo, minlength=len(counts) * ways)
+    if _is_torch(x):
+        import torch
+        xs = x[torch.as_tensor(perm, device=x.device)]
+    else:
+        xs = np.asarray(x)[perm]
+    p = Pack(xs, None, ele_np[perm], new_counts)
+    p.spread, p.m_real, p.real_counts = ways, len(counts), counts
+    return p
+
+
+def resident(data, stress=False, spread_small=False):
     """{'energy': tuple|list, 'force': tuple|list} -> {'energy': Pack, 'force': Pack}: the caller-held handles that
     keep a descriptor set in HBM across calls.  The packs are snapshots: later changes of the source arrays do not
-    reach them (build new ones)."""
+    reach them (build new ones).  spread_small: energy sets of up to 64 structures become spread packs (spread_energy),
+    which the K* assembly of kernels/device.py understands; plain packs are what everything else expects."""
     from .utilities import list_to_tuple
     out = {}
     E = data.get("energy")
     if E is not None and len(E) > 0:
-        out["energy"] = pack_energy(list_to_tuple(E, mode='energy') if isinstance(E, list) else E)
+        E = list_to_tuple(E, mode='energy') if isinstance(E, list) else E
+        if spread_small and not isinstance(E, Pack) and len(E[2]) <= SPREAD_MAX_GROUPS:
+            out["energy"] = spread_energy(E)      # prediction-side packs only: see spread_energy
+        else:
+            out["energy"] = pack_energy(E)
     F = data.get("force")
     if F is not None and len(F) > 0:
         out["force"] = pack_force(list_to_tuple(F, stress=stress) if isinstance(F, list) else F)

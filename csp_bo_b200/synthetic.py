@@ -23,7 +23,16 @@ def _base():
     return _cache["big"]
 
 
-def force_set(n_atoms, seed=0, single_element=False):
+def _mix(d):
+    """Fixed non-negative [24, d] mixing matrix: descriptors of another length d (e.g. 50 = AgI.json's nmax = lmax = 4,
+    90 = nmax = lmax = 5; SO3.py:205) with the group sizes, species and positive cosines of the X1_big rows."""
+    key = ("mix", d)
+    if key not in _cache:
+        _cache[key] = np.random.default_rng(1234 + d).uniform(0.0, 1.0, size=(24, d)) / np.sqrt(24.0)
+    return _cache[key]
+
+
+def force_set(n_atoms, seed=0, single_element=False, d=24):
     """Stacked force tuple (X, dXdR, ELE, indices) with `n_atoms` groups (3*n_atoms force rows)."""
     x, dx, ele, counts = _base()
     off = np.concatenate(([0], np.cumsum(counts)))
@@ -33,6 +42,9 @@ def force_set(n_atoms, seed=0, single_element=False):
     fac = np.exp(rng.normal(0.0, 0.05, size=len(rows)))
     X = x[rows] * fac[:, None]
     dX = dx[rows] * fac[:, None, None]
+    if d != 24:
+        M = _mix(d)
+        X, dX = X @ M, np.einsum("nfk,fd->ndk", dX, M)
     E = np.full(len(rows), 14, dtype=np.int32) if single_element else ele[rows].astype(np.int32)
     return (np.ascontiguousarray(X), np.ascontiguousarray(dX), E, [int(c) for c in counts[pick]])
 

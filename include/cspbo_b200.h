@@ -335,6 +335,11 @@ int cspbo_so3_compute(cspbo_so3 *h, int n_atoms, const double *positions, const 
                       const int *pbc, int stress, int *n_seq, int *n_coefs);
 /* Copy the results of the last compute to HOST buffers: x[n,nc], dxdr[n_seq,nc,3], rdxdr[n_seq,nc,3,3]
  * (NULL to skip; needs stress=1), seq[n_seq,2] (int64). */
+/* The results of the last cspbo_so3_compute where they are: DEVICE pointers to x [n_atoms, n_coefs],
+ * dxdr [n_seq, n_coefs, 3] and rdxdr [n_seq, n_coefs, 3, 3] (null unless computed with stress), owned by the handle
+ * and valid until its next compute / destroy.  Lets the MD path (gaussianprocess.py:335-351) pack K* without a round
+ * trip of the derivatives through the host. */
+int cspbo_so3_device_ptrs(const cspbo_so3 *h, double **x, double **dxdr, double **rdxdr);
 int cspbo_so3_fetch(const cspbo_so3 *h, double *x, double *dxdr, double *rdxdr, long long *seq);
 
 #ifdef __cplusplus
