@@ -101,6 +101,30 @@ def test_gpu_descriptor_larger_cell_vs_oracle():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("pbc", [(True, True, True), (True, False, True), (False, False, False)])
+def test_gpu_neighbour_cells_unwrapped_positions_and_mixed_pbc(pbc):
+    """The linked-cell neighbour search of csrc/so3.cu: atoms far outside the unit cell (wrap shifts), a triclinic cell with
+    one axis thinner than rcut (several images of one cell) and non-periodic axes, against the oracle's plain image loop;
+    `seq` must come out identical (same pair order), the descriptors within 1e-10."""
+    from csp_bo_b200.SO3 import SO3
+    from oracle import so3_reference as so
+    rng = np.random.default_rng(11)
+    cell = np.array([[7.9, 0.0, 0.0], [1.1, 3.1, 0.0], [-0.7, 0.9, 9.6]])       # heights ~7.9, 3.1 (< rcut), 9.6
+    frac = rng.uniform(0, 1, (40, 3))
+    frac += rng.integers(-2, 3, size=(40, 3))                                    # some atoms lie cells away from the origin
+    pos = frac @ cell
+    num = rng.choice([8, 78], size=40)
+    st = so.Structure(pos, num, cell, pbc=list(pbc))
+    ref = so.so3_calculate(st, nmax=3, lmax=2, rcut=3.6, alpha=2.0, stress=True)
+    d = SO3(nmax=3, lmax=2, rcut=3.6, alpha=2.0, derivative=True, stress=True).calculate(st)
+    assert np.array_equal(d["seq"], ref["seq"])
+    for k in ("x", "dxdr", "rdxdr"):
+        assert max_norm_err(d[k], ref[k]) < 1e-10, k
+    dev = SO3(nmax=3, lmax=2, rcut=3.6, alpha=2.0, derivative=True, stress=True).calculate_device(st)
+    assert np.array_equal(dev["seq"], ref["seq"]) and max_norm_err(dev["dxdr"].cpu().numpy(), ref["dxdr"]) < 1e-10
+
+
+@pytest.mark.gpu
 def test_full_pipeline_descriptor_to_forces(oracle_built):
     """Structures -> SO3 (GPU) -> training tuples -> GaussianProcess.fit -> predict_structure, against the
     same chain on the CPU oracle (NumPy SO3 + reference C++ kernels + SciPy)."""
