@@ -88,6 +88,7 @@ SIGNATURES = {
     "cspbo_so3_compute": [c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
     "cspbo_so3_device_ptrs": [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)],
     "cspbo_so3_fetch": [c_vp, c_vp, c_vp, c_vp, c_vp],
+    "cspbo_lj_compute": [c_int, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp],
     "cspbo_gp_add_noise": [c_vp, c_int, c_int, c_dbl, c_dbl],
     "cspbo_gp_cholesky_solve": [c_vp, c_int, c_vp, c_int, ctypes.POINTER(c_dbl)],
     "cspbo_gp_cho_solve": [c_vp, c_int, c_vp, c_int],

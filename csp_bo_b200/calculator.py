@@ -89,3 +89,56 @@ class GPR(_Base):
         if peratom:
             return self.results["energy"] / len(self.results["forces"])
         return self.results["energy"]
+
+
+class LJ():
+    """Pairwise shifted Lennard-Jones base potential (reference cspbo/calculator.py:68-177, which copies ase's `lj.py`):
+    `calculate(atoms)` -> (energy, forces [n,3], stress [n,6] | None) that the GP subtracts from its training targets and
+    adds back to its predictions (gaussianprocess.py:457-462,686-692).  Same constructor dictionary, __str__,
+    load_from_dict and save_dict; the pair sums run on the GPU (cspbo_lj_compute: linked-cell neighbour search + one
+    kernel) and ase is not needed."""
+
+    def __init__(self, parameters=None):
+        _parameters = {'name': 'LJ', 'rc': 5.0, 'sigma': 1.0, 'epsilon': 1.0}
+        if parameters is not None:
+            _parameters.update(parameters)
+        self.load_from_dict(_parameters)
+
+    def __str__(self):
+        return "LJ(eps: {:.3f}, sigma: {:.3f}, cutoff: {:.3f})".format(self.epsilon, self.sigma, self.rc)
+
+    def load_from_dict(self, dict0):
+        self._parameters = dict0
+        self.name = self._parameters["name"]
+        self.epsilon = self._parameters["epsilon"]
+        self.sigma = self._parameters["sigma"]
+        self.rc = self._parameters["rc"]
+
+    def save_dict(self):
+        return self._parameters
+
+    def calculate(self, atoms):
+        import ctypes
+        import numpy as np
+        from . import _lib
+        c_vp = ctypes.c_void_p
+        pos = np.ascontiguousarray(atoms.positions, dtype=np.float64)
+        cell = np.ascontiguousarray(np.asarray(atoms.get_cell()), dtype=np.float64)
+        pbc = np.broadcast_to(np.asarray(atoms.pbc), (3,)).astype(np.int32)
+        periodic = np.linalg.matrix_rank(cell) == 3          # ase: atoms.number_of_lattice_vectors == 3
+        if not periodic:                                     # a molecule: any non-singular frame, no images
+            cell_s, pbc = np.eye(3), np.zeros(3, dtype=np.int32)
+        else:
+            cell_s = cell
+        n = len(pos)
+        e, f, s = np.zeros(n), np.zeros((n, 3)), np.zeros((n, 3, 3))
+        _lib.check(_lib.load().cspbo_lj_compute(n, c_vp(pos.ctypes.data), c_vp(np.ascontiguousarray(cell_s).ctypes.data),
+                                                c_vp(np.ascontiguousarray(pbc).ctypes.data), float(self.rc), float(self.sigma),
+                                                float(self.epsilon), c_vp(e.ctypes.data), c_vp(f.ctypes.data), c_vp(s.ctypes.data)))
+        stress = None
+        if periodic:
+            # ase.constraints.full_3x3_to_voigt_6_stress: (xx, yy, zz, yz, xz, xy), off-diagonals symmetrised
+            voigt = np.stack((s[:, 0, 0], s[:, 1, 1], s[:, 2, 2], (s[:, 1, 2] + s[:, 2, 1]) / 2, (s[:, 0, 2] + s[:, 2, 0]) / 2,
+                              (s[:, 0, 1] + s[:, 1, 0]) / 2), axis=1)
+            stress = voigt / abs(np.linalg.det(cell))
+        return float(e.sum()), f, stress

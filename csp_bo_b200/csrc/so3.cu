@@ -401,6 +401,108 @@ struct cspbo_so3 {
     double *d_x = nullptr, *d_dxdr = nullptr, *d_rdxdr = nullptr;
 };
 
+// All (i, j, image) pairs with 0 < |r_j + o.cell - r_i| < rcut in (i, j, o) order (SO3.py:317-359; also the neighbour
+// list of the LJ base potential, calculator.py:131-133).
+struct Pair { int i, j; int o[3]; double rel[3]; };
+
+static int neighbour_pairs(int n_atoms, const double *pos, const double *cell, const int *pbc, double rcut, std::vector<Pair> &pairs)
+{
+    // ---- neighbour pairs (SO3.py:317-359): |r_j + offset.cell - r_i| < rcut, zero-offset self excluded
+    double inv[9];
+    {
+        const double *c = cell;
+        const double det = c[0] * (c[4] * c[8] - c[5] * c[7]) - c[1] * (c[3] * c[8] - c[5] * c[6]) + c[2] * (c[3] * c[7] - c[4] * c[6]);
+        if (fabs(det) < 1e-300) { set_error("neighbour search: singular cell"); return CSPBO_E_ARG; }
+        inv[0] = (c[4] * c[8] - c[5] * c[7]) / det; inv[1] = (c[2] * c[7] - c[1] * c[8]) / det; inv[2] = (c[1] * c[5] - c[2] * c[4]) / det;
+        inv[3] = (c[5] * c[6] - c[3] * c[8]) / det; inv[4] = (c[0] * c[8] - c[2] * c[6]) / det; inv[5] = (c[2] * c[3] - c[0] * c[5]) / det;
+        inv[6] = (c[3] * c[7] - c[4] * c[6]) / det; inv[7] = (c[1] * c[6] - c[0] * c[7]) / det; inv[8] = (c[0] * c[4] - c[1] * c[3]) / det;
+    }
+    // fractional coordinates and the cell heights along the reciprocal directions
+    double hgt[3];
+    for (int k = 0; k < 3; k++) hgt[k] = 1.0 / sqrt(inv[k] * inv[k] + inv[3 + k] * inv[3 + k] + inv[6 + k] * inv[6 + k]);
+    std::vector<double> frac((size_t)std::max(n_atoms, 1) * 3);
+    for (int a = 0; a < n_atoms; a++)
+        for (int k = 0; k < 3; k++)
+            frac[(size_t)a * 3 + k] = pos[3 * a] * inv[k] + pos[3 * a + 1] * inv[3 + k] + pos[3 * a + 2] * inv[6 + k];
+    pairs.clear();
+    const double rc2 = rcut * rcut;
+    // Linked cells in fractional coordinates (a 192-atom structure: 0.53 ms for the all-pairs x images scan, 0.05 ms
+    // with cells).  Along a periodic axis the atoms are wrapped into [0,1) (wrap shift w) and binned into nc cells of
+    // thickness >= rcut where the cell is thick enough, else one cell searched over several images; a non-periodic axis
+    // is one cell without images.  Candidates of atom i are then put in (j, offset) order, which keeps the pair list --
+    // and with it the summation order of the kernels -- exactly what the plain double loop over (i, j, offset) gives.
+    int nc[3], reach[3];
+    for (int k = 0; k < 3; k++) {
+        if (!pbc[k]) { nc[k] = 1; reach[k] = 0; continue; }
+        nc[k] = std::max(1, std::min(64, (int)floor(hgt[k] / rcut)));
+        reach[k] = (int)ceil(rcut / (hgt[k] / nc[k]) - 1e-12);
+        if (reach[k] < 1) reach[k] = 1;
+    }
+    std::vector<int> wrap((size_t)std::max(n_atoms, 1) * 3, 0), cidx((size_t)std::max(n_atoms, 1) * 3, 0);
+    std::vector<int> cell_head((size_t)nc[0] * nc[1] * nc[2] + 1, 0), cell_atoms((size_t)std::max(n_atoms, 1));
+    for (int a = 0; a < n_atoms; a++) {
+        for (int k = 0; k < 3; k++) {
+            if (!pbc[k]) continue;
+            const double f = frac[(size_t)a * 3 + k];
+            const int w = (int)floor(f);
+            wrap[(size_t)a * 3 + k] = w;
+            int c = (int)((f - w) * nc[k]);
+            cidx[(size_t)a * 3 + k] = std::min(std::max(c, 0), nc[k] - 1);
+        }
+        cell_head[(size_t)((cidx[(size_t)a * 3] * nc[1] + cidx[(size_t)a * 3 + 1]) * nc[2] + cidx[(size_t)a * 3 + 2]) + 1]++;
+    }
+    for (size_t c = 1; c < cell_head.size(); c++) cell_head[c] += cell_head[c - 1];
+    {
+        std::vector<int> fill(cell_head.begin(), cell_head.end() - 1);
+        for (int a = 0; a < n_atoms; a++)
+            cell_atoms[(size_t)fill[(size_t)((cidx[(size_t)a * 3] * nc[1] + cidx[(size_t)a * 3 + 1]) * nc[2] + cidx[(size_t)a * 3 + 2])]++] = a;
+    }
+    struct Cand { int j, o[3]; double rel[3]; };
+    std::vector<Cand> cand;
+    for (int i = 0; i < n_atoms; i++) {
+        cand.clear();
+        const int *ci = &cidx[(size_t)i * 3], *wi = &wrap[(size_t)i * 3];
+        for (int da = -reach[0]; da <= reach[0]; da++)
+            for (int db = -reach[1]; db <= reach[1]; db++)
+                for (int dc = -reach[2]; dc <= reach[2]; dc++) {
+                    const int dd[3] = {da, db, dc};
+                    int cc[3], sh[3];
+                    for (int k = 0; k < 3; k++) {
+                        const int t = ci[k] + dd[k];
+                        sh[k] = (t >= 0) ? t / nc[k] : -((-t + nc[k] - 1) / nc[k]);     // floor division
+                        cc[k] = t - sh[k] * nc[k];
+                    }
+                    const size_t cell_id = (size_t)((cc[0] * nc[1] + cc[1]) * nc[2] + cc[2]);
+                    for (int q = cell_head[cell_id]; q < cell_head[cell_id + 1]; q++) {
+                        const int j = cell_atoms[(size_t)q];
+                        const int *wj = &wrap[(size_t)j * 3];
+                        // image offset relative to the UNWRAPPED positions: r = pos_j + o.cell - pos_i
+                        const int o[3] = {sh[0] - wj[0] + wi[0], sh[1] - wj[1] + wi[1], sh[2] - wj[2] + wi[2]};
+                        double r[3];
+                        for (int k = 0; k < 3; k++)
+                            r[k] = pos[3 * j + k] + o[0] * cell[k] + o[1] * cell[3 + k] + o[2] * cell[6 + k] - pos[3 * i + k];
+                        const double d2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+                        if (d2 < rc2 && d2 > 1e-24) cand.push_back({j, {o[0], o[1], o[2]}, {r[0], r[1], r[2]}});
+                    }
+                }
+        std::sort(cand.begin(), cand.end(), [](const Cand &x, const Cand &y) {
+            if (x.j != y.j) return x.j < y.j;
+            if (x.o[0] != y.o[0]) return x.o[0] < y.o[0];
+            if (x.o[1] != y.o[1]) return x.o[1] < y.o[1];
+            return x.o[2] < y.o[2];
+        });
+        for (size_t q = 0; q < cand.size(); q++) {
+            // when a periodic axis has fewer cells than 2*reach+1 the same (j, offset) is met through several cell shifts
+            if (q > 0 && cand[q].j == cand[q - 1].j && cand[q].o[0] == cand[q - 1].o[0] && cand[q].o[1] == cand[q - 1].o[1] &&
+                cand[q].o[2] == cand[q - 1].o[2])
+                continue;
+            const Cand &c = cand[q];
+            pairs.push_back({i, c.j, {c.o[0], c.o[1], c.o[2]}, {c.rel[0], c.rel[1], c.rel[2]}});
+        }
+    }
+    return CSPBO_OK;
+}
+
 extern "C" int cspbo_so3_create(int nmax, int lmax, double rcut, double alpha, int cutoff, int weight_on, cspbo_so3 **out)
 {
     if (!out) { set_error("so3_create: null"); return CSPBO_E_ARG; }
@@ -467,99 +569,10 @@ extern "C" int cspbo_so3_compute(cspbo_so3 *h, int n_atoms, const double *pos, c
     static const bool trace = getenv("CSPBO_SO3_TRACE") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
-    // ---- neighbour pairs (SO3.py:317-359): |r_j + offset.cell - r_i| < rcut, zero-offset self excluded
-    double inv[9];
-    {
-        const double *c = cell;
-        const double det = c[0] * (c[4] * c[8] - c[5] * c[7]) - c[1] * (c[3] * c[8] - c[5] * c[6]) + c[2] * (c[3] * c[7] - c[4] * c[6]);
-        if (fabs(det) < 1e-300) { set_error("so3_compute: singular cell"); return CSPBO_E_ARG; }
-        inv[0] = (c[4] * c[8] - c[5] * c[7]) / det; inv[1] = (c[2] * c[7] - c[1] * c[8]) / det; inv[2] = (c[1] * c[5] - c[2] * c[4]) / det;
-        inv[3] = (c[5] * c[6] - c[3] * c[8]) / det; inv[4] = (c[0] * c[8] - c[2] * c[6]) / det; inv[5] = (c[2] * c[3] - c[0] * c[5]) / det;
-        inv[6] = (c[3] * c[7] - c[4] * c[6]) / det; inv[7] = (c[1] * c[6] - c[0] * c[7]) / det; inv[8] = (c[0] * c[4] - c[1] * c[3]) / det;
-    }
-    // fractional coordinates and the cell heights along the reciprocal directions
-    double hgt[3];
-    for (int k = 0; k < 3; k++) hgt[k] = 1.0 / sqrt(inv[k] * inv[k] + inv[3 + k] * inv[3 + k] + inv[6 + k] * inv[6 + k]);
-    std::vector<double> frac((size_t)std::max(n_atoms, 1) * 3);
-    for (int a = 0; a < n_atoms; a++)
-        for (int k = 0; k < 3; k++)
-            frac[(size_t)a * 3 + k] = pos[3 * a] * inv[k] + pos[3 * a + 1] * inv[3 + k] + pos[3 * a + 2] * inv[6 + k];
-    struct Pair { int i, j; int o[3]; double rel[3]; };
     std::vector<Pair> pairs;
-    const double rc2 = P.rcut * P.rcut;
-    // Linked cells in fractional coordinates (a 192-atom structure: 0.53 ms for the all-pairs x images scan, 0.05 ms
-    // with cells).  Along a periodic axis the atoms are wrapped into [0,1) (wrap shift w) and binned into nc cells of
-    // thickness >= rcut where the cell is thick enough, else one cell searched over several images; a non-periodic axis
-    // is one cell without images.  Candidates of atom i are then put in (j, offset) order, which keeps the pair list --
-    // and with it the summation order of the kernels -- exactly what the plain double loop over (i, j, offset) gives.
-    int nc[3], reach[3];
-    for (int k = 0; k < 3; k++) {
-        if (!pbc[k]) { nc[k] = 1; reach[k] = 0; continue; }
-        nc[k] = std::max(1, std::min(64, (int)floor(hgt[k] / P.rcut)));
-        reach[k] = (int)ceil(P.rcut / (hgt[k] / nc[k]) - 1e-12);
-        if (reach[k] < 1) reach[k] = 1;
-    }
-    std::vector<int> wrap((size_t)std::max(n_atoms, 1) * 3, 0), cidx((size_t)std::max(n_atoms, 1) * 3, 0);
-    std::vector<int> cell_head((size_t)nc[0] * nc[1] * nc[2] + 1, 0), cell_atoms((size_t)std::max(n_atoms, 1));
-    for (int a = 0; a < n_atoms; a++) {
-        for (int k = 0; k < 3; k++) {
-            if (!pbc[k]) continue;
-            const double f = frac[(size_t)a * 3 + k];
-            const int w = (int)floor(f);
-            wrap[(size_t)a * 3 + k] = w;
-            int c = (int)((f - w) * nc[k]);
-            cidx[(size_t)a * 3 + k] = std::min(std::max(c, 0), nc[k] - 1);
-        }
-        cell_head[(size_t)((cidx[(size_t)a * 3] * nc[1] + cidx[(size_t)a * 3 + 1]) * nc[2] + cidx[(size_t)a * 3 + 2]) + 1]++;
-    }
-    for (size_t c = 1; c < cell_head.size(); c++) cell_head[c] += cell_head[c - 1];
     {
-        std::vector<int> fill(cell_head.begin(), cell_head.end() - 1);
-        for (int a = 0; a < n_atoms; a++)
-            cell_atoms[(size_t)fill[(size_t)((cidx[(size_t)a * 3] * nc[1] + cidx[(size_t)a * 3 + 1]) * nc[2] + cidx[(size_t)a * 3 + 2])]++] = a;
-    }
-    struct Cand { int j, o[3]; double rel[3]; };
-    std::vector<Cand> cand;
-    for (int i = 0; i < n_atoms; i++) {
-        cand.clear();
-        const int *ci = &cidx[(size_t)i * 3], *wi = &wrap[(size_t)i * 3];
-        for (int da = -reach[0]; da <= reach[0]; da++)
-            for (int db = -reach[1]; db <= reach[1]; db++)
-                for (int dc = -reach[2]; dc <= reach[2]; dc++) {
-                    const int dd[3] = {da, db, dc};
-                    int cc[3], sh[3];
-                    for (int k = 0; k < 3; k++) {
-                        const int t = ci[k] + dd[k];
-                        sh[k] = (t >= 0) ? t / nc[k] : -((-t + nc[k] - 1) / nc[k]);     // floor division
-                        cc[k] = t - sh[k] * nc[k];
-                    }
-                    const size_t cell_id = (size_t)((cc[0] * nc[1] + cc[1]) * nc[2] + cc[2]);
-                    for (int q = cell_head[cell_id]; q < cell_head[cell_id + 1]; q++) {
-                        const int j = cell_atoms[(size_t)q];
-                        const int *wj = &wrap[(size_t)j * 3];
-                        // image offset relative to the UNWRAPPED positions: r = pos_j + o.cell - pos_i
-                        const int o[3] = {sh[0] - wj[0] + wi[0], sh[1] - wj[1] + wi[1], sh[2] - wj[2] + wi[2]};
-                        double r[3];
-                        for (int k = 0; k < 3; k++)
-                            r[k] = pos[3 * j + k] + o[0] * cell[k] + o[1] * cell[3 + k] + o[2] * cell[6 + k] - pos[3 * i + k];
-                        const double d2 = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-                        if (d2 < rc2 && d2 > 1e-24) cand.push_back({j, {o[0], o[1], o[2]}, {r[0], r[1], r[2]}});
-                    }
-                }
-        std::sort(cand.begin(), cand.end(), [](const Cand &x, const Cand &y) {
-            if (x.j != y.j) return x.j < y.j;
-            if (x.o[0] != y.o[0]) return x.o[0] < y.o[0];
-            if (x.o[1] != y.o[1]) return x.o[1] < y.o[1];
-            return x.o[2] < y.o[2];
-        });
-        for (size_t q = 0; q < cand.size(); q++) {
-            // when a periodic axis has fewer cells than 2*reach+1 the same (j, offset) is met through several cell shifts
-            if (q > 0 && cand[q].j == cand[q - 1].j && cand[q].o[0] == cand[q - 1].o[0] && cand[q].o[1] == cand[q - 1].o[1] &&
-                cand[q].o[2] == cand[q - 1].o[2])
-                continue;
-            const Cand &c = cand[q];
-            pairs.push_back({i, c.j, {c.o[0], c.o[1], c.o[2]}, {c.rel[0], c.rel[1], c.rel[2]}});
-        }
+        const int rcn = neighbour_pairs(n_atoms, pos, cell, pbc, P.rcut, pairs);
+        if (rcn) return rcn;
     }
     // loop order above is already (i, j, offset): the deterministic summation order of K2 / K3
     const int np = (int)pairs.size();
@@ -690,5 +703,80 @@ extern "C" int cspbo_so3_fetch(const cspbo_so3 *h, double *x, double *dxdr, doub
         if (!h->stress) { set_error("so3_fetch: stress terms were not computed"); return CSPBO_E_ARG; }
         CSPBO_CUDA(cudaMemcpy(rdxdr, h->d_rdxdr, (size_t)h->n_seq * h->ncoefs * 9 * 8, cudaMemcpyDeviceToHost));
     }
+    return CSPBO_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// LJ base potential (reference cspbo/calculator.py:68-177, itself ase's pairwise LJ): energy, forces and per-atom
+// 3x3 stress sums of a shifted 12-6 potential, subtracted from the training targets / added to the predictions of the
+// GP (gaussianprocess.py:457-462,686-692).  One thread per atom over its neighbour pairs, in pair order.
+// ------------------------------------------------------------------------------------------
+namespace cspbo {
+__global__ void lj_atom_kernel(int n_atoms, const int *__restrict__ pair_start, const double *__restrict__ rel, double sigma,
+                               double epsilon, double e0, double *__restrict__ energies, double *__restrict__ forces,
+                               double *__restrict__ stresses)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_atoms) return;
+    double e = 0.0, f[3] = {0.0, 0.0, 0.0}, st[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = pair_start[i]; p < pair_start[i + 1]; p++) {
+        const double d[3] = {rel[3 * p], rel[3 * p + 1], rel[3 * p + 2]};          // pointing towards the neighbour
+        const double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        const double s2 = sigma * sigma / r2, c6 = s2 * s2 * s2, c12 = c6 * c6;
+        e += 0.5 * (4.0 * epsilon * (c12 - c6) - e0);
+        const double g = -24.0 * epsilon * (2.0 * c12 - c6) / r2;
+        for (int a = 0; a < 3; a++) {
+            f[a] += g * d[a];
+            for (int b = 0; b < 3; b++) st[3 * a + b] += 0.5 * g * d[a] * d[b];
+        }
+    }
+    energies[i] = e;
+    for (int a = 0; a < 3; a++) forces[3 * i + a] = f[a];
+    for (int a = 0; a < 9; a++) stresses[9 * i + a] = st[a];
+}
+}  // namespace cspbo
+
+extern "C" int cspbo_lj_compute(int n_atoms, const double *pos, const double *cell, const int *pbc, double rc, double sigma,
+                                double epsilon, double *energies, double *forces, double *stresses)
+{
+    if (n_atoms < 0 || !pos || !cell || !pbc || !energies || !forces || !stresses || !(rc > 0) || !(sigma > 0)) {
+        set_error("lj_compute: bad argument");
+        return CSPBO_E_ARG;
+    }
+    if (n_atoms == 0) return CSPBO_OK;
+    std::vector<Pair> pairs;
+    int rc_ = neighbour_pairs(n_atoms, pos, cell, pbc, rc, pairs);
+    if (rc_) return rc_;
+    const int np = (int)pairs.size();
+    std::vector<int> pair_start((size_t)n_atoms + 1, 0);
+    std::vector<double> rel((size_t)std::max(np, 1) * 3);
+    for (int p = 0; p < np; p++) {
+        pair_start[(size_t)pairs[(size_t)p].i + 1]++;
+        for (int k = 0; k < 3; k++) rel[(size_t)p * 3 + k] = pairs[(size_t)p].rel[k];
+    }
+    for (int i = 0; i < n_atoms; i++) pair_start[(size_t)i + 1] += pair_start[(size_t)i];
+    int *d_ps = nullptr;
+    double *d_rel = nullptr, *d_out = nullptr;
+    std::vector<void *> tmp;
+    auto A = [&](size_t bytes, void **q) { int r = dev_alloc_cached(bytes, q); if (!r) tmp.push_back(*q); return r; };
+    auto cleanup = [&]() { for (void *q : tmp) dev_free_cached(q); };
+    if ((rc_ = A(((size_t)n_atoms + 1) * 4, (void **)&d_ps)) || (rc_ = A(rel.size() * 8, (void **)&d_rel)) ||
+        (rc_ = A((size_t)n_atoms * 13 * 8, (void **)&d_out))) { cleanup(); return rc_; }
+    cudaError_t e = cudaMemcpyAsync(d_ps, pair_start.data(), ((size_t)n_atoms + 1) * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rel, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const double sr6 = pow(sigma / rc, 6.0);
+        lj_atom_kernel<<<(n_atoms + 127) / 128, 128>>>(n_atoms, d_ps, d_rel, sigma, epsilon, 4.0 * epsilon * (sr6 * sr6 - sr6), d_out,
+                                                          d_out + n_atoms, d_out + (size_t)n_atoms * 4);
+        g_launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(energies, d_out, (size_t)n_atoms * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(forces, d_out + n_atoms, (size_t)n_atoms * 3 * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(stresses, d_out + (size_t)n_atoms * 4, (size_t)n_atoms * 9 * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    cleanup();
+    if (e != cudaSuccess) { set_error("lj_compute: %s", cudaGetErrorString(e)); return CSPBO_E_CUDA; }
     return CSPBO_OK;
 }

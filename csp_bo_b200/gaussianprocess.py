@@ -356,7 +356,11 @@ class GaussianProcess():
         else:
             raise NotImplementedError("unknow descriptors {:s}".format(str(dict0["descriptor"].get("_type"))))
         if "base_potential" in dict0:
-            raise NotImplementedError("base potentials (LJ) live in the reference's calculator.py")
+            from .calculator import LJ
+            if dict0["base_potential"]["name"] != "LJ":
+                raise NotImplementedError("unknow base potential {:s}".format(str(dict0["base_potential"]["name"])))
+            self.base_potential = LJ()
+            self.base_potential.load_from_dict(dict0["base_potential"])
         self.kernel.device = device
         self.noise_e = dict0["noise"]["energy"]
         self.f_coef = dict0["noise"]["f_coef"]
@@ -382,6 +386,61 @@ class GaussianProcess():
                 pts_to_add["force"].append((d['x'][_i, :], d['dxdr'][ids], force[fid], ele[_i]))
             pts_to_add["db"].append((atoms, energy, force, row["energy_in"], row["force_in"]))
         self.set_train_pts(pts_to_add, "w")
+
+    def add_structure(self, data, N_max=10, tol_e_var=1.2, tol_f_var=1.2, add_force=True):
+        """Active-learning selection (gaussianprocess.py:673-744): predict (E, F) and their standard deviations for the
+        structure `data = (atoms, energy, force)` with the current model -- K*, K*.alpha and diag(k) - diag(K* K^-1 K*^T)
+        all on the device -- and propose its energy when E_std > tol_e_var * noise_e, and up to N_max of its forces whose
+        std exceeds tol_f_var * noise_f and whose descriptor is new among those already picked (utilities.new_pt).
+        Returns (pts_to_add, N_pts, errors) like the reference; the caller feeds pts_to_add to set_train_pts(.., 'a+')."""
+        from .utilities import convert_train_data, new_pt
+        tol_e_var *= self.noise_e
+        tol_f_var *= self.noise_f
+        pts_to_add = {"energy": [], "force": [], "db": []}
+        (atoms, energy, force) = data
+        if self.base_potential is not None:
+            energy_off, force_off, _ = self.compute_base_potential(atoms)
+        else:
+            energy_off, force_off = 0, np.zeros((len(atoms), 3))
+        energy = energy - energy_off
+        force = np.asarray(force, dtype=np.float64) - force_off
+        my_data = convert_train_data([(atoms, energy, force)], self.descriptor)
+        if self.alpha_ is not None:
+            E, E1, E_std, F, F1, F_std = self.validate_data(my_data, return_std=True)
+            E_std = E_std[0]
+            F_std = F_std.reshape((len(atoms), 3))
+        else:
+            E = E1 = [energy]
+            F = F1 = force.flatten()
+            E_std = 2 * tol_e_var
+            F_std = 2 * tol_f_var * np.ones((len(atoms), 3))
+        energy_in = bool(E_std > tol_e_var)
+        if energy_in:
+            pts_to_add["energy"] = my_data["energy"]
+        force_in = []
+        if add_force:
+            xs_added = []
+            for f_id in range(len(atoms)):
+                include = False
+                if np.max(F_std[f_id]) > tol_f_var:
+                    X = my_data["energy"][0][0][f_id]
+                    _ele = my_data["energy"][0][2][f_id]
+                    include = len(xs_added) == 0 or new_pt((X, _ele), xs_added)
+                if include:
+                    force_in.append(f_id)
+                    xs_added.append((X, _ele))
+                    pts_to_add["force"].append(my_data["force"][f_id])
+                if len(force_in) == N_max:
+                    break
+        N_pts = int(energy_in) + len(force_in)
+        if N_pts > 0:
+            pts_to_add["db"].append((atoms, energy, force, energy_in, force_in))
+        errors = (E[0] + energy_off, E1[0] + energy_off, E_std, F + force_off.flatten(), F1 + force_off.flatten(), F_std)
+        return pts_to_add, N_pts, errors
+
+    def compute_base_potential(self, atoms):
+        """(energy, forces, stress) offsets of the base potential (gaussianprocess.py:746-751)."""
+        return self.base_potential.calculate(atoms)
 
     # ------------------------------------------------------------------ prediction
     def predict(self, X, stress=False, total_E=False, return_std=False, return_cov=False):

@@ -43,6 +43,21 @@ def tuple_to_list(data, mode='force'):
     return out
 
 
+def new_pt(data, Refs, d_tol=1e-1, eps=1e-8):
+    """Is the descriptor (X, ele) farther than d_tol (in 1 - cos^2) from every same-species reference?
+    (cspbo/utilities.py:32-42, used by the active-learning selection of add_structure; the reference's
+    `norm(X1 + eps)` is kept as written)."""
+    (X, ele) = data
+    X = X / (np.linalg.norm(X) + eps)
+    for (X1, ele1) in Refs:
+        if ele1 == ele:
+            X1 = X1 / np.linalg.norm(X1 + eps)
+            d = X @ X1.T
+            if 1 - d ** 2 < d_tol:
+                return False
+    return True
+
+
 # ---------------------------------------------------------------------------------------------
 # metrics printed by the reference's example scripts (cspbo/utilities.py:44-90)
 def rmse(true, predicted):

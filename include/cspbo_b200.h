@@ -342,6 +342,12 @@ int cspbo_so3_compute(cspbo_so3 *h, int n_atoms, const double *positions, const 
 int cspbo_so3_device_ptrs(const cspbo_so3 *h, double **x, double **dxdr, double **rdxdr);
 int cspbo_so3_fetch(const cspbo_so3 *h, double *x, double *dxdr, double *rdxdr, long long *seq);
 
+/* LJ base potential (reference cspbo/calculator.py:68-177): per-atom energies [n], forces [n,3] and 3x3 stress sums
+ * [n,9] (0.5 * sum_j f_ij (x) d_ij, not yet divided by the volume) of the shifted 12-6 potential with cutoff rc; host
+ * pointers in and out, neighbour search + one kernel inside. */
+int cspbo_lj_compute(int n_atoms, const double *pos, const double *cell, const int *pbc, double rc, double sigma,
+                     double epsilon, double *energies, double *forces, double *stresses);
+
 #ifdef __cplusplus
 }
 #endif

@@ -250,3 +250,69 @@ def test_predict_gemv_shapes(n, N):
     # deterministic: chunk partial sums are added in a fixed order
     again = gp.predict_mean(Ks.cuda(), al.cuda()).cpu().numpy()
     assert np.array_equal(got, again)
+
+
+def test_lj_base_potential_matches_reference_restatement():
+    """calculator.LJ (GPU pair sums) against the plain-Python restatement of calculator.py:117-177, plus F = -dE/dr."""
+    from csp_bo_b200.asedb import Structure
+    from csp_bo_b200.calculator import LJ
+    from oracle.lj_reference import lj_calculate
+    rng = np.random.default_rng(3)
+    cell = np.array([[5.1, 0.0, 0.0], [0.6, 4.7, 0.0], [-0.3, 0.4, 6.2]])
+    grid = np.array([(i, j, k) for i in range(2) for j in range(2) for k in range(3)], dtype=float) / [2, 2, 3]
+    pos = (grid + rng.normal(0, 0.02, grid.shape)) @ cell
+    st = Structure(pos, [29] * len(pos), cell)
+    lj = LJ({"rc": 4.5, "sigma": 2.3, "epsilon": 0.4})
+    assert str(lj) == "LJ(eps: 0.400, sigma: 2.300, cutoff: 4.500)" and lj.save_dict()["name"] == "LJ"
+    E, F, S = lj.calculate(st)
+    Er, Fr, Sr = lj_calculate(pos, cell, [True] * 3, sigma=2.3, epsilon=0.4, rc=4.5)
+    assert abs(E - Er) <= 1e-12 * abs(Er) and max_norm_err(F, Fr) < 1e-11 and max_norm_err(S, Sr) < 1e-11
+    h = 1e-5
+    for a, k in ((0, 0), (5, 2)):
+        p1, p2 = pos.copy(), pos.copy()
+        p1[a, k] += h; p2[a, k] -= h
+        fd = -(lj.calculate(Structure(p1, [29] * len(pos), cell))[0] - lj.calculate(Structure(p2, [29] * len(pos), cell))[0]) / (2 * h)
+        assert abs(fd - F[a, k]) < 1e-6 * max(1.0, abs(F[a, k]))
+
+
+def test_add_structure_selection(problem):
+    """Active-learning selection (gaussianprocess.py:673-744) on the device variance: thresholds, the N_max cap, the
+    new_pt filter, the errors tuple, and the base-potential offsets taken out of the targets and put back in `errors`."""
+    from csp_bo_b200.SO3 import SO3
+    from csp_bo_b200.asedb import Structure
+    from csp_bo_b200.calculator import LJ
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from csp_bo_b200.kernels import Dot_mb
+    from csp_bo_b200.utilities import convert_train_data, new_pt
+    rng = np.random.default_rng(8)
+    desc = SO3(nmax=3, lmax=3, rcut=3.5, alpha=2.0, derivative=True, stress=False)
+    cell = np.diag([5.2, 5.2, 7.8])
+    grid = np.array([(i, j, k) for i in range(2) for j in range(2) for k in range(3)], dtype=float) * 2.6
+
+    def struct(seed):
+        r = np.random.default_rng(seed)
+        return Structure(grid + r.normal(0, 0.15, grid.shape), [78, 8] * 6, cell)
+
+    train = [(struct(s), float(rng.normal(-3, 0.1)) * 12, rng.normal(0, 0.5, (12, 3))) for s in range(3)]
+    for base in (None, LJ({"rc": 4.0, "sigma": 2.0, "epsilon": 0.05})):
+        model = GaussianProcess(Dot_mb(para=[10.0, 0.1], zeta=2), descriptor=desc, base_potential=base, f_coef=10, noise_e=[0.01, 0.002, 0.1])
+        # before any fit: everything is proposed (alpha_ is None, gaussianprocess.py:698-702)
+        st, e, f = struct(11), -35.0, rng.normal(0, 0.5, (12, 3))
+        pts, n, errs = model.add_structure((st, e, f.copy()), N_max=4)
+        assert n == 5 and len(pts["energy"]) == 1 and len(pts["force"]) == 4 and pts["db"][0][3] is True
+        model.fit(convert_train_data(train, desc), show=False, opt=False)
+        pts, n, errs = model.add_structure((st, e, f.copy()), N_max=3, tol_e_var=1e-6, tol_f_var=1e-6)
+        assert len(pts["energy"]) == 1 and 1 <= len(pts["force"]) <= 3 and n == 1 + len(pts["force"])
+        picked = pts["db"][0][4]
+        X = pts["energy"][0][0]
+        for a, b in zip(picked[:-1], picked[1:]):            # every pick is new w.r.t. the earlier ones
+            assert new_pt((X[b], 78 if b % 2 == 0 else 8), [(X[a], 78 if a % 2 == 0 else 8)]) or (a % 2) != (b % 2)
+        E0, E1, E_std, F0, F1, F_std = errs
+        # the reference adds the TOTAL base-potential energy back onto the PER-ATOM energies (gaussianprocess.py:743): kept
+        off = model.compute_base_potential(st)[0] if base is not None else 0.0
+        assert abs(E0 - ((e - off) / 12 + off)) < 1e-9 and np.allclose(F0, f.flatten())
+        Ep, Fp, _, Es, Fs = model.predict_structure(st, stress=False, return_std=True)
+        assert abs(E1 - ((Ep - off) / 12 + off)) < 1e-7 * max(1.0, abs(Ep)) and np.allclose(F1, Fp.flatten(), atol=1e-7)
+        assert abs(E_std - Es) < 1e-7 and np.allclose(F_std, Fs, atol=1e-7)
+        pts, n, _ = model.add_structure((st, e, f.copy()), tol_e_var=1e9, tol_f_var=1e9)
+        assert n == 0 and pts == {"energy": [], "force": [], "db": []}
