@@ -28,7 +28,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
                        const struct TraceArgs *trace = nullptr);
 struct PanelArgs { long long ld; int nbw; long long row0_a, row0_b; };
 struct PassArgs { int npass, side; long long off; };
-struct TraceArgs { const double *alpha, *w; double *partial; long long ld, row0, col0; };
+struct TraceArgs { const double *alpha, *w; double *partial; long long ld, row0, col0; int packed; long long slab0; };
 
 // deterministic sum of the per-warp partial traces (fixed tree, one CTA)
 __global__ void trace_sum_kernel(const double *__restrict__ part, long long n, double *__restrict__ out, int accumulate)
@@ -386,8 +386,43 @@ extern "C" int cspbo_block_trace(const cspbo_block_desc *desc, const cspbo_pack 
     int rc = scratch_get(SCRATCH_GRAD, (size_t)nparts * sizeof(double), &sp);
     if (rc) return rc;
     CSPBO_CUDA(cudaMemsetAsync(sp, 0, (size_t)nparts * sizeof(double)));
-    const TraceArgs tr = {alpha, W, static_cast<double *>(sp), ldw, row0, col0};
+    const TraceArgs tr = {alpha, W, static_cast<double *>(sp), ldw, row0, col0, 0, 0};
     rc = build_block_device(d, a, b, 0, 0, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 1, nullptr, 0, -1, 0, 1, 0, 0, nullptr, nullptr, &tr);
+    if (rc) return rc;
+    trace_sum_kernel<<<1, 1024>>>(static_cast<const double *>(sp), nparts, result, accumulate);
+    g_launches++;
+    CSPBO_CUDA(cudaGetLastError());
+    return CSPBO_OK;
+}
+
+// The same for a SLAB of rows in packed (panel-layout) order: the A blocks [a_blk0, a_blk1) of pack a against all of
+// pack b, matrix row of packed position p = row0 + p * nc1 (column: col0 + q * nc2), Wslab = rows [slab_row0, ...) of
+// K^-1 in full (leading dimension ldw): what one rank contributes to the sharded hyper-gradient trace.
+extern "C" int cspbo_block_trace_slab(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b, const double *alpha,
+                                      const double *Wslab, long long ldw, long long row0, long long col0, long long slab_row0,
+                                      int a_blk0, int a_blk1, double *result, int accumulate)
+{
+    if (!desc || !a || !b || !alpha || !Wslab || !result) { set_error("block_trace_slab: null argument"); return CSPBO_E_ARG; }
+    cspbo_block_desc d = *desc;
+    if (d.family != CSPBO_RBF || !(d.l > 0.0)) { set_error("block_trace_slab: RBF blocks only"); return CSPBO_E_ARG; }
+    if (d.block < CSPBO_KEE || d.block > CSPBO_KFF || d.stress) { set_error("block_trace_slab: bad block"); return CSPBO_E_ARG; }
+    const int nc1 = d.block == CSPBO_KFF ? 3 : 0, nc2 = d.block == CSPBO_KEE ? 0 : 3;
+    if ((nc1 ? a->nc < 3 : a->nc != 0) || (nc2 ? b->nc < 3 : b->nc != 0)) { set_error("block_trace_slab: pack kinds do not match the block"); return CSPBO_E_ARG; }
+    if (a->row_classes != 1 || b->row_classes != 1) { set_error("block_trace_slab: packs with row_classes = 1 only"); return CSPBO_E_ARG; }
+    a_blk0 = std::max(a_blk0, 0); a_blk1 = std::min(a_blk1, (int)a->n_blocks);
+    if (row0 < 0 || col0 < 0 || slab_row0 > row0 + (long long)a_blk0 * 8 * std::max(nc1, 1)) { set_error("block_trace_slab: bad offsets"); return CSPBO_E_ARG; }
+    if (a_blk1 <= a_blk0 || b->m == 0) {
+        if (!accumulate) CSPBO_CUDA(cudaMemsetAsync(result, 0, sizeof(double)));
+        return CSPBO_OK;
+    }
+    d.with_grad = 1; d.use_tol = 0; d.symmetric = 0;
+    const long long nparts = (long long)(a_blk1 - a_blk0) * b->n_blocks * 4;
+    void *sp = nullptr;
+    int rc = scratch_get(SCRATCH_GRAD, (size_t)nparts * sizeof(double), &sp);
+    if (rc) return rc;
+    CSPBO_CUDA(cudaMemsetAsync(sp, 0, (size_t)nparts * sizeof(double)));
+    const TraceArgs tr = {alpha, Wslab, static_cast<double *>(sp), ldw, row0, col0, 1, slab_row0};
+    rc = build_block_device(d, a, b, 0, 0, nullptr, nullptr, 0, 0, 0, 0, 0, 0, 0, 1, nullptr, a_blk0, a_blk1, 0, 1, 0, 0, nullptr, nullptr, &tr);
     if (rc) return rc;
     trace_sum_kernel<<<1, 1024>>>(static_cast<const double *>(sp), nparts, result, accumulate);
     g_launches++;

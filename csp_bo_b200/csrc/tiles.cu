@@ -85,6 +85,10 @@ struct TileParams {
     const double *tr_alpha, *tr_w;
     double *tr_partial;
     long long tr_ld, tr_row0, tr_col0;
+    // tr_packed (sharded LML gradient): rows / columns are PACKED positions (r = tr_row0 + (block*8 + slot) * NC1 + k, the
+    // panel-layout order) and tr_w is a slab of full rows of K^-1 starting at matrix row tr_slab0: w = a_r a_c - tr_w[(r - tr_slab0) * tr_ld + c]
+    int tr_packed;
+    long long tr_slab0;
     long long si, sk, sj, sl;  // out index = i*si + k*sk + j*sj + l*sl
     // sharded symmetric build (one process per GPU): rank r owns the A blocks a with a % nranks == r
     // and stores row block a at local block a / nranks of outs[r]; mirrored tiles are stored
@@ -492,14 +496,14 @@ block_tile_kernel(const TileParams p)
                 if (gj < 0) continue;
 #pragma unroll
                 for (int k = 0; k < NC1; k++) {
-                    const long long r = p.tr_row0 + (long long)gi * NC1 + k;
+                    const long long r = p.tr_row0 + (p.tr_packed ? (long long)a_blk * 8 + ar : (long long)gi) * NC1 + k;
                     const double ar_ = p.tr_alpha[r];
 #pragma unroll
                     for (int l = 0; l < NC2; l++) {
-                        const long long c = p.tr_col0 + (long long)gj * NC2 + l;
+                        const long long c = p.tr_col0 + (p.tr_packed ? (long long)b_blk * 8 + bq + e : (long long)gj) * NC2 + l;
                         const long long lo = r < c ? r : c, hi = r < c ? c : r;
-                        const double w = ar_ * p.tr_alpha[c] - p.tr_w[lo * p.tr_ld + hi];
-                        sum = fma(accg[e][k][l], w, sum);
+                        const double kinv = p.tr_packed ? p.tr_w[(r - p.tr_slab0) * p.tr_ld + c] : p.tr_w[lo * p.tr_ld + hi];
+                        sum = fma(accg[e][k][l], ar_ * p.tr_alpha[c] - kinv, sum);
                     }
                 }
             }
@@ -693,7 +697,7 @@ static int launch_ks(int mode, int fam, bool z2, const TileParams &p, int nwarps
 // Panel-layout arguments of build_block_device (cspbo_block_build_panel).
 struct PanelArgs { long long ld; int nbw; long long row0_a, row0_b; };
 // Trace mode of the RBF dK/dl kernels (cspbo_block_trace).
-struct TraceArgs { const double *alpha, *w; double *partial; long long ld, row0, col0; };
+struct TraceArgs { const double *alpha, *w; double *partial; long long ld, row0, col0; int packed; long long slab0; };
 // Stress passes of one launch: npass column triplets of side `side` (0 = A, 1 = B), pass q stored at out + q*off.
 struct PassArgs { int npass, side; long long off; };
 
@@ -726,6 +730,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.trace = trace ? 1 : 0;
     p.tr_alpha = trace ? trace->alpha : nullptr; p.tr_w = trace ? trace->w : nullptr; p.tr_partial = trace ? trace->partial : nullptr;
     p.tr_ld = trace ? trace->ld : 0; p.tr_row0 = trace ? trace->row0 : 0; p.tr_col0 = trace ? trace->col0 : 0;
+    p.tr_packed = trace ? trace->packed : 0; p.tr_slab0 = trace ? trace->slab0 : 0;
     p.npass = passes ? std::max(passes->npass, 1) : 1;
     p.pass_side = passes ? passes->side : 0;
     p.pass_off = passes ? passes->off : 0;

@@ -755,7 +755,8 @@ class ShardedCovariance:
     the local rows afterwards.
     """
 
-    def __init__(self, kernel, data, group=None, nbw=384):
+    def __init__(self, kernel, data, group=None, nbw=384, grad_semantics=False):
+        """grad_semantics: build the K of `k_total_with_grad` instead of `k_total`'s (kernels/device.py: k_total_device)."""
         import torch
         import torch.distributed as dist
         from .kernels import device as kdev
@@ -764,7 +765,8 @@ class ShardedCovariance:
             raise ValueError("nbw must be a multiple of 24")
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.h = kdev._hyper(kernel, quirk=True)
+        self.grad_semantics = bool(grad_semantics)
+        self.h = kdev._hyper(kernel, quirk=not grad_semantics)
         self.pe, self.pf = kdev._tuples(data)
         self.mE = self.pe.m if self.pe else 0
         self.mF = self.pf.m if self.pf else 0
@@ -813,7 +815,7 @@ class ShardedCovariance:
             self._panel(_lib.KEF, h["zef"], h["sef"], self.pe, self.pf, 0, self.NE_pad)
         if self.pf:
             self._panel(_lib.KFF, h["zff"], h["sff"], self.pf, self.pf, self.NE_pad, self.NE_pad, tol=tol,
-                        use_tol=(h["family"] == _lib.RBF))
+                        use_tol=(h["family"] == _lib.RBF and not self.grad_semantics))
         self._barrier()                    # peer stores have landed
         dev = self.local.device
         if self.pe:
@@ -884,6 +886,126 @@ def fit_sharded(kernel, data, y, noise_e, f_coef, group=None, nbw=384, tol=1e-10
     chol.local = None
     cov.close()                          # the distributed rows are no longer needed: U is replicated
     return (alpha, solver) if return_solver else alpha
+
+
+# ----------------------------------------------------------------------------- sharded LML + gradient
+def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=None, nbw=384):
+    """log marginal likelihood (and its gradient w.r.t. the kernel parameters and the noise) of
+    gaussianprocess.py:453-503 with K distributed over the ranks: panel-layout build, sharded Cholesky, and the
+    gradient as fused traces --
+
+      * diag(Ky^-1): every rank inverts the factor only against the identity columns of ITS panels (one triangular solve
+        per owned panel, the zigzag ownership balances the N^3/3 flops), the pieces are summed by one all-reduce of an
+        N-vector;
+      * Dot: dK/dsigma = 2K/sigma and the block-constant dK/dsigma0 need nothing else (two scalars from alpha and one
+        extra solve for 1_E);
+      * RBF: the same panel solves continued to full rows of Ky^-1, contracted with the dK/dl tiles of those rows inside
+        the tile-kernel epilogue (cspbo_block_trace_slab), partial traces summed by an all-reduce.
+
+    Neither K_gradient [N,N,3] nor Ky^-1 exists anywhere: per rank one panel's rows of Ky^-1 (nbw x N) at a time.
+    y in the caller's [E; F] order.  Returns MLL or (MLL, grad) -- identical numbers on every rank."""
+    import torch
+    import torch.distributed as dist
+    from .kernels import device as kdev
+    cov = ShardedCovariance(kernel, data, group=group, nbw=nbw, grad_semantics=eval_gradient)
+    npar = len(kernel.parameters()) + 1
+    cov.build(noise_e, f_coef)
+    chol = ShardedCholesky(cov.local, cov.N, nbw, cov.rank, cov.world, True, group)
+    chol.factor()
+    try:
+        chol.check()
+    except _lib.CspboError as exc:
+        cov.close()
+        if exc.code == 5:
+            return (-np.inf, np.zeros(npar)) if eval_gradient else -np.inf
+        raise
+    dev = chol.U.device
+    perm = torch.as_tensor(cov.permutation(), device=dev)
+    yt = torch.as_tensor(np.asarray(y, dtype=np.float64).reshape(-1) if not isinstance(y, torch.Tensor) else y.reshape(-1),
+                         dtype=torch.float64, device=dev)
+    Nreal, NE, Ntot = yt.numel(), cov.mE, cov.N
+    yp = torch.zeros(Ntot, dtype=torch.float64, device=dev)
+    yp[perm] = yt
+    ap = chol.solve(yp)                                    # alpha in panel order (0 on the identity padding rows)
+    MLL = float(-0.5 * torch.dot(yp, ap) - 0.5 * chol.logdet() - Nreal / 2 * np.log(2 * np.pi))
+    chol.local = None
+    if not eval_gradient:
+        cov.close()
+        return MLL
+    U, W, me = chol.U, cov.world, cov.rank
+    ne, nf = float(noise_e), float(f_coef * noise_e)
+    is_e = torch.zeros(Ntot, dtype=torch.bool, device=dev)
+    is_e[: cov.mE] = True
+    is_f = torch.zeros(Ntot, dtype=torch.bool, device=dev)
+    is_f[cov.NE_pad:] = True
+    d = torch.where(is_e, ne * ne, 0.0) + torch.where(is_f, nf * nf, 0.0)          # noise on the real rows (pads: 0)
+    b = torch.where(is_e, 2 * ne, 0.0) + torch.where(is_f, 2 * f_coef ** 2 * ne, 0.0)
+    rbf = kernel.name != 'Dot_mb'
+    dinv = torch.zeros(Ntot, dtype=torch.float64, device=dev)
+    tr = torch.zeros(1, dtype=torch.float64, device=dev)
+    if rbf:
+        h = kdev._hyper(kernel, quirk=False)
+        l = kernel.l
+        fscale = torch.ones(Ntot, dtype=torch.float64, device=dev)       # 1/N_i of the energy rows (rbf_kernel.py:55-60,157)
+        if cov.pe:
+            fscale[: cov.mE] = 1.0 / torch.as_tensor(cov.pe.counts[cov.order_e], dtype=torch.float64, device=dev)
+        aps = ap * fscale
+        lib = _lib.load()
+
+        def trace(block, a, bp, row0, col0, slab0, blk0, blk1, scale_grad, slab):
+            desc = BlockDesc(_lib.RBF, block, float(h["zee"]), float(h["sigma2"]), 0.0, float(l), 0.0, 0, 1, 0, 1.0, float(scale_grad), 0)
+            _lib.check(lib.cspbo_block_trace_slab(ctypes.byref(desc), a.handle, bp.handle, c_vp(aps.data_ptr()), c_vp(slab.data_ptr()),
+                                                  int(slab.shape[1]), int(row0), int(col0), int(slab0), int(blk0), int(blk1),
+                                                  c_vp(tr.data_ptr()), 1))
+    for s in range(chol.S):
+        if superblock_owner(s, W, True) != me:
+            continue
+        j0, j1 = s * nbw, min((s + 1) * nbw, Ntot)
+        hj = j1 - j0
+        E = torch.zeros((Ntot - j0, hj), dtype=torch.float64, device=dev)
+        E[:hj].fill_diagonal_(1.0)
+        # Ky = U^T U: Y = (U^T)^-1 E_J has zeros above row j0, so only the trailing triangle is solved
+        Y = torch.linalg.solve_triangular(U[j0:, j0:].T, E, upper=False)
+        dinv[j0:j1] = (Y * Y).sum(dim=0)
+        if rbf and j0 < cov.mE or (rbf and j0 >= cov.NE_pad):
+            Ypad = torch.zeros((Ntot, hj), dtype=torch.float64, device=dev)
+            Ypad[j0:] = Y
+            slab = torch.linalg.solve_triangular(U, Ypad, upper=True).T.contiguous()     # rows J of Ky^-1, [hj, Ntot]
+            slab *= fscale[None, :]
+            slab *= fscale[j0:j1, None]
+            if j0 < cov.mE:                     # energy rows: E-E, and E-F twice (K_FE = K_EF^T contributes the same)
+                g = nbw // 8
+                trace(_lib.KEE, cov.pe, cov.pe, 0, 0, j0, s * g, (s + 1) * g, 1.0 / (l * l * l), slab)
+                if cov.pf:
+                    trace(_lib.KEF, cov.pe, cov.pf, 0, cov.NE_pad, j0, s * g, (s + 1) * g, 2.0, slab)
+            else:                               # force rows: F-F
+                g = nbw // 24
+                sf = s - cov.NE_pad // nbw
+                trace(_lib.KFF, cov.pf, cov.pf, cov.NE_pad, cov.NE_pad, j0, sf * g, (sf + 1) * g, 1.0, slab)
+            del slab, Ypad
+        del Y, E
+    red = torch.cat((dinv, tr))
+    if W > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.SUM, group=group)
+    dinv, trv = red[:Ntot], float(red[Ntot])
+    a2 = ap * ap
+    sigma = kernel.sigma
+    g_s = (1.0 / sigma) * float(torch.dot(ap, yp) - torch.dot(d, a2) - Nreal + torch.dot(d, dinv))
+    g_noise = 0.5 * float(torch.dot(b, a2 - dinv))
+    if rbf:
+        # sum_ij (alpha alpha^T - Ky^-1)_ij dK/dl_ij: the alpha alpha^T part is in the slab traces already
+        grad = np.array([g_s, 0.5 * trv, g_noise])
+    else:
+        g_s0 = 0.0
+        if NE > 0:
+            ones = torch.zeros(Ntot, dtype=torch.float64, device=dev)
+            ones[: cov.mE] = 1.0
+            u = chol.solve(ones)
+            c0 = 0.8 * 2 * kernel.sigma ** 2 * kernel.sigma0
+            g_s0 = 0.5 * c0 * float(ap[: cov.mE].sum() ** 2 - u[: cov.mE].sum())
+        grad = np.array([g_s, g_s0, g_noise])
+    cov.close()
+    return MLL, grad
 
 
 # ----------------------------------------------------------------------------- sharded prediction

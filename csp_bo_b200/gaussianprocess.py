@@ -273,6 +273,10 @@ class GaussianProcess():
             from .packing import resident
             self._packs = resident(self._train_dict())
         data = self._packs
+        if _world_size() > 1:
+            # one process per GPU: K distributed, sharded Cholesky, gradient traces per owned panel (distributed.lml_sharded)
+            from .distributed import lml_sharded
+            return lml_sharded(kernel, data, self.y_train[:, 0], params[-1], self.f_coef, eval_gradient=eval_gradient)
         K = kdev.k_total_device(kernel, data, grad_semantics=eval_gradient)       # the ONE N x N array of the evaluation
         N, NE = K.shape[0], self._n_energy()
         y = torch.from_numpy(np.ascontiguousarray(self.y_train[:, 0])).cuda()

@@ -296,6 +296,13 @@ int cspbo_gp_inverse_diag(double *L, int N, double *diag_out);
  * added in a fixed order: the result is deterministic. */
 int cspbo_block_trace(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b, const double *alpha,
                       const double *W, long long ldw, long long row0, long long col0, double *result, int accumulate);
+/* One rank's share of the same trace when K is distributed (csp_bo_b200/distributed.py: lml_sharded): the 8-group blocks
+ * [a_blk0, a_blk1) of pack a against ALL of pack b, rows and columns in PACKED order (matrix row of packed position p is
+ * row0 + p*nc1, column col0 + q*nc2: the panel layout of cspbo_block_build_panel), Wslab = the full rows
+ * [slab_row0, ...) of K^-1 (row-major, leading dimension ldw), alpha in the same packed order. */
+int cspbo_block_trace_slab(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b, const double *alpha,
+                           const double *Wslab, long long ldw, long long row0, long long col0, long long slab_row0,
+                           int a_blk0, int a_blk1, double *result, int accumulate);
 /* Building blocks of the sharded Cholesky K = U^T U (row-major; rows of U live where the rows of K live;
  * csp_bo_b200/distributed.py: ShardedCholesky).  All asynchronous on `stream` (a cudaStream_t); matrices are row-major
  * views given by pointer + leading dimension.  Distributed restatement of the single scipy `cholesky` of

@@ -217,6 +217,37 @@ def test_sharded_covariance_world1(fam, n_struct, n_atoms, nbw):
     assert float((ref - alpha).abs().max() / ref.abs().max()) < 1e-6
 
 
+@pytest.mark.parametrize("fam,n_struct,n_atoms,nbw", [("dot", 5, 40, 24), ("rbf", 30, 100, 48), ("rbf", 50, 0, 24), ("dot", 0, 70, 48),
+                                                      ("rbf", 0, 70, 48)])
+def test_lml_sharded_world1_matches_dense(fam, n_struct, n_atoms, nbw):
+    """distributed.lml_sharded (panel-layout K, sharded Cholesky, per-panel triangular solves for diag(K^-1), dK/dl traces
+    over row slabs of K^-1) against the dense single-GPU evaluation of GaussianProcess.log_marginal_likelihood."""
+    from csp_bo_b200.distributed import lml_sharded
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from csp_bo_b200.kernels import Dot_mb, RBF_mb
+    from csp_bo_b200.utilities import tuple_to_list
+    kernel = Dot_mb(para=[18.555440586011372, 0.05], zeta=2) if fam == "dot" else RBF_mb(para=[6.244955524643115, 0.5611029935713949], zeta=2)
+    data, y = _mixed_problem(max(n_struct, 1), max(n_atoms, 1))
+    lists = {}
+    if n_struct:
+        lists["energy"] = [(x, float(y[i]), ele) for i, (x, ele) in enumerate(tuple_to_list(data["energy"], mode='energy'))]
+    else:
+        data.pop("energy"); y = y[1:]
+    if n_atoms:
+        ne = n_struct
+        lists["force"] = [(x, dx, y[ne + 3 * i: ne + 3 * i + 3], ele) for i, (x, dx, ele) in enumerate(tuple_to_list(data["force"]))]
+    else:
+        data.pop("force"); y = y[:n_struct]
+    model = GaussianProcess(kernel, f_coef=20.0, noise_e=[0.01, 0.002, 0.1])
+    model.set_train_pts(lists)
+    params = np.array(kernel.parameters() + [0.01])
+    lml, grad = model.log_marginal_likelihood(params, eval_gradient=True)
+    lml_s, grad_s = lml_sharded(kernel, data, y, 0.01, 20.0, eval_gradient=True, nbw=nbw)
+    assert abs(lml - lml_s) <= 1e-9 * abs(lml)
+    assert max_norm_err(grad_s, grad) < 1e-7, (grad_s, grad)
+    assert abs(lml_sharded(kernel, data, y, 0.01, 20.0, nbw=nbw) - model.log_marginal_likelihood(params)) <= 1e-9 * abs(lml)
+
+
 def _cov_rank_main(rank, world, port, out):
     import torch
     import torch.distributed as dist
@@ -256,7 +287,20 @@ def _cov_rank_main(rank, world, port, out):
         from csp_bo_b200.distributed import predict_sharded
         m2, s2 = predict_sharded(model, test, return_std=True)
         err4 = float(max(np.abs(m2 - mean).max() / np.abs(mean).max(), np.abs(s2 - std).max() / np.abs(std).max()))
-        out[rank] = max(err, err2, err3 * 1e-2, err4 * 1e2)
+        # LML + gradient over the ranks (what fit(opt=True) evaluates under torchrun) against the dense algebra
+        from csp_bo_b200.distributed import lml_sharded
+        params = np.array(kernel.parameters() + [0.01])
+        lml_s, grad_s = model.log_marginal_likelihood(params, eval_gradient=True)          # sharded: world > 1
+        dense = GaussianProcess(kernel, f_coef=20.0, noise_e=[0.01, 0.002, 0.1])
+        dense.set_train_pts({"energy": E, "force": F})
+        import csp_bo_b200.gaussianprocess as gpm
+        ws, gpm._world_size = gpm._world_size, (lambda: 1)
+        try:
+            lml_d, grad_d = dense.log_marginal_likelihood(params, eval_gradient=True)
+        finally:
+            gpm._world_size = ws
+        err5 = max(abs(lml_s - lml_d) / abs(lml_d), float(np.abs(grad_s - grad_d).max() / np.abs(grad_d).max()) * 1e-1)
+        out[rank] = max(err, err2, err3 * 1e-2, err4 * 1e2, err5)
     finally:
         dist.destroy_process_group()
 
