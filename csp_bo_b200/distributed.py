@@ -938,8 +938,9 @@ def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=Non
     is_e[: cov.mE] = True
     is_f = torch.zeros(Ntot, dtype=torch.bool, device=dev)
     is_f[cov.NE_pad:] = True
-    d = torch.where(is_e, ne * ne, 0.0) + torch.where(is_f, nf * nf, 0.0)          # noise on the real rows (pads: 0)
-    b = torch.where(is_e, 2 * ne, 0.0) + torch.where(is_f, 2 * f_coef ** 2 * ne, 0.0)
+    is_e, is_f = is_e.to(torch.float64), is_f.to(torch.float64)
+    d = is_e * (ne * ne) + is_f * (nf * nf)                                        # noise on the real rows (pads: 0)
+    b = is_e * (2 * ne) + is_f * (2 * f_coef ** 2 * ne)
     rbf = kernel.name != 'Dot_mb'
     dinv = torch.zeros(Ntot, dtype=torch.float64, device=dev)
     tr = torch.zeros(1, dtype=torch.float64, device=dev)
