@@ -212,6 +212,9 @@ def run_ours(args):
     lib = _lib.load()
     _lib.check(lib.cspbo_set_device(local))
     if world > 1:
+        # NCCL kernels on high-priority streams: the 1-element "slab k is finished everywhere" all-reduces of the
+        # host-bound build must not queue behind the pending CTAs of the next slab's tile kernel
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     X, pairs = workload()

@@ -214,7 +214,10 @@ class ShardedSymmetricBlock:
             self._barrier()
         return self.local
 
-    SLAB_FRACTIONS = (0.0, 0.03, 0.1, 0.2, 0.35, 0.5, 0.65, 0.8, 1.0)
+    # 16 equal slabs measured best of (8 graded, 16 equal, 4, 12 front-loaded) at N = 2: 75.9 ms against 79-83 (tools/e2e_n_probe.py);
+    # the symmetric build finishes its first rows last-but-cheapest, so a host-bound build cannot beat
+    # T (1 - u^2) + u D with u = min(1, D / 2T) (T: build, D: copy-back time): 64 ms at N = 2, D itself at N = 8
+    SLAB_FRACTIONS = tuple(i / 16 for i in range(17))
 
     def slab_slots(self, fractions=None):
         """Block-slot boundaries of the row slabs of build_to_host: the same on every rank and aligned to superblock
