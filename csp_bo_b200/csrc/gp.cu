@@ -7,6 +7,7 @@
 #include <cusolverDn.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -326,7 +327,10 @@ struct StreamHandles {
     cusolverDnHandle_t solver;
     double *work;
     int lwork;
+    double *chol_scratch;     // fused diagonal-block kernel: 2 barrier words (zero between launches)
 };
+
+int chol_diag_launch(double *D, long long ld, int h, unsigned *bar, int *info_dev, cudaStream_t st);
 
 // inv = L^-1 for the h x h Cholesky factor that potrf left in D (row-major upper U == column-major lower L,
 // L(i,k) = D[k*ld + i]); inv is column-major lower with leading dimension h, the operand of the wide trmm.
@@ -415,10 +419,11 @@ static int stream_handles(cudaStream_t st, StreamHandles **out)
         cublasDestroy(g_sh[0].blas);
         cusolverDnDestroy(g_sh[0].solver);
         cudaFree(g_sh[0].work);
+        cudaFree(g_sh[0].chol_scratch);
         for (int i = 1; i < g_nsh; i++) g_sh[i - 1] = g_sh[i];
         g_nsh--;
     }
-    StreamHandles h = {st, dev, nullptr, nullptr, nullptr, 0};
+    StreamHandles h = {st, dev, nullptr, nullptr, nullptr, 0, nullptr};
     if (cublasCreate(&h.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return CSPBO_E_SOLVER; }
     if (cusolverDnCreate(&h.solver) != CUSOLVER_STATUS_SUCCESS) { cublasDestroy(h.blas); set_error("cusolverDnCreate failed"); return CSPBO_E_SOLVER; }
     cublasSetStream(h.blas, st);
@@ -438,17 +443,30 @@ extern "C" int cspbo_gp_chol_diag(double *D, long long ld, int h, double *inv, i
     StreamHandles *sh;
     int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
     if (rc) return rc;
-    int lwork = 0;
-    cusolverStatus_t s = cusolverDnDpotrf_bufferSize(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, &lwork);
-    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
-    if (lwork > sh->lwork) {
-        CSPBO_CUDA(cudaStreamSynchronize(sh->stream));
-        cudaFree(sh->work); sh->work = nullptr; sh->lwork = 0;
-        CSPBO_CUDA(cudaMalloc(&sh->work, (size_t)lwork * sizeof(double)));
-        sh->lwork = lwork;
+    // CSPBO_CHOL_DIAG=fused selects the single-kernel factorisation of chol.cu (h <= 384).  Measured on B200 it is correct to
+    // 1e-15 but SLOWER than cuSOLVER's potrf for this block size (0.26 vs 0.17 ms alone, 0.40 vs 0.30 ms per panel inside the
+    // running factorisation, profiles/chol_probe_r02.md), so cuSOLVER stays the default.
+    static const bool use_fused = getenv("CSPBO_CHOL_DIAG") && !strcmp(getenv("CSPBO_CHOL_DIAG"), "fused");
+    if (use_fused && h <= 384) {
+        if (!sh->chol_scratch) {
+            CSPBO_CUDA(cudaMalloc(&sh->chol_scratch, 64));
+            CSPBO_CUDA(cudaMemset(sh->chol_scratch, 0, 64));
+        }
+        rc = chol_diag_launch(D, ld, h, reinterpret_cast<unsigned *>(sh->chol_scratch), info_dev, sh->stream);
+        if (rc) return rc;
+    } else {
+        int lwork = 0;
+        cusolverStatus_t s = cusolverDnDpotrf_bufferSize(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, &lwork);
+        if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
+        if (lwork > sh->lwork) {
+            CSPBO_CUDA(cudaStreamSynchronize(sh->stream));
+            cudaFree(sh->work); sh->work = nullptr; sh->lwork = 0;
+            CSPBO_CUDA(cudaMalloc(&sh->work, (size_t)lwork * sizeof(double)));
+            sh->lwork = lwork;
+        }
+        s = cusolverDnDpotrf(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, sh->work, sh->lwork, info_dev);
+        if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf failed (status %d)", (int)s); return CSPBO_E_SOLVER; }
     }
-    s = cusolverDnDpotrf(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, sh->work, sh->lwork, info_dev);
-    if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf failed (status %d)", (int)s); return CSPBO_E_SOLVER; }
     if (h > 512) { set_error("gp_chol_diag: diagonal block of %d rows is too large (max 512)", h); return CSPBO_E_ARG; }
     const size_t smem = (size_t)(1 + kInvWarps) * h * sizeof(double);     // <= 36 KB
     const unsigned grid = (unsigned)((h + kInvWarps - 1) / kInvWarps);

@@ -300,3 +300,37 @@ def test_panel_and_cholesky_entry_points_reject_bad_arguments():
     assert lib.cspbo_gp_chol_diag(c_vp(Dn.data_ptr()), 8, 8, c_vp(inv.data_ptr()), c_vp(info.data_ptr()), st) == 0
     torch.cuda.synchronize()
     assert int(info.item()) > 0
+
+
+@pytest.mark.parametrize("h", [33, 192, 384])
+def test_fused_diagonal_block_factorisation_matches_cusolver(h):
+    """csrc/chol.cu (opt-in CSPBO_CHOL_DIAG=fused): the single-kernel Cholesky of a diagonal block, run in a child
+    process with the switch set, against cuSOLVER's potrf through the same entry point."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import ctypes, sys, torch
+        sys.path.insert(0, %r)
+        from csp_bo_b200 import _lib
+        lib = _lib.load(); c_vp = ctypes.c_void_p
+        h = %d
+        g = torch.Generator(device="cuda").manual_seed(1)
+        A = torch.randn(h, h, dtype=torch.float64, device="cuda", generator=g)
+        D0 = A @ A.T / h + torch.eye(h, dtype=torch.float64, device="cuda")
+        rows = torch.zeros(h, h + 7, dtype=torch.float64, device="cuda"); rows[:, :h] = D0
+        inv = torch.zeros(h, h, dtype=torch.float64, device="cuda"); info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        st = c_vp(torch.cuda.current_stream().cuda_stream)
+        assert lib.cspbo_gp_chol_diag(c_vp(rows.data_ptr()), h + 7, h, c_vp(inv.data_ptr()), c_vp(info.data_ptr()), st) == 0
+        torch.cuda.synchronize()
+        U = torch.triu(rows[:, :h])
+        print(float((U.T @ U - D0).abs().max()), float((inv @ U - torch.eye(h, dtype=torch.float64, device="cuda")).abs().max()), int(info))
+        bad = -torch.eye(h, dtype=torch.float64, device="cuda")
+        assert lib.cspbo_gp_chol_diag(c_vp(bad.data_ptr()), h, h, c_vp(inv.data_ptr()), c_vp(info.data_ptr()), st) == 0
+        torch.cuda.synchronize(); print(int(info))
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), h)
+    env = dict(os.environ, CSPBO_CHOL_DIAG="fused")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    l1, l2 = out.stdout.strip().splitlines()[-2:]
+    ferr, ierr, info = l1.split()
+    assert float(ferr) < 1e-13 and float(ierr) < 1e-12 and int(info) == 0
+    assert int(l2) == 1          # first non-positive pivot reported like cuSOLVER's devInfo
