@@ -880,6 +880,9 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
             cudaGetLastError();
         }
     }
+    // (d in (24, 56], K_FF with pow / exp in the epilogue: the KS = 14 instantiations spill 150-700 bytes around the libm
+    // calls; re-reading the A fragments per B tile instead -- the CHUNKED kernel with one chunk -- removes most of the spill
+    // but was measured SLOWER, RBF d = 50: 69.8 -> 73.2 ms, tools/ks14_probe.py, so the spilling variants stay)
     const int rc_launch = (a->ks == 6) ? launch_ks<6, false>(mode, fam, z2, p, nwarps, smem, st)
                           : (a->ks == 14) ? launch_ks<14, false>(mode, fam, z2, p, nwarps, smem, st)
                                           : launch_ks<6, true>(mode, fam, z2, p, nwarps, smem, st);
