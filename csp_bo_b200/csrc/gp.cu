@@ -327,10 +327,12 @@ struct StreamHandles {
     cusolverDnHandle_t solver;
     double *work;
     int lwork;
-    double *chol_scratch;     // fused diagonal-block kernel: 2 barrier words (zero between launches)
 };
 
-int chol_diag_launch(double *D, long long ld, int h, unsigned *bar, int *info_dev, cudaStream_t st);
+int chol_diag_launch(double *D, long long ld, int h, int *info_dev, cudaStream_t st);
+#ifndef CSPBO_CHOL_FUSED_DEFAULT
+#define CSPBO_CHOL_FUSED_DEFAULT false
+#endif
 
 // inv = L^-1 for the h x h Cholesky factor that potrf left in D (row-major upper U == column-major lower L,
 // L(i,k) = D[k*ld + i]); inv is column-major lower with leading dimension h, the operand of the wide trmm.
@@ -419,11 +421,10 @@ static int stream_handles(cudaStream_t st, StreamHandles **out)
         cublasDestroy(g_sh[0].blas);
         cusolverDnDestroy(g_sh[0].solver);
         cudaFree(g_sh[0].work);
-        cudaFree(g_sh[0].chol_scratch);
         for (int i = 1; i < g_nsh; i++) g_sh[i - 1] = g_sh[i];
         g_nsh--;
     }
-    StreamHandles h = {st, dev, nullptr, nullptr, nullptr, 0, nullptr};
+    StreamHandles h = {st, dev, nullptr, nullptr, nullptr, 0};
     if (cublasCreate(&h.blas) != CUBLAS_STATUS_SUCCESS) { set_error("cublasCreate failed"); return CSPBO_E_SOLVER; }
     if (cusolverDnCreate(&h.solver) != CUSOLVER_STATUS_SUCCESS) { cublasDestroy(h.blas); set_error("cusolverDnCreate failed"); return CSPBO_E_SOLVER; }
     cublasSetStream(h.blas, st);
@@ -443,18 +444,18 @@ extern "C" int cspbo_gp_chol_diag(double *D, long long ld, int h, double *inv, i
     StreamHandles *sh;
     int rc = stream_handles(static_cast<cudaStream_t>(stream), &sh);
     if (rc) return rc;
-    // CSPBO_CHOL_DIAG=fused selects the single-kernel factorisation of chol.cu (h <= 384).  Measured on B200 it is correct to
-    // 1e-15 but SLOWER than cuSOLVER's potrf for this block size (0.26 vs 0.17 ms alone, 0.40 vs 0.30 ms per panel inside the
-    // running factorisation, profiles/chol_probe_r02.md), so cuSOLVER stays the default.
-    static const bool use_fused = getenv("CSPBO_CHOL_DIAG") && !strcmp(getenv("CSPBO_CHOL_DIAG"), "fused");
-    if (use_fused && h <= 384) {
-        if (!sh->chol_scratch) {
-            CSPBO_CUDA(cudaMalloc(&sh->chol_scratch, 64));
-            CSPBO_CUDA(cudaMemset(sh->chol_scratch, 0, 64));
-        }
-        rc = chol_diag_launch(D, ld, h, reinterpret_cast<unsigned *>(sh->chol_scratch), info_dev, sh->stream);
-        if (rc) return rc;
-    } else {
+    // CSPBO_CHOL_DIAG: "fused" = the cluster-resident single-kernel factorisation of chol.cu (h <= 384; falls back to
+    // cuSOLVER when the stream's SM partition does not take an 8-CTA cluster), "cusolver" = cuSOLVER potrf.
+    static const bool use_fused = getenv("CSPBO_CHOL_DIAG") ? !strcmp(getenv("CSPBO_CHOL_DIAG"), "fused") : CSPBO_CHOL_FUSED_DEFAULT;
+    static bool fused_ok = true;
+    bool done = false;
+    if (use_fused && fused_ok && h <= 384) {
+        rc = chol_diag_launch(D, ld, h, info_dev, sh->stream);
+        if (rc == CSPBO_OK) done = true;
+        else if (rc == CSPBO_E_CUDA) fused_ok = false;      // no cluster on this partition: cuSOLVER from now on
+        else return rc;
+    }
+    if (!done) {
         int lwork = 0;
         cusolverStatus_t s = cusolverDnDpotrf_bufferSize(sh->solver, CUBLAS_FILL_MODE_LOWER, h, D, (int)ld, &lwork);
         if (s != CUSOLVER_STATUS_SUCCESS) { set_error("potrf_bufferSize failed (%d)", (int)s); return CSPBO_E_SOLVER; }
