@@ -435,6 +435,12 @@ def run_ours(args):
             legs = extra_legs(full, X, fp64_peak()[0])
         except Exception as exc:
             legs = {"error": str(exc)[:300]}
+    elif world > 1 and not args.no_legs:
+        # N > 1: one LML + gradient evaluation per kernel family over the ranks (what fit(opt=True) evaluates per L-BFGS step)
+        try:
+            legs = lml_sharded_legs(full, m, world, barrier)
+        except Exception as exc:
+            legs = {"error": str(exc)[:300]}
 
     # ---- one MD / validation step (config 1 of BASELINE.json): SO3 descriptor of a 192-atom Pt/H/O structure
     # + K* against a 16-energy + 409-force model + K*.alpha, through GaussianProcess.predict_structure.
@@ -618,6 +624,29 @@ def extra_legs(full, X, peak):
                      "lml": float(lml), "grad": [float(g) for g in grad]}
         del model
         torch.cuda.empty_cache()
+    return out
+
+
+def lml_sharded_legs(full, m, world, barrier):
+    """distributed.lml_sharded on the headline force set (N = 3m), Dot and RBF: panel-layout build + sharded Cholesky +
+    per-panel solves for diag(K^-1) (+ row slabs of K^-1 contracted with dK/dl tiles for RBF)."""
+    import torch
+    import torch.distributed as dist
+    from csp_bo_b200.distributed import lml_sharded
+    from csp_bo_b200.kernels import Dot_mb, RBF_mb
+    y = np.random.default_rng(0).standard_normal(3 * m)
+    out = {}
+    for name, kern in (("lml_grad_dot", Dot_mb(para=[SIGMA, SIGMA0], zeta=2)),
+                       ("lml_grad_rbf", RBF_mb(para=[6.244955524643115, 0.5611029935713949], zeta=2))):
+        ts = []
+        for _ in range(2):
+            barrier(); t0 = time.perf_counter()
+            lml, grad = lml_sharded(kern, {"force": full}, y, 0.005, 30.0, eval_gradient=True)
+            barrier(); ts.append((time.perf_counter() - t0) * 1e3)
+        t = torch.tensor([min(ts)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out[name] = {"what": "lml_sharded(eval_gradient=True), N = %d, %s, %d GPUs" % (3 * m, kern.name, world), "ms": float(t),
+                     "lml": float(lml), "grad": [float(g) for g in grad]}
     return out
 
 
