@@ -415,7 +415,9 @@ extern "C" int cspbo_block_trace_slab(const cspbo_block_desc *desc, const cspbo_
         if (!accumulate) CSPBO_CUDA(cudaMemsetAsync(result, 0, sizeof(double)));
         return CSPBO_OK;
     }
-    d.with_grad = 1; d.use_tol = 0; d.symmetric = 0;
+    // a == b (K_EE, K_FF): dK/dl and K^-1 are symmetric, so the blocks b >= a of the slab's rows, off-diagonal tiles counted
+    // twice, give the same total once every rank has added its rows -- half the tiles
+    d.with_grad = 1; d.use_tol = 0; d.symmetric = (a == b && d.block != CSPBO_KEF) ? 1 : 0;
     const long long nparts = (long long)(a_blk1 - a_blk0) * b->n_blocks * 4;
     void *sp = nullptr;
     int rc = scratch_get(SCRATCH_GRAD, (size_t)nparts * sizeof(double), &sp);

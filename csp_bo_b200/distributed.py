@@ -956,10 +956,10 @@ def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=Non
         aps = ap * fscale
         lib = _lib.load()
 
-        def trace(block, a, bp, row0, col0, slab0, blk0, blk1, scale_grad, slab):
+        def trace(block, a, bp, row0, col0, slab0, blk0, blk1, scale_grad, wptr, ldw):
             desc = BlockDesc(_lib.RBF, block, float(h["zee"]), float(h["sigma2"]), 0.0, float(l), 0.0, 0, 1, 0, 1.0, float(scale_grad), 0)
-            _lib.check(lib.cspbo_block_trace_slab(ctypes.byref(desc), a.handle, bp.handle, c_vp(aps.data_ptr()), c_vp(slab.data_ptr()),
-                                                  int(slab.shape[1]), int(row0), int(col0), int(slab0), int(blk0), int(blk1),
+            _lib.check(lib.cspbo_block_trace_slab(ctypes.byref(desc), a.handle, bp.handle, c_vp(aps.data_ptr()), c_vp(wptr),
+                                                  int(ldw), int(row0), int(col0), int(slab0), int(blk0), int(blk1),
                                                   c_vp(tr.data_ptr()), 1))
     for s in range(chol.S):
         if superblock_owner(s, W, True) != me:
@@ -971,22 +971,24 @@ def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=Non
         # Ky = U^T U: Y = (U^T)^-1 E_J has zeros above row j0, so only the trailing triangle is solved
         Y = torch.linalg.solve_triangular(U[j0:, j0:].T, E, upper=False)
         dinv[j0:j1] = (Y * Y).sum(dim=0)
-        if rbf and j0 < cov.mE or (rbf and j0 >= cov.NE_pad):
-            Ypad = torch.zeros((Ntot, hj), dtype=torch.float64, device=dev)
-            Ypad[j0:] = Y
-            slab = torch.linalg.solve_triangular(U, Ypad, upper=True).T.contiguous()     # rows J of Ky^-1, [hj, Ntot]
-            slab *= fscale[None, :]
+        if rbf and (j0 < cov.mE or j0 >= cov.NE_pad):
+            # rows J of Ky^-1 = (U^-1 Y)^T; only the columns from j0 on are needed (the traces below walk the blocks
+            # b >= a, off-diagonal tiles twice), and those depend on the trailing triangle alone
+            slab = torch.linalg.solve_triangular(U[j0:, j0:], Y, upper=True).T.contiguous()      # [hj, Ntot - j0]
+            slab *= fscale[None, j0:]
             slab *= fscale[j0:j1, None]
-            if j0 < cov.mE:                     # energy rows: E-E, and E-F twice (K_FE = K_EF^T contributes the same)
+            wptr = slab.data_ptr() - 8 * j0             # so that column c of the matrix is slab[:, c - j0]
+            ldw = slab.shape[1]
+            if j0 < cov.mE:                     # energy rows: E-E (symmetric), and E-F twice (K_FE = K_EF^T contributes the same)
                 g = nbw // 8
-                trace(_lib.KEE, cov.pe, cov.pe, 0, 0, j0, s * g, (s + 1) * g, 1.0 / (l * l * l), slab)
+                trace(_lib.KEE, cov.pe, cov.pe, 0, 0, j0, s * g, (s + 1) * g, 1.0 / (l * l * l), wptr, ldw)
                 if cov.pf:
-                    trace(_lib.KEF, cov.pe, cov.pf, 0, cov.NE_pad, j0, s * g, (s + 1) * g, 2.0, slab)
-            else:                               # force rows: F-F
+                    trace(_lib.KEF, cov.pe, cov.pf, 0, cov.NE_pad, j0, s * g, (s + 1) * g, 2.0, wptr, ldw)
+            else:                               # force rows: F-F (symmetric)
                 g = nbw // 24
                 sf = s - cov.NE_pad // nbw
-                trace(_lib.KFF, cov.pf, cov.pf, cov.NE_pad, cov.NE_pad, j0, sf * g, (sf + 1) * g, 1.0, slab)
-            del slab, Ypad
+                trace(_lib.KFF, cov.pf, cov.pf, cov.NE_pad, cov.NE_pad, j0, sf * g, (sf + 1) * g, 1.0, wptr, ldw)
+            del slab
         del Y, E
     red = torch.cat((dinv, tr))
     if W > 1:

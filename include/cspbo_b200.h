@@ -298,8 +298,10 @@ int cspbo_block_trace(const cspbo_block_desc *desc, const cspbo_pack *a, const c
                       const double *W, long long ldw, long long row0, long long col0, double *result, int accumulate);
 /* One rank's share of the same trace when K is distributed (csp_bo_b200/distributed.py: lml_sharded): the 8-group blocks
  * [a_blk0, a_blk1) of pack a against ALL of pack b, rows and columns in PACKED order (matrix row of packed position p is
- * row0 + p*nc1, column col0 + q*nc2: the panel layout of cspbo_block_build_panel), Wslab = the full rows
- * [slab_row0, ...) of K^-1 (row-major, leading dimension ldw), alpha in the same packed order. */
+ * row0 + p*nc1, column col0 + q*nc2: the panel layout of cspbo_block_build_panel), Wslab = the rows [slab_row0, ...) of
+ * K^-1 (row-major, leading dimension ldw; Wslab[(r - slab_row0)*ldw + c] must be valid for every column c the slab's
+ * tiles touch), alpha in the same packed order.  When a == b only the blocks b >= a are evaluated and the off-diagonal
+ * tiles count twice (both factors are symmetric): columns left of the slab's first row are then never read. */
 int cspbo_block_trace_slab(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b, const double *alpha,
                            const double *Wslab, long long ldw, long long row0, long long col0, long long slab_row0,
                            int a_blk0, int a_blk1, double *result, int accumulate);
