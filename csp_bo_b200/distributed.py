@@ -417,6 +417,10 @@ class ShardedCholesky:
         self.max_chunk = 4      # neighbouring superblocks updated by one dgemm (world 1 only)
         self.bulk_sms = int(os.environ.get("CSPBO_BULK_SMS", "0"))
         self.depth = max(1, int(os.environ.get("CSPBO_CHOL_DEPTH", "3")))    # panels of look-ahead
+        # trailing updates two panels at a time (k = 2 nbw): pays where the factorisation is bound by the bulk dgemms
+        # (world <= 4); at world 8 the diagonal chain is the limit and the one-panel delay of the bulk would only hurt
+        pair = os.environ.get("CSPBO_CHOL_PAIR")
+        self.pair_updates = ((world <= 4) if pair is None else bool(int(pair))) and self.depth >= 2
         self.cuda = bool(getattr(self.ops, "cuda", False))
         dev = local2d.device
         self.U = torch.empty((self.N, self.N), dtype=torch.float64, device=dev)
@@ -574,6 +578,46 @@ class ShardedCholesky:
                         if trace is not None:
                             trace.append(("lookahead", s, t5, mark(SP)))
                     e_look[s] = record(SP)
+            # ------------------------------------------------------------------ bulk updates of this rank's rows
+            # (issued before the deeper look-ahead below: with paired updates the look-ahead of THIS iteration may wait for an
+            # e_first event that is recorded here)
+            with on(SU):
+                wait(SU, e_wide)
+
+                def bulk(todo, p0, p1, key):
+                    """rows of the superblocks `todo` -= U[p0:p1, cols(t)]^T U[p0:p1, cols(t):]; records e_first[key] after the
+                    first dgemm (or at once when there is nothing to do)"""
+                    i, first = 0, True
+                    while i < len(todo):
+                        # superblocks that are neighbours in the matrix AND in this rank's buffer (world 1, zigzag turns)
+                        # share one dgemm: the few extra nbw x nbw blocks left of their diagonals are never read again
+                        j = i + 1
+                        while j < len(todo) and j - i < self.max_chunk and todo[j] == todo[j - 1] + 1 and \
+                                todo[j] // W == todo[j - 1] // W + 1:
+                            j += 1
+                        t = todo[i]
+                        lr, c0 = (t // W) * nbw, t * nbw
+                        ht = min((todo[j - 1] + 1) * nbw, N) - c0
+                        ops.update(loc[lr:lr + ht, c0:N], U[p0:p1, c0:c0 + ht], U[p0:p1, c0:N], su)
+                        if first:
+                            e_first[key] = record(SU)
+                            first = False
+                        i = j
+                    if first:
+                        e_first[key] = record(SU)
+
+                if not self.pair_updates:
+                    bulk([t for t in mine if t >= s + D + 1], r0, r1, s)      # rows s+D+1 (if mine) now carry panel s
+                elif s % 2 == 0 and s + 1 < S:
+                    pass    # first panel of a pair: its bulk update waits for its partner (one dgemm with k = 2 nbw)
+                elif s % 2 == 1:
+                    # panel s-1 alone on the one superblock that needs it before the pair reaches it (rows s+D), then both
+                    # panels together on everything below: k = 2 nbw dgemms run at 34 instead of 28-29 TFLOP/s
+                    pa0 = (s - 1) * nbw
+                    bulk([t for t in mine if t == s + D], pa0, r0, s - 1)
+                    bulk([t for t in mine if t >= s + D + 1], pa0, r1, s)
+                else:
+                    bulk([t for t in mine if t >= s + D + 1], r0, r1, s)      # unpaired last panel
             # ------------------------------------------------------------------ deeper look-ahead: rows s+2 .. s+D
             with on(SL):
                 for d in range(2, D + 1):
@@ -586,30 +630,8 @@ class ShardedCholesky:
                     ht = min(c0 + nbw, N) - c0
                     ops.update(loc[lr:lr + ht, c0:N], U[r0:r1, c0:c0 + ht], U[r0:r1, c0:N], sl)
                     e_sl[t] = record(SL)
-            # ------------------------------------------------------------------ bulk updates of this rank's rows
-            with on(SU):
-                wait(SU, e_wide)
-                todo = [t for t in mine if t >= s + D + 1]
-                i, first = 0, True
-                while i < len(todo):
-                    # superblocks that are neighbours in the matrix AND in this rank's buffer (world 1, zigzag turns)
-                    # share one dgemm: the few extra nbw x nbw blocks left of their diagonals are never read again
-                    j = i + 1
-                    while j < len(todo) and j - i < self.max_chunk and todo[j] == todo[j - 1] + 1 and \
-                            todo[j] // W == todo[j - 1] // W + 1:
-                        j += 1
-                    t = todo[i]
-                    lr, c0 = (t // W) * nbw, t * nbw
-                    ht = min((todo[j - 1] + 1) * nbw, N) - c0
-                    ops.update(loc[lr:lr + ht, c0:N], U[r0:r1, c0:c0 + ht], U[r0:r1, c0:N], su)
-                    if first:
-                        e_first[s] = record(SU)      # rows s+D+1 (if they are mine) now carry panel s
-                        first = False
-                    i = j
-                if first:
-                    e_first[s] = record(SU)
-                for d in (e_first, e_look, e_wtrmm, e_sl):
-                    d.pop(s - R - D - 2, None)
+            for d in (e_first, e_look, e_wtrmm, e_sl):
+                d.pop(s - R - D - 2, None)
         self.host_ms = (_time.perf_counter() - host_t0) * 1e3     # host time spent issuing the whole factorisation
         if cuda:
             cur = torch.cuda.current_stream()
