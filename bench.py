@@ -236,7 +236,8 @@ def run_ours(args):
         # neighbours in packed order (with single blocks dealt cyclically they are ~8 N blocks apart, and the CTAs that straddle
         # the diagonal idle half their warps: measured 14.01 -> 13.71 ms at N = 8, tools/sb_probe.py); packed columns:
         # full-row stores (local + NVLink)
-        sh = ShardedSymmetricBlock(full, _lib.KFF, sb_blocks=4, zigzag=True, packed_cols=True)
+        # balance=True: inside every cycle of N superblocks the heaviest goes to the rank with the least work so far (tile pairs)
+        sh = ShardedSymmetricBlock(full, _lib.KFF, sb_blocks=4, zigzag=True, packed_cols=True, balance=True)
         algo_pairs = (pairs + len(X[0])) / 2 / world
 
         def step():
@@ -407,7 +408,7 @@ def run_ours(args):
                 from csp_bo_b200.distributed import local_positions
                 from oracle import cpu_reference as cr
                 subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=False, stdout=subprocess.DEVNULL)
-                pos = local_positions(sh.n_blocks, rank, world, sh.sb_blocks, sh.zigzag)[:16]
+                pos = sh.positions(rank)[:16]
                 groups = sh.order[pos]
                 off = np.concatenate(([0], np.cumsum(X[3])))
                 rows = np.concatenate([np.arange(off[g], off[g + 1]) for g in groups])

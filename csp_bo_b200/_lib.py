@@ -81,7 +81,8 @@ SIGNATURES = {
     "cspbo_block_build_sharded_ex": [ctypes.POINTER(BlockDesc), c_vp, c_int, c_int, ctypes.POINTER(c_vp), c_int, c_int, c_int],
     "cspbo_block_build_sharded_ld": [ctypes.POINTER(BlockDesc), c_vp, c_int, c_int, ctypes.POINTER(c_vp), c_int, c_int, c_int, c_ll],
     "cspbo_block_build_sharded_slab": [ctypes.POINTER(BlockDesc), c_vp, c_int, c_int, ctypes.POINTER(c_vp), c_int, c_int, c_int, c_ll,
-                                       c_int, c_int, c_vp],
+                                       c_int, c_int, c_vp, c_vp, c_vp],
+    "cspbo_pack_block_work": [c_vp, c_vp, c_ll],
     "cspbo_block_build_panel": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_int, c_int, ctypes.POINTER(c_vp), c_ll, c_int, c_ll, c_ll],
     "cspbo_so3_create": [c_int, c_int, c_dbl, c_dbl, c_int, c_int, ctypes.POINTER(c_vp)],
     "cspbo_so3_destroy": [c_vp],

@@ -25,7 +25,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
                        int accumulate, cudaStream_t st, int rank = 0, int nranks = 1, double *const *outs = nullptr,
                        int a_begin = 0, int a_end = -1, int diag = 0, int sb_blocks = 1, int zigzag = 0,
                        int packed_cols = 0, const struct PanelArgs *panel = nullptr, const struct PassArgs *passes = nullptr,
-                       const struct TraceArgs *trace = nullptr);
+                       const struct TraceArgs *trace = nullptr, const int *sb_perm = nullptr, const int *sb_inv = nullptr);
 struct PanelArgs { long long ld; int nbw; long long row0_a, row0_b; };
 struct PassArgs { int npass, side; long long off; };
 struct TraceArgs { const double *alpha, *w; double *partial; long long ld, row0, col0; int packed; long long slab0; };
@@ -546,13 +546,32 @@ extern "C" int cspbo_block_build_sharded_ex(const cspbo_block_desc *desc, const 
 extern "C" int cspbo_block_build_sharded_ld(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
                                             double *const *outs, int sb_blocks, int zigzag, int packed_cols, long long ld)
 {
-    return cspbo_block_build_sharded_slab(desc, a, rank, nranks, outs, sb_blocks, zigzag, packed_cols, ld, 0, -1, nullptr);
+    return cspbo_block_build_sharded_slab(desc, a, rank, nranks, outs, sb_blocks, zigzag, packed_cols, ld, 0, -1, nullptr, nullptr, nullptr);
+}
+
+// work[a] = tile pairs of the symmetric build that belong to row block a: sum over b >= a and species of T(a,e) T(b,e)
+extern "C" int cspbo_pack_block_work(const cspbo_pack *a, double *work, long long n)
+{
+    if (!a || !work || n < a->n_blocks) { set_error("pack_block_work: bad argument"); return CSPBO_E_ARG; }
+    const int nb = (int)a->n_blocks, ns = (int)a->species.size();
+    std::vector<double> suffix((size_t)std::max(ns, 1), 0.0);      // sum over b >= a of T(b, e)
+    for (int blk = nb - 1; blk >= 0; blk--) {
+        double w = 0.0;
+        for (int e = 0; e < ns; e++) {
+            const double t = a->h_tile_start[(size_t)blk * ns + e + 1] - a->h_tile_start[(size_t)blk * ns + e];
+            suffix[(size_t)e] += t;
+            w += t * suffix[(size_t)e];
+        }
+        work[blk] = w;
+    }
+    return CSPBO_OK;
 }
 
 extern "C" int cspbo_block_build_sharded_slab(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
                                               double *const *outs, int sb_blocks, int zigzag, int packed_cols, long long ld,
-                                              int slot0, int slot1, void *stream)
+                                              int slot0, int slot1, void *stream, const int *sb_perm, const int *sb_inv)
 {
+    if ((sb_perm == nullptr) != (sb_inv == nullptr)) { set_error("block_build_sharded: sb_perm and sb_inv go together"); return CSPBO_E_ARG; }
     if (!desc || !a || !outs) { set_error("block_build_sharded: null argument"); return CSPBO_E_ARG; }
     if (sb_blocks < 1) { set_error("block_build_sharded: sb_blocks must be >= 1"); return CSPBO_E_ARG; }
     if (packed_cols && a->row_classes != 1) { set_error("block_build_sharded: packed_cols needs a pack with row_classes = 1"); return CSPBO_E_ARG; }
@@ -577,7 +596,7 @@ extern "C" int cspbo_block_build_sharded_slab(const cspbo_block_desc *desc, cons
         si = 3 * ld; sk = ld; sj = 3; sl = 1;
     }
     return build_block_device(d, a, a, 0, 0, outs[rank], nullptr, si, sk, sj, sl, 0, static_cast<cudaStream_t>(stream), rank, nranks, outs,
-                              slot0, slot1, 0, sb_blocks, zigzag, packed_cols);
+                              slot0, slot1, 0, sb_blocks, zigzag, packed_cols, nullptr, nullptr, nullptr, sb_perm, sb_inv);
 }
 
 extern "C" int cspbo_block_build_panel(const cspbo_block_desc *desc, const cspbo_pack *a, const cspbo_pack *b, int rank, int nranks,

@@ -101,6 +101,9 @@ struct TileParams {
     int sharded, nranks, rank;
     int sb_blocks, zigzag, packed_cols, a_slots;   // a_slots: blocks (incl. a ragged tail) this rank enumerates
     int a_slot0;   // sharded == 1: first block slot of this launch in the rank's buffer (row-slab pipelining)
+    // sharded == 1, optional work-balanced ownership: the dealing formula runs on VIRTUAL superblock indices; sb_perm[v] is the
+    // real superblock at virtual index v (-1: none), sb_inv its inverse.  Null = identity.
+    const int *sb_perm, *sb_inv;
     double *outs[kMaxRanks];
     // sharded == 2, "panel layout": the blocks of SEVERAL packs (energies, forces) live in one distributed matrix of
     // leading dimension ldo whose rows are dealt to the ranks by superblocks of nbw ROWS (zigzag); a pack starts at a
@@ -293,7 +296,9 @@ block_tile_kernel(const TileParams p)
     } else if (p.sharded) {   // a_idx-th block of this rank's buffer -> global block id
         const int cyc = a_idx / p.sb_blocks, within = a_idx - cyc * p.sb_blocks;
         const int pos = (p.zigzag && (cyc & 1)) ? p.nranks - 1 - p.rank : p.rank;
-        a_blk = (cyc * p.nranks + pos) * p.sb_blocks + within;
+        int sreal = cyc * p.nranks + pos;
+        if (p.sb_perm) sreal = p.sb_perm[sreal];
+        a_blk = sreal < 0 ? p.a_nblk : sreal * p.sb_blocks + within;
     }
     const int b_blk = p.diag ? a_blk : q;
     // symmetric build: only blocks with b >= a are computed (mirrored at write time)
@@ -545,11 +550,12 @@ block_tile_kernel(const TileParams p)
             col_j0 = p.pb.col0 + (long long)b_blk * C;
             mirror = p.pair || b_blk != a_blk;
         } else {
-            const int sa = a_blk / p.sb_blocks, sb = b_blk / p.sb_blocks;
-            row_i0 = ((long long)(sa / p.nranks) * p.sb_blocks + (a_blk - sa * p.sb_blocks)) * R;
+            const int sb = b_blk / p.sb_blocks;
+            const int vb = p.sb_inv ? p.sb_inv[sb] : sb;          // virtual superblock of the B rows
+            row_i0 = (long long)a_idx * R;                        // a_idx is this block's slot in the rank's buffer
             col_i0 = (long long)a_blk * R;
-            peer = p.outs[sb_owner(sb, p.nranks, p.zigzag)];
-            row_j0 = ((long long)(sb / p.nranks) * p.sb_blocks + (b_blk - sb * p.sb_blocks)) * C;
+            peer = p.outs[sb_owner(vb, p.nranks, p.zigzag)];
+            row_j0 = ((long long)(vb / p.nranks) * p.sb_blocks + (b_blk - sb * p.sb_blocks)) * C;
             col_j0 = (long long)b_blk * C;
             mirror = b_blk != a_blk;
         }
@@ -581,15 +587,16 @@ block_tile_kernel(const TileParams p)
         // sharded symmetric build: rows are block-cyclic over ranks in packed order, columns keep the
         // caller's group ids.  Own tile -> local HBM, mirrored tile -> peer HBM of the owner of b.
         double *mine = p.outs[p.rank];
-        const int sa = a_blk / p.sb_blocks, sb = b_blk / p.sb_blocks;
-        const long long lrow_i = ((long long)(sa / p.nranks) * p.sb_blocks + (a_blk - sa * p.sb_blocks)) * 8 + ar;
+        const int sb = b_blk / p.sb_blocks;
+        const int vb = p.sb_inv ? p.sb_inv[sb] : sb;
+        const long long lrow_i = (long long)a_idx * 8 + ar;
         const long long ci = gi;
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const int gj = p.B.slot_group[b_blk * 8 + bq + e];
             if (gj < 0) continue;
-            double *peer = p.outs[sb_owner(sb, p.nranks, p.zigzag)];
-            const long long lrow_j = ((long long)(sb / p.nranks) * p.sb_blocks + (b_blk - sb * p.sb_blocks)) * 8 + bq + e;
+            double *peer = p.outs[sb_owner(vb, p.nranks, p.zigzag)];
+            const long long lrow_j = ((long long)(vb / p.nranks) * p.sb_blocks + (b_blk - sb * p.sb_blocks)) * 8 + bq + e;
             const long long cj = gj;
 #pragma unroll
             for (int k = 0; k < NC1; k++)
@@ -715,7 +722,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
                        double *out, double *out_grad, long long si, long long sk, long long sj, long long sl,
                        int accumulate, cudaStream_t st, int rank, int nranks, double *const *outs, int a_begin, int a_end,
                        int diag, int sb_blocks, int zigzag, int packed_cols, const PanelArgs *panel, const PassArgs *passes,
-                       const TraceArgs *trace)
+                       const TraceArgs *trace, const int *sb_perm, const int *sb_inv)
 {
     if (a->ks != b->ks || a->d != b->d) {
         set_error("block_build: packs have different descriptor lengths (%d vs %d)", a->d, b->d);
@@ -757,6 +764,12 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.a_nblk = (a_end < 0 || p.sharded) ? (int)a->n_blocks : std::min(a_end, (int)a->n_blocks);
     p.a_slots = p.sharded ? sharded_superblocks((int)a->n_blocks, p.rank, p.nranks, p.sb_blocks, p.zigzag) * p.sb_blocks : 0;
     p.a_slot0 = 0;
+    p.sb_perm = (p.sharded && !panel) ? sb_perm : nullptr;
+    p.sb_inv = (p.sharded && !panel) ? sb_inv : nullptr;
+    if (p.sb_perm) {      // permuted ownership: every rank enumerates all cycles, slots without a superblock are skipped
+        const int nsb = ((int)a->n_blocks + p.sb_blocks - 1) / p.sb_blocks;
+        p.a_slots = ((nsb + p.nranks - 1) / p.nranks) * p.sb_blocks;
+    }
     if (p.sharded && !panel && a_end >= 0) {      // a slab [a_begin, a_end) of this rank's block slots
         p.a_slot0 = std::min(std::max(a_begin, 0), p.a_slots);
         p.a_slots = std::max(std::min(a_end, p.a_slots) - p.a_slot0, 0);

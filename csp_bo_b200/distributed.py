@@ -53,7 +53,32 @@ def local_positions(n_blocks, rank, world, sb_blocks=1, zigzag=False):
     return np.asarray(pos, dtype=np.int64)
 
 
-def assemble_full(parts, order, m, ncomp=3, sb_blocks=1, zigzag=False, packed_cols=False):
+def balanced_superblock_perm(weights, world, zigzag=False):
+    """Work-balanced ownership for the sharded symmetric build.  The dealing formula (superblock_owner) is kept but applied
+    to VIRTUAL indices: inside every cycle of `world` consecutive superblocks the heaviest one goes to the rank with the
+    least work so far, and so on.  Returns (perm, inv): perm[v] = real superblock at virtual index v (-1 = none, length
+    cycles * world), inv[s] = virtual index of superblock s.  Only superblocks of one cycle change places, so slab k of all
+    ranks still covers a contiguous range of packed row blocks (what build_to_host relies on)."""
+    w = np.asarray(weights, dtype=np.float64)
+    nsb = len(w)
+    ncyc = (nsb + world - 1) // world
+    perm = np.full(ncyc * world, -1, dtype=np.int32)
+    inv = np.zeros(max(nsb, 1), dtype=np.int32)
+    load = np.zeros(world)
+    for c in range(ncyc):
+        sbs = sorted(range(c * world, min((c + 1) * world, nsb)), key=lambda t: (-w[t], t))
+        free = list(range(world))
+        for t in sbs:
+            r = min(free, key=lambda q: (load[q], q))
+            free.remove(r)
+            load[r] += w[t]
+            pos = world - 1 - r if (zigzag and c & 1) else r
+            perm[c * world + pos] = t
+            inv[t] = c * world + pos
+    return perm, inv
+
+
+def assemble_full(parts, order, m, ncomp=3, sb_blocks=1, zigzag=False, packed_cols=False, positions=None):
     """Rebuild the dense matrix in the caller's group order from per-rank row blocks.
 
     parts[r]: array [sharded_rows(r), ncomp, m*ncomp] (K_FF) or [sharded_rows(r), m] (K_EE, ncomp=1)
@@ -70,7 +95,7 @@ def assemble_full(parts, order, m, ncomp=3, sb_blocks=1, zigzag=False, packed_co
     else:
         full = np.empty((m,) + tuple(parts[0].shape[1:]), dtype=parts[0].dtype)
     for r in range(world):
-        pos = local_positions(n_blocks, r, world, sb_blocks, zigzag)
+        pos = local_positions(n_blocks, r, world, sb_blocks, zigzag) if positions is None else np.asarray(positions[r])
         g = np.where(pos >= 0, order[np.maximum(pos, 0)], -1)
         keep = np.nonzero(g >= 0)[0]
         if len(keep) == 0:
@@ -127,13 +152,14 @@ def _open_peers(lib, own, group, world, rank):
     return ptrs, peers
 
 
-def gather_row_blocks(local, n_blocks, rank, world, group=None, sb_blocks=1, zigzag=False):
+def gather_row_blocks(local, n_blocks, rank, world, group=None, sb_blocks=1, zigzag=False, rows=None):
     """all_gather of the (unequal) per-rank row blocks; device-agnostic (NCCL on CUDA tensors, gloo on
     CPU tensors; CUDA tensors under gloo are staged through the host).  Returns the list of per-rank arrays,
     trimmed to their true row counts."""
     import torch
     import torch.distributed as dist
-    max_rows = max(sharded_rows(n_blocks, r, world, sb_blocks, zigzag) for r in range(world))
+    rows = [sharded_rows(n_blocks, r, world, sb_blocks, zigzag) for r in range(world)] if rows is None else list(rows)
+    max_rows = max(rows)
     via_host = local.is_cuda and dist.get_backend(group) != "nccl"
     dev = "cpu" if via_host else local.device
     pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=dev)
@@ -142,7 +168,7 @@ def gather_row_blocks(local, n_blocks, rank, world, group=None, sb_blocks=1, zig
     dist.all_gather(parts, pad, group=group)
     if via_host:
         parts = [p.to(local.device) for p in parts]
-    return [p[: sharded_rows(n_blocks, r, world, sb_blocks, zigzag)] for r, p in enumerate(parts)]
+    return [p[: rows[r]] for r, p in enumerate(parts)]
 
 
 # ----------------------------------------------------------------------------- device side
@@ -157,10 +183,12 @@ class _RawCuda:
 class ShardedSymmetricBlock:
     """K_FF(X,X) or K_EE(X,X) of one packed training set, distributed over the ranks of `group`."""
 
-    def __init__(self, pack, block=_lib.KFF, group=None, sb_blocks=1, zigzag=False, packed_cols=False):
+    def __init__(self, pack, block=_lib.KFF, group=None, sb_blocks=1, zigzag=False, packed_cols=False, balance=False):
         """sb_blocks / zigzag / packed_cols: the ownership and column order of cspbo_block_build_sharded_ex
         (include/cspbo_b200.h); the defaults are the plain block-cyclic layout, ShardedCholesky.from_block
-        needs packed_cols=True and wide superblocks (the panels of the factorisation)."""
+        needs packed_cols=True and wide superblocks (the panels of the factorisation).  balance=True deals the
+        superblocks by their actual work (tile pairs, cspbo_pack_block_work) instead of by position: see
+        balanced_superblock_perm; not for from_block, which factorises the plain zigzag layout."""
         import torch
         import torch.distributed as dist
         self.lib = _lib.load()
@@ -176,8 +204,20 @@ class ShardedSymmetricBlock:
         # peer) are whole 32-byte sectors / 128-byte lines; caller-order columns keep the dense pitch
         self.ld = ((self.ncols + 15) // 16) * 16 if self.packed_cols else self.ncols
         self.row_shape = (3, self.ld) if block == _lib.KFF else (self.ld,)
-        self.rows = int(self.lib.cspbo_sharded_rows_ex(pack.handle, self.rank, self.world, self.sb_blocks, int(self.zigzag)))
-        assert self.rows == sharded_rows(self.n_blocks, self.rank, self.world, self.sb_blocks, self.zigzag)
+        self.balance = bool(balance) and self.world > 1
+        self._perm = self._inv = self._perm_dev = self._inv_dev = None
+        if self.balance:
+            work = np.zeros(self.n_blocks)
+            _lib.check(self.lib.cspbo_pack_block_work(pack.handle, c_vp(work.ctypes.data), len(work)))
+            nsb = (self.n_blocks + self.sb_blocks - 1) // self.sb_blocks
+            wsb = np.add.reduceat(work, np.arange(0, self.n_blocks, self.sb_blocks))[:nsb]
+            self._perm, self._inv = balanced_superblock_perm(wsb, self.world, self.zigzag)
+            self._perm_dev = torch.as_tensor(self._perm, device="cuda")
+            self._inv_dev = torch.as_tensor(self._inv, device="cuda")
+            self.rows = 8 * self.sb_blocks * (len(self._perm) // self.world)      # every cycle has a slot on every rank
+        else:
+            self.rows = int(self.lib.cspbo_sharded_rows_ex(pack.handle, self.rank, self.world, self.sb_blocks, int(self.zigzag)))
+            assert self.rows == sharded_rows(self.n_blocks, self.rank, self.world, self.sb_blocks, self.zigzag)
         order = np.empty(self.n_blocks * 8, dtype=np.int32)
         _lib.check(self.lib.cspbo_pack_order(pack.handle, c_vp(order.ctypes.data), len(order)))
         self.order = order
@@ -188,6 +228,26 @@ class ShardedSymmetricBlock:
         self._ptrs, self._peers = _open_peers(self.lib, ptr, group, self.world, self.rank)
         self._full = torch.as_tensor(_RawCuda(ptr.value, (max(self.rows, 1),) + self.row_shape), device="cuda")[: self.rows]
         self.local = self._full[..., : self.ncols]        # [rows, 3, 3m] / [rows, m] view of the pitched buffer
+
+    def positions(self, rank=None):
+        """Packed positions (block*8 + slot) of the group rows of `rank`'s buffer, in buffer order; -1 where a slot holds no
+        group row (ragged tail, or a cycle that gave this rank no superblock)."""
+        rank = self.rank if rank is None else rank
+        if not self.balance:
+            return local_positions(self.n_blocks, rank, self.world, self.sb_blocks, self.zigzag)
+        pos = []
+        W, sb = self.world, self.sb_blocks
+        for c in range(len(self._perm) // W):
+            p = W - 1 - rank if (self.zigzag and c & 1) else rank
+            t = int(self._perm[c * W + p])
+            for b in range(t * sb, (t + 1) * sb):
+                pos.extend(range(b * 8, b * 8 + 8) if (t >= 0 and b < self.n_blocks) else [-1] * 8)
+        return np.asarray(pos, dtype=np.int64)
+
+    def _perm_ptrs(self):
+        if not self.balance:
+            return None, None
+        return c_vp(self._perm_dev.data_ptr()), c_vp(self._inv_dev.data_ptr())
 
     def local2d(self):
         """The local rows as a [rows * ncomp, N] matrix view (row pitch self.ld)."""
@@ -207,9 +267,10 @@ class ShardedSymmetricBlock:
             self._barrier()
         desc = BlockDesc(family, self.block, float(zeta), float(sigma2), float(sigma02), float(l), float(tol),
                          int(bool(use_tol)), 0, 0, float(scale), 1.0, 1)
-        _lib.check(self.lib.cspbo_block_build_sharded_ld(ctypes.byref(desc), self.pack.handle, self.rank, self.world,
-                                                         self._ptrs, self.sb_blocks, int(self.zigzag), int(self.packed_cols),
-                                                         self.ld))
+        pp, pi = self._perm_ptrs()
+        _lib.check(self.lib.cspbo_block_build_sharded_slab(ctypes.byref(desc), self.pack.handle, self.rank, self.world,
+                                                           self._ptrs, self.sb_blocks, int(self.zigzag), int(self.packed_cols),
+                                                           self.ld, 0, -1, None, pp, pi))
         if sync:
             self._barrier()
         return self.local
@@ -250,10 +311,11 @@ class ShardedSymmetricBlock:
         my_slots = self.rows // 8
         rowb = self.ncomp * self.ld * 8                     # bytes per group row of the pitched device buffer
         width = self.ncols * 8
+        pp, pi = self._perm_ptrs()
         for s0, s1 in zip(cuts[:-1], cuts[1:]):
             _lib.check(self.lib.cspbo_block_build_sharded_slab(ctypes.byref(desc), self.pack.handle, self.rank, self.world,
                                                                self._ptrs, self.sb_blocks, int(self.zigzag), int(self.packed_cols),
-                                                               self.ld, int(s0), int(s1), c_vp(sb.cuda_stream)))
+                                                               self.ld, int(s0), int(s1), c_vp(sb.cuda_stream), pp, pi))
             ev = torch.cuda.Event()
             ev.record(sb)
             with torch.cuda.stream(sc):
@@ -278,8 +340,9 @@ class ShardedSymmetricBlock:
         lay = dict(sb_blocks=self.sb_blocks, zigzag=self.zigzag)
         if self.world == 1:
             return assemble_full([self.local], self.order, self.m, self.ncomp, packed_cols=self.packed_cols, **lay)
-        parts = gather_row_blocks(self.local, self.n_blocks, self.rank, self.world, self.group, **lay)
-        return assemble_full(parts, self.order, self.m, self.ncomp, packed_cols=self.packed_cols, **lay)
+        allpos = [self.positions(r) for r in range(self.world)]
+        parts = gather_row_blocks(self.local, self.n_blocks, self.rank, self.world, self.group, rows=[len(q) for q in allpos], **lay)
+        return assemble_full(parts, self.order, self.m, self.ncomp, packed_cols=self.packed_cols, positions=allpos, **lay)
 
     def close(self):
         import torch
@@ -437,8 +500,8 @@ class ShardedCholesky:
     @classmethod
     def from_block(cls, sh, ops=None):
         """Factorise the matrix a ShardedSymmetricBlock(packed_cols=True) has built, in place."""
-        if not sh.packed_cols:
-            raise ValueError("ShardedCholesky needs a block built with packed_cols=True")
+        if not sh.packed_cols or sh.balance:
+            raise ValueError("ShardedCholesky needs a block built with packed_cols=True and the plain (unbalanced) ownership")
         N = sh.m * sh.ncomp
         return cls(sh.local2d(), N, 8 * sh.sb_blocks * sh.ncomp, sh.rank, sh.world, sh.zigzag, sh.group, ops)
 

@@ -253,10 +253,17 @@ int cspbo_block_build_sharded_ld(const cspbo_block_desc *desc, const cspbo_pack 
  * slots [slot0, slot1) of this rank's buffer are computed (slot1 < 0: all).  Slabs taken in ascending order by every
  * rank have this property: once ALL ranks have finished their slab k, the rows of slab k are final on every rank
  * (mirrored tiles only ever come from row blocks that are not later in packed order), so a host-bound build can copy
- * slab k out while slab k+1 is computed (csp_bo_b200/distributed.py: ShardedSymmetricBlock.build_to_host). */
+ * slab k out while slab k+1 is computed (csp_bo_b200/distributed.py: ShardedSymmetricBlock.build_to_host).
+ * sb_perm / sb_inv (DEVICE int arrays, both or neither; NULL = identity): work-balanced ownership.  The dealing formula
+ * (rank of superblock s, its place in the owner's buffer) is applied to VIRTUAL indices; sb_perm[v] is the real superblock
+ * at virtual index v (-1 = none; length ceil(nsb / nranks) * nranks) and sb_inv[s] the virtual index of real superblock s.
+ * A permutation that only shuffles superblocks inside each cycle of `nranks` keeps the slab property above. */
 int cspbo_block_build_sharded_slab(const cspbo_block_desc *desc, const cspbo_pack *a, int rank, int nranks,
                                    double *const *outs, int sb_blocks, int zigzag, int packed_cols, long long ld,
-                                   int slot0, int slot1, void *stream);
+                                   int slot0, int slot1, void *stream, const int *sb_perm, const int *sb_inv);
+/* work[a] (n >= number of 8-group blocks) = tile pairs of the symmetric build that belong to row block a (sum over the
+ * blocks b >= a and the species of T(a,e) T(b,e)): the weights a work-balanced ownership is computed from. */
+int cspbo_pack_block_work(const cspbo_pack *a, double *work, long long n);
 
 /* Panel layout: the whole covariance [[K_EE, K_EF], [K_FE, K_FF]] (base.py:13-14) as ONE distributed matrix, the input
  * of the sharded Cholesky.  Global rows = columns: each pack in packed order (cspbo_pack_order), starting at a multiple

@@ -287,3 +287,23 @@ def test_panel_layout_host_logic():
     assert np.all(packed[mE:NE_pad] == 0)                                            # identity padding rows
     assert np.array_equal(packed[NE_pad:].reshape(mF, 3), y[mE:].reshape(mF, 3)[of])  # forces, 3 rows per atom
     assert np.array_equal(packed[perm], y)
+
+
+def test_balanced_superblock_perm_properties():
+    """Work-balanced ownership of the sharded build: a permutation of the superblocks that only moves them inside their
+    cycle of `world` (so row slabs stay contiguous ranges of packed blocks), with inverse, and loads no worse than the
+    positional zigzag dealing."""
+    from csp_bo_b200.distributed import balanced_superblock_perm, superblock_owner
+    rng = np.random.default_rng(0)
+    for nsb, W, z in ((26, 8, True), (209, 8, True), (13, 4, False), (5, 8, True), (1, 2, True), (16, 2, True)):
+        w = np.sort(rng.uniform(1, 3, nsb))[::-1] * np.linspace(2, 0.1, nsb)
+        perm, inv = balanced_superblock_perm(w, W, z)
+        assert len(perm) == -(-nsb // W) * W and sorted(int(t) for t in perm if t >= 0) == list(range(nsb))
+        load, plain = np.zeros(W), np.zeros(W)
+        for v, t in enumerate(perm):
+            if t >= 0:
+                assert inv[t] == v and t // W == v // W
+                load[superblock_owner(v, W, z)] += w[t]
+        for t in range(nsb):
+            plain[superblock_owner(t, W, z)] += w[t]
+        assert load.max() <= plain.max() * (1 + 1e-12)

@@ -64,7 +64,7 @@ def _rank_main(rank, world, port, out):
         ref, _ = build_block(_lib.RBF, _lib.KFF, p, p, 2.0, sigma2=39.0, l=0.56, tol=1e-10, use_tol=True, device=True)
         err = 0.0
         # plain block-cyclic rows / caller-order columns, and the superblock + zigzag + packed-column layout of the fit
-        for kw in (dict(), dict(sb_blocks=4, zigzag=True, packed_cols=True)):
+        for kw in (dict(), dict(sb_blocks=4, zigzag=True, packed_cols=True), dict(sb_blocks=2, zigzag=True, packed_cols=True, balance=True)):
             sh = ShardedSymmetricBlock(p, _lib.KFF, **kw)
             sh._full.zero_()             # rows of padding slots are never written: give them a defined value
             torch.cuda.synchronize()

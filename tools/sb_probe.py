@@ -13,8 +13,8 @@ X = synthetic.force_set(6667, seed=0)
 full = packing.Pack(torch.from_numpy(X[0]).cuda(), torch.from_numpy(X[1]).cuda(), X[2], X[3])
 S2 = 18.555440586011372 ** 2 * 2.0
 res = {}
-for sb in (1, 2, 4, 8, 16):
-    sh = ShardedSymmetricBlock(full, _lib.KFF, sb_blocks=sb, zigzag=True, packed_cols=True)
+for sb, bal in ((1, False), (4, False), (1, True), (2, True), (4, True), (8, True)):
+    sh = ShardedSymmetricBlock(full, _lib.KFF, sb_blocks=sb, zigzag=True, packed_cols=True, balance=bal)
     for _ in range(3):
         sh.build(_lib.DOT, 2.0, scale=S2, sync=False)
     torch.cuda.synchronize()
@@ -29,7 +29,7 @@ for sb in (1, 2, 4, 8, 16):
     tmin = t.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
-    res[sb] = [round(float(t), 3), round(float(tmin), 3)]
+    res["%d%s" % (sb, "b" if bal else "")] = [round(float(t), 3), round(float(tmin), 3)]
     sh.close()
 if rank == 0:
     print(json.dumps({"world": world, "ms_max_min_over_ranks_by_sb_blocks": res}))
