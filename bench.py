@@ -357,7 +357,7 @@ def run_ours(args):
             how = "K_FF + noise -> cuSOLVER potrf/potrs -> alpha"
         else:
             from csp_bo_b200.distributed import ShardedSymmetricBlock, fit_alpha_sharded
-            shf = ShardedSymmetricBlock(full, _lib.KFF, sb_blocks=FIT_SB_BLOCKS, zigzag=True, packed_cols=True)
+            shf = ShardedSymmetricBlock(full, _lib.KFF, sb_blocks=FIT_SB_BLOCKS, zigzag=True, packed_cols=True, balance=True)
             for i in range(3):
                 barrier(); t0 = time.perf_counter()
                 shf.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
@@ -383,7 +383,7 @@ def run_ours(args):
             shf.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
             order = torch.as_tensor(np.asarray(shf.order[:m], dtype=np.int64), device="cuda")
             ap, yp = alpha.reshape(m, 3)[order].reshape(-1), y.reshape(m, 3)[order].reshape(-1)      # packed order
-            pos = torch.as_tensor(local_positions(shf.n_blocks, rank, world, shf.sb_blocks, shf.zigzag), device="cuda")
+            pos = torch.as_tensor(shf.positions(rank), device="cuda")
             keep = (pos >= 0) & (pos < m)
             rows3 = (pos.clamp(min=0)[:, None] * 3 + torch.arange(3, device="cuda")[None, :]).reshape(-1)
             keep3 = keep[:, None].expand(-1, 3).reshape(-1)

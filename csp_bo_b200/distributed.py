@@ -188,7 +188,7 @@ class ShardedSymmetricBlock:
         (include/cspbo_b200.h); the defaults are the plain block-cyclic layout, ShardedCholesky.from_block
         needs packed_cols=True and wide superblocks (the panels of the factorisation).  balance=True deals the
         superblocks by their actual work (tile pairs, cspbo_pack_block_work) instead of by position: see
-        balanced_superblock_perm; not for from_block, which factorises the plain zigzag layout."""
+        balanced_superblock_perm (ShardedCholesky.from_block follows the same ownership)."""
         import torch
         import torch.distributed as dist
         self.lib = _lib.load()
@@ -470,12 +470,16 @@ class ShardedCholesky:
     """
     RING = 4
 
-    def __init__(self, local2d, N, nbw, rank, world, zigzag=False, group=None, ops=None):
+    def __init__(self, local2d, N, nbw, rank, world, zigzag=False, group=None, ops=None, owner_inv=None):
+        """owner_inv: optional inverse of a within-cycle ownership permutation (balanced_superblock_perm): panel s then
+        belongs to the rank the dealing formula gives for virtual index owner_inv[s]; its place in the owner's buffer,
+        (s // world) * nbw, is the same because the permutation never leaves the cycle."""
         import torch
         self.torch = torch
         self.local, self.N, self.nbw = local2d, int(N), int(nbw)
         self.rank, self.world, self.zigzag, self.group = rank, world, bool(zigzag), group
         self.ops = ops if ops is not None else _DeviceOps()
+        self.owner_inv = None if owner_inv is None else [int(v) for v in owner_inv]
         self.S = (self.N + self.nbw - 1) // self.nbw
         self.max_chunk = 4      # neighbouring superblocks updated by one dgemm (world 1 only)
         self.bulk_sms = int(os.environ.get("CSPBO_BULK_SMS", "0"))
@@ -500,12 +504,16 @@ class ShardedCholesky:
     @classmethod
     def from_block(cls, sh, ops=None):
         """Factorise the matrix a ShardedSymmetricBlock(packed_cols=True) has built, in place."""
-        if not sh.packed_cols or sh.balance:
-            raise ValueError("ShardedCholesky needs a block built with packed_cols=True and the plain (unbalanced) ownership")
+        if not sh.packed_cols:
+            raise ValueError("ShardedCholesky needs a block built with packed_cols=True")
         N = sh.m * sh.ncomp
-        return cls(sh.local2d(), N, 8 * sh.sb_blocks * sh.ncomp, sh.rank, sh.world, sh.zigzag, sh.group, ops)
+        return cls(sh.local2d(), N, 8 * sh.sb_blocks * sh.ncomp, sh.rank, sh.world, sh.zigzag, sh.group, ops,
+                   owner_inv=sh._inv if sh.balance else None)
 
     def _owner(self, s):
+        if self.owner_inv is not None:
+            assert self.owner_inv[s] // self.world == s // self.world
+            s = self.owner_inv[s]
         return superblock_owner(s, self.world, self.zigzag)
 
     def add_noise(self, noise2):
