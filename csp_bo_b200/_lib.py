@@ -8,7 +8,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_PKG, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libcspbo_b200.so")
+LIB_PATH = os.environ.get("CSPBO_LIB") or os.path.join(LIB_DIR, "libcspbo_b200.so")     # CSPBO_LIB: A/B builds of the library
 
 c_int, c_dbl, c_ll, c_vp = ctypes.c_int, ctypes.c_double, ctypes.c_longlong, ctypes.c_void_p
 

@@ -50,6 +50,8 @@ def build(force=False, verbose_ptxas=False):
             if os.environ.get("CSPBO_TUNE"):      # e.g. CSPBO_TUNE="6,2,48": warps per CTA, CTAs per SM, KB per stage
                 w, c, kb = os.environ["CSPBO_TUNE"].split(",")
                 cmd += ["-DCSPBO_WARPS=" + w, "-DCSPBO_CTAS=" + c, "-DCSPBO_STAGE_KB=" + kb]
+            if os.environ.get("CSPBO_DEFS"):      # extra -D switches for experiments, e.g. CSPBO_DEFS="CSPBO_LIBM_EXP"
+                cmd += ["-D" + d for d in os.environ["CSPBO_DEFS"].split(",")]
             if verbose_ptxas:
                 cmd += ["-Xptxas", "-v"]
             _run(cmd)

@@ -217,8 +217,11 @@ __device__ __forceinline__ Weights pair_weights(double c, bool valid, const Tile
         else if (MODE == MODE_KEF) { w.w1 = z * cm1; w.w2 = 0.0; }
         else { w.w1 = cz + p.sigma02; w.w2 = 0.0; }  // sigma2 applied through p.scale
     } else {
-                // (a 256-entry-table exp with a degree-4 polynomial, 9 instead of 17 FP64 instructions, was measured
-        // SLOWER here: K_EE RBF 18.3 -> 21.1 ms; the dependent L1 lookup is not hidden at 3 warps per scheduler)
+        // (a 256-entry-table exp with a degree-4 polynomial, 9 instead of 17 FP64 instructions, was measured
+        // SLOWER here: K_EE RBF 18.3 -> 21.1 ms; the dependent L1 lookup is not hidden at 3 warps per scheduler.  Round 2
+        // repeated it with a 16-entry 2^(i/16) table in SHARED memory + degree-5 polynomial, 11 FP64 instructions, 1.4e-13
+        // accurate: K_EE 16.8 -> 18.2 ms, K_EF 73.7 -> 74.0, K_FF 119.0 -> 118.3 (tools/rbf_probe.py): the epilogue is bound
+        // by its dependent chain, not by FP64 issue slots, and libm's all-ALU polynomial pipelines better)
         const double K = p.sigma2 * exp(-(1.0 - cz) * p.inv2l2);
         const double dKdD = K * p.inv2l2;
         const double gl = (cz - 1.0) * p.inv_l3 + 2.0 * p.inv_l;  // (D-1)/l^3 + 2/l
