@@ -173,9 +173,7 @@ def k_total_with_stress_device(kernel, data1, data2, tol=1e-10):
         K[:ne1, ne2:] /= _counts(e1)[:, None]
     if f1 and e2:
         out, _ = build_block(fam, _lib.KEF, e2, f1, h["zef"], sigma2=h["sigma2"], l=h["l"], stress=True,
-                             scale=h["sef"], device=True)                    # [ne2 (x spread), m1, 9]
-        if e2.spread > 1:
-            out = out.view(ne2, e2.spread, m1, 9).sum(dim=1)
+                             scale=h["sef"], device=True)                    # [ne2, m1, 9] (spread packs are folded by build_block)
         out = out / _counts(e2)[:, None, None]
         K[ne1:, :ne2] = out[:, :, :3].reshape(ne2, 3 * m1).T
         Ks[:, :ne2] = out[:, :, 3:].reshape(ne2, 6 * m1).T

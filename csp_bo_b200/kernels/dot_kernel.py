@@ -49,13 +49,14 @@ def _force_packs(X1, X2, stress, on_dev):
 def kee_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False):
     """Energy-energy block [m1, m2] (and dC/dsigma, dC/dsigma0 when grad=True)."""
     X1, X2 = _energy(X1), _energy(X2)
-    a, b = pack_energy(X1), pack_energy(X2)
+    # small energy sets are packed spread over the tile slots (packing.spread_energy): 8x the CTAs for a K* row
+    a, b = pack_energy(X1, spread_small=True), pack_energy(X2, spread_small=True)
     C, _ = build_block(_lib.DOT, _lib.KEE, a, b, zeta, sigma2=sigma ** 2, sigma02=sigma0 ** 2, scale=sigma ** 2)
-    C /= (a.counts[:, None] * b.counts[None, :])
+    C /= (a.real_counts[:, None] * b.real_counts[None, :])
     if grad:
         C1 = 2 * C / sigma
         # the reference's d/dsigma0 is this constant (dot_kernel.py:57), reproduced as is
-        C2 = 0.8 * 2 * sigma ** 2 * sigma0 * np.ones([a.m, b.m])
+        C2 = 0.8 * 2 * sigma ** 2 * sigma0 * np.ones([a.m_real, b.m_real])
         return C, C1, C2
     return C
 
@@ -63,10 +64,10 @@ def kee_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False):
 def kef_C(X1, X2, sigma=1.0, sigma0=1.0, zeta=2.0, grad=False, stress=False, transpose=False):
     """Energy-force block [m1, 3*m2] (K_FE when transpose=True; + stress block when stress=True)."""
     X1, X2 = _energy(X1), _force(X2, stress)
-    a, b = pack_energy(X1), pack_force(X2)
-    m1, m2 = a.m, b.m
+    a, b = pack_energy(X1, spread_small=True), pack_force(X2)
+    m1, m2 = a.m_real, b.m
     out, _ = build_block(_lib.DOT, _lib.KEF, a, b, zeta, stress=stress, scale=1.0)
-    out /= a.counts[:, None, None]
+    out /= a.real_counts[:, None, None]
     out *= -sigma * sigma
     C = out[:, :, :3].reshape([m1, m2 * 3])
     Cs = out[:, :, 3:].reshape([m1, m2 * 6]) if stress else np.zeros([m1, m2 * 6])

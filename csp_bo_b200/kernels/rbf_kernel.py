@@ -14,8 +14,8 @@ from .dot_kernel import _energy, _force, _force_packs
 def kee_C(X1, X2, sigma=1.0, l=1.0, zeta=2.0, grad=False):
     """Energy-energy block; with grad=True also (dC/dsigma, dC/dl)."""
     X1, X2 = _energy(X1), _energy(X2)
-    a, b = pack_energy(X1), pack_energy(X2)
-    norm = a.counts[:, None] * b.counts[None, :]
+    a, b = pack_energy(X1, spread_small=True), pack_energy(X2, spread_small=True)
+    norm = a.real_counts[:, None] * b.real_counts[None, :]
     C, C_l = build_block(_lib.RBF, _lib.KEE, a, b, zeta, sigma2=sigma * sigma, l=l, with_grad=grad)
     C /= norm
     if grad:
@@ -28,19 +28,19 @@ def kee_C(X1, X2, sigma=1.0, l=1.0, zeta=2.0, grad=False):
 def kef_C(X1, X2, sigma=1.0, l=1.0, zeta=2.0, grad=False, stress=False, transpose=False):
     """Energy-force block; K_FE with transpose=True; stress block or (dC/dsigma, dC/dl) on request."""
     X1, X2 = _energy(X1), _force(X2, stress)
-    a, b = pack_energy(X1), pack_force(X2)
-    m1, m2 = a.m, b.m
+    a, b = pack_energy(X1, spread_small=True), pack_force(X2)
+    m1, m2 = a.m_real, b.m
     with_grad = grad and not stress   # the reference gives stress priority (rbf_kernel.py:127-145)
     out, out_l = build_block(_lib.RBF, _lib.KEF, a, b, zeta, sigma2=sigma * sigma, l=l, stress=stress,
                              with_grad=with_grad)
-    out /= a.counts[:, None, None]
+    out /= a.real_counts[:, None, None]
     C = out[:, :, :3].reshape([m1, m2 * 3])
     Cs = np.zeros([m1, m2 * 6])
     C_s = C_l = None
     if stress:
         Cs = out[:, :, 3:].reshape([m1, m2 * 6])
     elif grad:
-        out_l /= a.counts[:, None, None]
+        out_l /= a.real_counts[:, None, None]
         C_l = out_l.reshape([m1, m2 * 3])
         C_s = (2 / sigma) * C
     if transpose:

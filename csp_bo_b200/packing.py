@@ -102,11 +102,14 @@ class Pack:
 # that was updated in place (MD loops, finite differences, NEB images reusing buffers) can never be served from a
 # stale copy.  Residency is explicit: build the packs once with `resident()` (or `Pack(...)`) and pass THEM wherever a
 # stacked tuple is accepted -- that is what GaussianProcess does with its training set.
-def pack_energy(X):
-    """Stacked energy tuple (X, ELE, indices) -> Pack; a Pack passes through."""
+def pack_energy(X, spread_small=False):
+    """Stacked energy tuple (X, ELE, indices) -> Pack; a Pack passes through.  spread_small: sets of up to
+    SPREAD_MAX_GROUPS structures are packed spread over the tile slots (spread_energy), which build_block understands."""
     if isinstance(X, Pack):
         return X
     x, ele, indices = X
+    if spread_small and len(indices) <= SPREAD_MAX_GROUPS:
+        return spread_energy(X)
     return Pack(x, None, ele, indices)
 
 
@@ -122,7 +125,7 @@ def pack_force(X, row_range=None, row_classes=1):
 
 
 SPREAD_WAYS = 8
-SPREAD_MAX_GROUPS = 64
+SPREAD_MAX_GROUPS = 64      # larger sets: the host-side regrouping (two argsorts + a row gather) costs more than the kernel gains
 
 
 def spread_energy(X, ways=SPREAD_WAYS):
@@ -193,6 +196,9 @@ def build_block(family, block, a, b, zeta, sigma2=1.0, sigma02=0.0, l=1.0, tol=0
     device=True (or when `out` is a CUDA tensor)."""
     lib = _lib.load()
     grad = bool(with_grad) and family == _lib.RBF
+    if a.spread > 1 or b.spread > 1:
+        return _build_block_spread(family, block, a, b, zeta, sigma2, sigma02, l, tol, use_tol, with_grad, stress, scale,
+                                   scale_grad, symmetric, out, out_grad, device)
     shp, shp_g = out_shapes(block, a.m, b.m, stress)
     if out is not None and _is_torch(out) and out.is_cuda:
         device = True
@@ -219,6 +225,52 @@ def build_block(family, block, a, b, zeta, sigma2=1.0, sigma02=0.0, l=1.0, tol=0
     _lib.check(lib.cspbo_block_build(ctypes.byref(desc), a.handle, b.handle, _ptr(out),
                                      _ptr(out_grad) if grad else None, mem, 0))
     return out, (out_grad if grad else None)
+
+
+def _build_block_spread(family, block, a, b, zeta, sigma2, sigma02, l, tol, use_tol, with_grad, stress, scale, scale_grad,
+                        symmetric, out, out_grad, device):
+    """build_block for spread energy packs (spread_energy): the block of the pseudo-structures is built on the device and
+    its rows / columns are added up `spread` by `spread` into the real structures' entries; results have the shapes of the
+    real groups.  K_EE and K_EF only (force packs are never spread)."""
+    import torch
+    if block == _lib.KFF:
+        raise ValueError("spread packs are energy packs: K_EE / K_EF only")
+    pa, pb = _plain_view(a), _plain_view(b)
+    tmp, tmp_g = build_block(family, block, pa, pb, zeta, sigma2, sigma02, l, tol, use_tol, with_grad, stress, scale, scale_grad,
+                             symmetric, device=True)
+
+    def fold(t):
+        if t is None:
+            return None
+        if block == _lib.KEE:
+            return t.view(a.m_real, a.spread, b.m_real, b.spread).sum(dim=(1, 3))
+        return t.view(a.m_real, a.spread, b.m, t.shape[-1]).sum(dim=1)        # K_EF: side a is the energy pack
+    res, res_g = fold(tmp), fold(tmp_g)
+    want_dev = device or (out is not None and _is_torch(out) and out.is_cuda)
+
+    def deliver(r, dst):
+        if r is None:
+            return None
+        if dst is None:
+            return r if want_dev else r.cpu().numpy()
+        if _is_torch(dst):
+            dst.view(r.shape).copy_(r)
+        else:
+            dst.reshape(r.shape)[...] = r.cpu().numpy()
+        return dst
+    return deliver(res, out), deliver(res_g, out_grad)
+
+
+class _PlainView:
+    """A spread pack seen as the plain pack of its pseudo-structures (what the C side holds)."""
+
+    def __init__(self, p):
+        self._p, self.spread, self.m, self.handle = p, 1, p.m, p.handle
+        self.n, self.d, self.nc = p.n, p.d, p.nc
+
+
+def _plain_view(p):
+    return _PlainView(p) if p.spread > 1 else p
 
 
 def block_diag(family, block, a, zeta, sigma2=1.0, sigma02=0.0, l=1.0, scale=1.0):
