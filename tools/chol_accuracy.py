@@ -35,3 +35,18 @@ def e(a):
     return dict(alpha_rel=float((a - truth).abs().max() / truth.abs().max()), pred_rel=float((Kt @ a - pt).abs().max() / pt.abs().max()))
 print(json.dumps(dict(N=N, cusolver=e(a_cus), **{k: e(v) for k, v in res.items()},
                       residual_truth=float((y - (K @ truth + nf2 * truth)).abs().max()))))
+
+# ---- the reference's own solver on the same matrix: SciPy cholesky + cho_solve (gaussianprocess.py:116,127) on the host
+if len(sys.argv) > 2 and sys.argv[2] == "scipy":
+    import time
+    from scipy.linalg import cho_factor, cho_solve
+    Kh = K.cpu().numpy()
+    Kh[np.diag_indices(N)] += nf2
+    t0 = time.perf_counter()
+    a_sp = cho_solve(cho_factor(Kh, lower=True, overwrite_a=True, check_finite=False), y.cpu().numpy(), check_finite=False)
+    t_sp = time.perf_counter() - t0
+    a_sp = torch.from_numpy(a_sp).cuda()
+    psp = Kt @ a_sp
+    cmp_ = lambda a: float((Kt @ a - psp).abs().max() / psp.abs().max())
+    print(json.dumps(dict(scipy_seconds=round(t_sp, 1), scipy_vs_truth=e(a_sp), pred_rel_vs_scipy=dict(cusolver=cmp_(a_cus), refined=cmp_(truth),
+                                                                                                     **{k: cmp_(v) for k, v in res.items()}))))
