@@ -379,7 +379,6 @@ def run_ours(args):
             r = gp.predict_mean(out.view(3 * m, 3 * m), alpha) + nf2 * alpha - y
             rr = torch.stack(((r * r).sum(), (y * y).sum()))
         else:
-            from csp_bo_b200.distributed import local_positions
             shf.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
             order = torch.as_tensor(np.asarray(shf.order[:m], dtype=np.int64), device="cuda")
             ap, yp = alpha.reshape(m, 3)[order].reshape(-1), y.reshape(m, 3)[order].reshape(-1)      # packed order
@@ -405,7 +404,6 @@ def run_ours(args):
         try:
             sh.build(_lib.DOT, ZETA, scale=SIGMA * SIGMA * ZETA, sync=True)
             if rank == 0:
-                from csp_bo_b200.distributed import local_positions
                 from oracle import cpu_reference as cr
                 subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "port"], check=False, stdout=subprocess.DEVNULL)
                 pos = sh.positions(rank)[:16]
