@@ -622,7 +622,8 @@ def extra_legs(full, X, peak):
         lml, grad = model.log_marginal_likelihood(params, eval_gradient=True)
         torch.cuda.synchronize()
         out[name] = {"what": "log_marginal_likelihood(eval_gradient=True), N = %d, %s" % (N, kern.name), "ms": (time.perf_counter() - t0) * 1e3,
-                     "peak_extra_memory_in_N2_doubles": (torch.cuda.max_memory_allocated() - base) / (8.0 * N * N),
+                     "peak_extra_memory_in_N2_doubles": (torch.cuda.max_memory_allocated() - base + gp.inverse_workspace_bytes(N)) / (8.0 * N * N),
+                     "peak_memory_note": "torch allocator peak (the one N x N array) + the factor-inverse workspace of csrc/dense.cu (leaf results + chunk buffer, about N^2/16 + N*384 doubles)",
                      "lml": float(lml), "grad": [float(g) for g in grad]}
         del model
         torch.cuda.empty_cache()

@@ -96,6 +96,7 @@ SIGNATURES = {
     "cspbo_gp_cholesky_inverse": [c_vp, c_int, c_vp],
     "cspbo_gp_cholesky_inverse_inplace": [c_vp, c_int, c_int],
     "cspbo_gp_inverse_diag": [c_vp, c_int, c_vp],
+    "cspbo_gp_inverse_workspace_bytes": [c_int],
     "cspbo_block_trace_slab": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_ll, c_int, c_int, c_vp, c_int],
     "cspbo_block_trace": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_vp, c_int],
     "cspbo_gp_predict": [c_vp, c_int, c_int, c_vp, c_vp],
@@ -107,7 +108,8 @@ SIGNATURES = {
                               ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
 }
 _RESTYPE = {"cspbo_last_error": ctypes.c_char_p, "cspbo_launch_count": c_ll, "cspbo_pack_bytes": c_ll,
-            "cspbo_pack_pair_count": c_ll, "cspbo_sharded_rows": c_ll, "cspbo_sharded_rows_ex": c_ll}
+            "cspbo_pack_pair_count": c_ll, "cspbo_sharded_rows": c_ll, "cspbo_sharded_rows_ex": c_ll,
+            "cspbo_gp_inverse_workspace_bytes": c_ll}
 
 # reference-named shims (libdot_builder.py:5-9, librbf_builder.py:5-12)
 SHIM_SYMBOLS = {

@@ -21,7 +21,7 @@ CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
 NVCC = os.path.join(CUDA_HOME, "bin", "nvcc")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-CU_SOURCES = ["api.cu", "pack.cu", "tiles.cu", "gp.cu", "chol.cu", "so3.cu"]
+CU_SOURCES = ["api.cu", "pack.cu", "tiles.cu", "gp.cu", "dense.cu", "chol.cu", "so3.cu"]
 HEADERS = [os.path.join(SRC, "common.h"), os.path.join(SRC, "shim_common.h"), os.path.join(INC, "cspbo_b200.h")]
 
 

@@ -249,11 +249,39 @@ extern "C" int cspbo_gp_cho_solve(const double *L, int N, double *B, int nrhs)
     return CSPBO_OK;
 }
 
+namespace cspbo {
+int dense_factor_inverse(double *L, int N, long long ld, int what);      // dense.cu
+long long dense_workspace_bytes(int N);
+// cuSOLVER below CSPBO_DENSE_MIN rows (default 1024: the recursion's launches are not worth it) or with CSPBO_DENSE=0
+static bool use_dense(int N)
+{
+    const int on = getenv("CSPBO_DENSE") ? atoi(getenv("CSPBO_DENSE")) : 1;             // read per call: tests switch it
+    const int nmin = getenv("CSPBO_DENSE_MIN") ? atoi(getenv("CSPBO_DENSE_MIN")) : 1024;
+    return on != 0 && N >= nmin;
+}
+}  // namespace cspbo
+
+extern "C" long long cspbo_gp_inverse_workspace_bytes(int N)
+{
+    return (N > 0 && use_dense(N)) ? dense_workspace_bytes(N) : 0;
+}
+
 // In place: the factor L (column-major lower == row-major upper triangle of the buffer) -> K^-1, same triangle
 // (cuSOLVER potri).  With mirror != 0 the other triangle is filled too.
 extern "C" int cspbo_gp_cholesky_inverse_inplace(double *L, int N, int mirror)
 {
     if (!L || N <= 0) { set_error("gp_cholesky_inverse_inplace: bad argument"); return CSPBO_E_ARG; }
+    if (use_dense(N)) {      // recursive dgemm-rich sweeps (dense.cu): 2-3x cuSOLVER's potri at N = 20 001
+        const int rcd = dense_factor_inverse(L, N, N, 1);
+        if (rcd) return rcd;
+        if (mirror) {
+            const long long total = (long long)N * N;
+            symmetrize_kernel<<<(unsigned)((total + 255) / 256), 256>>>(L, N);
+            g_launches++;
+        }
+        CSPBO_CUDA(cudaGetLastError());
+        return CSPBO_OK;
+    }
     cusolverDnHandle_t h;
     int rc = solver_handle(&h);
     if (rc) return rc;
@@ -289,6 +317,14 @@ extern "C" int cspbo_gp_cholesky_inverse(const double *L, int N, double *Kinv)
 extern "C" int cspbo_gp_inverse_diag(double *L, int N, double *diag_out)
 {
     if (!L || !diag_out || N <= 0) { set_error("gp_inverse_diag: bad argument"); return CSPBO_E_ARG; }
+    if (use_dense(N)) {
+        const int rcd = dense_factor_inverse(L, N, N, 0);
+        if (rcd) return rcd;
+        row_sumsq_upper_kernel<<<(unsigned)((N + 7) / 8), 256>>>(L, N, diag_out);
+        g_launches++;
+        CSPBO_CUDA(cudaGetLastError());
+        return CSPBO_OK;
+    }
     cusolverDnHandle_t h;
     int rc = solver_handle(&h);
     if (rc) return rc;
@@ -345,9 +381,13 @@ int chol_diag_launch(double *D, long long ld, int h, int *info_dev, cudaStream_t
 constexpr int kInvWarps = 8;
 
 template <int KPER>      // rows per lane: h <= 32 * KPER
-__global__ void __launch_bounds__(kInvWarps * 32, 2) tri_inverse_kernel(const double *__restrict__ D, long long ld, int h, double *__restrict__ inv)
+__global__ void __launch_bounds__(kInvWarps * 32, 2) tri_inverse_kernel(const double *__restrict__ D, long long ld, int h, double *__restrict__ inv, int ntot)
 {
     extern __shared__ double tsm[];          // [h] reciprocal diagonal | [8][h] staged rows of D
+    // batched form (gridDim.y leaves): leaf y is the h x h diagonal block y of an ntot x ntot factor, the last one ragged
+    D += (long long)blockIdx.y * h * (ld + 1);
+    inv += (long long)blockIdx.y * h * h;
+    h = min(h, ntot - (int)blockIdx.y * h);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     double *rdiag = tsm;
     double *rows = tsm + h;
@@ -405,6 +445,22 @@ __global__ void __launch_bounds__(kInvWarps * 32, 2) tri_inverse_kernel(const do
             if (i < h) inv[(long long)j * h + i] = (i >= j) ? bv[u] : 0.0;
         }
     }
+}
+
+// inv[y][h_y * h_y] = inverse of the y-th nb x nb diagonal block of the N x N column-major lower factor L (the last block
+// is ragged; column-major lower with leading dimension h_y, zeros above the diagonal): the leaves of dense.cu's
+// recursive triangular inverse, all in one launch.
+int tri_inverse_leaves(const double *L, long long ld, int N, int nb, double *inv, cudaStream_t st)
+{
+    if (nb < 1 || nb > 512) { set_error("tri_inverse_leaves: leaf of %d rows (max 512)", nb); return CSPBO_E_ARG; }
+    const size_t smem = (size_t)(1 + kInvWarps) * nb * sizeof(double);
+    const dim3 grid((unsigned)((nb + kInvWarps - 1) / kInvWarps), (unsigned)((N + nb - 1) / nb));
+    if (nb <= 192) tri_inverse_kernel<6><<<grid, kInvWarps * 32, smem, st>>>(L, ld, nb, inv, N);
+    else if (nb <= 384) tri_inverse_kernel<12><<<grid, kInvWarps * 32, smem, st>>>(L, ld, nb, inv, N);
+    else tri_inverse_kernel<16><<<grid, kInvWarps * 32, smem, st>>>(L, ld, nb, inv, N);
+    g_launches++;
+    CSPBO_CUDA(cudaGetLastError());
+    return CSPBO_OK;
 }
 
 static StreamHandles g_sh[16];
@@ -471,9 +527,9 @@ extern "C" int cspbo_gp_chol_diag(double *D, long long ld, int h, double *inv, i
     if (h > 512) { set_error("gp_chol_diag: diagonal block of %d rows is too large (max 512)", h); return CSPBO_E_ARG; }
     const size_t smem = (size_t)(1 + kInvWarps) * h * sizeof(double);     // <= 36 KB
     const unsigned grid = (unsigned)((h + kInvWarps - 1) / kInvWarps);
-    if (h <= 192) tri_inverse_kernel<6><<<grid, kInvWarps * 32, smem, sh->stream>>>(D, ld, h, inv);
-    else if (h <= 384) tri_inverse_kernel<12><<<grid, kInvWarps * 32, smem, sh->stream>>>(D, ld, h, inv);
-    else tri_inverse_kernel<16><<<grid, kInvWarps * 32, smem, sh->stream>>>(D, ld, h, inv);
+    if (h <= 192) tri_inverse_kernel<6><<<grid, kInvWarps * 32, smem, sh->stream>>>(D, ld, h, inv, h);
+    else if (h <= 384) tri_inverse_kernel<12><<<grid, kInvWarps * 32, smem, sh->stream>>>(D, ld, h, inv, h);
+    else tri_inverse_kernel<16><<<grid, kInvWarps * 32, smem, sh->stream>>>(D, ld, h, inv, h);
     CSPBO_CUDA(cudaGetLastError());
     g_launches += 2;
     return CSPBO_OK;

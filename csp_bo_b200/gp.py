@@ -62,7 +62,7 @@ def cho_solve(L, Bt):
 
 
 def cholesky_inverse(L):
-    """K^-1 from the in-place factor (cuSOLVER potri), CUDA tensor [N,N]."""
+    """K^-1 from the in-place factor (csrc/dense.cu from 1024 rows on, cuSOLVER potri below), CUDA tensor [N,N]."""
     import torch
     lib = _lib.load()
     N = L.shape[0]
@@ -78,8 +78,15 @@ def cholesky_inverse_inplace(L, mirror=False):
 
 
 def inverse_diag(L):
-    """diag(K^-1) from the in-place factor, which is destroyed (trtri in place + row sums of squares): no second N x N array."""
+    """diag(K^-1) from the in-place factor, which is destroyed (triangular inverse in place, csrc/dense.cu, + row sums of
+    squares): no second N x N array."""
     import torch
     out = torch.empty(L.shape[0], dtype=torch.float64, device=L.device)
     _lib.check(_lib.load().cspbo_gp_inverse_diag(c_vp(L.data_ptr()), int(L.shape[0]), c_vp(out.data_ptr())))
     return out
+
+
+def inverse_workspace_bytes(N):
+    """Device workspace (library block cache, not torch's allocator) that inverse_diag / cholesky_inverse* use for an
+    N x N factor: leaf results + the chunk buffer of the out-of-place triangular products."""
+    return int(_lib.load().cspbo_gp_inverse_workspace_bytes(int(N)))

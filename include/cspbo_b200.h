@@ -287,13 +287,19 @@ int cspbo_gp_cholesky_solve(double *K, int N, double *y_inout, int nrhs, double 
  * column-major, i.e. a row-major [nrhs, N] matrix such as K* itself; overwritten with X.
  * gaussianprocess.py:166 (cho_solve) and the K^-1 K*^T of :174,:382 */
 int cspbo_gp_cho_solve(const double *L, int N, double *B, int nrhs);
-/* Kinv = (L L^T)^-1 (cuSOLVER potri), full symmetric matrix.  gaussianprocess.py:497 */
+/* Kinv = (L L^T)^-1, full symmetric matrix.  gaussianprocess.py:497 (cho_solve against the identity).  From 1024 rows
+ * on the inverse is formed by the recursive sweeps of csrc/dense.cu -- batched leaf inverses + large cuBLAS trmm / syrk
+ * products, 2.7x cuSOLVER's potri on B200 at N = 20 001 -- below that (or with CSPBO_DENSE=0) by cuSOLVER potri. */
 int cspbo_gp_cholesky_inverse(const double *L, int N, double *Kinv);
 /* The same in place: the factor in the buffer becomes K^-1 (row-major upper triangle; mirror != 0 fills both). */
 int cspbo_gp_cholesky_inverse_inplace(double *L, int N, int mirror);
-/* diag_out[N] = diag((L L^T)^-1), destroying the factor (cuSOLVER trtri in place + a row-wise sum of squares): all the
- * Dot kernel's hyper-gradient needs of K^-1, with no second N x N array.  gaussianprocess.py:490-499 */
+/* diag_out[N] = diag((L L^T)^-1), destroying the factor (triangular inverse in place -- csrc/dense.cu, 4.3x cuSOLVER's
+ * trtri at N = 20 001 -- + a row-wise sum of squares): all the Dot kernel's hyper-gradient needs of K^-1, with no second
+ * N x N array.  gaussianprocess.py:490-499 */
 int cspbo_gp_inverse_diag(double *L, int N, double *diag_out);
+/* Bytes of device workspace the two calls above take from the library's block cache for an N x N factor (leaf results +
+ * the chunk buffer of the out-of-place triangular products: about N^2/16 doubles at large N); 0 on the cuSOLVER path. */
+long long cspbo_gp_inverse_workspace_bytes(int N);
 /* Hyper-gradient trace of an RBF block without materialising dK/dl (gaussianprocess.py:496-499, rbf_kernel.cpp:87-92,
  * 239-246, 621-629): *result (device double) = [accumulate ? *result : 0] +
  *     sum over the block's entries (r, c) of  desc->scale_grad * dK/dl[r, c] * (alpha[r] alpha[c] - W[min(r,c)*ldw + max(r,c)])
