@@ -985,20 +985,52 @@ def fit_sharded(kernel, data, y, noise_e, f_coef, group=None, nbw=384, tol=1e-10
 
 
 # ----------------------------------------------------------------------------- sharded LML + gradient
+_SLAB_UNIT = 96          # rows: a multiple of the 8-row energy blocks and the 24-row force blocks of the packs
+_SLAB_MAX = int(os.environ.get('CSPBO_SLAB_MAX', '2304'))         # columns of one triangular solve (wide right-hand sides run at dgemm-like rates, thin ones do not)
+_TRACE_ROWS = 8000.0     # RBF: the dK/dl trace of a slab row costs about as much as this many rows of a triangular solve
+
+
+def _inverse_slabs(Ntot, NE_pad, rank, world, rbf, nbw=384, max_cols=_SLAB_MAX):
+    """Column ranges [j0, j1) of K^-1 that `rank` works out in lml_sharded.  Every rank holds the whole factor after
+    ShardedCholesky.factor(), so the inverse work is dealt independently of who factorised what: CONTIGUOUS ranges whose
+    cost -- (Ntot - j)^2 per column for the triangular solves against the trailing triangle, plus a term linear in
+    (Ntot - j) for the RBF dK/dl traces -- is equal over the ranks, cut into slabs of at most `max_cols` columns that do
+    not straddle the energy / force boundary NE_pad.  Boundaries are multiples of 96 rows (of nbw when that is not a
+    multiple of 96), i.e. aligned to the packs' blocks for the trace kernels; the last slab may be ragged."""
+    unit = _SLAB_UNIT if nbw % _SLAB_UNIT == 0 else nbw
+    assert NE_pad % unit == 0 and unit % 24 == 0, (NE_pad, unit)
+    nU = (Ntot + unit - 1) // unit
+    rem = (Ntot - np.arange(nU, dtype=np.float64) * unit)
+    cum = np.concatenate(([0.0], np.cumsum(rem * rem + (_TRACE_ROWS * rem if rbf else 0.0))))
+    cut = [int(np.searchsorted(cum, cum[-1] * r / world, side='left')) for r in range(world + 1)]
+    cut[0], cut[-1] = 0, nU
+    lo, hi = cut[rank] * unit, min(cut[rank + 1] * unit, Ntot)
+    out = []
+    j0 = lo
+    while j0 < hi:
+        j1 = min(j0 + max_cols, hi)
+        if j0 < NE_pad < j1:
+            j1 = NE_pad
+        out.append((j0, j1))
+        j0 = j1
+    return out
+
+
 def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=None, nbw=384):
     """log marginal likelihood (and its gradient w.r.t. the kernel parameters and the noise) of
     gaussianprocess.py:453-503 with K distributed over the ranks: panel-layout build, sharded Cholesky, and the
     gradient as fused traces --
 
-      * diag(Ky^-1): every rank inverts the factor only against the identity columns of ITS panels (one triangular solve
-        per owned panel, the zigzag ownership balances the N^3/3 flops), the pieces are summed by one all-reduce of an
-        N-vector;
+      * diag(Ky^-1): every rank inverts the factor only against the identity columns of ITS column range (contiguous
+        ranges of equal cost, _inverse_slabs; one triangular solve of the trailing triangle per slab of up to 2304
+        columns -- wide right-hand sides, which cuBLAS' trsm runs several times faster than one 384-column panel at a
+        time), the pieces are summed by one all-reduce of an N-vector;
       * Dot: dK/dsigma = 2K/sigma and the block-constant dK/dsigma0 need nothing else (two scalars from alpha and one
         extra solve for 1_E);
-      * RBF: the same panel solves continued to full rows of Ky^-1, contracted with the dK/dl tiles of those rows inside
+      * RBF: the same slab solves continued to full rows of Ky^-1, contracted with the dK/dl tiles of those rows inside
         the tile-kernel epilogue (cspbo_block_trace_slab), partial traces summed by an all-reduce.
 
-    Neither K_gradient [N,N,3] nor Ky^-1 exists anywhere: per rank one panel's rows of Ky^-1 (nbw x N) at a time.
+    Neither K_gradient [N,N,3] nor Ky^-1 exists anywhere: per rank one slab's rows of Ky^-1 (<= 2304 x N) at a time.
     y in the caller's [E; F] order.  Returns MLL or (MLL, grad) -- identical numbers on every rank."""
     import torch
     import torch.distributed as dist
@@ -1054,35 +1086,34 @@ def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=Non
             _lib.check(lib.cspbo_block_trace_slab(ctypes.byref(desc), a.handle, bp.handle, c_vp(aps.data_ptr()), c_vp(wptr),
                                                   int(ldw), int(row0), int(col0), int(slab0), int(blk0), int(blk1),
                                                   c_vp(tr.data_ptr()), 1))
-    for s in range(chol.S):
-        if superblock_owner(s, W, True) != me:
-            continue
-        j0, j1 = s * nbw, min((s + 1) * nbw, Ntot)
+    for j0, j1 in _inverse_slabs(Ntot, cov.NE_pad, me, W, rbf, nbw):
         hj = j1 - j0
         E = torch.zeros((Ntot - j0, hj), dtype=torch.float64, device=dev)
         E[:hj].fill_diagonal_(1.0)
         # Ky = U^T U: Y = (U^T)^-1 E_J has zeros above row j0, so only the trailing triangle is solved
         Y = torch.linalg.solve_triangular(U[j0:, j0:].T, E, upper=False)
+        del E
         dinv[j0:j1] = (Y * Y).sum(dim=0)
         if rbf and (j0 < cov.mE or j0 >= cov.NE_pad):
             # rows J of Ky^-1 = (U^-1 Y)^T; only the columns from j0 on are needed (the traces below walk the blocks
             # b >= a, off-diagonal tiles twice), and those depend on the trailing triangle alone
             slab = torch.linalg.solve_triangular(U[j0:, j0:], Y, upper=True).T.contiguous()      # [hj, Ntot - j0]
+            del Y
             slab *= fscale[None, j0:]
             slab *= fscale[j0:j1, None]
             wptr = slab.data_ptr() - 8 * j0             # so that column c of the matrix is slab[:, c - j0]
             ldw = slab.shape[1]
             if j0 < cov.mE:                     # energy rows: E-E (symmetric), and E-F twice (K_FE = K_EF^T contributes the same)
-                g = nbw // 8
-                trace(_lib.KEE, cov.pe, cov.pe, 0, 0, j0, s * g, (s + 1) * g, 1.0 / (l * l * l), wptr, ldw)
+                b0, b1 = j0 // 8, (j1 + 7) // 8
+                trace(_lib.KEE, cov.pe, cov.pe, 0, 0, j0, b0, b1, 1.0 / (l * l * l), wptr, ldw)
                 if cov.pf:
-                    trace(_lib.KEF, cov.pe, cov.pf, 0, cov.NE_pad, j0, s * g, (s + 1) * g, 2.0, wptr, ldw)
+                    trace(_lib.KEF, cov.pe, cov.pf, 0, cov.NE_pad, j0, b0, b1, 2.0, wptr, ldw)
             else:                               # force rows: F-F (symmetric)
-                g = nbw // 24
-                sf = s - cov.NE_pad // nbw
-                trace(_lib.KFF, cov.pf, cov.pf, cov.NE_pad, cov.NE_pad, j0, sf * g, (sf + 1) * g, 1.0, wptr, ldw)
+                b0, b1 = (j0 - cov.NE_pad) // 24, (j1 - cov.NE_pad + 23) // 24
+                trace(_lib.KFF, cov.pf, cov.pf, cov.NE_pad, cov.NE_pad, j0, b0, b1, 1.0, wptr, ldw)
             del slab
-        del Y, E
+        else:
+            del Y
     red = torch.cat((dinv, tr))
     if W > 1:
         dist.all_reduce(red, op=dist.ReduceOp.SUM, group=group)

@@ -307,3 +307,25 @@ def test_balanced_superblock_perm_properties():
         for t in range(nsb):
             plain[superblock_owner(t, W, z)] += w[t]
         assert load.max() <= plain.max() * (1 + 1e-12)
+
+
+@pytest.mark.parametrize("Ntot,NE_pad,nbw", [(20001, 0, 384), (15354 + 24, 5376, 384), (1000, 96, 48), (96, 96, 96), (50, 0, 384)])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_inverse_slabs_partition_the_columns(Ntot, NE_pad, nbw, world):
+    """distributed._inverse_slabs: the ranks' slabs tile [0, Ntot) exactly once, in order, never straddle the energy /
+    force boundary, stay block-aligned and under the column cap; costs are balanced at production sizes."""
+    from csp_bo_b200.distributed import _inverse_slabs, _SLAB_MAX
+    for rbf in (False, True):
+        cover, cost = [], []
+        for r in range(world):
+            sl = _inverse_slabs(Ntot, NE_pad, r, world, rbf, nbw)
+            cost.append(sum((Ntot - (a + b) / 2.0) ** 2 * (b - a) for a, b in sl))
+            cover += sl
+        assert cover[0][0] == 0 and cover[-1][1] == Ntot
+        unit = 96 if nbw % 96 == 0 else nbw
+        for (a, b), nxt in zip(cover, cover[1:] + [(Ntot, Ntot)]):
+            assert a < b <= Ntot and b == nxt[0] and b - a <= _SLAB_MAX
+            assert a % unit == 0 and (b % unit == 0 or b == Ntot)
+            assert not (a < NE_pad < b)
+        if Ntot >= 15000 and not rbf and world > 1:
+            assert max(cost) <= 1.12 * (sum(cost) / world)
