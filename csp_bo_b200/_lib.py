@@ -97,6 +97,7 @@ SIGNATURES = {
     "cspbo_gp_cholesky_inverse_inplace": [c_vp, c_int, c_int],
     "cspbo_gp_inverse_diag": [c_vp, c_int, c_vp],
     "cspbo_gp_inverse_workspace_bytes": [c_int],
+    "cspbo_gp_tri_inverse_inplace": [c_vp, c_int],
     "cspbo_block_trace_slab": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_ll, c_int, c_int, c_vp, c_int],
     "cspbo_block_trace": [ctypes.POINTER(BlockDesc), c_vp, c_vp, c_vp, c_vp, c_ll, c_ll, c_ll, c_vp, c_int],
     "cspbo_gp_predict": [c_vp, c_int, c_int, c_vp, c_vp],

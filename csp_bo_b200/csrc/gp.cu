@@ -314,17 +314,11 @@ extern "C" int cspbo_gp_cholesky_inverse(const double *L, int N, double *Kinv)
 // diag_out[N] = diag((L L^T)^-1), destroying L: the factor is inverted in place (cuSOLVER trtri, N^3/3 flop, no second
 // N x N array) and (K^-1)_ii = sum_j (L^-1)_ji^2 is a row-wise sum of squares of what is left.  This is all the Dot
 // kernel's hyper-gradient needs of K^-1 (dK/dsigma = 2K/sigma, dK/dnoise diagonal; gaussianprocess.py:490-499).
-extern "C" int cspbo_gp_inverse_diag(double *L, int N, double *diag_out)
+namespace cspbo {
+// L -> L^-1 in place (column-major lower == row-major upper triangle of the buffer): dense.cu from 1024 rows on, cuSOLVER trtri below
+static int tri_inverse_inplace(double *L, int N)
 {
-    if (!L || !diag_out || N <= 0) { set_error("gp_inverse_diag: bad argument"); return CSPBO_E_ARG; }
-    if (use_dense(N)) {
-        const int rcd = dense_factor_inverse(L, N, N, 0);
-        if (rcd) return rcd;
-        row_sumsq_upper_kernel<<<(unsigned)((N + 7) / 8), 256>>>(L, N, diag_out);
-        g_launches++;
-        CSPBO_CUDA(cudaGetLastError());
-        return CSPBO_OK;
-    }
+    if (use_dense(N)) return dense_factor_inverse(L, N, N, 0);
     cusolverDnHandle_t h;
     int rc = solver_handle(&h);
     if (rc) return rc;
@@ -339,10 +333,25 @@ extern "C" int cspbo_gp_inverse_diag(double *L, int N, double *diag_out)
     int *info = reinterpret_cast<int *>(sc.small), hinfo = 0;
     s = cusolverDnXtrtri(h, CUBLAS_FILL_MODE_LOWER, CUBLAS_DIAG_NON_UNIT, (int64_t)N, CUDA_R_64F, L, (int64_t)N, sc.work, wdev, hbuf.data(),
                          whost, info);
-    row_sumsq_upper_kernel<<<(unsigned)((N + 7) / 8), 256>>>(L, N, diag_out);
-    g_launches++;
     cudaMemcpy(&hinfo, info, sizeof(int), cudaMemcpyDeviceToHost);
     if (s != CUSOLVER_STATUS_SUCCESS || hinfo != 0) { set_error("trtri failed (status %d, info %d)", (int)s, hinfo); return CSPBO_E_SOLVER; }
+    return CSPBO_OK;
+}
+}  // namespace cspbo
+
+extern "C" int cspbo_gp_tri_inverse_inplace(double *L, int N)
+{
+    if (!L || N <= 0) { set_error("gp_tri_inverse_inplace: bad argument"); return CSPBO_E_ARG; }
+    return tri_inverse_inplace(L, N);
+}
+
+extern "C" int cspbo_gp_inverse_diag(double *L, int N, double *diag_out)
+{
+    if (!L || !diag_out || N <= 0) { set_error("gp_inverse_diag: bad argument"); return CSPBO_E_ARG; }
+    const int rc = tri_inverse_inplace(L, N);
+    if (rc) return rc;
+    row_sumsq_upper_kernel<<<(unsigned)((N + 7) / 8), 256>>>(L, N, diag_out);
+    g_launches++;
     CSPBO_CUDA(cudaGetLastError());
     return CSPBO_OK;
 }

@@ -1016,6 +1016,64 @@ def _inverse_slabs(Ntot, NE_pad, rank, world, rbf, nbw=384, max_cols=_SLAB_MAX):
     return out
 
 
+class _BlockedSubstitution:
+    """Triangular solves of lml_sharded against the trailing triangle U[j0:, j0:] of the factor (Ky = U^T U) with a slab of
+    right-hand sides, as blocked substitutions over row blocks of `nbk` rows whose diagonal blocks are inverted
+    EXPLICITLY once (gp.tri_inverse_inplace, cached per block): every step is then one large dgemm plus one product
+    with a small triangle, which runs about twice as fast as cuBLAS' trsm at these shapes (tools/lml_sharded_probe.py).
+    Blocks sit on a global grid (multiples of nbk) so that all slabs of a rank share the inverses; a slab that starts
+    inside a block gets a ragged first block of its own."""
+
+    def __init__(self, U, Ntot, nbk=None):
+        self.U, self.N = U, Ntot
+        self.nbk = nbk or int(os.environ.get("CSPBO_SUB_BLOCK", "1024"))
+        self._inv = {}
+
+    def _blocks(self, j0):
+        out, a = [], j0
+        while a < self.N:
+            b = min((a // self.nbk + 1) * self.nbk, self.N)
+            out.append((a, b))
+            a = b
+        return out
+
+    def _inverse(self, a, b):
+        from . import gp
+        key = (a, b)
+        if key not in self._inv:
+            import torch
+            blk = self.U[a:b, a:b].clone(memory_format=torch.contiguous_format)        # a copy even when the slice IS the factor
+            self._inv[key] = gp.tri_inverse_inplace(blk)                              # U_kk^-1 (upper)
+        return self._inv[key]
+
+    def forward(self, j0, hj):
+        """Y = (U[j0:, j0:]^T)^-1 E, E = the first hj columns of the identity: [N - j0, hj]."""
+        import torch
+        U = self.U
+        Y = torch.empty((self.N - j0, hj), dtype=U.dtype, device=U.device)
+        for a, b in self._blocks(j0):
+            if a == j0:
+                T = torch.zeros((b - a, hj), dtype=U.dtype, device=U.device)
+            else:
+                T = torch.mm(U[j0:a, a:b].T, Y[: a - j0])          # L[a:b, j0:a] Y[:a]
+                T.neg_()
+            if a - j0 < hj:                                        # rows of E inside this block
+                n1 = min(b - j0, hj) - (a - j0)
+                T[:n1, a - j0: a - j0 + n1].diagonal().add_(1.0)
+            torch.mm(self._inverse(a, b).T, T, out=Y[a - j0: b - j0])
+        return Y
+
+    def backward(self, j0, Y):
+        """Z = U[j0:, j0:]^-1 Y, overwriting Y."""
+        import torch
+        U = self.U
+        for a, b in reversed(self._blocks(j0)):
+            T = Y[a - j0: b - j0]
+            T = T - torch.mm(U[a:b, b:], Y[b - j0:]) if b < self.N else T.clone()
+            torch.mm(self._inverse(a, b), T, out=Y[a - j0: b - j0])
+        return Y
+
+
 def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=None, nbw=384):
     """log marginal likelihood (and its gradient w.r.t. the kernel parameters and the noise) of
     gaussianprocess.py:453-503 with K distributed over the ranks: panel-layout build, sharded Cholesky, and the
@@ -1086,18 +1144,16 @@ def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=Non
             _lib.check(lib.cspbo_block_trace_slab(ctypes.byref(desc), a.handle, bp.handle, c_vp(aps.data_ptr()), c_vp(wptr),
                                                   int(ldw), int(row0), int(col0), int(slab0), int(blk0), int(blk1),
                                                   c_vp(tr.data_ptr()), 1))
+    sub = _BlockedSubstitution(U, Ntot)
     for j0, j1 in _inverse_slabs(Ntot, cov.NE_pad, me, W, rbf, nbw):
         hj = j1 - j0
-        E = torch.zeros((Ntot - j0, hj), dtype=torch.float64, device=dev)
-        E[:hj].fill_diagonal_(1.0)
         # Ky = U^T U: Y = (U^T)^-1 E_J has zeros above row j0, so only the trailing triangle is solved
-        Y = torch.linalg.solve_triangular(U[j0:, j0:].T, E, upper=False)
-        del E
+        Y = sub.forward(j0, hj)
         dinv[j0:j1] = (Y * Y).sum(dim=0)
         if rbf and (j0 < cov.mE or j0 >= cov.NE_pad):
             # rows J of Ky^-1 = (U^-1 Y)^T; only the columns from j0 on are needed (the traces below walk the blocks
             # b >= a, off-diagonal tiles twice), and those depend on the trailing triangle alone
-            slab = torch.linalg.solve_triangular(U[j0:, j0:], Y, upper=True).T.contiguous()      # [hj, Ntot - j0]
+            slab = sub.backward(j0, Y).T.contiguous()      # [hj, Ntot - j0]
             del Y
             slab *= fscale[None, j0:]
             slab *= fscale[j0:j1, None]

@@ -86,6 +86,12 @@ def inverse_diag(L):
     return out
 
 
+def tri_inverse_inplace(U):
+    """U (upper triangular CUDA tensor [n,n], contiguous; its lower triangle is ignored) -> U^-1 in place, lower triangle zeroed."""
+    _lib.check(_lib.load().cspbo_gp_tri_inverse_inplace(c_vp(U.data_ptr()), int(U.shape[0])))
+    return U.triu_()
+
+
 def inverse_workspace_bytes(N):
     """Device workspace (library block cache, not torch's allocator) that inverse_diag / cholesky_inverse* use for an
     N x N factor: leaf results + the chunk buffer of the out-of-place triangular products."""

@@ -297,7 +297,10 @@ int cspbo_gp_cholesky_inverse_inplace(double *L, int N, int mirror);
  * trtri at N = 20 001 -- + a row-wise sum of squares): all the Dot kernel's hyper-gradient needs of K^-1, with no second
  * N x N array.  gaussianprocess.py:490-499 */
 int cspbo_gp_inverse_diag(double *L, int N, double *diag_out);
-/* Bytes of device workspace the two calls above take from the library's block cache for an N x N factor (leaf results +
+/* The triangular factor itself inverted in place: the buffer's row-major upper triangle (= column-major lower L) becomes
+ * L^-1; the other triangle is scratch.  The diagonal-block inverses of distributed.lml_sharded's blocked substitutions. */
+int cspbo_gp_tri_inverse_inplace(double *L, int N);
+/* Bytes of device workspace the calls above take from the library's block cache for an N x N factor (leaf results +
  * the chunk buffer of the out-of-place triangular products: about N^2/16 doubles at large N); 0 on the cuSOLVER path. */
 long long cspbo_gp_inverse_workspace_bytes(int N);
 /* Hyper-gradient trace of an RBF block without materialising dK/dl (gaussianprocess.py:496-499, rbf_kernel.cpp:87-92,

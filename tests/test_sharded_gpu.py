@@ -310,3 +310,25 @@ def _cov_rank_main(rank, world, port, out):
 
 def test_sharded_covariance_two_ranks():
     _spawn2(_cov_rank_main, 29651, 1e-8)
+
+
+@pytest.mark.parametrize("N,nbk,j0,hj", [(1500, 256, 0, 384), (1500, 256, 288, 600), (2100, 1100, 96, 96), (700, 2048, 192, 508), (700, 2048, 0, 96), (1030, 128, 1000, 30)])
+def test_blocked_substitution_matches_triangular_solves(N, nbk, j0, hj):
+    """distributed._BlockedSubstitution (the slab solves of lml_sharded): explicit diagonal-block inverses + dgemm sweeps
+    against torch's triangular solves; ragged first and last blocks, slabs wider than a block, junk below U's diagonal."""
+    import torch
+    from csp_bo_b200.distributed import _BlockedSubstitution
+    g = torch.Generator(device="cuda").manual_seed(N + j0)
+    A = torch.randn(N, N + 30, dtype=torch.float64, device="cuda", generator=g)
+    U = torch.linalg.cholesky(A @ A.T / N + 0.5 * torch.eye(N, dtype=torch.float64, device="cuda"), upper=True)
+    Ujunk = U + torch.tril(torch.randn(N, N, dtype=torch.float64, device="cuda", generator=g), -1)   # the sharded factor's lower part is scratch
+    sub = _BlockedSubstitution(Ujunk, N, nbk=nbk)
+    E = torch.zeros((N - j0, hj), dtype=torch.float64, device="cuda")
+    E[:hj].fill_diagonal_(1.0)
+    Yref = torch.linalg.solve_triangular(U[j0:, j0:].T, E, upper=False)
+    Y = sub.forward(j0, hj)
+    assert float((Y - Yref).abs().max()) <= 1e-11 * float(Yref.abs().max())
+    Zref = torch.linalg.solve_triangular(U[j0:, j0:], Yref, upper=True)
+    Z = sub.backward(j0, Y)
+    assert float((Z - Zref).abs().max()) <= 1e-11 * float(Zref.abs().max())
+    assert torch.equal(torch.triu(Ujunk), U)          # the factor itself is left alone
