@@ -262,6 +262,11 @@ block_tile_kernel(const TileParams p)
     constexpr int NC1 = (MODE == MODE_KFF) ? 3 : 1;
     constexpr int NC2 = (MODE == MODE_KEE) ? 1 : 3;
     constexpr bool GRAD = (FAM == FAM_RBF_GRAD);
+#ifdef CSPBO_KEE_SINGLE_CHAIN
+    constexpr bool DUAL = false;
+#else
+    constexpr bool DUAL = (MODE == MODE_KEE);
+#endif
     constexpr int HALF = KS / 2;
     const int nch = CHUNKED ? p.nch : 1;
     const int halft = HALF * nch;                        // 128-bit fragment rows per vector of a tile
@@ -385,6 +390,9 @@ block_tile_kernel(const TileParams p)
                 for (int v1 = 0; v1 < NV1; v1++)
 #pragma unroll
                     for (int v2 = 0; v2 < NV2; v2++) H[v1][v2][0] = H[v1][v2][1] = 0.0;
+                // K_EE has ONE accumulator pair per tile pair, so its KS DMMAs would form one dependent chain: the odd
+                // k-steps go to a second pair (two chains of KS/2) that is added at the end
+                double G0 = 0.0, G1 = 0.0;
 
                 const double2 *bt = reinterpret_cast<const double2 *>(sB + (size_t)tb * p.B.tile_doubles);
                 for (int ch = 0; ch < nch; ch++) {
@@ -403,12 +411,17 @@ block_tile_kernel(const TileParams p)
                         for (int v2 = 0; v2 < NV2; v2++)
 #pragma unroll
                             for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h], b[v2].x);
+                        if (DUAL) {
+                            dmma(G0, G1, a[0][2 * h + 1], b[0].y);
+                        } else {
 #pragma unroll
-                        for (int v2 = 0; v2 < NV2; v2++)
+                            for (int v2 = 0; v2 < NV2; v2++)
 #pragma unroll
-                            for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h + 1], b[v2].y);
+                                for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h + 1], b[v2].y);
+                        }
                     }
                 }
+                if (DUAL) { H[0][0][0] += G0; H[0][0][1] += G1; }
 
                 const unsigned vb = __ldg(p.B.tile_valid + b_tile0 + tb);
 #pragma unroll
