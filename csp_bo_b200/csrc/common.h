@@ -39,7 +39,7 @@ constexpr int kSlots = 8;
 // Grow-only device scratch buffers, cached per (device, slot) so that host-pointer calls do not
 // cudaMalloc / cudaFree gigabytes on every call (measured: 2 ms typical, but outliers of 0.2-2 s).
 // Not thread safe across concurrent builds in one process; cspbo_release_scratch() frees them.
-enum { SCRATCH_OUT = 0, SCRATCH_GRAD = 1, SCRATCH_X = 2, SCRATCH_DX = 3, SCRATCH_DEST = 4, SCRATCH_GEMV = 5, SCRATCH_SLOTS = 6 };
+enum { SCRATCH_OUT = 0, SCRATCH_GRAD = 1, SCRATCH_X = 2, SCRATCH_DX = 3, SCRATCH_DEST = 4, SCRATCH_GEMV = 5, SCRATCH_PLANES = 6, SCRATCH_SLOTS = 7 };
 int scratch_get(int slot, size_t bytes, void **ptr);
 
 // Small caching allocator for the pack's device arrays: blocks released by cspbo_pack_destroy are kept

@@ -65,6 +65,9 @@ struct TileParams {
     int pass_side;          //   pass_side (0 = A: K_FF stress rows, 1 = B: K_EF stress columns) and stores at out + q*pass_off
     long long pass_off;
     int tbc;  // B tiles per shared-memory chunk
+    int bsplit;      // > 1 (small problems): gridDim.y CTAs share one (A block, B block) pair, CTA y takes the B-tile runs
+                     //      y, y + bsplit, ... and stores its partial block into plane y (out + y * pass_off); the planes are
+                     //      summed in a fixed order by plane_reduce_kernel
     int strip;  // A-block groups per rasterisation strip
     int symmetric;
     int split;       // 1: the warps of a CTA share ONE A block and split its tiles (small problems: 4x more
@@ -253,7 +256,9 @@ __device__ __forceinline__ Weights pair_weights(double c, bool valid, const Tile
 // tile pair accumulate over the chunks with the A fragments re-read from global memory (L1) per chunk instead of living
 // in registers for the whole sweep, so any d runs at the register budget of the d <= 24 kernel (dot_kernel.cpp:257-289
 // loops `i < d` for any d; SO3.py:205 gives d = 90 at nmax = lmax = 5).
-template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED>
+// BS: the B-run split instantiations (p.bsplit > 1, small problems); a separate instantiation so that the code of the
+// large builds stays exactly what it was (a run-time switch cost RBF K_EE 2-3 %).
+template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED, bool BS = false>
 __global__ void __launch_bounds__(kMaxWarps * 32, (KS <= 6 && FAM != FAM_RBF_GRAD && !CHUNKED) ? kMinCtas : (kMinCtas > 1 ? 2 : 1))
 block_tile_kernel(const TileParams p)
 {
@@ -265,17 +270,21 @@ block_tile_kernel(const TileParams p)
 #ifdef CSPBO_KEE_SINGLE_CHAIN
     constexpr bool DUAL = false;
 #else
-    constexpr bool DUAL = (MODE == MODE_KEE);
+    constexpr bool DUAL = (MODE == MODE_KEE) && (BS || FAM != FAM_DOT);
 #endif
+    // (measured, tools/kee_probe.py: two chains are 15 % faster for small K_EE builds and 1-2 % for RBF at any size, but
+    // 3-5 % slower for large Dot K_EE builds, whose 6 warps per scheduler hide the chain anyway; a run-time switch cost
+    // the large builds 5-8 %, so the choice is made at compile time)
     constexpr int HALF = KS / 2;
     const int nch = CHUNKED ? p.nch : 1;
     const int halft = HALF * nch;                        // 128-bit fragment rows per vector of a tile
     const bool staged = CHUNKED ? (p.staged != 0) : true;
     // stress variants: pass q (blockIdx.y) works on derivative vectors 1+3q .. 3+3q of one side
-    const int pass = blockIdx.y;
+    const int pass = BS ? 0 : blockIdx.y;
+    const int zb = BS ? blockIdx.y : 0, nzb = BS ? p.bsplit : 1;
     const int voffA = p.A.voff + ((p.npass > 1 && p.pass_side == 0) ? 3 * pass : 0);
     const int voffB = p.B.voff + ((p.npass > 1 && p.pass_side == 1) ? 3 * pass : 0);
-    double *const out = p.out + pass * p.pass_off;
+    double *const out = p.out + blockIdx.y * p.pass_off;
 
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31;
@@ -342,6 +351,8 @@ block_tile_kernel(const TileParams p)
 
     ChunkIter cur;
     cur.start(p, b_blk);
+    if (BS)
+        for (int s = 0; s < zb && !cur.done(p); s++) cur.next(p, b_blk);
     auto issue = [&](const ChunkIter &c, int st) {
         const unsigned bytes = (unsigned)(c.nt(p) * p.B.tile_doubles * (int)sizeof(double));
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of this stage are done
@@ -352,6 +363,8 @@ block_tile_kernel(const TileParams p)
     for (int it = 0; !cur.done(p); it++) {
         ChunkIter nxt = cur;
         nxt.next(p, b_blk);
+        if (BS)
+            for (int s = 1; s < nzb && !nxt.done(p); s++) nxt.next(p, b_blk);
         const int st = it & 1;
         // prefetch the next run into the other stage (its last readers passed the barrier below)
         if (staged && !nxt.done(p) && threadIdx.x == 0) issue(nxt, st ^ 1);
@@ -390,8 +403,8 @@ block_tile_kernel(const TileParams p)
                 for (int v1 = 0; v1 < NV1; v1++)
 #pragma unroll
                     for (int v2 = 0; v2 < NV2; v2++) H[v1][v2][0] = H[v1][v2][1] = 0.0;
-                // K_EE has ONE accumulator pair per tile pair, so its KS DMMAs would form one dependent chain: the odd
-                // k-steps go to a second pair (two chains of KS/2) that is added at the end
+                // K_EE has ONE accumulator pair per tile pair, so its KS DMMAs form one dependent chain: in the latency-bound
+                // cases the odd k-steps go to a second pair (two chains of KS/2) that is added at the end
                 double G0 = 0.0, G1 = 0.0;
 
                 const double2 *bt = reinterpret_cast<const double2 *>(sB + (size_t)tb * p.B.tile_doubles);
@@ -663,11 +676,34 @@ block_tile_kernel(const TileParams p)
     }
 }
 
+// out[i, k, j, l] (caller strides) = [accumulate ? out : 0] + sum_z planes[z][i, k, j, l] (dense planes), z in order
+__global__ void plane_reduce_kernel(const double *__restrict__ planes, long long plane, int nz, int nc1, int m2, int nc2, double *__restrict__ out,
+                                    long long si, long long sk, long long sj, long long sl, int accumulate)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= plane) return;
+    double s = 0.0;
+    for (int z = 0; z < nz; z++) s += planes[(long long)z * plane + idx];
+    const int l = (int)(idx % nc2);
+    long long r = idx / nc2;
+    const int j = (int)(r % m2);
+    r /= m2;
+    const int k = (int)(r % nc1);
+    const long long i = r / nc1;
+    const long long o = i * si + k * sk + j * sj + l * sl;
+    out[o] = accumulate ? out[o] + s : s;
+}
+
 // ------------------------------------------------------------------------------------------
-template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED>
+template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED, bool BS = false>
 static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t st)
 {
-    auto kern = block_tile_kernel<MODE, FAM, KS, Z2, CHUNKED>;
+    if (!BS && p.bsplit > 1) {      // build_block_device only asks for the split where these instantiations exist
+        if (FAM != FAM_RBF_GRAD && !CHUNKED) return launch_one<MODE, (FAM == FAM_RBF_GRAD ? FAM_RBF : FAM), KS, Z2, false, true>(p, nwarps, smem, st);
+        set_error("block_build: B-run split without an instantiation");
+        return CSPBO_E_ARG;
+    }
+    auto kern = block_tile_kernel<MODE, FAM, KS, Z2, CHUNKED, BS>;
     // the opt-in is a per-device attribute of the function: remember it per device ordinal (a thread may switch
     // devices through cspbo_set_device); races between threads only repeat a cheap idempotent call
     static size_t configured[64] = {};
@@ -683,7 +719,7 @@ static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t
     const long long grid = (long long)npg * p.b_nblk;
     if (grid <= 0) return CSPBO_OK;
     if (grid > 0x7fffffffLL) { set_error("block_build: grid too large"); return CSPBO_E_ARG; }
-    kern<<<dim3((unsigned)grid, (unsigned)std::max(p.npass, 1)), nwarps * 32, smem, st>>>(p);
+    kern<<<dim3((unsigned)grid, (unsigned)std::max(std::max(p.npass, p.bsplit), 1)), nwarps * 32, smem, st>>>(p);
     g_launches++;
     {
         cudaError_t e = cudaGetLastError();
@@ -863,7 +899,40 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
         if (tile_bytes <= (size_t)96 * 1024) stage_bytes = tile_bytes;
         else p.staged = 0;
     }
-    const int tbc = p.staged ? (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, stage_bytes / tile_bytes)) : maxTb;
+    int tbc = p.staged ? (int)std::max<size_t>(1, std::min<size_t>((size_t)maxTb, stage_bytes / tile_bytes)) : maxTb;
+    // Small problems whose (A block, B block) pairs are few but long (a K_EE of some dozens of 192-atom structures: one
+    // CTA per pair walked 0.4 ms alone while most SMs idled): bsplit CTAs share a pair, each taking every bsplit-th run
+    // of B tiles, and their partial blocks are summed in a fixed order afterwards (deterministic; no atomics).
+    p.bsplit = 1;
+    long long plane = 0;
+    const int nc1 = (mode == MODE_KFF) ? 3 : 1, nc2 = (mode == MODE_KEE) ? 1 : 3;
+    const int bsplit_env = getenv("CSPBO_BSPLIT") ? atoi(getenv("CSPBO_BSPLIT")) : -1;     // 0 / 1 = off, n = force (tests, experiments)
+    if (p.split && !p.sharded && !diag && !trace && p.npass == 1 && fam != FAM_RBF_GRAD && st == nullptr && a_begin <= 0 && a_end < 0 &&
+        !chunked && out && bsplit_env != 0 && bsplit_env != 1) {
+        // tiles of the heaviest B block and tile pairs of the heaviest block pair
+        long long tsum = 0, pairs = 0;
+        for (int q = 0; q < (int)b->n_blocks; q++) {
+            long long t = 0;
+            for (int ea = 0; ea < nsA; ea++)
+                if (emap[(size_t)ea] >= 0) t += b->h_tile_start[(size_t)q * nsB + emap[(size_t)ea] + 1] - b->h_tile_start[(size_t)q * nsB + emap[(size_t)ea]];
+            tsum = std::max(tsum, t);
+        }
+        for (int ea = 0; ea < nsA; ea++)
+            if (emap[(size_t)ea] >= 0)
+                pairs += (long long)(a->h_tile_start[(size_t)ea + 1] - a->h_tile_start[(size_t)ea]) *
+                         (b->h_tile_start[(size_t)emap[(size_t)ea] + 1] - b->h_tile_start[(size_t)emap[(size_t)ea]]);     // block 0 x block 0 (the fullest)
+        const long long ctas = d.symmetric ? (long long)a_mine * (p.b_nblk + 1) / 2 : (long long)a_mine * p.b_nblk;
+        const long long dmma_per_cta = pairs * (a->ks) * (mode == MODE_KFF ? 16 : (mode == MODE_KEF ? 4 : 1));
+        // as many CTAs as the SMs hold at once (6 / 4 / 3 per SM for K_EE / K_EF / K_FF at their register and stage sizes)
+        const long long resident = (mode == MODE_KEE ? 6LL : (mode == MODE_KEF ? 4LL : 3LL)) * sms;
+        int nz = (int)std::min<long long>(16, resident / std::max<long long>(ctas, 1));
+        if (bsplit_env > 1) nz = bsplit_env;
+        plane = (long long)a->m * nc1 * b->m * nc2;
+        if (nz >= 2 && tsum >= 2 * nz && (dmma_per_cta >= 20000 || bsplit_env > 1) && plane * nz * (long long)sizeof(double) <= (64LL << 20)) {
+            tbc = (int)std::max<long long>(1, std::min<long long>(tbc, tsum / (2 * nz)));      // at least ~2 runs per CTA
+            p.bsplit = nz;
+        }
+    }
     p.tbc = tbc;
     // the stage buffers double as the scratch of the split-mode reduction (NACC accumulators per thread of 3 warps)
     const int nacc = 2 * (mode == MODE_KFF ? 9 : (mode == MODE_KEF ? 3 : 1)) * (fam == FAM_RBF_GRAD ? 2 : 1);
@@ -912,9 +981,26 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     // (d in (24, 56], K_FF with pow / exp in the epilogue: the KS = 14 instantiations spill 150-700 bytes around the libm
     // calls; re-reading the A fragments per B tile instead -- the CHUNKED kernel with one chunk -- removes most of the spill
     // but was measured SLOWER, RBF d = 50: 69.8 -> 73.2 ms, tools/ks14_probe.py, so the spilling variants stay)
-    const int rc_launch = (a->ks == 6) ? launch_ks<6, false>(mode, fam, z2, p, nwarps, smem, st)
+    double *final_out = p.out;
+    const long long fsi = p.si, fsk = p.sk, fsj = p.sj, fsl = p.sl;
+    if (p.bsplit > 1) {
+        void *sp = nullptr;
+        const int rcs = scratch_get(SCRATCH_PLANES, (size_t)plane * p.bsplit * sizeof(double), &sp);
+        if (rcs) { if (emap_dev) dev_free_cached(emap_dev); return rcs; }
+        p.out = static_cast<double *>(sp);
+        p.pass_off = plane;
+        p.accumulate = 0;
+        p.si = (long long)nc1 * b->m * nc2; p.sk = (long long)b->m * nc2; p.sj = nc2; p.sl = 1;     // dense planes [m1, nc1, m2, nc2]
+    }
+    int rc_launch = (a->ks == 6) ? launch_ks<6, false>(mode, fam, z2, p, nwarps, smem, st)
                           : (a->ks == 14) ? launch_ks<14, false>(mode, fam, z2, p, nwarps, smem, st)
                                           : launch_ks<6, true>(mode, fam, z2, p, nwarps, smem, st);
+    if (p.bsplit > 1 && rc_launch == CSPBO_OK) {
+        plane_reduce_kernel<<<(unsigned)((plane + 255) / 256), 256, 0, st>>>(p.out, plane, p.bsplit, nc1, b->m, nc2, final_out, fsi, fsk, fsj, fsl,
+                                                                             accumulate);
+        g_launches++;
+        if (cudaGetLastError() != cudaSuccess) { set_error("plane_reduce_kernel launch failed"); rc_launch = CSPBO_E_CUDA; }
+    }
     if (emap_dev) {
         cudaStreamSynchronize(st);
         dev_free_cached(emap_dev);

@@ -334,3 +334,39 @@ def test_fused_diagonal_block_factorisation_matches_cusolver(h):
     ferr, ierr, info = l1.split()
     assert float(ferr) < 1e-13 and float(ierr) < 1e-12 and int(info) == 0
     assert int(l2) == 1          # first non-positive pivot reported like cuSOLVER's devInfo
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_b_run_split_matches_the_unsplit_build(single, monkeypatch):
+    """Small problems: gridDim.y CTAs share a block pair (each takes every n-th run of B tiles) and plane_reduce_kernel
+    sums their partial blocks (tiles.cu, bsplit).  Same numbers as the one-CTA-per-pair build to rounding, for every block
+    kind, symmetric and not, written into a strided sub-block of a larger matrix, and twice the same bits (deterministic)."""
+    import torch
+    from csp_bo_b200 import _lib, synthetic
+    from csp_bo_b200.kernels import Dot_mb, RBF_mb
+    from csp_bo_b200.kernels import device as kdev
+    from csp_bo_b200.packing import resident
+    E = synthetic.energy_set(40, seed=5, single_element=single, rows_per_structure=96)
+    F = synthetic.force_set(160, seed=6, single_element=single)
+    E2 = synthetic.energy_set(9, seed=7, single_element=single, rows_per_structure=96)
+    F2 = synthetic.force_set(50, seed=8, single_element=single)
+    d1, d2 = resident({"energy": E, "force": F}), resident({"energy": E2, "force": F2})
+    launches = {}
+    for kern in (Dot_mb(para=[18.5, 0.01], zeta=2), RBF_mb(para=[6.2, 0.56], zeta=2), Dot_mb(para=[18.5, 0.01], zeta=3)):
+        res = {}
+        for mode in ("1", "5", "auto", "5"):
+            if mode == "auto":
+                monkeypatch.delenv("CSPBO_BSPLIT", raising=False)
+            else:
+                monkeypatch.setenv("CSPBO_BSPLIT", mode)
+            n0 = _lib.launch_count()
+            K = kdev.k_total_device(kern, d1)                      # symmetric K_EE / K_FF + K_EF into one matrix
+            Ks = kdev.k_total_device(kern, d2, d1)                 # K*: non-symmetric blocks
+            launches.setdefault(mode, _lib.launch_count() - n0)
+            res.setdefault(mode, []).append((K, Ks))
+        (K1, Ks1), (K5, Ks5), (K5b, Ks5b) = res["1"][0], res["5"][0], res["5"][1]
+        Ka, Ksa = res["auto"][0]
+        for ref, got in ((K1, K5), (Ks1, Ks5), (K1, Ka), (Ks1, Ksa)):
+            assert float((ref - got).abs().max()) <= 1e-13 * float(ref.abs().max())
+        assert torch.equal(K5, K5b) and torch.equal(Ks5, Ks5b)
+    assert launches["5"] > launches["1"]                           # the forced split really ran (one reduce launch per block)

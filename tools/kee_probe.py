@@ -8,7 +8,7 @@ from tools.sweep import block_line, epack, peaks
 
 fp64, _ = peaks()
 for single in (False, True):
-    for n_struct in (41, 83, 208, 416, 833):
+    for n_struct in [int(v) for v in os.environ.get('KEE_SIZES', '41,83,208,416,833').split(',')]:
         pe = epack(n_struct, single)
         for fam in (_lib.DOT, _lib.RBF):
             r = block_line(fam, _lib.KEE, pe, pe, True, "%d structures of 192 atoms%s" % (n_struct, ", single species" if single else ""), fp64)
