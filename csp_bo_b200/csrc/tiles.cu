@@ -60,6 +60,7 @@ struct TileParams {
     int a_begin;  // first A block of this launch (row-slab pipelining of host-bound builds); a_nblk is the end
     int emap[kMaxSpecies];  // species bucket of A -> bucket of B holding the same species id, or -1
     const int *emap_dev;    // the same map in device memory when A has more than kMaxSpecies buckets (else null)
+    int kc;                 // KS = 14 kernels (24 < d <= 56): k-steps that hold features, ceil(d / 4); the rest of the 14 multiply zeros and are skipped
     int nch, staged;        // chunked kernels (d > 56): k-chunks of 6 steps per tile; staged = B tiles go through shared memory
     int npass;              // stress variants: gridDim.y passes, pass q uses derivative vectors 1+3q .. 3+3q of the side
     int pass_side;          //   pass_side (0 = A: K_FF stress rows, 1 = B: K_EF stress columns) and stores at out + q*pass_off
@@ -76,6 +77,7 @@ struct TileParams {
     int diag;        // 1: one warp per block, b = a, only the (i,i) group pairs are stored: out[i, NC1, NC2]
     int accumulate;  // 1: out += result (reference `pout +=` semantics), 0: out = result
     double zeta, sigma2, sigma02, inv2l2, inv_l, inv_l3, tol;
+    int zint;        // zeta when it is an integer in [1, 8] (other than the Z2 instantiations' 2), else 0
     int use_tol;
     double scale, scale_grad;
     double *out, *out_grad;
@@ -209,6 +211,17 @@ __device__ __forceinline__ Weights pair_weights(double c, bool valid, const Tile
     double cm2, cm1, cz;  // c^(z-2), c^(z-1), c^z
     if (Z2) {
         cm2 = 1.0; cm1 = c; cz = c * c;
+    } else if (p.zint != 0) {
+        // integer zeta (1, 3, 4, ...): the powers by multiplication (a uniform branch) instead of libm's pow, which costs
+        // the zeta = 3 K_FF a quarter of its run time (tools/ks14_probe.py)
+        if (p.zint == 1) {
+            cm2 = 1.0 / c;
+        } else {
+            cm2 = 1.0;
+            for (int i = 2; i < p.zint; i++) cm2 *= c;
+        }
+        cm1 = c * cm2;
+        cz = c * cm1;
     } else {
         cm2 = pow(c, z - 2.0);   // reference: d2 = pow(dx, zeta-2); d1 = dx*d2  (dot_kernel.cpp:265-267)
         cm1 = c * cm2;
@@ -258,7 +271,8 @@ __device__ __forceinline__ Weights pair_weights(double c, bool valid, const Tile
 // loops `i < d` for any d; SO3.py:205 gives d = 90 at nmax = lmax = 5).
 // BS: the B-run split instantiations (p.bsplit > 1, small problems); a separate instantiation so that the code of the
 // large builds stays exactly what it was (a run-time switch cost RBF K_EE 2-3 %).
-template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED, bool BS = false>
+// VK (KS = 14 only): the k-steps beyond p.kc = ceil(d / 4) are skipped -- d = 30 / 40 / 50 need 8 / 10 / 13 of the 14.
+template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED, bool BS = false, bool VK = false>
 __global__ void __launch_bounds__(kMaxWarps * 32, (KS <= 6 && FAM != FAM_RBF_GRAD && !CHUNKED) ? kMinCtas : (kMinCtas > 1 ? 2 : 1))
 block_tile_kernel(const TileParams p)
 {
@@ -276,6 +290,7 @@ block_tile_kernel(const TileParams p)
     // 3-5 % slower for large Dot K_EE builds, whose 6 warps per scheduler hide the chain anyway; a run-time switch cost
     // the large builds 5-8 %, so the choice is made at compile time)
     constexpr int HALF = KS / 2;
+    constexpr bool VARK = VK;
     const int nch = CHUNKED ? p.nch : 1;
     const int halft = HALF * nch;                        // 128-bit fragment rows per vector of a tile
     const bool staged = CHUNKED ? (p.staged != 0) : true;
@@ -412,6 +427,11 @@ block_tile_kernel(const TileParams p)
                     if (CHUNKED) load_a(ch);
 #pragma unroll
                     for (int h = 0; h < HALF; h++) {
+                        // VK: the unrolled steps beyond p.kc are skipped under a uniform predicate (their operands are zero
+                        // padding: same bits either way).  Measured at 10 002 force rows (tools/ks14_probe.py): K_FF Dot d = 30 /
+                        // 40 / 50: 63.0 -> 39.6 / 47.6 / 59.5 ms; with nothing to skip the predicates cost K_EE 18 % and RBF
+                        // K_FF 5 %, hence a separate instantiation that launch_one picks only where it pays
+                        if (VARK && 2 * h >= p.kc) continue;
                         // one 128-bit LDS per B vector = operands of k-steps 2h and 2h+1; the 16 accumulators
                         // of a k-step are independent, so consecutive DMMAs never wait on each other
                         double2 b[NV2];
@@ -424,6 +444,7 @@ block_tile_kernel(const TileParams p)
                         for (int v2 = 0; v2 < NV2; v2++)
 #pragma unroll
                             for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h], b[v2].x);
+                        if (VARK && 2 * h + 1 >= p.kc) continue;
                         if (DUAL) {
                             dmma(G0, G1, a[0][2 * h + 1], b[0].y);
                         } else {
@@ -695,15 +716,18 @@ __global__ void plane_reduce_kernel(const double *__restrict__ planes, long long
 }
 
 // ------------------------------------------------------------------------------------------
-template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED, bool BS = false>
+template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED, bool BS = false, bool VK = false>
 static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t st)
 {
+    if constexpr (KS == 14 && !CHUNKED && !VK) {
+        if (p.kc <= 12 || (p.kc == 13 && MODE != MODE_KEE)) return launch_one<MODE, FAM, KS, Z2, CHUNKED, BS, true>(p, nwarps, smem, st);
+    }
     if (!BS && p.bsplit > 1) {      // build_block_device only asks for the split where these instantiations exist
         if (FAM != FAM_RBF_GRAD && !CHUNKED) return launch_one<MODE, (FAM == FAM_RBF_GRAD ? FAM_RBF : FAM), KS, Z2, false, true>(p, nwarps, smem, st);
         set_error("block_build: B-run split without an instantiation");
         return CSPBO_E_ARG;
     }
-    auto kern = block_tile_kernel<MODE, FAM, KS, Z2, CHUNKED, BS>;
+    auto kern = block_tile_kernel<MODE, FAM, KS, Z2, CHUNKED, BS, VK>;
     // the opt-in is a per-device attribute of the function: remember it per device ordinal (a thread may switch
     // devices through cspbo_set_device); races between threads only repeat a cheap idempotent call
     static size_t configured[64] = {};
@@ -794,6 +818,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     p.pass_side = passes ? passes->side : 0;
     p.pass_off = passes ? passes->off : 0;
     p.zeta = d.zeta; p.sigma2 = d.sigma2; p.sigma02 = d.sigma02;
+    p.zint = (d.zeta >= 1.0 && d.zeta <= 8.0 && d.zeta == (double)(int)d.zeta) ? (int)d.zeta : 0;
     p.inv2l2 = d.family == CSPBO_RBF ? 1.0 / (2.0 * d.l * d.l) : 0.0;
     p.inv_l = d.family == CSPBO_RBF ? 1.0 / d.l : 0.0;
     p.inv_l3 = d.family == CSPBO_RBF ? p.inv_l / (d.l * d.l) : 0.0;
@@ -894,6 +919,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     // side) the B fragments are read straight from global memory
     const bool chunked = a->ks != 6 && a->ks != 14;
     p.nch = chunked ? a->ks / 6 : 1;
+    p.kc = std::min((a->d + 3) / 4, (int)a->ks);
     p.staged = 1;
     if (chunked && tile_bytes > stage_bytes) {
         if (tile_bytes <= (size_t)96 * 1024) stage_bytes = tile_bytes;

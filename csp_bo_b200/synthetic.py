@@ -49,7 +49,7 @@ def force_set(n_atoms, seed=0, single_element=False, d=24):
     return (np.ascontiguousarray(X), np.ascontiguousarray(dX), E, [int(c) for c in counts[pick]])
 
 
-def energy_set(n_structures, seed=1, single_element=False, rows_per_structure=192):
+def energy_set(n_structures, seed=1, single_element=False, rows_per_structure=192, d=24):
     """Stacked energy tuple (X, ELE, indices): structures of `rows_per_structure` atoms drawn from the
     X2_EE fixture rows (Cpp_code/Kff_QZ/X2_EE.npy: 16 structures x 192 atoms)."""
     _base()
@@ -58,6 +58,8 @@ def energy_set(n_structures, seed=1, single_element=False, rows_per_structure=19
     rows = rng.integers(0, len(x), size=n_structures * rows_per_structure)
     fac = np.exp(rng.normal(0.0, 0.05, size=len(rows)))
     X = x[rows] * fac[:, None]
+    if d != 24:
+        X = X @ _mix(d)
     E = np.full(len(rows), 14, dtype=np.int32) if single_element else ele[rows].astype(np.int32)
     return (np.ascontiguousarray(X), E, [rows_per_structure] * n_structures)
 
