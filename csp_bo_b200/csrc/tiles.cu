@@ -60,7 +60,7 @@ struct TileParams {
     int a_begin;  // first A block of this launch (row-slab pipelining of host-bound builds); a_nblk is the end
     int emap[kMaxSpecies];  // species bucket of A -> bucket of B holding the same species id, or -1
     const int *emap_dev;    // the same map in device memory when A has more than kMaxSpecies buckets (else null)
-    int kc;                 // KS = 14 kernels (24 < d <= 56): k-steps that hold features, ceil(d / 4); the rest of the 14 multiply zeros and are skipped
+    int kc;                 // unchunked kernels: k-steps that hold features, ceil(d / 4); the rest of the KS multiply zeros (VK instantiations skip them)
     int nch, staged;        // chunked kernels (d > 56): k-chunks of 6 steps per tile; staged = B tiles go through shared memory
     int npass;              // stress variants: gridDim.y passes, pass q uses derivative vectors 1+3q .. 3+3q of the side
     int pass_side;          //   pass_side (0 = A: K_FF stress rows, 1 = B: K_EF stress columns) and stores at out + q*pass_off
@@ -271,7 +271,7 @@ __device__ __forceinline__ Weights pair_weights(double c, bool valid, const Tile
 // loops `i < d` for any d; SO3.py:205 gives d = 90 at nmax = lmax = 5).
 // BS: the B-run split instantiations (p.bsplit > 1, small problems); a separate instantiation so that the code of the
 // large builds stays exactly what it was (a run-time switch cost RBF K_EE 2-3 %).
-// VK (KS = 14 only): the k-steps beyond p.kc = ceil(d / 4) are skipped -- d = 30 / 40 / 50 need 8 / 10 / 13 of the 14.
+// VK: the k-steps beyond p.kc = ceil(d / 4) are skipped -- d = 30 / 40 / 50 need 8 / 10 / 13 of the 14, d = 9 / 18 need 3 / 5 of the 6.
 template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED, bool BS = false, bool VK = false>
 __global__ void __launch_bounds__(kMaxWarps * 32, (KS <= 6 && FAM != FAM_RBF_GRAD && !CHUNKED) ? kMinCtas : (kMinCtas > 1 ? 2 : 1))
 block_tile_kernel(const TileParams p)
@@ -719,8 +719,9 @@ __global__ void plane_reduce_kernel(const double *__restrict__ planes, long long
 template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED, bool BS = false, bool VK = false>
 static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t st)
 {
-    if constexpr (KS == 14 && !CHUNKED && !VK) {
-        if (p.kc <= 12 || (p.kc == 13 && MODE != MODE_KEE)) return launch_one<MODE, FAM, KS, Z2, CHUNKED, BS, true>(p, nwarps, smem, st);
+    if constexpr (!CHUNKED && !VK) {      // d = 9 / 12 / 18 need 3 / 3 / 5 of the 6 k-steps, d = 30 / 40 / 50 need 8 / 10 / 13 of the 14
+        // (one skippable step pays only for the Dot K_FF kernels: -14 % at d = 18, -6 % at d = 50; the others lose 1-2 % to the predicates)
+        if (p.kc <= KS - 2 || (p.kc == KS - 1 && MODE == MODE_KFF && FAM == FAM_DOT)) return launch_one<MODE, FAM, KS, Z2, CHUNKED, BS, true>(p, nwarps, smem, st);
     }
     if (!BS && p.bsplit > 1) {      // build_block_device only asks for the split where these instantiations exist
         if (FAM != FAM_RBF_GRAD && !CHUNKED) return launch_one<MODE, (FAM == FAM_RBF_GRAD ? FAM_RBF : FAM), KS, Z2, false, true>(p, nwarps, smem, st);
