@@ -1,7 +1,7 @@
 """Registers / spills / shared memory of every tile-kernel instantiation (ptxas -v), as a table.
 
     python tools/resource_usage.py [> profiles/resource_usage_rNN.txt]
-Template arguments: MODE (0 K_EE, 1 K_EF, 2 K_FF), FAM (0 Dot, 1 RBF, 2 RBF with dK/dl), KS, zeta==2, CHUNKED.
+Template arguments: MODE (0 K_EE, 1 K_EF, 2 K_FF), FAM (0 Dot, 1 RBF, 2 RBF with dK/dl), KS, zeta==2, CHUNKED, BS (B-run split), VK (skips zero k-steps).
 """
 import os
 import re

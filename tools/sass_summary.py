@@ -14,11 +14,14 @@ for ln in txt.splitlines():
     elif cur is not None and re.search(r"/\*[0-9a-f]{4}\*/", ln):
         funcs[cur].append(ln)
 KEYS = ["DMMA", "DFMA", "DMUL", "DADD", "UBLKCP", "SYNCS", "LDS.128", "LDG.E.128", "LDG", "STG", "STS", "STL", "LDL", "MUFU", "BAR", "SHFL", "CALL"]
-want = ["block_tile_kernel<2, 0, 6, true, false>", "block_tile_kernel<2, 0, 14, true, false>", "block_tile_kernel<2, 0, 6, true, true>",
-        "block_tile_kernel<2, 1, 6, true, false>", "block_tile_kernel<2, 2, 6, true, false>", "block_tile_kernel<2, 2, 14, true, false>",
-        "block_tile_kernel<1, 0, 6, true, false>", "block_tile_kernel<0, 0, 6, true, false>", "block_tile_kernel<0, 1, 6, true, false>"]
+T = ", false, false>"      # BS (B-run split), VK (skips zero k-steps)
+want = ["block_tile_kernel<2, 0, 6, true, false" + T, "block_tile_kernel<2, 0, 14, true, false" + T, "block_tile_kernel<2, 0, 14, true, false, false, true>",
+        "block_tile_kernel<2, 0, 6, true, true" + T,
+        "block_tile_kernel<2, 1, 6, true, false" + T, "block_tile_kernel<2, 2, 6, true, false" + T, "block_tile_kernel<2, 2, 14, true, false" + T,
+        "block_tile_kernel<1, 0, 6, true, false" + T, "block_tile_kernel<0, 0, 6, true, false" + T, "block_tile_kernel<0, 1, 6, true, false" + T,
+        "block_tile_kernel<0, 1, 6, true, false, true, false>"]
 print("# SASS instruction mix of the tile kernels (cuobjdump -sass csp_bo_b200/lib/libcspbo_b200.so, sm_100a)\n")
-print("Template arguments: MODE (0 K_EE, 1 K_EF, 2 K_FF), FAM (0 Dot, 1 RBF, 2 RBF + dK/dl), KS, zeta == 2, CHUNKED.")
+print("Template arguments: MODE (0 K_EE, 1 K_EF, 2 K_FF), FAM (0 Dot, 1 RBF, 2 RBF + dK/dl), KS, zeta == 2, CHUNKED, BS (B-run split), VK (skips zero k-steps).")
 print("`STL`/`LDL` = local-memory (spill) instructions; registers and spill bytes per instantiation: profiles/resource_usage_r02.txt.\n")
 print("| kernel | instr | " + " | ".join(KEYS) + " |")
 print("|---|---|" + "---|" * len(KEYS))
