@@ -237,7 +237,10 @@ __device__ __forceinline__ Weights pair_weights(double c, bool valid, const Tile
         // SLOWER here: K_EE RBF 18.3 -> 21.1 ms; the dependent L1 lookup is not hidden at 3 warps per scheduler.  Round 2
         // repeated it with a 16-entry 2^(i/16) table in SHARED memory + degree-5 polynomial, 11 FP64 instructions, 1.4e-13
         // accurate: K_EE 16.8 -> 18.2 ms, K_EF 73.7 -> 74.0, K_FF 119.0 -> 118.3 (tools/rbf_probe.py): the epilogue is bound
-        // by its dependent chain, not by FP64 issue slots, and libm's all-ALU polynomial pipelines better)
+        // by its dependent chain, not by FP64 issue slots, and libm's all-ALU polynomial pipelines better.  A third try made
+        // the exp BRANCH-FREE (libm's inlined range check ends the basic block between the two exps of a thread): same
+        // reduction and degree-11 polynomial with one clamp, 2e-16 accurate -- K_EE 16.9 -> 16.7 / 162.8 -> 168.0 ms,
+        // K_EF 73.8 -> 75.5, K_FF 116.1 -> 116.5: no gain either, dropped)
         const double K = p.sigma2 * exp(-(1.0 - cz) * p.inv2l2);
         const double dKdD = K * p.inv2l2;
         const double gl = (cz - 1.0) * p.inv_l3 + 2.0 * p.inv_l;  // (D-1)/l^3 + 2/l
