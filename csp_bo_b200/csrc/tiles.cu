@@ -60,7 +60,7 @@ struct TileParams {
     int a_begin;  // first A block of this launch (row-slab pipelining of host-bound builds); a_nblk is the end
     int emap[kMaxSpecies];  // species bucket of A -> bucket of B holding the same species id, or -1
     const int *emap_dev;    // the same map in device memory when A has more than kMaxSpecies buckets (else null)
-    int kc;                 // unchunked kernels: k-steps that hold features, ceil(d / 4); the rest of the KS multiply zeros (VK instantiations skip them)
+    int kc;                 // k-steps that hold features, ceil(d / 4) (chunked kernels: those of the last chunk); the rest of the KS multiply zeros (VK instantiations skip them)
     int nch, staged;        // chunked kernels (d > 56): k-chunks of 6 steps per tile; staged = B tiles go through shared memory
     int npass;              // stress variants: gridDim.y passes, pass q uses derivative vectors 1+3q .. 3+3q of the side
     int pass_side;          //   pass_side (0 = A: K_FF stress rows, 1 = B: K_EF stress columns) and stores at out + q*pass_off
@@ -434,7 +434,7 @@ block_tile_kernel(const TileParams p)
                         // padding: same bits either way).  Measured at 10 002 force rows (tools/ks14_probe.py): K_FF Dot d = 30 /
                         // 40 / 50: 63.0 -> 39.6 / 47.6 / 59.5 ms; with nothing to skip the predicates cost K_EE 18 % and RBF
                         // K_FF 5 %, hence a separate instantiation that launch_one picks only where it pays
-                        if (VARK && 2 * h >= p.kc) continue;
+                        if (VARK && (!CHUNKED || ch == nch - 1) && 2 * h >= p.kc) continue;
                         // one 128-bit LDS per B vector = operands of k-steps 2h and 2h+1; the 16 accumulators
                         // of a k-step are independent, so consecutive DMMAs never wait on each other
                         double2 b[NV2];
@@ -447,7 +447,7 @@ block_tile_kernel(const TileParams p)
                         for (int v2 = 0; v2 < NV2; v2++)
 #pragma unroll
                             for (int v1 = 0; v1 < NV1; v1++) dmma(H[v1][v2][0], H[v1][v2][1], a[v1][2 * h], b[v2].x);
-                        if (VARK && 2 * h + 1 >= p.kc) continue;
+                        if (VARK && (!CHUNKED || ch == nch - 1) && 2 * h + 1 >= p.kc) continue;
                         if (DUAL) {
                             dmma(G0, G1, a[0][2 * h + 1], b[0].y);
                         } else {
@@ -722,9 +722,10 @@ __global__ void plane_reduce_kernel(const double *__restrict__ planes, long long
 template <int MODE, int FAM, int KS, bool Z2, bool CHUNKED, bool BS = false, bool VK = false>
 static int launch_one(const TileParams &p, int nwarps, size_t smem, cudaStream_t st)
 {
-    if constexpr (!CHUNKED && !VK) {      // d = 9 / 12 / 18 need 3 / 3 / 5 of the 6 k-steps, d = 30 / 40 / 50 need 8 / 10 / 13 of the 14
-        // (one skippable step pays only for the Dot K_FF kernels: -14 % at d = 18, -6 % at d = 50; the others lose 1-2 % to the predicates)
-        if (p.kc <= KS - 2 || (p.kc == KS - 1 && MODE == MODE_KFF && FAM == FAM_DOT)) return launch_one<MODE, FAM, KS, Z2, CHUNKED, BS, true>(p, nwarps, smem, st);
+    if constexpr (!VK) {      // d = 9 / 12 / 18 need 3 / 3 / 5 of the 6 k-steps, d = 30 / 40 / 50 need 8 / 10 / 13 of the 14; chunked: the LAST chunk of d = 60 / 75 needs 3 / 1 of its 6
+        // (one skippable step pays only for the unchunked Dot K_FF kernels: -14 % at d = 18, -6 % at d = 50; the others lose 1-2 % to the
+        // predicates.  Chunked, 10 002 force rows: d = 60 / 75: 74.7 / 99.4 ms against 86.5 / 115.4 ms for the padded 72 / 96)
+        if (p.kc <= KS - 2 || (p.kc == KS - 1 && MODE == MODE_KFF && FAM == FAM_DOT && !CHUNKED)) return launch_one<MODE, FAM, KS, Z2, CHUNKED, BS, true>(p, nwarps, smem, st);
     }
     if (!BS && p.bsplit > 1) {      // build_block_device only asks for the split where these instantiations exist
         if (FAM != FAM_RBF_GRAD && !CHUNKED) return launch_one<MODE, (FAM == FAM_RBF_GRAD ? FAM_RBF : FAM), KS, Z2, false, true>(p, nwarps, smem, st);
@@ -923,7 +924,7 @@ int build_block_device(const cspbo_block_desc &d, const cspbo_pack *a, const csp
     // side) the B fragments are read straight from global memory
     const bool chunked = a->ks != 6 && a->ks != 14;
     p.nch = chunked ? a->ks / 6 : 1;
-    p.kc = std::min((a->d + 3) / 4, (int)a->ks);
+    p.kc = std::min((a->d + 3) / 4, (int)a->ks) - (chunked ? 6 * (p.nch - 1) : 0);      // chunked: k-steps of the last chunk
     p.staged = 1;
     if (chunked && tile_bytes > stage_bytes) {
         if (tile_bytes <= (size_t)96 * 1024) stage_bytes = tile_bytes;

@@ -62,7 +62,8 @@ def both(libs, family, name, args, out_shapes, init=0.0):
                                          (90, 2.0, 5), (140, 3.0, 6), (57, 2.5, 7), (450, 2.0, 8),
                                          # 24 < d <= 56: the KS = 14 kernels skip the k-steps beyond ceil(d / 4) (VK instantiations)
                                          (25, 2.0, 20), (30, 2.5, 21), (40, 2.0, 22), (48, 3.0, 23), (49, 2.0, 24), (53, 2.0, 25),
-                                         (3, 2.0, 29), (9, 2.0, 30), (12, 3.0, 31), (18, 2.0, 32), (20, 2.5, 33), (21, 2.0, 34)])
+                                         (3, 2.0, 29), (9, 2.0, 30), (12, 3.0, 31), (18, 2.0, 32), (20, 2.5, 33), (21, 2.0, 34),
+                                         (60, 2.0, 37), (75, 2.0, 38), (92, 3.0, 39), (97, 2.0, 40)])      # chunked: ragged last chunk
 def test_dot_entry_points(libs, d, zeta, seed):
     rng = np.random.default_rng(seed)
     x1, _, e1, g1, m1 = make_side(rng, 11, d, 0)
@@ -92,7 +93,7 @@ def test_dot_entry_points(libs, d, zeta, seed):
 
 @pytest.mark.parametrize("d,zeta,l,seed", [(24, 2.0, 0.56, 10), (24, 3.0, 0.9, 11), (50, 2.0, 0.5, 12), (7, 2.5, 1.3, 13),
                                            (90, 2.0, 0.7, 14), (140, 2.5, 0.9, 15), (450, 2.0, 0.6, 16),
-                                           (30, 2.0, 0.6, 26), (40, 2.5, 0.8, 27), (52, 2.0, 0.5, 28), (9, 2.0, 0.6, 35), (18, 2.0, 0.7, 36)])
+                                           (30, 2.0, 0.6, 26), (40, 2.5, 0.8, 27), (52, 2.0, 0.5, 28), (9, 2.0, 0.6, 35), (18, 2.0, 0.7, 36), (60, 2.0, 0.6, 41), (75, 2.5, 0.8, 42)])
 def test_rbf_entry_points(libs, d, zeta, l, seed):
     rng = np.random.default_rng(seed)
     x1, _, e1, g1, m1 = make_side(rng, 10, d, 0)
