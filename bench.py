@@ -624,6 +624,8 @@ def extra_legs(full, X, peak):
         out[name] = {"what": "log_marginal_likelihood(eval_gradient=True), N = %d, %s" % (N, kern.name), "ms": (time.perf_counter() - t0) * 1e3,
                      "peak_extra_memory_in_N2_doubles": (torch.cuda.max_memory_allocated() - base + gp.inverse_workspace_bytes(N)) / (8.0 * N * N),
                      "peak_memory_note": "torch allocator peak (the one N x N array) + the factor-inverse workspace of csrc/dense.cu (leaf results + chunk buffer, about N^2/16 + N*384 doubles)",
+                     "resident_cache_in_N2_doubles": 1.0 if getattr(model, "_lml_cache", None) is not None else 0.0,
+                     "resident_cache_note": "Dot_mb keeps K(sigma = 1, sigma0 = 0) across the evaluations of one hyper-optimisation (GaussianProcess._dot_scaled_K; CSPBO_LML_CACHE=0 turns it off: 285 ms per evaluation instead of 183)",
                      "lml": float(lml), "grad": [float(g) for g in grad]}
         del model
         torch.cuda.empty_cache()

@@ -68,6 +68,7 @@ class GaussianProcess():
         self.L_ = None            # CUDA tensor: cuSOLVER factor of K + noise (its lower triangle, column-major)
         self._alpha_dev = None
         self._packs = None        # the training set as resident packs, snapshot taken by fit()
+        self._lml_cache = None    # Dot_mb: (packs, zeta, K(sigma = 1, sigma0 = 0), P) of the hyper-optimisation (_dot_scaled_K)
         self._packs_pred = None   # the same for K* builds (small energy sets spread over the tile slots)
         self.N_energy = 0
         self.N_forces = 0
@@ -229,6 +230,7 @@ class GaussianProcess():
         hyper_bounds = self.kernel.bounds + [self.noise_bounds]
         if opt:
             params, _ = self.optimize(obj_func, hyper_params, hyper_bounds)
+            self._lml_cache = None            # the optimisation's cached unit-sigma K (Dot_mb) is not needed any longer
             self.kernel.update(params[:-1])
             self.noise_e = params[-1]
             self.noise_f = self.f_coef * params[-1]
@@ -264,11 +266,52 @@ class GaussianProcess():
                            options={'maxiter': 10, 'ftol': 1e-2})
         return opt_res.x, opt_res.fun
 
+    def _dot_scaled_K(self, kernel, data):
+        """Dot_mb only: the training covariance of k_total_with_grad is K(sigma, sigma0) = sigma^2 (K1 + sigma0^2 P) with
+        K1 = K(1, 0) and P_ij = (valid same-species row pairs of structures i, j) / (N_i N_j) on the energy block
+        (dot_kernel.cpp:45-47, dot_kernel.py:45,129-130,260): the descriptor-dependent part does not change while L-BFGS-B
+        moves (sigma, sigma0, noise), so it is built ONCE per training set and every further evaluation is a 1 ms
+        rescale instead of a 104 ms build (N = 20 001).  Costs one more resident N x N array; skipped (returns None)
+        when that does not fit comfortably or with CSPBO_LML_CACHE=0."""
+        import os
+        import torch
+        from .kernels import Dot_mb
+        if os.environ.get("CSPBO_LML_CACHE", "1") == "0":
+            return None
+        c = getattr(self, "_lml_cache", None)
+        if c is None or c[0] is not data or c[1] != float(kernel.zeta):
+            self._lml_cache = None
+            N = int(self.y_train.shape[0])
+            free, _ = torch.cuda.mem_get_info()
+            if free < 3 * 8 * N * N:
+                return None
+            unit = Dot_mb(para=[1.0, 0.0], zeta=kernel.zeta)
+            K1 = kdev.k_total_device(unit, data, grad_semantics=True)
+            P = None
+            if "energy" in data:
+                one = Dot_mb(para=[1.0, 1.0], zeta=kernel.zeta)
+                NE = self._n_energy()
+                P = kdev.k_total_device(one, {"energy": data["energy"]}, grad_semantics=True) - K1[:NE, :NE]
+            c = self._lml_cache = (data, float(kernel.zeta), K1, P)
+        s2 = float(kernel.sigma) ** 2
+        K = torch.mul(c[2], s2)
+        if c[3] is not None:
+            NE = c[3].shape[0]
+            K[:NE, :NE].add_(c[3], alpha=s2 * float(kernel.sigma0) ** 2)
+        return K
+
     def log_marginal_likelihood(self, params, eval_gradient=False, clone_kernel=False):
         """gaussianprocess.py:453-503, evaluated on the device."""
         import torch
         kernel = self.kernel
         kernel.update(params[:-1])
+        if self._packs is not None:
+            # the packs are fit()'s snapshot: points added since (set_train_pts without a refit) make them stale for the
+            # likelihood of the CURRENT training set, which is what the reference evaluates (gaussianprocess.py:456-464)
+            rows = (self._packs["energy"].m_real if "energy" in self._packs else 0) + \
+                   (3 * self._packs["force"].m if "force" in self._packs else 0)
+            if rows != int(self.y_train.shape[0]):
+                self._packs = None
         if self._packs is None:
             from .packing import resident
             self._packs = resident(self._train_dict())
@@ -277,7 +320,9 @@ class GaussianProcess():
             # one process per GPU: K distributed, sharded Cholesky, gradient traces per owned panel (distributed.lml_sharded)
             from .distributed import lml_sharded
             return lml_sharded(kernel, data, self.y_train[:, 0], params[-1], self.f_coef, eval_gradient=eval_gradient)
-        K = kdev.k_total_device(kernel, data, grad_semantics=eval_gradient)       # the ONE N x N array of the evaluation
+        K = self._dot_scaled_K(kernel, data) if (eval_gradient and kernel.name == 'Dot_mb') else None
+        if K is None:
+            K = kdev.k_total_device(kernel, data, grad_semantics=eval_gradient)   # the ONE N x N array of the evaluation
         N, NE = K.shape[0], self._n_energy()
         y = torch.from_numpy(np.ascontiguousarray(self.y_train[:, 0])).cuda()
         try:

@@ -349,3 +349,38 @@ def test_recursive_factor_inverse_matches_direct_inverse(N, nb, monkeypatch):
     monkeypatch.setenv("CSPBO_DENSE", "0")                # the cuSOLVER path
     assert float((gp.inverse_diag(factor()) - dinv).abs().max()) / scale < 1e-12
     assert float((torch.triu(gp.cholesky_inverse_inplace(factor())) - torch.triu(Kinv)).abs().max()) / scale < 1e-12
+
+
+@pytest.mark.parametrize("zeta,subset", [(2.0, "both"), (3.0, "both"), (2.0, "force"), (2.0, "energy")])
+def test_dot_lml_cache_gives_the_same_numbers(problem, zeta, subset, monkeypatch):
+    """GaussianProcess._dot_scaled_K: K(sigma, sigma0) = sigma^2 (K(1, 0) + sigma0^2 P) cached across the L-BFGS-B
+    evaluations of a Dot_mb fit -- same LML and gradient as building K afresh, for changing (sigma, sigma0, noise),
+    and a new training set drops the cache."""
+    from csp_bo_b200.gaussianprocess import GaussianProcess
+    from csp_bo_b200.kernels import Dot_mb
+    train_x, y, _ = problem
+    data = train_lists(train_x, y)
+    if subset != "both":
+        data = {subset: data[subset]}
+
+    def model_for(d):
+        m = GaussianProcess(Dot_mb(para=[18.5, 0.05], bounds=KERNELS[0][2], zeta=zeta), f_coef=20, noise_e=[0.01, 0.002, 0.1])
+        m.set_train_pts(d)
+        return m
+    cached, fresh = model_for(data), model_for(data)
+    for params in ([18.5, 0.05, 0.01], [7.25, 0.8, 0.02], [33.0, 0.011, 0.004]):
+        monkeypatch.setenv("CSPBO_LML_CACHE", "1")
+        l1, g1 = cached.log_marginal_likelihood(np.array(params), eval_gradient=True)
+        assert cached._lml_cache is not None
+        monkeypatch.setenv("CSPBO_LML_CACHE", "0")
+        l0, g0 = fresh.log_marginal_likelihood(np.array(params), eval_gradient=True)
+        assert abs(l1 - l0) <= 1e-10 * abs(l0)
+        assert np.allclose(g1, g0, rtol=1e-8, atol=1e-8 * np.abs(g0).max())
+    monkeypatch.setenv("CSPBO_LML_CACHE", "1")
+    key = cached._lml_cache[0]
+    cached.set_train_pts(data, mode="a+")       # more points, no refit: the likelihood is that of the CURRENT training set
+    l2, _ = cached.log_marginal_likelihood(np.array([18.5, 0.05, 0.01]), eval_gradient=True)
+    assert cached._lml_cache[0] is not key
+    twice = {k: v + v for k, v in data.items()}
+    ref2, _ = model_for(twice).log_marginal_likelihood(np.array([18.5, 0.05, 0.01]), eval_gradient=True)
+    assert abs(l2 - ref2) <= 1e-9 * abs(ref2)
