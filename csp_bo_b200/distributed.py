@@ -900,16 +900,57 @@ class ShardedCovariance:
     def _local_rows(self, g0, g1):
         return panel_local_rows(self.mine, self.nbw, g0, g1)
 
-    def build(self, noise_e, f_coef, tol=1e-10):
-        """Build K + noise into the distributed rows (gaussianprocess.py:105-113)."""
-        torch, h, nbw = self.torch, self.h, self.nbw
+    def build(self, noise_e, f_coef, tol=1e-10, cache=None):
+        """Build K + noise into the distributed rows (gaussianprocess.py:105-113).
+
+        cache (a dict the caller keeps across calls on ONE training set; Dot_mb only): the covariance of a Dot kernel is
+        K(sigma, sigma0) = sigma^2 (K(1, 0) + sigma0^2 P), P on the energy block only, so this rank's rows of K(1, 0) and
+        of P are built once and every later call is a local rescale -- no tile kernels, no peer stores (the sharded twin
+        of GaussianProcess._dot_scaled_K; costs N^2 / world more doubles per rank while the cache lives)."""
+        torch = self.torch
+        if cache is not None and self.h["family"] == _lib.DOT:
+            sig = (self.N, self.mE, self.rows, float(self.h["zee"]), float(self.h["zff"]), self.grad_semantics)
+            if cache.get("sig") != sig:
+                real = self.h
+                self.h = dict(real, sigma2=1.0, sigma02=0.0, see=1.0, sef=-1.0, sff=float(real["zff"]))
+                self._build_raw(tol)
+                K1, P, le = self.local.clone(), None, None
+                if self.pe:
+                    self.h = dict(self.h, sigma02=1.0)
+                    self._build_raw(tol, energy_only=True)
+                    le, _ = self._local_rows(0, self.mE)
+                    le = torch.as_tensor(le, dtype=torch.long, device=K1.device)
+                    P = self.local[le][:, : self.mE] - K1[le][:, : self.mE]
+                self.h = real
+                cache.clear()
+                cache.update(sig=sig, K1=K1, P=P, le=le)
+            s2 = float(self.h["see"])                                   # sigma^2
+            torch.mul(cache["K1"], s2, out=self.local)
+            if cache["P"] is not None and len(cache["le"]):
+                rows = self.local[cache["le"]]
+                rows[:, : self.mE] += (s2 * float(self.h["sigma02"])) * cache["P"]
+                self.local[cache["le"]] = rows
+        else:
+            self._build_raw(tol)
+        # noise on the diagonal, identity on the padding rows
+        dev = self.local.device
+        for rng, val in (((0, self.mE), float(noise_e) ** 2), ((self.mE, self.NE_pad), 1.0),
+                         ((self.NE_pad, self.N), (float(f_coef) * float(noise_e)) ** 2)):
+            lr, gr = self._local_rows(*rng)
+            if len(lr):
+                self.local[torch.as_tensor(lr, device=dev), torch.as_tensor(gr, device=dev)] += val
+        return self.local
+
+    def _build_raw(self, tol=1e-10, energy_only=False):
+        """The blocks of K (no noise) into the distributed rows, 1/N_i normalisations of the energy rows / columns applied."""
+        torch, h = self.torch, self.h
         self.local.zero_()
         self._barrier()                    # every buffer is zeroed before peers store mirrored tiles into it
         if self.pe:
             self._panel(_lib.KEE, h["zee"], h["see"], self.pe, self.pe, 0, 0)
-        if self.pe and self.pf:
+        if self.pe and self.pf and not energy_only:
             self._panel(_lib.KEF, h["zef"], h["sef"], self.pe, self.pf, 0, self.NE_pad)
-        if self.pf:
+        if self.pf and not energy_only:
             self._panel(_lib.KFF, h["zff"], h["sff"], self.pf, self.pf, self.NE_pad, self.NE_pad, tol=tol,
                         use_tol=(h["family"] == _lib.RBF and not self.grad_semantics))
         self._barrier()                    # peer stores have landed
@@ -927,13 +968,6 @@ class ShardedCovariance:
             if len(lf):
                 lt = torch.as_tensor(lf, device=dev)
                 self.local[lt, : self.mE] = self.local[lt, : self.mE] / ce[None, :]
-        # noise on the diagonal, identity on the padding rows
-        for rng, val in (((0, self.mE), float(noise_e) ** 2), ((self.mE, self.NE_pad), 1.0),
-                         ((self.NE_pad, self.N), (float(f_coef) * float(noise_e)) ** 2)):
-            lr, gr = self._local_rows(*rng)
-            if len(lr):
-                self.local[torch.as_tensor(lr, device=dev), torch.as_tensor(gr, device=dev)] += val
-        return self.local
 
     def permutation(self):
         return panel_permutation(self.order_e, self.order_f, self.NE_pad)
@@ -1074,7 +1108,7 @@ class _BlockedSubstitution:
         return Y
 
 
-def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=None, nbw=384):
+def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=None, nbw=384, cache=None):
     """log marginal likelihood (and its gradient w.r.t. the kernel parameters and the noise) of
     gaussianprocess.py:453-503 with K distributed over the ranks: panel-layout build, sharded Cholesky, and the
     gradient as fused traces --
@@ -1089,13 +1123,15 @@ def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=Non
         the tile-kernel epilogue (cspbo_block_trace_slab), partial traces summed by an all-reduce.
 
     Neither K_gradient [N,N,3] nor Ky^-1 exists anywhere: per rank one slab's rows of Ky^-1 (<= 2304 x N) at a time.
+    cache: a dict kept by the caller across the evaluations of one hyper-optimisation on one training set (Dot_mb only,
+    ShardedCovariance.build): the tile kernels then run for the first evaluation only.
     y in the caller's [E; F] order.  Returns MLL or (MLL, grad) -- identical numbers on every rank."""
     import torch
     import torch.distributed as dist
     from .kernels import device as kdev
     cov = ShardedCovariance(kernel, data, group=group, nbw=nbw, grad_semantics=eval_gradient)
     npar = len(kernel.parameters()) + 1
-    cov.build(noise_e, f_coef)
+    cov.build(noise_e, f_coef, cache=cache if eval_gradient else None)
     chol = ShardedCholesky(cov.local, cov.N, nbw, cov.rank, cov.world, True, group)
     chol.factor()
     try:

@@ -14,6 +14,7 @@ Device residency: K is assembled block by block straight into one CUDA matrix
 device.  Only alpha-sized vectors and predictions cross PCIe.
 """
 import json
+import os
 import warnings
 
 import numpy as np
@@ -319,7 +320,14 @@ class GaussianProcess():
         if _world_size() > 1:
             # one process per GPU: K distributed, sharded Cholesky, gradient traces per owned panel (distributed.lml_sharded)
             from .distributed import lml_sharded
-            return lml_sharded(kernel, data, self.y_train[:, 0], params[-1], self.f_coef, eval_gradient=eval_gradient)
+            cache = None
+            if kernel.name == 'Dot_mb' and os.environ.get("CSPBO_LML_CACHE", "1") != "0":
+                # the sharded twin of _dot_scaled_K: every rank keeps its rows of K(1, 0) while L-BFGS-B runs
+                c = self._lml_cache
+                if not (isinstance(c, tuple) and c[0] is data and isinstance(c[1], dict)):
+                    c = self._lml_cache = (data, {})
+                cache = c[1]
+            return lml_sharded(kernel, data, self.y_train[:, 0], params[-1], self.f_coef, eval_gradient=eval_gradient, cache=cache)
         K = self._dot_scaled_K(kernel, data) if (eval_gradient and kernel.name == 'Dot_mb') else None
         if K is None:
             K = kdev.k_total_device(kernel, data, grad_semantics=eval_gradient)   # the ONE N x N array of the evaluation

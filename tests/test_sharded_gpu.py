@@ -249,6 +249,16 @@ def test_lml_sharded_world1_matches_dense(fam, n_struct, n_atoms, nbw):
     assert abs(lml - lml_s) <= 1e-9 * abs(lml)
     assert max_norm_err(grad_s, grad) < 1e-7, (grad_s, grad)
     assert abs(lml_sharded(kernel, data, y, 0.01, 20.0, nbw=nbw) - model.log_marginal_likelihood(params)) <= 1e-9 * abs(lml)
+    if fam == "dot":
+        # Dot_mb: the rows of K(sigma = 1, sigma0 = 0) cached across evaluations (ShardedCovariance.build): same numbers
+        # while (sigma, sigma0, noise) move
+        cache = {}
+        for sig, sig0, ne in ((18.5, 0.05, 0.01), (7.0, 0.7, 0.02), (31.0, 0.02, 0.005)):
+            kernel.update([sig, sig0])
+            a = lml_sharded(kernel, data, y, ne, 20.0, eval_gradient=True, nbw=nbw, cache=cache)
+            b = lml_sharded(kernel, data, y, ne, 20.0, eval_gradient=True, nbw=nbw)
+            assert "K1" in cache
+            assert abs(a[0] - b[0]) <= 1e-11 * abs(b[0]) and max_norm_err(a[1], b[1]) < 1e-9
 
 
 def _cov_rank_main(rank, world, port, out):
@@ -303,6 +313,16 @@ def _cov_rank_main(rank, world, port, out):
         finally:
             gpm._world_size = ws
         err5 = max(abs(lml_s - lml_d) / abs(lml_d), float(np.abs(grad_s - grad_d).max() / np.abs(grad_d).max()) * 1e-1)
+        # Dot_mb under world 2: the regressor keeps every rank's rows of K(1, 0) across evaluations (second call: cached)
+        from csp_bo_b200.kernels import Dot_mb
+        dk = Dot_mb(para=[18.5, 0.05], zeta=2)
+        md = GaussianProcess(dk, f_coef=20.0, noise_e=[0.01, 0.002, 0.1])
+        md.set_train_pts({"energy": E, "force": F})
+        md.log_marginal_likelihood(np.array([18.5, 0.05, 0.01]), eval_gradient=True)
+        l_c, g_c = md.log_marginal_likelihood(np.array([9.0, 0.4, 0.02]), eval_gradient=True)
+        assert isinstance(md._lml_cache[1], dict) and "K1" in md._lml_cache[1]
+        l_f, g_f = lml_sharded(dk, md._packs, md.y_train[:, 0], 0.02, 20.0, eval_gradient=True)
+        err5 = max(err5, abs(l_c - l_f) / abs(l_f) * 1e2, float(np.abs(g_c - g_f).max() / np.abs(g_f).max()))     # rounding of the rescale x conditioning
         out[rank] = max(err, err2, err3 * 1e-2, err4 * 1e2, err5)
     finally:
         dist.destroy_process_group()
