@@ -1058,10 +1058,29 @@ class _BlockedSubstitution:
     Blocks sit on a global grid (multiples of nbk) so that all slabs of a rank share the inverses; a slab that starts
     inside a block gets a ragged first block of its own."""
 
-    def __init__(self, U, Ntot, nbk=None):
+    def __init__(self, U, Ntot, nbk=None, group=None, world=1, rank=0):
         self.U, self.N = U, Ntot
         self.nbk = nbk or int(os.environ.get("CSPBO_SUB_BLOCK", "1024"))
         self._inv = {}
+        if world > 1:
+            self._share_grid_inverses(group, world, rank)
+
+    def _share_grid_inverses(self, group, world, rank):
+        """world > 1: the rank whose columns start at 0 needs the inverse of EVERY grid block (20 at N = 20 001: two thirds
+        of its share of the substitution work at world = 8), the last rank only a few.  The factor is replicated, so the
+        grid blocks are inverted round-robin and summed into place by one all-reduce of a zero-initialised buffer
+        (N x nbk doubles; gloo, the one-GPU test mode, has all-reduce for CUDA tensors but no all-gather)."""
+        import torch
+        import torch.distributed as dist
+        nb = (self.N + self.nbk - 1) // self.nbk
+        buf = torch.zeros((nb, self.nbk, self.nbk), dtype=self.U.dtype, device=self.U.device)
+        for b in range(rank, nb, world):
+            a, e = b * self.nbk, min((b + 1) * self.nbk, self.N)
+            buf[b, : e - a, : e - a] = self._invert(a, e)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        for b in range(nb):
+            a, e = b * self.nbk, min((b + 1) * self.nbk, self.N)
+            self._inv[(a, e)] = buf[b, : e - a, : e - a]
 
     def _blocks(self, j0):
         out, a = [], j0
@@ -1071,13 +1090,16 @@ class _BlockedSubstitution:
             a = b
         return out
 
-    def _inverse(self, a, b):
+    def _invert(self, a, b):
+        import torch
         from . import gp
+        blk = self.U[a:b, a:b].clone(memory_format=torch.contiguous_format)            # a copy even when the slice IS the factor
+        return gp.tri_inverse_inplace(blk)                                            # U_kk^-1 (upper)
+
+    def _inverse(self, a, b):
         key = (a, b)
         if key not in self._inv:
-            import torch
-            blk = self.U[a:b, a:b].clone(memory_format=torch.contiguous_format)        # a copy even when the slice IS the factor
-            self._inv[key] = gp.tri_inverse_inplace(blk)                              # U_kk^-1 (upper)
+            self._inv[key] = self._invert(a, b)
         return self._inv[key]
 
     def forward(self, j0, hj):
@@ -1180,7 +1202,7 @@ def lml_sharded(kernel, data, y, noise_e, f_coef, eval_gradient=False, group=Non
             _lib.check(lib.cspbo_block_trace_slab(ctypes.byref(desc), a.handle, bp.handle, c_vp(aps.data_ptr()), c_vp(wptr),
                                                   int(ldw), int(row0), int(col0), int(slab0), int(blk0), int(blk1),
                                                   c_vp(tr.data_ptr()), 1))
-    sub = _BlockedSubstitution(U, Ntot)
+    sub = _BlockedSubstitution(U, Ntot, group=group, world=W, rank=me)
     for j0, j1 in _inverse_slabs(Ntot, cov.NE_pad, me, W, rbf, nbw):
         hj = j1 - j0
         # Ky = U^T U: Y = (U^T)^-1 E_J has zeros above row j0, so only the trailing triangle is solved
