@@ -375,3 +375,16 @@ def test_b_run_split_matches_the_unsplit_build(single, monkeypatch):
             assert float((ref - got).abs().max()) <= 1e-13 * float(ref.abs().max())
         assert torch.equal(K5, K5b) and torch.equal(Ks5, Ks5b)
     assert launches["5"] > launches["1"]                           # the forced split really ran (one reduce launch per block)
+    # reference `pout +=` semantics through the split: accumulate = 1 adds the summed planes onto what `out` held
+    import ctypes
+    from csp_bo_b200._lib import BlockDesc, c_vp
+    pe = d1["energy"]
+    desc = BlockDesc(_lib.DOT, _lib.KEE, 2.0, 1.0, 0.01, 1.0, 0.0, 0, 0, 0, 342.25, 1.0, 1)
+    outs = {}
+    for mode in ("1", "5"):
+        monkeypatch.setenv("CSPBO_BSPLIT", mode)
+        out = torch.full((pe.m, pe.m), 0.75, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.load().cspbo_block_build(ctypes.byref(desc), pe.handle, pe.handle, c_vp(out.data_ptr()), None, 1, 1))
+        outs[mode] = out
+    assert float((outs["1"] - outs["5"]).abs().max()) <= 1e-13 * float(outs["1"].abs().max())
+    assert float(outs["5"].min()) > 0.75
