@@ -478,10 +478,10 @@ def run_ours(args):
     achieved = algo_pairs * FLOP_PER_PAIR / (kern_ms * 1e-3) / 1e12
     # DRAM bytes per launch are an ncu figure (profiles/kff_traffic_r02.md, same kernel and workload), not measured in
     # this run: caller-order output (N = 1) 16.25 GB, packed-column output (N > 1, the whole matrix) 3.60 GB
-    traffic = 16.25e9 if world == 1 else 3.60e9 / world
+    traffic = 16.48e9 if world == 1 else 3.60e9 / world
     tensor_flops = algo_pairs * 32 * 24          # the 16 length-d dot products only: what the DMMA pipe executes
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/kff_traffic_r02.md (not measured in this run)",
+                "traffic": traffic, "traffic_source": "ncu dram__bytes_read+write per launch: profiles/kff_r02_final_ncu.csv (N = 1, caller-order output: 24-byte pieces, inherent to the layout kff_C must return), profiles/kff_traffic_r02.md (N > 1, packed columns); not measured in this run",
                 "algorithmic_bytes_per_step": (8.0 * 9 * m * m + 113e6) / world,
                 "peak_source": "builder-measured DMMA peak: " + peak_src,
                 "algorithmic_flops_per_step": algo_pairs * FLOP_PER_PAIR,
