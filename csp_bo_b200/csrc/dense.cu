@@ -10,8 +10,8 @@
 //
 // The nb x nb diagonal leaves are inverted / squared up front in ONE batched launch each (they only depend on the
 // leaf itself); everything else is a large triangular-times-general product (cuBLAS trmm), a syrk or a dgemm.  The
-// triangular products are out of place (cuBLAS documents the out-of-place trmm as its parallel form; the in-place one was
-// not measured), chunked through a workspace of a few per cent of N^2, and copied back.  Measured at N = 20 001 (tools/dense_probe.py): L^-1 83.5 ms (32 TFLOP/s, cuSOLVER trtri
+// triangular products are out of place (cuBLAS' trmm with C = B, the BLAS in-place form, was measured 36 % slower: 115 /
+// 213 ms), chunked through a workspace of a few per cent of N^2, and copied back.  Measured at N = 20 001 (tools/dense_probe.py): L^-1 83.5 ms (32 TFLOP/s, cuSOLVER trtri
 // 356 ms), K^-1 165 ms (cuSOLVER potri 454 ms).  Splitting the trmm / syrk calls further into dgemms by hand (down to
 // 2048 rows) was measured 6 % SLOWER than handing cuBLAS the whole triangle; workspace 96 / 192 / 384 / 800 MB: 84.9 /
 // 83.5 / 82.6 / 82.4 ms.

@@ -37,5 +37,5 @@ if len(sys.argv) > 1:
 else:
     N = "20001"
     for env, extra in (({"CSPBO_DENSE": "0"}, ["gemm"]), ({}, []), ({"CSPBO_DENSE_WS_MB": "96"}, []),
-                       ({"CSPBO_DENSE_WS_MB": "384"}, []), ({"CSPBO_DENSE_WS_MB": "800"}, []), ({"CSPBO_DENSE_NB": "256"}, [])):
+                       ({"CSPBO_DENSE_WS_MB": "800"}, []), ({"CSPBO_DENSE_NB": "256"}, [])):
         subprocess.run([sys.executable, __file__, N] + extra, env=dict(os.environ, **env))
