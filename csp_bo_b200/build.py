@@ -39,7 +39,7 @@ def _run(cmd):
 
 def build(force=False, verbose_ptxas=False):
     os.makedirs(LIB, exist_ok=True)
-    objs = []
+    objs, cmds = [], []
     for s in CU_SOURCES:
         src = os.path.join(SRC, s)
         obj = os.path.join(LIB, s.replace(".cu", ".o"))
@@ -54,7 +54,13 @@ def build(force=False, verbose_ptxas=False):
                 cmd += ["-D" + d for d in os.environ["CSPBO_DEFS"].split(",")]
             if verbose_ptxas:
                 cmd += ["-Xptxas", "-v"]
-            _run(cmd)
+            cmds.append(cmd)
+    if cmds:
+        # the translation units are independent: compile them side by side (tiles.cu, 156 kernel instantiations, takes a
+        # minute on its own; the others finish in its shadow)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 1)) as pool:
+            list(pool.map(_run, cmds))
     main = os.path.join(LIB, "libcspbo_b200.so")
     if force or _stale(main, objs):
         _run([NVCC] + ARCH + ["-shared", "-o", main] + objs +
